@@ -1,0 +1,201 @@
+/*
+ * prosper_b200.h -- C ABI of the B200-native truncated-EM (Expectation Truncation) engine.
+ *
+ * This is the drop-in boundary for ONE hot path of ml-uol/prosper: the per-iteration
+ *     select_Hprimes -> E_step -> M_step
+ * of the sparse-coding models in prosper/em/camodels/*_et.py.  The reference has no
+ * native boundary (it is pure Python/NumPy behind the CAModel operator API), so the entry
+ * points below are what a ctypes binding of that operator API needs; each one cites the
+ * reference interface it replaces.  The reference-side stub is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain C, no C++/torch types; every function returns 0 on success or a negative
+ *     PET_E* code, with the text available from pet_last_error() (thread-local).
+ *   - all floating point is IEEE float64, all matrices row-major; `ld*` are leading
+ *     dimensions in ELEMENTS.
+ *   - pointers named *_dev must be device pointers on the engine's device, pointers
+ *     named *_host must be host pointers (pinned memory makes the copies asynchronous);
+ *     pointers with neither suffix may be either (resolved with cudaPointerGetAttributes).
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  Calls
+ *     enqueue work on it and return without synchronising unless they return host
+ *     scalars/arrays (stated per function).
+ *   - no CPU fallback exists: pet_create fails if no sm_100 device is present.
+ */
+#ifndef PROSPER_B200_H
+#define PROSPER_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PET_ABI_VERSION 1
+
+/* error codes */
+#define PET_OK          0
+#define PET_EINVAL     -1   /* bad argument / unsupported configuration           */
+#define PET_ECUDA      -2   /* CUDA runtime error (see pet_last_error)             */
+#define PET_ENOMEM     -3   /* device allocation failed                            */
+#define PET_ESTATE     -4   /* call order violated (e.g. E-step before set_data)   */
+#define PET_ENUMERIC   -5   /* non-finite value where the reference asserts finite */
+
+/* model kinds: the concrete CAModel subclasses (prosper/em/camodels/*_et.py) */
+#define PET_MODEL_BSC   0   /* bsc_et.py  BSC_ET  */
+#define PET_MODEL_MCA   1   /* mca_et.py  MCA_ET  */
+#define PET_MODEL_MMCA  2   /* mmca_et.py MMCA_ET */
+#define PET_MODEL_TSC   3   /* tsc_et.py  TSC_ET  */
+#define PET_MODEL_DSC   4   /* dsc_et.py  DSC_ET  */
+#define PET_MODEL_GSC   5   /* gsc_et.py  GSC     */
+
+typedef struct pet_engine pet_engine;
+
+/* Constructor arguments of CAModel.__init__(D, H, Hprime, gamma, ...)
+ * (camodels/__init__.py:60-102); `states` is DSC_ET's `states=` (dsc_et.py:135) and is
+ * fixed to {-1,0,1} for TSC (tsc_et.py:125). */
+typedef struct pet_config {
+    int32_t model;          /* PET_MODEL_*                                         */
+    int32_t device;         /* CUDA device ordinal                                  */
+    int64_t D, H, Hprime, gamma;
+    int32_t n_states;       /* K: number of latent values (TSC/DSC), else 0         */
+    const double *states;   /* K values, exactly one of them 0 (host pointer)       */
+    int64_t chunk_rows;     /* datapoints per pipeline chunk; 0 = choose            */
+} pet_config;
+
+/* model_params dict of the reference: W is (D,H) row-major exactly like the NumPy array
+ * (bsc_et.py:142 transposes internally, so do we); pi is a scalar (BSC/MCA/MMCA/TSC) or a
+ * K-vector (DSC, dsc_et.py:503); mu is BSC's optional offset (bsc_et.py:145-149). */
+typedef struct pet_params {
+    const double *W;        /* (D,H), host or device                                */
+    int64_t ldW;            /* >= H                                                 */
+    const double *pi_host;  /* n_pi values                                          */
+    int32_t n_pi;
+    double sigma;
+    const double *mu;       /* (D,) or NULL (= zeros), host or device               */
+} pet_params;
+
+/* The annealing values the hot path reads through anneal['...'] (bsc_et.py:152,187,247). */
+typedef struct pet_anneal {
+    double T;               /* anneal['T']                                          */
+    double Ncut_factor;     /* anneal['Ncut_factor']                                */
+    int32_t anneal_prior;   /* anneal['anneal_prior'] != 0                          */
+} pet_anneal;
+
+/* Everything M_step reduces over datapoints, laid out as ONE contiguous float64 buffer so
+ * that the reference's 7-9 MPI collectives per iteration (bsc_et.py:225,258,266,373-374,
+ * 387,417) become one all-reduce.  Offsets/sizes are returned by pet_stats_layout. */
+typedef struct pet_stats_layout {
+    int64_t total;          /* number of doubles                                    */
+    int64_t off_Wp, rows_Wp, cols_Wp, ld_Wp;   /* numerator, stored (D+1, H): row D = sum_n <s> */
+    int64_t off_Wq, rows_Wq, cols_Wq, ld_Wq;   /* (H,H) for BSC/TSC/DSC, (D,H) for MCA/MMCA   */
+    int64_t off_scalars;    /* [0]=n_used [1]=sum_n log sum_c exp(logpj) [2]=sigma stat
+                               [3..3+n_counts) = per-value activity counts                  */
+    int64_t n_scalars;
+} pet_stats_layout;
+
+/* ---- lifecycle ------------------------------------------------------------------- */
+int  pet_abi_version(void);
+const char *pet_last_error(void);
+int  pet_create(const pet_config *cfg, pet_engine **out);
+void pet_destroy(pet_engine *e);
+
+/* ---- state space (camodels/__init__.py:21-47, tsc_et.py:23-80, dsc_et.py:56-63) ---- */
+int64_t pet_num_states(const pet_engine *e);    /* rows of state_matrix                    */
+int64_t pet_num_columns(const pet_engine *e);   /* columns of logpj                        */
+/* state_matrix as float64 (S,Hprime) into host memory, reference row order */
+int  pet_state_matrix(const pet_engine *e, double *out_host);
+
+/* ---- data ------------------------------------------------------------------------ */
+/* Bind my_data['y'] (n,D).  The engine keeps its own padded device copy (ld rounded up,
+ * one extra all-ones column used by the statistics GEMM).  With a host pointer the copy is
+ * issued chunk-wise on an internal copy stream and overlaps the compute of earlier chunks;
+ * nothing blocks the caller. */
+int  pet_set_data(pet_engine *e, const double *y, int64_t n, int64_t ld, void *stream);
+int64_t pet_num_data(const pet_engine *e);
+
+/* ---- the three operators --------------------------------------------------------- */
+/* select_Hprimes(model_params, data) -> data['candidates']  (bsc_et.py:98-115,
+ * mca_et.py:88-111, mmca_et.py:95-124, tsc_et.py:142-212, dsc_et.py:347-410).
+ * cand_out (n,Hprime) int64, host or device, may be NULL (kept internally). */
+int  pet_select_hprimes(pet_engine *e, const pet_params *p, int64_t *cand_out, void *stream);
+
+/* Override the internally kept candidates (my_data['candidates'] supplied by the caller). */
+int  pet_set_candidates(pet_engine *e, const int64_t *cand, void *stream);
+
+/* E_step(anneal, model_params, my_data) -> {'logpj': (n,C)}  (bsc_et.py:119-192, ...).
+ * logpj_out (n,C) host or device. */
+int  pet_e_step(pet_engine *e, const pet_anneal *a, const pet_params *p,
+                double *logpj_out, int64_t ld_logpj, void *stream);
+
+/* First half of M_step: per-datapoint log-denominators log sum_c exp(logpj) used by the
+ * truncation rule (bsc_et.py:222,247-258) and by L (bsc_et.py:265).  `logpj` NULL = evaluate
+ * the E-step on the fly (fused path, nothing of size n*C is materialised).
+ * logdenom_out_dev (n,) device, may be NULL (kept internally). */
+int  pet_log_denominators(pet_engine *e, const pet_anneal *a, const pet_params *p,
+                          const double *logpj, int64_t ld_logpj, int32_t flags,
+                          double *logdenom_out_dev, void *stream);
+/* engine-owned (n,) device array the call above fills (valid until the next pet_set_data) */
+const double *pet_log_denominators_ptr(const pet_engine *e);
+
+/* `flags` of pet_log_denominators / pet_m_step_stats */
+#define PET_PASS_SELECT        1  /* (re)run select_Hprimes inside this pass (fused step)      */
+#define PET_PASS_REUSE_SCORES  2  /* same params as the previous pass: reuse its score matrix  */
+
+/* k-th largest of n device doubles (replaces parallel.allsort(...)[-k], parallel.py:87-110).
+ * Result written to *out_dev (device). */
+int  pet_kth_largest(pet_engine *e, const double *vals_dev, int64_t n, int64_t k,
+                     double *out_dev, void *stream);
+
+/* Second half of M_step, local part: accumulate the packed sufficient statistics of this
+ * rank's datapoints (bsc_et.py:334-366,395-415 and the model-specific equivalents).
+ * use_cut != 0 keeps only datapoints whose log-denominator is >= *cut_dev (strict > for DSC,
+ * dsc_et.py:832); requires pet_log_denominators to have run when the data is not re-evaluated.
+ * `logpj` NULL = fused path.  stats_dev: pet_stats_layout.total doubles, overwritten. */
+int  pet_m_step_stats(pet_engine *e, const pet_anneal *a, const pet_params *p,
+                      const double *logpj, int64_t ld_logpj, int32_t flags,
+                      int32_t use_cut, const double *cut_dev,
+                      double *stats_dev, void *stream);
+int  pet_stats_layout_get(const pet_engine *e, pet_stats_layout *out);
+
+/* Second half of M_step, replicated part: from the (all-reduced) statistics produce the
+ * new W (D,H) on the device (lstsq / pinv / element-wise update: bsc_et.py:377-380,
+ * tsc_et.py:493, dsc_et.py:732-735, mca_et.py:343-348, mmca_et.py:383-394).  The scalar
+ * updates (pi, sigma, L) are O(1) host arithmetic on stats[off_scalars..] and are done by
+ * the caller exactly as the reference writes them.  W_new_dev (D,H) ld=H, device.
+ * info_host[0] = number of pivots treated as zero (rank deficiency). Synchronises. */
+int  pet_m_step_solve(pet_engine *e, const pet_params *p, const double *stats_dev,
+                      double *W_new_dev, int32_t *info_host, void *stream);
+
+/* ---- building blocks exported for tests / benchmarks ------------------------------ */
+/* C(M,N) = A.B with both operands K-contiguous: A(M,K) lda, B(N,K) ldb (FP64 tensor-core
+ * tiles).  Device pointers, 16-byte aligned, even lda/ldb. */
+int  pet_dgemm_kk(int64_t M, int64_t N, int64_t K, const double *A_dev, int64_t lda,
+                  const double *B_dev, int64_t ldb, double *C_dev, int64_t ldc,
+                  double alpha, double beta, void *stream);
+/* C(M,N) = A^T.B with A(K,M) lda, B(K,N) ldb (reduction over rows, split-K inside;
+ * workspace_dev holds splits*M*ldc doubles, query with C_dev == NULL -> returns splits). */
+int  pet_dgemm_mn(int64_t M, int64_t N, int64_t K, const double *A_dev, int64_t lda,
+                  const double *B_dev, int64_t ldb, double *C_dev, int64_t ldc,
+                  int32_t accumulate, double *workspace_dev, int64_t workspace_doubles,
+                  void *stream);
+/* Solve X.A = B for X with A (n,n) symmetric positive semi-definite (pivots below
+ * tol are dropped, giving the minimum-norm behaviour of lstsq for dead units).
+ * A is overwritten by its Cholesky factor; B (m,n) overwritten by X. Synchronises. */
+int  pet_spd_solve_right(int64_t n, int64_t m, double *A_dev, int64_t lda,
+                         double *B_dev, int64_t ldb, double *work_dev,
+                         int32_t *info_host, void *stream);
+int64_t pet_spd_solve_work_doubles(int64_t n, int64_t lda);   /* size of work_dev */
+
+/* Device time per stage since pet_enable_timing(e,1), measured with CUDA events on the
+ * caller's stream around every launch group: out[0..5] = total ms of [0]=prepare
+ * (transpose+Gram) [1]=score GEMM [2]=posterior kernel [3]=statistics GEMM [4]=solve
+ * [5]=kth-largest; out[6..11] = how many spans each total sums.  Synchronises. */
+int  pet_stage_times_ms(pet_engine *e, double *out_host12);
+int  pet_enable_timing(pet_engine *e, int32_t on);
+/* number of kernels launched by the engine since creation (bench.py's gpu_launches) */
+int64_t pet_launch_count(const pet_engine *e);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PROSPER_B200_H */

@@ -1,0 +1,82 @@
+// Shared helpers for the prosper_b200 CUDA sources (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+#include "../../include/prosper_b200.h"
+
+namespace pet {
+
+void set_error(const char *fmt, ...);
+extern thread_local int64_t g_launches;   // kernels launched on this thread (all engines)
+
+#define PET_CUDA(expr)                                                                     \
+    do {                                                                                   \
+        cudaError_t _e = (expr);                                                           \
+        if (_e != cudaSuccess) {                                                           \
+            pet::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),         \
+                           __FILE__, __LINE__);                                            \
+            return PET_ECUDA;                                                              \
+        }                                                                                  \
+    } while (0)
+
+#define PET_LAUNCH_CHECK()                                                                 \
+    do {                                                                                   \
+        pet::g_launches++;                                                                 \
+        cudaError_t _e = cudaGetLastError();                                               \
+        if (_e != cudaSuccess) {                                                           \
+            pet::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e),     \
+                           __FILE__, __LINE__);                                            \
+            return PET_ECUDA;                                                              \
+        }                                                                                  \
+    } while (0)
+
+#define PET_CHECK(expr)                                                                    \
+    do {                                                                                   \
+        int _r = (expr);                                                                   \
+        if (_r != PET_OK) return _r;                                                       \
+    } while (0)
+
+static inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+static inline int64_t ceil_div(int64_t x, int64_t m) { return (x + m - 1) / m; }
+
+// ---- device helpers ---------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+// 16-byte async copy global->shared; src_bytes in {0,8,16}, the rest is zero-filled.
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src, int src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(src_bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+}
+
+// FP64 tensor-core tile: D(8x8) = A(8x4, row) * B(4x8, col) + C.  Fragment ownership
+// (PTX ISA, mma.m8n8k4 .f64): a0 = A[lane/4][lane%4]; b0 = B[lane%4][lane/4];
+// c0,c1 = C[lane/4][2*(lane%4) + {0,1}].
+__device__ __forceinline__ void dmma_8x8x4(double &d0, double &d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(d0), "+d"(d1)
+                 : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+}  // namespace pet

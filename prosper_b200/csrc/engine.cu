@@ -1,0 +1,701 @@
+// C-ABI engine: owns the device-resident layout of the training shard and orchestrates the
+// per-iteration pipeline  prepare -> [chunk: score GEMM -> posterior kernel -> statistics GEMM]
+// -> (all-reduce by the caller) -> solve.   See include/prosper_b200.h for the contract.
+#include <math.h>
+#include <stdarg.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "common.cuh"
+#include "gl_kernel.cuh"
+
+namespace pet {
+
+thread_local std::string g_error;
+thread_local int64_t g_launches = 0;
+
+void set_error(const char *fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_error = buf;
+}
+
+// kernels / launchers implemented in the other translation units
+int dgemm_kk(int64_t M, int64_t N, int64_t K, const double *A, int64_t lda, const double *B, int64_t ldb,
+             double *C, int64_t ldc, double alpha, int accumulate, cudaStream_t st);
+int dgemm_mn(int64_t M, int64_t N, int64_t K, const double *A, int64_t lda, const double *B, int64_t ldb,
+             double *C, int64_t ldc, int accumulate, double *work, int64_t work_doubles, int sm_count,
+             cudaStream_t st);
+int dgemm_mn_splits(int64_t M, int64_t N, int64_t K, int sm_count);
+int spd_solve_right(int64_t n, int64_t m, double *A, int64_t lda, double *B, int64_t ldb, double *work,
+                    cudaStream_t st);
+int64_t spd_solve_work_doubles(int64_t n, int64_t lda);
+int kth_largest(const double *vals, int64_t n, int64_t k, double *out, unsigned long long *state, int sm_count,
+                cudaStream_t st);
+int launch_transpose_w(double *Wt, int64_t ldk, const double *W, int64_t ldw, int D, int H, cudaStream_t st);
+int launch_gram_diag(const double *G, int64_t ldg, int H, double *wn2, double *invn, cudaStream_t st);
+int launch_subtract_mu(double *Y, int64_t ldy, int64_t n, int D, const double *mu, cudaStream_t st);
+int launch_rownorm_pad(double *Y, int64_t ldy, int64_t n, int D, double *yy, cudaStream_t st);
+int launch_cand_to_i64(int64_t *out, const int *in, int64_t count, cudaStream_t st);
+int launch_cand_from_i64(int *out, const int64_t *in, int64_t count, int H, cudaStream_t st);
+int launch_add_diag(double *Wq, int64_t ld, const double *colsum, int H, cudaStream_t st);
+int launch_colsum(double *out, const double *M, int64_t ld, int64_t rows, int cols, cudaStream_t st);
+
+#include "statespace.cpp.inc"
+
+static bool is_device_ptr(const void *p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+
+enum Stage { ST_PREPARE = 0, ST_SCORE, ST_POST, ST_STATS, ST_SOLVE, ST_KSEL, ST_COUNT };
+
+struct StageTimer {
+    bool on = false;
+    std::vector<cudaEvent_t> pool;
+    size_t used = 0;
+    struct Span { int stage; cudaEvent_t a, b; };
+    std::vector<Span> spans;
+    double totals[ST_COUNT] = {0, 0, 0, 0, 0, 0};
+    int counts[ST_COUNT] = {0, 0, 0, 0, 0, 0};
+    cudaEvent_t get() {
+        if (used == pool.size()) { cudaEvent_t e; cudaEventCreate(&e); pool.push_back(e); }
+        return pool[used++];
+    }
+    void begin(int stage, cudaStream_t st) {
+        if (!on) return;
+        Span s{stage, get(), get()};
+        cudaEventRecord(s.a, st);
+        spans.push_back(s);
+    }
+    void end(cudaStream_t st) {
+        if (!on) return;
+        cudaEventRecord(spans.back().b, st);
+    }
+    void collect() {
+        for (auto &s : spans) {
+            cudaEventSynchronize(s.b);
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, s.a, s.b);
+            totals[s.stage] += ms;
+            counts[s.stage] += 1;
+        }
+        spans.clear();
+        used = 0;
+    }
+    void reset() { collect(); for (int i = 0; i < ST_COUNT; ++i) { totals[i] = 0; counts[i] = 0; } }
+};
+
+}  // namespace pet
+
+using namespace pet;
+
+struct pet_engine {
+    int model = 0, device = 0, sm_count = 148;
+    int D = 0, H = 0, Hp = 0, gamma = 0, K = 0, k0 = 0;
+    std::vector<double> values;     // latent values (K), binary: {0,1}
+    bool binary = true;
+    StateSpace ss;
+    int64_t C = 0;
+    GLStatic gls{};
+    int64_t ldY = 0, ldH = 0, chunk_rows = 0;
+
+    // device-resident shard
+    double *Y = nullptr; int64_t n = 0, n_cap = 0;
+    double *yy = nullptr; int *cand = nullptr; double *lse = nullptr;
+    bool yy_valid = false; int cand_state = 0;
+    std::vector<double> mu_applied;
+
+    // per-iteration
+    double *Wt = nullptr, *G = nullptr, *wn2 = nullptr, *invn = nullptr, *Wtmp = nullptr, *mu_dev = nullptr;
+    double *YW = nullptr; int64_t yw_rows = 0; bool yw_all = false;
+    double *Sbuf = nullptr, *S2buf = nullptr;
+    double *gemm_work = nullptr; int64_t gemm_work_doubles = 0;
+    double *solveA = nullptr, *solveB = nullptr, *solve_work = nullptr;
+    double *s2sum = nullptr;
+    double *stage_logpj = nullptr; int64_t stage_logpj_doubles = 0;
+    int64_t *stage_i64 = nullptr; int64_t stage_i64_count = 0;
+    unsigned long long *ksel_state = nullptr;
+    unsigned long long *d_states = nullptr; unsigned int *d_entries = nullptr; double *d_wlut = nullptr;
+
+    cudaStream_t copy_stream = nullptr;
+    std::vector<cudaEvent_t> chunk_ready; bool upload_pending = false;
+    cudaEvent_t compute_done = nullptr; bool compute_done_valid = false;
+    StageTimer timer;
+    int64_t launches0 = 0;
+};
+
+static int free_dev(void *p) { if (p) cudaFree(p); return 0; }
+
+template <typename T>
+static int dev_alloc(T **p, int64_t count) {
+    *p = nullptr;
+    if (count <= 0) count = 1;
+    cudaError_t e = cudaMalloc((void **)p, size_t(count) * sizeof(T));
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        set_error("cudaMalloc of %lld bytes failed: %s", (long long)(count * (int64_t)sizeof(T)), cudaGetErrorString(e));
+        return PET_ENOMEM;
+    }
+    return PET_OK;
+}
+
+extern "C" int pet_abi_version(void) { return PET_ABI_VERSION; }
+extern "C" const char *pet_last_error(void) { return g_error.c_str(); }
+
+extern "C" void pet_destroy(pet_engine *e) {
+    if (!e) return;
+    cudaSetDevice(e->device);
+    cudaDeviceSynchronize();
+    free_dev(e->Y); free_dev(e->yy); free_dev(e->cand); free_dev(e->lse);
+    free_dev(e->Wt); free_dev(e->G); free_dev(e->wn2); free_dev(e->invn); free_dev(e->Wtmp); free_dev(e->mu_dev);
+    free_dev(e->YW); free_dev(e->Sbuf); free_dev(e->S2buf); free_dev(e->gemm_work);
+    free_dev(e->solveA); free_dev(e->solveB); free_dev(e->solve_work); free_dev(e->s2sum);
+    free_dev(e->stage_logpj); free_dev(e->stage_i64); free_dev(e->ksel_state);
+    free_dev(e->d_states); free_dev(e->d_entries); free_dev(e->d_wlut);
+    for (auto ev : e->chunk_ready) cudaEventDestroy(ev);
+    for (auto ev : e->timer.pool) cudaEventDestroy(ev);
+    if (e->compute_done) cudaEventDestroy(e->compute_done);
+    if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
+    delete e;
+}
+
+extern "C" int pet_create(const pet_config *cfg, pet_engine **out) {
+    if (!cfg || !out) { set_error("pet_create: null argument"); return PET_EINVAL; }
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        set_error("no CUDA device: prosper_b200 has no CPU path");
+        return PET_ECUDA;
+    }
+    if (cfg->device < 0 || cfg->device >= ndev) { set_error("device %d out of range", cfg->device); return PET_EINVAL; }
+    PET_CUDA(cudaSetDevice(cfg->device));
+    cudaDeviceProp prop;
+    PET_CUDA(cudaGetDeviceProperties(&prop, cfg->device));
+    if (prop.major != 10) {
+        set_error("device %d is sm_%d%d; this library is built for sm_100a only", cfg->device, prop.major, prop.minor);
+        return PET_EINVAL;
+    }
+    if (cfg->model != PET_MODEL_BSC && cfg->model != PET_MODEL_TSC && cfg->model != PET_MODEL_DSC) {
+        set_error("model kind %d is not handled by this engine entry point", cfg->model);
+        return PET_EINVAL;
+    }
+    if (cfg->D < 1 || cfg->H < 1 || cfg->Hprime < 1 || cfg->gamma < 1 || cfg->Hprime > cfg->H ||
+        cfg->gamma > cfg->Hprime) {   // camodels/__init__.py:90-91
+        set_error("need 1 <= gamma <= Hprime <= H and D >= 1");
+        return PET_EINVAL;
+    }
+    if (cfg->Hprime > PET_MAXHP || cfg->gamma > PET_MAXG) {
+        set_error("Hprime <= %d and gamma <= %d supported", PET_MAXHP, PET_MAXG);
+        return PET_EINVAL;
+    }
+    pet_engine *e = new pet_engine();
+    e->model = cfg->model; e->device = cfg->device; e->sm_count = prop.multiProcessorCount;
+    e->D = (int)cfg->D; e->H = (int)cfg->H; e->Hp = (int)cfg->Hprime; e->gamma = (int)cfg->gamma;
+    e->ldY = round_up(e->D + 1, 8);
+    e->ldH = round_up(e->H, 8);
+
+    std::vector<std::vector<int>> rows;
+    GLStatic &g = e->gls;
+    memset(&g, 0, sizeof(g));
+    if (e->model == PET_MODEL_BSC) {
+        e->values = {0.0, 1.0}; e->k0 = 0; e->K = 2; e->binary = true;
+        enum_binary(e->Hp, e->gamma, rows);
+        g.has_null = 1; g.n_blocks = 1; g.block_val[0] = 1.0; g.block_vidx[0] = 0;
+        g.zbase = 0; g.select_mode = SEL_BSC; g.diag_from_colsum = 1;
+    } else {
+        std::vector<double> vals;
+        if (e->model == PET_MODEL_TSC) vals = {-1.0, 0.0, 1.0};
+        else {
+            if (!cfg->states || cfg->n_states < 2) { delete e; set_error("DSC needs the latent values (states)"); return PET_EINVAL; }
+            vals.assign(cfg->states, cfg->states + cfg->n_states);
+        }
+        int k0 = -1;
+        for (size_t k = 0; k < vals.size(); ++k) if (vals[k] == 0.0) { if (k0 >= 0) k0 = -2; else k0 = (int)k; }
+        if (k0 < 0) { delete e; set_error("states must contain exactly one 0"); return PET_EINVAL; }
+        if ((int)vals.size() - 1 > PET_MAXV) { delete e; set_error("at most %d non-zero latent values", PET_MAXV); return PET_EINVAL; }
+        e->values = vals; e->k0 = k0; e->K = (int)vals.size(); e->binary = false;
+        if (e->model == PET_MODEL_TSC) {
+            enum_product(e->Hp, e->K, k0, e->gamma, 0, rows);     // null and singletons included (tsc_et.py:76)
+            g.has_null = 0; g.n_blocks = 0; g.zbase = e->Hp; g.select_mode = SEL_TSC;
+        } else {
+            enum_product(e->Hp, e->K, k0, e->gamma, 2, rows);     // dsc_et.py:59-61
+            g.has_null = 1; g.zbase = e->H; g.select_mode = SEL_DSC;
+            int b = 0;
+            for (int k = 0; k < e->K; ++k) if (k != k0) { g.block_val[b] = vals[k]; g.block_vidx[b] = b; ++b; }
+            g.n_blocks = b;
+        }
+        g.diag_from_colsum = 0;
+    }
+    int rc = build_state_space(e->ss, e->Hp, rows, e->values, e->k0);
+    if (rc != PET_OK) { delete e; return rc; }
+    g.H = e->H; g.Hp = e->Hp; g.S = (int)e->ss.S; g.ldH = (int)e->ldH;
+    g.n_cnt = e->K - 1;
+    { int v = 0; for (int k = 0; k < e->K; ++k) if (k != e->k0) g.vals[v++] = e->values[k]; }
+    e->C = g.has_null + (int64_t)g.n_blocks * e->H + e->ss.S;
+    g.C = (int)e->C;
+    g.entries_per_lane = e->ss.entries_per_lane;
+    g.n_out = e->ss.n_out;
+    if (gl_smem_bytes(g, 4) > 227 * 1024) {
+        delete e;
+        set_error("H=%d with %lld states needs more shared memory than one SM has", e->H, (long long)e->ss.S);
+        return PET_EINVAL;
+    }
+
+#define TRY(x) do { rc = (x); if (rc != PET_OK) { pet_destroy(e); return rc; } } while (0)
+#define TRYC(x) do { cudaError_t _c = (x); if (_c != cudaSuccess) { set_error("%s: %s", #x, cudaGetErrorString(_c)); pet_destroy(e); return PET_ECUDA; } } while (0)
+    TRY(dev_alloc(&e->d_states, std::max<int64_t>(1, e->ss.S)));
+    TRY(dev_alloc(&e->d_entries, (int64_t)e->ss.entries.size()));
+    TRY(dev_alloc(&e->d_wlut, (int64_t)e->ss.wlut.size()));
+    if (e->ss.S) TRYC(cudaMemcpy(e->d_states, e->ss.records.data(), e->ss.S * 8, cudaMemcpyHostToDevice));
+    TRYC(cudaMemcpy(e->d_entries, e->ss.entries.data(), e->ss.entries.size() * 4, cudaMemcpyHostToDevice));
+    TRYC(cudaMemcpy(e->d_wlut, e->ss.wlut.data(), e->ss.wlut.size() * 8, cudaMemcpyHostToDevice));
+    g.states = e->d_states; g.entries = e->d_entries; g.wlut = e->d_wlut;
+
+    // chunking: posterior / score buffers of ~128 MB each
+    int64_t cr = cfg->chunk_rows > 0 ? cfg->chunk_rows : (int64_t(128) << 20) / (e->ldH * 8);
+    cr = std::max<int64_t>(128, std::min<int64_t>(cr, 1 << 20));
+    e->chunk_rows = round_up(cr, 128);
+
+    TRY(dev_alloc(&e->Wt, e->ldH * e->ldY));
+    TRY(dev_alloc(&e->G, e->ldH * e->ldH));
+    TRY(dev_alloc(&e->wn2, e->ldH)); TRY(dev_alloc(&e->invn, e->ldH));
+    TRY(dev_alloc(&e->Wtmp, (int64_t)e->D * e->ldH));
+    TRY(dev_alloc(&e->mu_dev, e->ldY));
+    TRY(dev_alloc(&e->Sbuf, e->chunk_rows * e->ldH));
+    if (e->model == PET_MODEL_DSC) { TRY(dev_alloc(&e->S2buf, e->chunk_rows * e->ldH)); TRY(dev_alloc(&e->s2sum, e->ldH)); }
+    {
+        int splits = dgemm_mn_splits(e->D + 1, e->H, e->chunk_rows, e->sm_count);
+        e->gemm_work_doubles = int64_t(splits) * (e->D + 1) * e->ldH;
+        TRY(dev_alloc(&e->gemm_work, e->gemm_work_doubles));
+    }
+    TRY(dev_alloc(&e->solveA, (int64_t)e->H * e->ldH));
+    TRY(dev_alloc(&e->solveB, (int64_t)e->D * e->ldH));
+    TRY(dev_alloc(&e->solve_work, spd_solve_work_doubles(e->H, e->ldH)));
+    TRY(dev_alloc(&e->ksel_state, 2 + 256));
+    TRYC(cudaMemset(e->Wt, 0, e->ldH * e->ldY * 8));
+    TRYC(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+    TRYC(cudaEventCreateWithFlags(&e->compute_done, cudaEventDisableTiming));
+#undef TRY
+#undef TRYC
+    e->launches0 = g_launches;
+    *out = e;
+    return PET_OK;
+}
+
+extern "C" int64_t pet_num_states(const pet_engine *e) { return e ? e->ss.S : -1; }
+extern "C" int64_t pet_num_columns(const pet_engine *e) { return e ? e->C : -1; }
+extern "C" int64_t pet_num_data(const pet_engine *e) { return e ? e->n : -1; }
+extern "C" int64_t pet_launch_count(const pet_engine *e) { return e ? (g_launches - e->launches0) : -1; }
+extern "C" int pet_state_matrix(const pet_engine *e, double *out_host) {
+    if (!e || !out_host) { set_error("pet_state_matrix: null argument"); return PET_EINVAL; }
+    memcpy(out_host, e->ss.matrix.data(), e->ss.matrix.size() * sizeof(double));
+    return PET_OK;
+}
+extern "C" int pet_enable_timing(pet_engine *e, int32_t on) {
+    if (!e) return PET_EINVAL;
+    e->timer.reset();
+    e->timer.on = on != 0;
+    return PET_OK;
+}
+extern "C" int pet_stage_times_ms(pet_engine *e, double *out) {
+    if (!e || !out) return PET_EINVAL;
+    e->timer.collect();
+    for (int i = 0; i < ST_COUNT; ++i) { out[i] = e->timer.totals[i]; out[ST_COUNT + i] = (double)e->timer.counts[i]; }
+    return PET_OK;
+}
+
+// ---- data ------------------------------------------------------------------------------
+static int ensure_rows(pet_engine *e, int64_t n) {
+    if (n <= e->n_cap) return PET_OK;
+    cudaDeviceSynchronize();
+    free_dev(e->Y); free_dev(e->yy); free_dev(e->cand); free_dev(e->lse); free_dev(e->YW);
+    e->Y = nullptr; e->yy = nullptr; e->cand = nullptr; e->lse = nullptr; e->YW = nullptr;
+    e->n_cap = 0;
+    PET_CHECK(dev_alloc(&e->Y, n * e->ldY));
+    PET_CHECK(dev_alloc(&e->yy, n));
+    PET_CHECK(dev_alloc(&e->cand, n * e->Hp));
+    PET_CHECK(dev_alloc(&e->lse, n));
+    // cache the whole score matrix when it is affordable (lets the truncated M-step skip the
+    // second score GEMM); otherwise one chunk
+    size_t free_b = 0, total_b = 0;
+    cudaMemGetInfo(&free_b, &total_b);
+    int64_t all_bytes = n * e->ldH * 8;
+    e->yw_all = all_bytes <= (int64_t)(free_b / 3);
+    e->yw_rows = e->yw_all ? n : std::min<int64_t>(n, e->chunk_rows);
+    PET_CHECK(dev_alloc(&e->YW, e->yw_rows * e->ldH));
+    e->n_cap = n;
+    return PET_OK;
+}
+
+extern "C" int pet_set_data(pet_engine *e, const double *y, int64_t n, int64_t ld, void *stream) {
+    if (!e || !y || n < 0 || ld < e->D) { set_error("pet_set_data: bad arguments"); return PET_EINVAL; }
+    cudaStream_t st = (cudaStream_t)stream;
+    PET_CUDA(cudaSetDevice(e->device));
+    PET_CHECK(ensure_rows(e, n));
+    e->n = n;
+    e->yy_valid = false;
+    e->cand_state = 0;
+    e->mu_applied.assign(e->D, 0.0);
+    if (n == 0) return PET_OK;
+    const int64_t nchunks = ceil_div(n, e->chunk_rows);
+    if (is_device_ptr(y)) {
+        PET_CUDA(cudaMemcpy2DAsync(e->Y, e->ldY * 8, y, ld * 8, size_t(e->D) * 8, n, cudaMemcpyDeviceToDevice, st));
+        e->upload_pending = false;
+    } else {
+        // the copy stream must not overwrite Y while earlier kernels still read it
+        if (e->compute_done_valid) PET_CUDA(cudaStreamWaitEvent(e->copy_stream, e->compute_done, 0));
+        while ((int64_t)e->chunk_ready.size() < nchunks) {
+            cudaEvent_t ev;
+            PET_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+            e->chunk_ready.push_back(ev);
+        }
+        for (int64_t c = 0; c < nchunks; ++c) {
+            int64_t r0 = c * e->chunk_rows, rows = std::min(e->chunk_rows, n - r0);
+            PET_CUDA(cudaMemcpy2DAsync(e->Y + r0 * e->ldY, e->ldY * 8, y + r0 * ld, ld * 8, size_t(e->D) * 8, rows,
+                                       cudaMemcpyHostToDevice, e->copy_stream));
+            PET_CUDA(cudaEventRecord(e->chunk_ready[c], e->copy_stream));
+        }
+        e->upload_pending = true;
+    }
+    return PET_OK;
+}
+
+// ---- per-iteration preparation ---------------------------------------------------------
+static int load_W(pet_engine *e, const pet_params *p, cudaStream_t st) {
+    if (!p || !p->W || p->ldW < e->H || !p->pi_host || p->n_pi < 1) { set_error("bad model parameters"); return PET_EINVAL; }
+    const double *Wsrc = p->W;
+    int64_t ldw = p->ldW;
+    if (!is_device_ptr(p->W)) {
+        PET_CUDA(cudaMemcpy2DAsync(e->Wtmp, e->ldH * 8, p->W, p->ldW * 8, size_t(e->H) * 8, e->D, cudaMemcpyHostToDevice, st));
+        Wsrc = e->Wtmp; ldw = e->ldH;
+    }
+    PET_CHECK(launch_transpose_w(e->Wt, e->ldY, Wsrc, ldw, e->D, e->H, st));
+    return PET_OK;
+}
+
+static int apply_mu(pet_engine *e, const pet_params *p, cudaStream_t st) {
+    // BSC only: y - mu (bsc_et.py:169,335,396).  The shard is stored shifted by the mu in force.
+    std::vector<double> mu(e->D, 0.0);
+    if (p->mu) {
+        if (is_device_ptr(p->mu)) PET_CUDA(cudaMemcpyAsync(mu.data(), p->mu, e->D * 8, cudaMemcpyDeviceToHost, st));
+        else memcpy(mu.data(), p->mu, e->D * 8);
+        PET_CUDA(cudaStreamSynchronize(st));
+    }
+    if (e->mu_applied.size() != (size_t)e->D) e->mu_applied.assign(e->D, 0.0);
+    bool same = true;
+    std::vector<double> delta(e->D);
+    for (int d = 0; d < e->D; ++d) { delta[d] = mu[d] - e->mu_applied[d]; same &= (delta[d] == 0.0); }
+    if (same) return PET_OK;
+    if (e->upload_pending) {   // all chunks must have landed before shifting in place
+        PET_CUDA(cudaStreamWaitEvent(st, e->chunk_ready[ceil_div(e->n, e->chunk_rows) - 1], 0));
+    }
+    PET_CUDA(cudaMemcpyAsync(e->mu_dev, delta.data(), e->D * 8, cudaMemcpyHostToDevice, st));
+    PET_CUDA(cudaStreamSynchronize(st));
+    PET_CHECK(launch_subtract_mu(e->Y, e->ldY, e->n, e->D, e->mu_dev, st));
+    e->mu_applied = mu;
+    e->yy_valid = false;
+    return PET_OK;
+}
+
+static int prepare(pet_engine *e, const pet_params *p, cudaStream_t st) {
+    e->timer.begin(ST_PREPARE, st);
+    PET_CHECK(load_W(e, p, st));
+    if (e->model == PET_MODEL_BSC) PET_CHECK(apply_mu(e, p, st));
+    // G = W^T W  (H,H); its diagonal gives ||W_h||^2 (bsc_et.py:111 recomputes this per datapoint)
+    PET_CHECK(dgemm_kk(e->H, e->H, e->D, e->Wt, e->ldY, e->Wt, e->ldY, e->G, e->ldH, 1.0, 0, st));
+    PET_CHECK(launch_gram_diag(e->G, e->ldH, e->H, e->wn2, e->invn, st));
+    e->timer.end(st);
+    return PET_OK;
+}
+
+// model-specific log-prior constants
+static int fill_iter(const pet_engine *e, const pet_anneal *a, const pet_params *p, GLIter &it) {
+    memset(&it, 0, sizeof(it));
+    if (!a || !(a->T > 0.0)) { set_error("annealing temperature T must be > 0"); return PET_EINVAL; }
+    if (!(p->sigma > 0.0)) { set_error("sigma must be > 0"); return PET_EINVAL; }
+    it.beta = 1.0 / a->T;                          // bsc_et.py:152
+    it.pre1 = -1.0 / 2.0 / p->sigma / p->sigma;    // bsc_et.py:153
+    it.anneal_prior = a->anneal_prior ? 1 : 0;
+    const GLStatic &g = e->gls;
+    if (e->model == PET_MODEL_BSC) {
+        double pi = p->pi_host[0];
+        double pil_bar = log(pi / (1.0 - pi));     // bsc_et.py:154
+        it.prior_null = 0.0; it.prior_block[0] = pil_bar; it.lp[0] = pil_bar; it.lp0 = 0.0;
+    } else if (e->model == PET_MODEL_TSC) {
+        double pi = p->pi_host[0];                 // tsc_et.py:316-322
+        it.lp[0] = log(pi / 2.0); it.lp[1] = log(pi / 2.0); it.lp0 = log(1.0 - pi);
+    } else {
+        if (p->n_pi != e->K) { set_error("DSC: pi must have K=%d entries", e->K); return PET_EINVAL; }
+        double l0 = log(p->pi_host[e->k0]);
+        it.lp0 = l0;
+        it.prior_null = e->H * l0;                 // dsc_et.py:550
+        int b = 0;
+        for (int k = 0; k < e->K; ++k) if (k != e->k0) {
+            it.lp[b] = log(p->pi_host[k]);
+            it.prior_block[b] = it.lp[b] + (e->H - 1) * l0;   // dsc_et.py:555
+            it.sel_prior[b] = it.prior_block[b];               // dsc_et.py:393
+            ++b;
+        }
+    }
+    (void)g;
+    return PET_OK;
+}
+
+static int ensure_chunk_inputs(pet_engine *e, int64_t c, int64_t r0, int64_t rows, cudaStream_t st) {
+    if (e->upload_pending) PET_CUDA(cudaStreamWaitEvent(st, e->chunk_ready[c], 0));
+    if (!e->yy_valid) PET_CHECK(launch_rownorm_pad(e->Y + r0 * e->ldY, e->ldY, rows, e->D, e->yy + r0, st));
+    return PET_OK;
+}
+
+static void mark_compute_done(pet_engine *e, cudaStream_t st) {
+    cudaEventRecord(e->compute_done, st);
+    e->compute_done_valid = true;
+}
+
+enum { PASS_SELECT = 1, PASS_REUSE_SCORES = 2 };
+
+// One sweep over the shard.  kflags: GLF_* for the posterior kernel.
+static int sweep(pet_engine *e, const pet_anneal *a, const pet_params *p, int kflags, int pass_flags,
+                 const double *logpj_user, int64_t ld_logpj, bool logpj_is_output, const double *cut_dev,
+                 double *stats_dev, cudaStream_t st) {
+    if (e->n <= 0) { set_error("no data bound (pet_set_data)"); return PET_ESTATE; }
+    if (!(kflags & GLF_SELECT) && e->cand_state == 0) { set_error("no candidates: run select_Hprimes first"); return PET_ESTATE; }
+    GLArgs ga;
+    memset(&ga, 0, sizeof(ga));
+    ga.st = e->gls;
+    PET_CHECK(fill_iter(e, a, p, ga.it));
+    const bool reuse = (pass_flags & PASS_REUSE_SCORES) && e->yw_all;
+    if (!reuse) PET_CHECK(prepare(e, p, st));
+    ga.flags = kflags;
+    if (e->model == PET_MODEL_DSC) ga.flags |= (kflags & GLF_USE_CUT) ? GLF_CUT_STRICT : 0;
+    ga.yy = e->yy; ga.wn2 = e->wn2; ga.invn = e->invn; ga.G = e->G;
+    ga.cand = e->cand; ga.lse = e->lse; ga.cut = cut_dev;
+    pet_stats_layout lay;
+    pet_stats_layout_get(e, &lay);
+    const bool do_stats = !(kflags & (GLF_LSE_ONLY | GLF_SELECT_ONLY));
+    if (do_stats) {
+        if (!stats_dev) { set_error("stats buffer is null"); return PET_EINVAL; }
+        PET_CUDA(cudaMemsetAsync(stats_dev, 0, lay.total * 8, st));
+        ga.Wq = stats_dev + lay.off_Wq;
+        ga.scalars = stats_dev + lay.off_scalars;
+        if (e->S2buf) PET_CUDA(cudaMemsetAsync(e->s2sum, 0, e->ldH * 8, st));
+    }
+    const bool user_logpj = (kflags & (GLF_READ_LOGPJ | GLF_WRITE_LOGPJ)) != 0;
+    const bool logpj_on_dev = user_logpj && is_device_ptr(logpj_user);
+    if (user_logpj && !logpj_on_dev) {
+        int64_t need = e->chunk_rows * e->C;
+        if (need > e->stage_logpj_doubles) {
+            cudaStreamSynchronize(st);
+            free_dev(e->stage_logpj); e->stage_logpj = nullptr; e->stage_logpj_doubles = 0;
+            PET_CHECK(dev_alloc(&e->stage_logpj, need));
+            e->stage_logpj_doubles = need;
+        }
+    }
+    const int64_t nchunks = ceil_div(e->n, e->chunk_rows);
+    for (int64_t c = 0; c < nchunks; ++c) {
+        const int64_t r0 = c * e->chunk_rows, rows = std::min(e->chunk_rows, e->n - r0);
+        PET_CHECK(ensure_chunk_inputs(e, c, r0, rows, st));
+        double *yw = e->yw_all ? e->YW + r0 * e->ldH : e->YW;
+        if (!reuse) {
+            e->timer.begin(ST_SCORE, st);
+            PET_CHECK(dgemm_kk(rows, e->H, e->D, e->Y + r0 * e->ldY, e->ldY, e->Wt, e->ldY, yw, e->ldH, 1.0, 0, st));
+            e->timer.end(st);
+        }
+        ga.n_rows = rows; ga.row0 = r0; ga.YW = yw; ga.S = e->Sbuf; ga.S2 = e->S2buf;
+        if (user_logpj) {
+            if (logpj_on_dev) { ga.logpj = const_cast<double *>(logpj_user); ga.ld_logpj = ld_logpj; }
+            else {
+                // stage this chunk; the kernel indexes logpj by GLOBAL row, so bias the pointer
+                ga.logpj = e->stage_logpj - r0 * e->C; ga.ld_logpj = e->C;
+                if (!logpj_is_output)
+                    PET_CUDA(cudaMemcpy2DAsync(e->stage_logpj, e->C * 8, logpj_user + r0 * ld_logpj, ld_logpj * 8,
+                                               size_t(e->C) * 8, rows, cudaMemcpyHostToDevice, st));
+            }
+        }
+        e->timer.begin(ST_POST, st);
+        PET_CHECK(launch_gl_kernel(ga, e->gamma, e->binary, e->sm_count, st));
+        e->timer.end(st);
+        if (user_logpj && !logpj_on_dev && logpj_is_output)
+            PET_CUDA(cudaMemcpy2DAsync(const_cast<double *>(logpj_user) + r0 * ld_logpj, ld_logpj * 8, e->stage_logpj,
+                                       e->C * 8, size_t(e->C) * 8, rows, cudaMemcpyDeviceToHost, st));
+        if (do_stats) {
+            e->timer.begin(ST_STATS, st);
+            // Wp^T (D+1, H) += Y_chunk^T . <S>_chunk ; row D (all-ones column of Y) = sum_n <s>
+            PET_CHECK(dgemm_mn(e->D + 1, e->H, rows, e->Y + r0 * e->ldY, e->ldY, e->Sbuf, e->ldH,
+                               stats_dev + lay.off_Wp, e->ldH, 1, e->gemm_work, e->gemm_work_doubles, e->sm_count, st));
+            if (e->S2buf) PET_CHECK(launch_colsum(e->s2sum, e->S2buf, e->ldH, rows, e->H, st));
+            e->timer.end(st);
+        }
+    }
+    e->yy_valid = true;
+    if (kflags & GLF_SELECT) e->cand_state = 1;
+    if (do_stats && e->S2buf)   // DSC: singleton second moments onto the diagonal (dsc_et.py:701)
+        PET_CHECK(launch_add_diag(stats_dev + lay.off_Wq, e->ldH, e->s2sum, e->H, st));
+    mark_compute_done(e, st);
+    return PET_OK;
+}
+
+extern "C" int pet_stats_layout_get(const pet_engine *e, pet_stats_layout *out) {
+    if (!e || !out) { set_error("pet_stats_layout_get: null argument"); return PET_EINVAL; }
+    memset(out, 0, sizeof(*out));
+    out->off_Wp = 0; out->rows_Wp = e->D + 1; out->cols_Wp = e->H; out->ld_Wp = e->ldH;
+    out->off_Wq = out->rows_Wp * out->ld_Wp; out->rows_Wq = e->H; out->cols_Wq = e->H; out->ld_Wq = e->ldH;
+    out->off_scalars = out->off_Wq + out->rows_Wq * out->ld_Wq;
+    out->n_scalars = 16;
+    out->total = out->off_scalars + out->n_scalars;
+    return PET_OK;
+}
+
+extern "C" int pet_select_hprimes(pet_engine *e, const pet_params *p, int64_t *cand_out, void *stream) {
+    if (!e) { set_error("null engine"); return PET_EINVAL; }
+    cudaStream_t st = (cudaStream_t)stream;
+    PET_CUDA(cudaSetDevice(e->device));
+    pet_anneal a{1.0, 0.0, 0};
+    PET_CHECK(sweep(e, &a, p, GLF_SELECT | GLF_SELECT_ONLY, 0, nullptr, 0, false, nullptr, nullptr, st));
+    if (cand_out) {
+        int64_t count = e->n * e->Hp;
+        if (is_device_ptr(cand_out)) PET_CHECK(launch_cand_to_i64(cand_out, e->cand, count, st));
+        else {
+            if (count > e->stage_i64_count) {
+                cudaStreamSynchronize(st);
+                free_dev(e->stage_i64); e->stage_i64 = nullptr; e->stage_i64_count = 0;
+                PET_CHECK(dev_alloc(&e->stage_i64, count));
+                e->stage_i64_count = count;
+            }
+            PET_CHECK(launch_cand_to_i64(e->stage_i64, e->cand, count, st));
+            PET_CUDA(cudaMemcpyAsync(cand_out, e->stage_i64, count * 8, cudaMemcpyDeviceToHost, st));
+            PET_CUDA(cudaStreamSynchronize(st));
+        }
+    }
+    return PET_OK;
+}
+
+extern "C" int pet_set_candidates(pet_engine *e, const int64_t *cand, void *stream) {
+    if (!e || !cand) { set_error("pet_set_candidates: null argument"); return PET_EINVAL; }
+    if (e->n <= 0) { set_error("no data bound"); return PET_ESTATE; }
+    cudaStream_t st = (cudaStream_t)stream;
+    PET_CUDA(cudaSetDevice(e->device));
+    int64_t count = e->n * e->Hp;
+    const int64_t *src = cand;
+    if (!is_device_ptr(cand)) {
+        if (count > e->stage_i64_count) {
+            cudaStreamSynchronize(st);
+            free_dev(e->stage_i64); e->stage_i64 = nullptr; e->stage_i64_count = 0;
+            PET_CHECK(dev_alloc(&e->stage_i64, count));
+            e->stage_i64_count = count;
+        }
+        PET_CUDA(cudaMemcpyAsync(e->stage_i64, cand, count * 8, cudaMemcpyHostToDevice, st));
+        src = e->stage_i64;
+    }
+    PET_CHECK(launch_cand_from_i64(e->cand, src, count, e->H, st));
+    e->cand_state = 1;
+    return PET_OK;
+}
+
+extern "C" int pet_e_step(pet_engine *e, const pet_anneal *a, const pet_params *p, double *logpj_out,
+                          int64_t ld_logpj, void *stream) {
+    if (!e || !logpj_out || ld_logpj < e->C) { set_error("pet_e_step: bad arguments"); return PET_EINVAL; }
+    cudaStream_t st = (cudaStream_t)stream;
+    PET_CUDA(cudaSetDevice(e->device));
+    PET_CHECK(sweep(e, a, p, GLF_WRITE_LOGPJ | GLF_LSE_ONLY, 0, logpj_out, ld_logpj, true, nullptr, nullptr, st));
+    if (!is_device_ptr(logpj_out)) PET_CUDA(cudaStreamSynchronize(st));
+    return PET_OK;
+}
+
+extern "C" int pet_log_denominators(pet_engine *e, const pet_anneal *a, const pet_params *p, const double *logpj,
+                                    int64_t ld_logpj, int32_t flags, double *logdenom_out_dev, void *stream) {
+    if (!e) { set_error("null engine"); return PET_EINVAL; }
+    cudaStream_t st = (cudaStream_t)stream;
+    PET_CUDA(cudaSetDevice(e->device));
+    int kf = GLF_LSE_ONLY | (logpj ? GLF_READ_LOGPJ : 0) | ((flags & PASS_SELECT) ? GLF_SELECT : 0);
+    PET_CHECK(sweep(e, a, p, kf, flags, logpj, ld_logpj, false, nullptr, nullptr, st));
+    if (logdenom_out_dev) PET_CUDA(cudaMemcpyAsync(logdenom_out_dev, e->lse, e->n * 8, cudaMemcpyDeviceToDevice, st));
+    return PET_OK;
+}
+
+extern "C" int pet_m_step_stats(pet_engine *e, const pet_anneal *a, const pet_params *p, const double *logpj,
+                                int64_t ld_logpj, int32_t flags, int32_t use_cut, const double *cut_dev,
+                                double *stats_dev, void *stream) {
+    if (!e || !stats_dev) { set_error("pet_m_step_stats: null argument"); return PET_EINVAL; }
+    if (use_cut && !cut_dev) { set_error("pet_m_step_stats: use_cut without a cut value"); return PET_EINVAL; }
+    cudaStream_t st = (cudaStream_t)stream;
+    PET_CUDA(cudaSetDevice(e->device));
+    int kf = (logpj ? GLF_READ_LOGPJ : 0) | ((flags & PASS_SELECT) ? GLF_SELECT : 0) | (use_cut ? GLF_USE_CUT : 0);
+    return sweep(e, a, p, kf, flags, logpj, ld_logpj, false, cut_dev, stats_dev, st);
+}
+
+extern "C" int pet_kth_largest(pet_engine *e, const double *vals_dev, int64_t n, int64_t k, double *out_dev,
+                               void *stream) {
+    if (!e || !vals_dev || !out_dev) { set_error("pet_kth_largest: null argument"); return PET_EINVAL; }
+    cudaStream_t st = (cudaStream_t)stream;
+    PET_CUDA(cudaSetDevice(e->device));
+    e->timer.begin(ST_KSEL, st);
+    PET_CHECK(kth_largest(vals_dev, n, k, out_dev, e->ksel_state, e->sm_count, st));
+    e->timer.end(st);
+    return PET_OK;
+}
+
+extern "C" const double *pet_log_denominators_ptr(const pet_engine *e) { return e ? e->lse : nullptr; }
+
+extern "C" int pet_m_step_solve(pet_engine *e, const pet_params *p, const double *stats_dev, double *W_new,
+                                int32_t *info_host, void *stream) {
+    if (!e || !stats_dev || !W_new) { set_error("pet_m_step_solve: null argument"); return PET_EINVAL; }
+    (void)p;
+    cudaStream_t st = (cudaStream_t)stream;
+    PET_CUDA(cudaSetDevice(e->device));
+    pet_stats_layout lay;
+    pet_stats_layout_get(e, &lay);
+    e->timer.begin(ST_SOLVE, st);
+    PET_CUDA(cudaMemcpyAsync(e->solveA, stats_dev + lay.off_Wq, (int64_t)e->H * e->ldH * 8, cudaMemcpyDeviceToDevice, st));
+    PET_CUDA(cudaMemcpyAsync(e->solveB, stats_dev + lay.off_Wp, (int64_t)e->D * e->ldH * 8, cudaMemcpyDeviceToDevice, st));
+    if (e->gls.diag_from_colsum)   // binary: <s_h s_h> = <s_h>  (bsc_et.py:350,356-358)
+        PET_CHECK(launch_add_diag(e->solveA, e->ldH, stats_dev + lay.off_Wp + (int64_t)e->D * e->ldH, e->H, st));
+    PET_CHECK(spd_solve_right(e->H, e->D, e->solveA, e->ldH, e->solveB, e->ldH, e->solve_work, st));
+    e->timer.end(st);
+    cudaMemcpyKind kind = is_device_ptr(W_new) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+    PET_CUDA(cudaMemcpy2DAsync(W_new, size_t(e->H) * 8, e->solveB, e->ldH * 8, size_t(e->H) * 8, e->D, kind, st));
+    double scal[2] = {0, 0};
+    PET_CUDA(cudaMemcpyAsync(scal, e->solve_work + (int64_t)e->H * e->ldH + round_up(e->H, 2), 16, cudaMemcpyDeviceToHost, st));
+    PET_CUDA(cudaStreamSynchronize(st));
+    if (info_host) info_host[0] = (int32_t)scal[1];
+    return PET_OK;
+}
+
+// ---- exported building blocks ------------------------------------------------------------
+extern "C" int pet_dgemm_kk(int64_t M, int64_t N, int64_t K, const double *A, int64_t lda, const double *B,
+                            int64_t ldb, double *C, int64_t ldc, double alpha, double beta, void *stream) {
+    if (beta != 0.0 && beta != 1.0) { set_error("pet_dgemm_kk: beta must be 0 or 1"); return PET_EINVAL; }
+    return dgemm_kk(M, N, K, A, lda, B, ldb, C, ldc, alpha, beta == 1.0, (cudaStream_t)stream);
+}
+
+extern "C" int pet_dgemm_mn(int64_t M, int64_t N, int64_t K, const double *A, int64_t lda, const double *B,
+                            int64_t ldb, double *C, int64_t ldc, int32_t accumulate, double *work,
+                            int64_t work_doubles, void *stream) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (!C) return dgemm_mn_splits(M, N, K, sms);
+    return dgemm_mn(M, N, K, A, lda, B, ldb, C, ldc, accumulate, work, work_doubles, sms, (cudaStream_t)stream);
+}
+
+extern "C" int pet_spd_solve_right(int64_t n, int64_t m, double *A, int64_t lda, double *B, int64_t ldb,
+                                   double *work, int32_t *info_host, void *stream) {
+    if (!A || !B || !work || (lda & 1) || (ldb & 1)) { set_error("pet_spd_solve_right: bad arguments"); return PET_EINVAL; }
+    cudaStream_t st = (cudaStream_t)stream;
+    PET_CHECK(spd_solve_right(n, m, A, lda, B, ldb, work, st));
+    double scal[2] = {0, 0};
+    PET_CUDA(cudaMemcpyAsync(scal, work + n * lda + round_up(n, 2), 16, cudaMemcpyDeviceToHost, st));
+    PET_CUDA(cudaStreamSynchronize(st));
+    if (info_host) info_host[0] = (int32_t)scal[1];
+    return PET_OK;
+}
+
+extern "C" int64_t pet_spd_solve_work_doubles(int64_t n, int64_t lda) { return spd_solve_work_doubles(n, lda); }

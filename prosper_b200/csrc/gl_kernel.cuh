@@ -1,0 +1,84 @@
+// Shared declarations of the "Gaussian-linear" ET posterior kernel (BSC / TSC / DSC).
+#pragma once
+#include "common.cuh"
+
+namespace pet {
+
+constexpr int PET_MAXV = 6;        // max number of non-zero latent values (K-1)
+constexpr int PET_MAXHP = 16;      // max H'
+constexpr int PET_MAXG = 8;        // max gamma (members per state record)
+
+// selection rules of the reference's select_Hprimes variants
+enum SelectMode {
+    SEL_BSC = 0,    // cosine score, ascending output order            (bsc_et.py:110-112)
+    SEL_NEGDIST,    // smallest ||W_h - y||^2, best first               (mmca_et.py:115-119)
+    SEL_TSC,        // top-H' of the 2H signed singletons, duplicates   (tsc_et.py:198-210)
+    SEL_DSC,        // top-H' distinct h over (K-1)H singletons         (dsc_et.py:398-408)
+    SEL_GIVEN,      // scores precomputed per (n,h) in the row buffer, smallest first (MCA)
+};
+
+// kernel behaviour flags
+enum {
+    GLF_SELECT      = 1 << 0,   // run the top-H' selection (else use cand_io as input)
+    GLF_WRITE_LOGPJ = 1 << 1,   // materialise logpj (compat E_step)
+    GLF_READ_LOGPJ  = 1 << 2,   // take logpj from the caller (compat M_step)
+    GLF_LSE_ONLY    = 1 << 3,   // stop after the log-denominator
+    GLF_USE_CUT     = 1 << 4,   // skip datapoints below the truncation cut
+    GLF_CUT_STRICT  = 1 << 5,   // '>' instead of '>=' (dsc_et.py:832)
+    GLF_SELECT_ONLY = 1 << 6,   // stop after selection
+};
+
+struct GLStatic {                 // fixed per engine
+    int H, Hp, S, C;
+    int ldH;                      // leading dimension of YW / S / G / Wq rows
+    int has_null;                 // column 0 = null state
+    int n_blocks;                 // all-H singleton blocks (BSC 1, DSC K-1, TSC 0)
+    double block_val[PET_MAXV];   // latent value of each block
+    int block_vidx[PET_MAXV];     // which count accumulator it feeds
+    int n_cnt;                    // number of non-zero latent values
+    double vals[PET_MAXV];        // value LUT by vidx
+    int zbase;                    // zero-entry count base for the state prior (H' TSC, H DSC, 0 BSC)
+    int select_mode;
+    int diag_from_colsum;         // binary: Wq diagonal = column sums of <s> (not scattered)
+    const unsigned long long *states;   // S records: 8 x (pos | vidx<<4), 0xFF = unused
+    const unsigned int *entries;  // moment gather lists, transposed [t][lane]
+    int entries_per_lane;
+    int n_out;                    // number of moment outputs (first + second moments)
+    const double *wlut;           // weight LUT for moment entries
+};
+
+struct GLIter {                   // per call
+    double beta, pre1;
+    int anneal_prior;
+    double prior_null;
+    double prior_block[PET_MAXV];
+    double lp[PET_MAXV];          // log-prior weight per non-zero value
+    double lp0;                   // log-prior weight of a zero entry
+    double sel_prior[PET_MAXV];   // TSC/DSC selection: per-block log prior
+};
+
+struct GLArgs {
+    GLStatic st;
+    GLIter it;
+    int flags;
+    int64_t n_rows;               // rows in this chunk
+    int64_t row0;                 // global index of the first row (for per-datapoint arrays)
+    const double *YW;             // (n_rows, ldH) scores of this chunk
+    const double *yy;             // (n,) squared norms (global index)
+    const double *wn2;            // (H,)  ||W_h||^2
+    const double *invn;           // (H,)  1/||W_h||
+    const double *G;              // (H, ldH) Gram matrix
+    int *cand;                    // (n, Hp) global index
+    double *logpj; int64_t ld_logpj;   // (n, C) global index (read or write)
+    double *lse;                  // (n,) global index (written, or read when GLF_USE_CUT)
+    const double *cut;            // device scalar
+    double *S;                    // (n_rows, ldH) chunk posterior matrix <s>
+    double *S2;                   // (n_rows, ldH) second moments of the singleton blocks (DSC) or NULL
+    double *Wq;                   // (H, ldH) atomic scatter target
+    double *scalars;              // [0]=n_used [1]=sum lse [2]=sigma stat [3..]=counts
+};
+
+int launch_gl_kernel(const GLArgs &a, int gamma, bool binary, int sm_count, cudaStream_t st);
+size_t gl_smem_bytes(const GLStatic &s, int warps);
+
+}  // namespace pet

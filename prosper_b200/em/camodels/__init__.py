@@ -1,0 +1,301 @@
+"""CAModel: base class of the ET sparse-coding models, bound to the CUDA engine.
+
+Interface follows prosper/em/camodels/__init__.py:53-375 (constructor attributes, `step`
+order, `standard_init`, `select_partial_data`, `compute_lpj`).  What differs is where the
+O(N) work happens: `select_Hprimes`, `E_step`, `M_step` and the fused `step` call the C ABI
+(include/prosper_b200.h) on device-resident data.
+"""
+import ctypes as C
+import itertools
+
+import numpy as np
+import torch
+
+from .. import Model
+from ... import _lib
+from ...utils import parallel
+from ...utils.datalog import dlog
+
+
+def generate_state_matrix(Hprime, gamma):
+    """Binary H'-vectors with 2..gamma ones -> (state_list, no_states, state_matrix, state_abs).
+
+    Host-side twin of camodels/__init__.py:21-47 (the engine enumerates the same order on its
+    own; tests check both against each other)."""
+    sl = [np.array(s, dtype=np.int8) for g in range(2, gamma + 1)
+          for s in itertools.combinations(range(Hprime), g)]
+    sm = np.zeros((len(sl), Hprime), dtype=np.uint8)
+    for i, s in enumerate(sl):
+        sm[i, s] = 1
+    return sl, len(sl), sm, sm.sum(axis=1)
+
+
+def _ptr(t):
+    """Device/host address of a torch tensor or NumPy array (None -> NULL)."""
+    if t is None:
+        return None
+    if isinstance(t, torch.Tensor):
+        return C.c_void_p(t.data_ptr())
+    return C.c_void_p(t.ctypes.data)
+
+
+class Engine(object):
+    """Thin RAII wrapper of a `pet_engine*`."""
+
+    def __init__(self, model_kind, D, H, Hprime, gamma, states=None, device=None, chunk_rows=0):
+        if not torch.cuda.is_available():
+            raise RuntimeError("prosper_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.lib = _lib.load()
+        self.device = torch.cuda.current_device() if device is None else int(device)
+        self._states = None if states is None else np.ascontiguousarray(states, dtype=np.float64)
+        cfg = _lib.Config(model_kind, self.device, D, H, Hprime, gamma,
+                          0 if states is None else len(self._states),
+                          None if states is None else self._states.ctypes.data_as(_lib.c_double_p), chunk_rows)
+        h = C.c_void_p()
+        _lib.check(self.lib.pet_create(C.byref(cfg), C.byref(h)))
+        self.h = h
+        self.D, self.H, self.Hprime, self.gamma = D, H, Hprime, gamma
+        self.S = int(self.lib.pet_num_states(h))
+        self.Cols = int(self.lib.pet_num_columns(h))
+        lay = _lib.StatsLayout()
+        _lib.check(self.lib.pet_stats_layout_get(h, C.byref(lay)))
+        self.layout = lay
+        self.tdev = torch.device('cuda', self.device)
+        self.stats = torch.zeros(lay.total, dtype=torch.float64, device=self.tdev)
+        self.cut = torch.zeros(1, dtype=torch.float64, device=self.tdev)
+        self.n = 0
+        self._keep = []
+
+    def __del__(self):
+        try:
+            if getattr(self, 'h', None):
+                self.lib.pet_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.tdev).cuda_stream)
+
+    def state_matrix(self):
+        out = np.empty((self.S, self.Hprime), dtype=np.float64)
+        _lib.check(self.lib.pet_state_matrix(self.h, out.ctypes.data_as(_lib.c_double_p)))
+        return out
+
+    # -- data ---------------------------------------------------------------------------
+    def set_data(self, y):
+        """y: (n,D) float64 NumPy array (host; pinned if it came from torch) or CUDA tensor."""
+        if isinstance(y, torch.Tensor):
+            if y.dtype != torch.float64 or y.dim() != 2 or y.stride(1) != 1:
+                y = y.to(torch.float64).contiguous()
+            n, ld = y.shape[0], y.stride(0)
+        else:
+            y = np.ascontiguousarray(y, dtype=np.float64)
+            n, ld = y.shape[0], y.shape[1]
+        assert y.shape[1] == self.D
+        self._keep = [y]                      # the async copy reads it after we return
+        _lib.check(self.lib.pet_set_data(self.h, _ptr(y), n, ld, self.stream()))
+        self.n = n
+        self.lse = torch.empty(max(n, 1), dtype=torch.float64, device=self.tdev)
+
+    # -- parameter marshalling ----------------------------------------------------------
+    def params(self, W, pi, sigma, mu=None):
+        if isinstance(W, torch.Tensor):
+            Wc = W if (W.dtype == torch.float64 and W.stride(-1) == 1) else W.to(torch.float64).contiguous()
+            ldW = Wc.stride(0)
+        else:
+            Wc = np.ascontiguousarray(W, dtype=np.float64)
+            ldW = Wc.shape[1]
+        pi_arr = np.atleast_1d(np.asarray(pi, dtype=np.float64)).copy()
+        mu_c = None
+        if mu is not None and np.any(np.asarray(mu) != 0):
+            mu_c = np.ascontiguousarray(mu, dtype=np.float64)
+        p = _lib.Params(_ptr(Wc), ldW, pi_arr.ctypes.data_as(_lib.c_double_p), len(pi_arr), float(sigma), _ptr(mu_c))
+        p._keep = (Wc, pi_arr, mu_c)
+        return p
+
+    @staticmethod
+    def anneal(anneal):
+        return _lib.Anneal(float(anneal['T']), float(anneal['Ncut_factor']), 1 if anneal['anneal_prior'] else 0)
+
+    # -- operators ----------------------------------------------------------------------
+    def select(self, p):
+        cand = np.empty((self.n, self.Hprime), dtype=np.int64)
+        _lib.check(self.lib.pet_select_hprimes(self.h, C.byref(p), _ptr(cand), self.stream()))
+        return cand
+
+    def set_candidates(self, cand):
+        cand = np.ascontiguousarray(cand, dtype=np.int64)
+        assert cand.shape == (self.n, self.Hprime)
+        _lib.check(self.lib.pet_set_candidates(self.h, _ptr(cand), self.stream()))
+        torch.cuda.current_stream(self.tdev).synchronize()
+
+    def e_step(self, a, p):
+        logpj = np.empty((self.n, self.Cols), dtype=np.float64)
+        _lib.check(self.lib.pet_e_step(self.h, C.byref(a), C.byref(p), _ptr(logpj), self.Cols, self.stream()))
+        return logpj
+
+    def log_denominators(self, a, p, logpj=None, flags=0):
+        _lib.check(self.lib.pet_log_denominators(self.h, C.byref(a), C.byref(p), _ptr(logpj),
+                                                 0 if logpj is None else logpj.shape[1], flags,
+                                                 _ptr(self.lse), self.stream()))
+        return self.lse[:self.n]
+
+    def kth_largest(self, vals, k):
+        _lib.check(self.lib.pet_kth_largest(self.h, _ptr(vals), vals.numel(), int(k), _ptr(self.cut), self.stream()))
+        return self.cut
+
+    def m_step_stats(self, a, p, logpj=None, flags=0, use_cut=False):
+        _lib.check(self.lib.pet_m_step_stats(self.h, C.byref(a), C.byref(p), _ptr(logpj),
+                                             0 if logpj is None else logpj.shape[1], flags,
+                                             1 if use_cut else 0, _ptr(self.cut) if use_cut else None,
+                                             _ptr(self.stats), self.stream()))
+        return self.stats
+
+    def solve(self, p, stats):
+        W_new = torch.empty((self.D, self.H), dtype=torch.float64, device=self.tdev)
+        info = C.c_int32(0)
+        _lib.check(self.lib.pet_m_step_solve(self.h, C.byref(p), _ptr(stats), _ptr(W_new), C.byref(info), self.stream()))
+        return W_new, int(info.value)
+
+    def scalars(self, stats):
+        lay = self.layout
+        return stats[lay.off_scalars:lay.off_scalars + lay.n_scalars].cpu().numpy()
+
+    def enable_timing(self, on=True):
+        _lib.check(self.lib.pet_enable_timing(self.h, 1 if on else 0))
+
+    def stage_times(self):
+        out = (C.c_double * 12)()
+        _lib.check(self.lib.pet_stage_times_ms(self.h, out))
+        names = ['prepare', 'score_gemm', 'posterior', 'stats_gemm', 'solve', 'kth']
+        return dict((nm, {'ms': out[i], 'spans': int(out[6 + i])}) for i, nm in enumerate(names))
+
+    def launch_count(self):
+        return int(self.lib.pet_launch_count(self.h))
+
+
+class CAModel(Model):
+    """Base of the ET models (camodels/__init__.py:53-193)."""
+
+    model_kind = None
+
+    def __init__(self, D, H, Hprime, gamma, to_learn=['W', 'pi', 'sigma'], comm=None):
+        Model.__init__(self, comm)
+        self.to_learn = to_learn
+        self.D, self.H, self.Hprime, self.gamma = D, H, Hprime, gamma
+        assert Hprime <= H
+        assert gamma <= Hprime
+        tol = 1e-5
+        self.noise_policy = {
+            'W': (-np.inf, +np.inf, False),
+            'pi': (tol, 1. - tol, False),
+            'sigma': (0., +np.inf, False),
+        }
+        self.state_list, self.no_states, self.state_matrix, self.state_abs = generate_state_matrix(Hprime, gamma)
+        self.cache_data = True          # keep the device copy of my_data['y'] between calls
+        self._engine = None
+        self._bound = None
+
+    # -- engine / data binding ------------------------------------------------------------
+    def _make_engine(self):
+        return Engine(self.model_kind, self.D, self.H, self.Hprime, self.gamma)
+
+    @property
+    def engine(self):
+        if self._engine is None:
+            self._engine = self._make_engine()
+        return self._engine
+
+    def invalidate_data(self):
+        """Forget the device copy of the data (call after mutating my_data['y'] in place)."""
+        self._bound = None
+
+    def _bind(self, my_data):
+        y = my_data['y']
+        if isinstance(y, torch.Tensor):
+            key = ('t', y.data_ptr(), tuple(y.shape), y._version)
+        else:
+            key = ('n', y.ctypes.data, y.shape, y.strides)
+        if self.cache_data and self._bound == key and self.engine.n == y.shape[0]:
+            return False
+        self.engine.set_data(y)
+        self._bound = key
+        return True
+
+    # -- reference interface --------------------------------------------------------------
+    def generate_data(self, model_params, my_N):
+        """camodels/__init__.py:104-122: Bernoulli(pi) latents, then generate_from_hidden."""
+        s = np.random.random(size=(my_N, self.H)) < model_params['pi']
+        return self.generate_from_hidden(model_params, {'s': s})
+
+    def select_partial_data(self, anneal, my_data):
+        """camodels/__init__.py:125-152."""
+        partial = anneal['partial']
+        if partial == 0 or partial == 1:
+            return my_data
+        my_N = my_data['y'].shape[0]
+        my_pN = int(np.ceil(my_N * partial))
+        if my_N == my_pN:
+            return my_data
+        sel = np.random.permutation(my_N)[:my_pN]
+        sel.sort()
+        return dict((k, v[sel]) for k, v in my_data.items())
+
+    def check_params(self, model_params):
+        return model_params
+
+    def step(self, anneal, model_params, my_data):
+        """One EM step in the order of camodels/__init__.py:163-193; the three starred calls
+        of the reference are fused into `_fused_step` (logpj is never materialised)."""
+        model_params = self.noisify_params(model_params, anneal)
+        model_params = self.check_params(model_params)
+        my_pdata = self.select_partial_data(anneal, my_data)
+        new_model_params = self._fused_step(anneal, model_params, my_pdata)
+        dlog.append_all(new_model_params)
+        dlog.append_all(anneal.as_dict())
+        return new_model_params
+
+    def _fused_step(self, anneal, model_params, my_data):
+        my_data = self.select_Hprimes(model_params, my_data)
+        suff = self.E_step(anneal, model_params, my_data)
+        return self.M_step(anneal, model_params, suff, my_data)
+
+    def standard_init(self, data):
+        """camodels/__init__.py:196-235; W noise is drawn on rank 0 and broadcast (the reference
+        relies on identically seeded ranks)."""
+        comm = self.comm
+        my_y = data['y']
+        if isinstance(my_y, torch.Tensor):
+            my_y = my_y.cpu().numpy()
+        my_N, D = my_y.shape
+        assert D == self.D
+        W_mean = parallel.allmean(my_y, axis=0, comm=comm)
+        sigma_sq = parallel.allmean((my_y - W_mean) ** 2, axis=0, comm=comm)
+        sigma_init = np.sqrt(sigma_sq).sum() / D
+        noise = np.random.normal(scale=sigma_init / 4., size=[D, self.H]) if comm.rank == 0 else None
+        noise = comm.bcast(noise)
+        return {'W': W_mean[:, None] + noise, 'pi': 1. / self.H, 'sigma': sigma_init}
+
+    def compute_lpj(self, anneal, model_params, my_data):
+        """camodels/__init__.py:238-253."""
+        assert 'y' in my_data, "Key 'y' in my_data dict not defined."
+        my_data = self.select_Hprimes(model_params, my_data)
+        my_suff_stat = self.E_step(anneal, model_params, my_data)
+        return my_suff_stat['logpj'], my_data['candidates']
+
+    # -- shared M-step plumbing -----------------------------------------------------------
+    def _global_cut(self, lse, N_use_target):
+        """k-th largest log-denominator over ALL ranks -> engine.cut (device scalar).
+
+        Replaces parallel.allsort(all_denoms)[-N_use] (bsc_et.py:252): the log-denominators are
+        all-gathered over NVLink (8 bytes per datapoint) and every rank runs the same radix
+        select, exactly as every MPI rank sorts the gathered array in the reference."""
+        comm, eng = self.comm, self.engine
+        if comm.size == 1:
+            return eng.kth_largest(lse, N_use_target)
+        nmax = int(comm.allreduce_max(lse.numel()))
+        pad = torch.full((nmax,), -float('inf'), dtype=torch.float64, device=lse.device)
+        pad[:lse.numel()] = lse
+        allv = torch.cat(comm.allgather_tensor(pad))
+        return eng.kth_largest(allv, N_use_target)

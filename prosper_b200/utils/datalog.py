@@ -1,0 +1,125 @@
+"""Rank-0 publish/subscribe of named values (the keys the hot path feeds).
+
+Mirrors the interface of prosper/utils/datalog.py (`dlog.set_handler / append / append_all /
+progress / close`, datalog.py:179-254) so that the models log the same keys the reference
+does (`W, pi, sigma, mu, L, N, N_use, Q, prior_mass` and the annealing values,
+camodels/__init__.py:190-191).  Handlers here: TextPrinter, StoreToTxt, Keep (in-memory).
+The HDF5 writer (`result.h5`) is SURVEY section 8 row f1 and not built yet.
+"""
+import sys
+
+import numpy as np
+
+
+class DataHandler(object):
+    def register(self, tblname):
+        pass
+
+    def append(self, tblname, value):
+        raise NotImplementedError
+
+    def append_all(self, valdict):
+        for k, v in valdict.items():
+            self.append(k, v)
+
+    def remove(self, tblname):
+        pass
+
+    def close(self):
+        pass
+
+
+class TextPrinter(DataHandler):
+    def append(self, tblname, value):
+        sys.stdout.write("  %8s = %s \n" % (tblname, value))
+
+
+class StoreToTxt(DataHandler):
+    def __init__(self, destination='terminal.txt'):
+        self.fd = open(destination, 'w')
+
+    def append(self, tblname, value):
+        self.fd.write("%s = %s\n" % (tblname, value))
+        self.fd.flush()
+
+    def close(self):
+        self.fd.close()
+
+
+class Keep(DataHandler):
+    """Collects every appended value in `self.values[name]` (used by tests and bench)."""
+
+    def __init__(self):
+        self.values = {}
+
+    def append(self, tblname, value):
+        self.values.setdefault(tblname, []).append(np.copy(value) if isinstance(value, np.ndarray) else value)
+
+    def last(self, name):
+        return self.values[name][-1]
+
+
+class DataLog(object):
+    def __init__(self, comm=None):
+        self.comm = comm
+        self.policy = []          # ordered (tblname or '*', handler)
+
+    def _rank(self):
+        if self.comm is not None:
+            return self.comm.rank
+        from . import parallel
+        return parallel.default_comm().rank
+
+    def _lookup(self, tblname):
+        return [h for (name, h) in self.policy if name == tblname or name == '*']
+
+    def set_handler(self, tblnames, handler_class, *args, **kargs):
+        if self._rank() != 0:
+            return None
+        if not issubclass(handler_class, DataHandler):
+            raise TypeError("handler_class must be a subclass of DataHandler")
+        handler = handler_class(*args, **kargs)
+        if isinstance(tblnames, str):
+            tblnames = (tblnames,)
+        for t in tblnames:
+            self.policy.append((t, handler))
+            handler.register(t)
+        return handler
+
+    def remove_handler(self, handler):
+        self.policy = [(n, h) for (n, h) in self.policy if h is not handler]
+
+    def ignored(self, tblname):
+        return self._rank() != 0 or not self._lookup(tblname)
+
+    def append(self, tblname, value):
+        if self._rank() != 0:
+            return
+        for h in self._lookup(tblname):
+            h.append(tblname, value)
+
+    def append_all(self, valdict):
+        for k, v in valdict.items():
+            self.append(k, v)
+
+    def progress(self, message, completed=None):
+        if self._rank() != 0:
+            return
+        if completed is None:
+            sys.stdout.write("[%s]\n" % message)
+        else:
+            sys.stdout.write("[%5.1f%%] %s\n" % (completed * 100., message))
+        sys.stdout.flush()
+
+    def close(self, quiet=False):
+        if self._rank() != 0:
+            return
+        seen = []
+        for _, h in self.policy:
+            if not any(h is s for s in seen):
+                h.close()
+                seen.append(h)
+        self.policy = []
+
+
+dlog = DataLog()

@@ -1,0 +1,143 @@
+"""Data-parallel plumbing: the reference's mpi4py communicator, on torch.distributed.
+
+Mirrors prosper/utils/parallel.py (stride_data :44-84, allsort :87-110, allmean :138-156,
+allsum :159-170, pprint :27-41) and the subset of the mpi4py communicator API the models
+call (`comm.rank`, `comm.size`, `comm.allreduce`, `comm.bcast`, `comm.Barrier`).  One process
+per GPU; NCCL for device tensors, gloo for host tensors (CPU tests run with gloo only).
+"""
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+class SerialComm(object):
+    """Single-process communicator (what the reference sees without mpirun)."""
+    rank = 0
+    size = 1
+
+    def allreduce(self, x):
+        return x
+
+    def allreduce_max(self, x):
+        return x
+
+    def bcast(self, x, root=0):
+        return x
+
+    def allreduce_tensor_(self, t):
+        return t
+
+    def allgather_tensor(self, t):
+        return [t]
+
+    def Barrier(self):
+        pass
+
+
+class TorchComm(object):
+    """torch.distributed process group with the mpi4py-style calls the models use."""
+
+    def __init__(self, group=None):
+        if not dist.is_initialized():
+            raise RuntimeError("torch.distributed is not initialised")
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.size = dist.get_world_size(group)
+        self.backend = dist.get_backend(group)
+
+    def _host_device(self):
+        # NCCL cannot reduce host tensors: stage small host values through the current GPU
+        return torch.device('cuda', torch.cuda.current_device()) if self.backend == 'nccl' else torch.device('cpu')
+
+    def allreduce(self, x):
+        """Sum of a Python scalar or NumPy array over ranks (comm.allreduce / Allreduce)."""
+        arr = np.asarray(x)
+        t = torch.as_tensor(arr.astype(np.float64 if arr.dtype.kind == 'f' else np.int64)).to(self._host_device())
+        if t.dim() == 0:
+            t = t.reshape(1)
+            dist.all_reduce(t, group=self.group)
+            v = t.cpu().numpy()[0]
+            return float(v) if arr.dtype.kind == 'f' else int(v)
+        dist.all_reduce(t, group=self.group)
+        return t.cpu().numpy()
+
+    def allreduce_max(self, x):
+        t = torch.as_tensor([float(x)], dtype=torch.float64).to(self._host_device())
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+        return float(t.cpu()[0])
+
+    def bcast(self, x, root=0):
+        obj = [x]
+        dist.broadcast_object_list(obj, src=root, group=self.group)
+        return obj[0]
+
+    def allreduce_tensor_(self, t):
+        """In-place sum of a tensor that already lives where the backend wants it."""
+        dist.all_reduce(t, group=self.group)
+        return t
+
+    def allgather_tensor(self, t):
+        """Gather equally-shaped tensors from all ranks."""
+        out = [torch.empty_like(t) for _ in range(self.size)]
+        dist.all_gather(out, t, group=self.group)
+        return out
+
+    def Barrier(self):
+        dist.barrier(group=self.group)
+
+
+def default_comm():
+    return TorchComm() if dist.is_available() and dist.is_initialized() else SerialComm()
+
+
+def pprint(obj="", comm=None, end='\n'):
+    comm = comm or default_comm()
+    if comm.rank != 0:
+        return
+    sys.stdout.write((obj if isinstance(obj, str) else repr(obj)) + end)
+    sys.stdout.flush()
+
+
+def stride_data(N, balanced=False, comm=None):
+    """Block distribution of N items over comm.size ranks -> (first, last).
+
+    Same rule as parallel.py:67-84: N // size each, the first N % size ranks get one more
+    (`balanced=True` drops the remainder).
+    """
+    comm = comm or default_comm()
+    base, residue = divmod(N, comm.size)
+    if balanced:
+        return base * comm.rank, base * (comm.rank + 1)
+    if comm.rank < residue:
+        first = (base + 1) * comm.rank
+        return first, first + base + 1
+    first = base * comm.rank + residue
+    return first, first + base
+
+
+def allsort(my_array, comm=None):
+    """All ranks get the globally sorted 1-D array (parallel.py:87-110)."""
+    comm = comm or default_comm()
+    if comm.size == 1:
+        return np.sort(my_array)
+    n = int(comm.allreduce(len(my_array)))
+    nmax = int(comm.allreduce_max(len(my_array)))
+    pad = np.full(nmax, np.inf)                 # +inf padding sorts last and is cut off below
+    pad[:len(my_array)] = my_array
+    t = torch.as_tensor(pad).to(comm._host_device())
+    parts = comm.allgather_tensor(t)
+    allv = np.sort(np.concatenate([p.cpu().numpy() for p in parts]))
+    return allv[:n]
+
+
+def allmean(my_a, axis=None, comm=None):
+    comm = comm or default_comm()
+    N = comm.allreduce(my_a.size if axis is None else my_a.shape[axis])
+    return comm.allreduce(np.sum(my_a, axis)) / N
+
+
+def allsum(my_a, axis=None, comm=None):
+    comm = comm or default_comm()
+    return comm.allreduce(np.sum(my_a, axis))
