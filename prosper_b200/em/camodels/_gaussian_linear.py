@@ -1,0 +1,91 @@
+"""Shared host logic of the Gaussian-linear ET models (BSC, TSC, DSC).
+
+All three evaluate ||y - sum_h s_h W_h||^2 over a truncated state space, so they share the
+device pipeline (score GEMM -> posterior kernel -> statistics GEMM -> all-reduce -> solve);
+what differs per model is O(1) host arithmetic: the truncation mass A, the likelihood
+constant and the prior update.  Subclasses provide `_truncation_mass`, `_likelihood_const`,
+`_update_prior` and `_pack_params`.
+"""
+import numpy as np
+
+from . import CAModel
+from ... import _lib
+from ...utils.datalog import dlog
+
+
+class GaussianLinearET(CAModel):
+
+    # -- hooks ----------------------------------------------------------------------------------
+    def _pack_params(self, model_params):
+        return self.engine.params(model_params['W'], model_params['pi'], model_params['sigma'])
+
+    def _truncation_mass(self, model_params):
+        raise NotImplementedError
+
+    def _likelihood_const(self, model_params, A):
+        raise NotImplementedError
+
+    def _update_prior(self, model_params, counts, N_use, A):
+        raise NotImplementedError
+
+    # -- the three operators ----------------------------------------------------------------------
+    def select_Hprimes(self, model_params, data):
+        self._bind(data)
+        data['candidates'] = self.engine.select(self._pack_params(model_params))
+        return data
+
+    def E_step(self, anneal, model_params, my_data):
+        eng = self.engine
+        self._bind(my_data)
+        eng.set_candidates(my_data['candidates'])
+        return {'logpj': eng.e_step(eng.anneal(anneal), self._pack_params(model_params))}
+
+    def M_step(self, anneal, model_params, my_suff_stat, my_data):
+        eng = self.engine
+        self._bind(my_data)
+        eng.set_candidates(my_data['candidates'])
+        logpj = np.ascontiguousarray(my_suff_stat['logpj'], dtype=np.float64)
+        return self._m_step(anneal, model_params, logpj, fused=False)
+
+    def _fused_step(self, anneal, model_params, my_data):
+        """select + E + M in one sweep over the shard; logpj (n x C) is never written to memory."""
+        self._bind(my_data)
+        return self._m_step(anneal, model_params, None, fused=True)
+
+    def _m_step(self, anneal, model_params, logpj, fused):
+        comm, eng = self.comm, self.engine
+        p = self._pack_params(model_params)
+        a = eng.anneal(anneal)
+        N = comm.allreduce(eng.n)
+        A = self._truncation_mass(model_params)
+        sel = _lib.PASS_SELECT if fused else 0
+        if anneal['Ncut_factor'] > 0.0:
+            # N_use = int(N * (1 - (1 - A) * Ncut)); cut = allsort(denoms)[-N_use]   (bsc_et.py:250-252)
+            N_use_target = int(N * (1 - (1 - A) * anneal['Ncut_factor']))
+            lse = eng.log_denominators(a, p, logpj, sel)
+            self._global_cut(lse, N_use_target)
+            stats = eng.m_step_stats(a, p, logpj, _lib.PASS_REUSE_SCORES if fused else 0, use_cut=True)
+        else:
+            stats = eng.m_step_stats(a, p, logpj, sel)
+        comm.allreduce_tensor_(stats)     # ONE collective replaces bsc_et.py:258,266,373-374,387,417
+        sc = eng.scalars(stats)
+        N_use = int(round(sc[0]))
+        self._log_before_L(N_use, A)
+        L = self._likelihood_const(model_params, A) + sc[1] / N_use
+        dlog.append('L', L)
+        if 'W' in self.to_learn:
+            W_dev, self.last_dropped_pivots = eng.solve(p, stats)
+            W_new = W_dev.cpu().numpy()
+        else:
+            W_new = model_params['W']
+        n_cnt = max(1, len(getattr(self, 'states', [0, 1])) - 1)
+        pi_new = self._update_prior(model_params, sc[3:3 + n_cnt], N_use, A) if 'pi' in self.to_learn else model_params['pi']
+        sigma_new = np.sqrt(sc[2] / self.D / N_use) if 'sigma' in self.to_learn else model_params['sigma']
+        dlog.append('N_use', N_use)
+        return self._result(model_params, W_new, pi_new, sigma_new)
+
+    def _log_before_L(self, N_use, A):
+        pass
+
+    def _result(self, model_params, W_new, pi_new, sigma_new):
+        return {'W': W_new, 'pi': pi_new, 'sigma': sigma_new, 'Q': 0.}

@@ -1,0 +1,152 @@
+"""Discrete Sparse Coding with Expectation Truncation on the B200 engine.
+
+Mirrors prosper/em/camodels/dsc_et.py (DSC_ET): select_Hprimes :347-410, E_step :492-585,
+M_step :587-774, get_scaling_factors :798-823, truncation with strict '>' :825-843,
+get_likelihood :845-870, standard_init :872-925.
+"""
+import itertools
+
+import numpy as np
+from scipy.special import gammaln
+
+from ._gaussian_linear import GaussianLinearET
+from . import CAModel
+from ... import _lib
+from ...utils import parallel
+from ...utils.datalog import dlog
+
+
+def get_states(states, Hprime, gamma):
+    """dsc_et.py:56-63: product states with 2 <= nnz <= gamma, itertools.product order."""
+    states = np.asarray(states)
+    K = len(states)
+    idx = np.indices((K,) * Hprime).reshape(Hprime, -1).T
+    s = states[idx]
+    nnz = (s != 0).sum(axis=1)
+    return s[(nnz <= gamma) & (nnz > 1)]
+
+
+class DSC_ET(GaussianLinearET):
+    model_kind = _lib.MODEL_DSC
+
+    def __init__(self, D, H, Hprime, gamma, states=np.array([-1., 0., 1.]), to_learn=['W', 'pi', 'sigma'], comm=None):
+        CAModel.__init__(self, D, H, Hprime, gamma, to_learn, comm)
+        if not type(states) == np.ndarray:
+            raise TypeError("DSC: states must be of type numpy.ndarray")        # dsc_et.py:139
+        if Hprime > H:
+            raise Exception("Hprime must be less or equal to H")
+        if gamma > Hprime:
+            raise Exception("gamma must be less or equal to Hprime")
+        self.states = states
+        self.K = states.shape[0]
+        self._K_0 = int(np.argwhere(states == 0.)[0, 0])
+        self._noise_policy = dict(self.noise_policy)
+        self.single_state_matrix = np.concatenate([np.eye(H) * states[i] for i in range(self.K) if i != self._K_0])
+        self.state_matrix = get_states(states, Hprime, gamma)
+        self.no_states = self.state_matrix.shape[0]
+        self.state_abs = np.stack([(self.state_matrix == states[i]).sum(axis=1) for i in range(self.K)]).astype(np.float64)
+        self.state_abs[self._K_0] = H - self.state_abs.sum(0) + self.state_abs[self._K_0]   # dsc_et.py:190-191
+
+    def _make_engine(self):
+        from . import Engine
+        return Engine(self.model_kind, self.D, self.H, self.Hprime, self.gamma, states=self.states)
+
+    def check_params(self, model_params):
+        """dsc_et.py:194-236."""
+        assert np.isfinite(model_params['W']).all()
+        assert np.isfinite(model_params['pi']).all()
+        assert np.isfinite(model_params['sigma']).all()
+        assert model_params['sigma'] >= 0.
+        return model_params
+
+    def generate_data(self, model_params, my_N):
+        """dsc_et.py:238-345 (default path): s_h ~ Categorical(pi) over `states`."""
+        pi, W, sigma = model_params['pi'], model_params['W'].T, model_params['sigma']
+        s = np.random.choice(self.states, size=(my_N, self.H), p=pi)
+        y = s @ W + np.random.normal(scale=sigma, size=(my_N, self.D))
+        return {'y': y, 's': s}
+
+    def noisify_params(self, model_params, anneal):
+        """dsc_et.py:412-490: as the base class, except pi gets uniform noise and is renormalised."""
+        comm = self.comm
+        for param, policy in self._noise_policy.items():
+            pvalue = model_params[param]
+            scale = anneal[param + "_noise"]
+            if scale == 0.0:
+                continue
+            if param == 'pi':
+                new = pvalue
+                if comm.rank == 0:
+                    new = pvalue + np.random.rand(*pvalue.shape) * scale
+                    new = new / new.sum()
+                pvalue = comm.bcast(new)
+            elif np.isscalar(pvalue):
+                new = 0
+                if comm.rank == 0:
+                    new = pvalue + np.random.normal(scale=scale)
+                    new = min(max(new, policy[0]), policy[1]) if new < policy[0] or new >= policy[1] else new
+                    if policy[2]:
+                        new = np.abs(new)
+                pvalue = comm.bcast(new)
+            else:
+                new = pvalue
+                if comm.rank == 0:
+                    low, up, absify = policy
+                    new = np.minimum(up, np.maximum(low, pvalue + np.random.normal(scale=scale, size=pvalue.shape)))
+                    if absify:
+                        new = np.abs(new)
+                pvalue = comm.bcast(new)
+            model_params[param] = pvalue
+        return model_params
+
+    def get_scaling_factors(self, pi):
+        """Prior mass of the truncated state space (dsc_et.py:798-823)."""
+        A = 0.0
+        for gp in itertools.product(range(self.gamma + 1), repeat=self.K - 1):
+            ngp = np.array(gp)
+            if ngp.sum() > self.gamma:
+                continue
+            abs_array = np.insert(ngp, self._K_0, self.H - ngp.sum())
+            cmb = np.exp(gammaln(abs_array.sum() + 1) - gammaln(abs_array + 1).sum())
+            A += cmb * np.prod(pi ** abs_array)
+        return A
+
+    def _truncation_mass(self, model_params):
+        A = self.get_scaling_factors(model_params['pi'])
+        dlog.append("prior_mass", A)                                         # dsc_et.py:643
+        return A
+
+    def _likelihood_const(self, model_params, A):
+        sigma = model_params['sigma']                                        # dsc_et.py:866 (no -log A)
+        return -0.5 * self.D * np.log(2 * np.pi * sigma ** 2)
+
+    def _update_prior(self, model_params, counts, N_use, A):
+        my_pi = np.zeros(self.K)
+        nz = [i for i in range(self.K) if i != self._K_0]
+        my_pi[nz] = counts[:len(nz)]
+        my_pi[self._K_0] = self.H * N_use - my_pi.sum()      # every state has H entries and posteriors sum to 1
+        pi_new = my_pi / my_pi.sum()                                         # dsc_et.py:740-741
+        eps = 1e-6                                                           # dsc_et.py:743-748
+        if np.any(pi_new < eps):
+            lo = pi_new < eps
+            hi = ~lo
+            pi_new[lo] += eps - pi_new[lo]
+            pi_new[hi] -= (eps * lo.sum()) / hi.sum()
+        if 'penalty' in self.__dict__:                                       # dsc_et.py:750-756
+            if self.penalty > pi_new[self._K_0]:
+                r = (1 - self.penalty) / (1 - pi_new[self._K_0])
+                pi_new[pi_new != 0] = pi_new[pi_new != 0] * r
+                pi_new[self._K_0] = self.penalty
+                pi_new /= pi_new.sum()
+        return pi_new
+
+    def standard_init(self, data):
+        """dsc_et.py:872-925: W/sigma as the base class, pi = sparsity 1-1/H on the zero state."""
+        comm = self.comm
+        base = CAModel.standard_init(self, data)
+        sparsity = 1. - (1. / self.H)
+        pi_init = np.random.rand(self.K - 1) if comm.rank == 0 else None
+        pi_init = comm.bcast(pi_init)
+        pi_init = (1 - sparsity) * pi_init / pi_init.sum()
+        base['pi'] = np.insert(pi_init, self._K_0, sparsity)
+        return base

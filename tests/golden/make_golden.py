@@ -1,0 +1,79 @@
+"""Mint golden vectors from the UNMODIFIED reference (run in the build container only).
+
+    python tests/golden/make_golden.py
+
+Imports /root/reference/prosper through oracle/ref_harness.py (fake mpi4py/tables, NumPy-2
+aliases), runs select_Hprimes / E_step / M_step of each model on small seeded
+inputs and stores inputs + every intermediate in tests/golden/<model>_<case>.npz.  The GPU box
+has no /root/reference, so tests only ever read the .npz files.
+Protocol per case: np.random.seed(seed); data = model.generate_data(gt, N);
+params = model.standard_init(data); one step at the given (T, Ncut_factor, anneal_prior).
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "..", ".."))
+from oracle import ref_harness  # noqa: E402
+
+ref_harness.load()
+from prosper.em.annealing import LinearAnnealing  # noqa: E402
+from prosper.utils.barstest import generate_bars_dict  # noqa: E402
+
+log = ref_harness.KeepLog().install()
+
+
+def run_case(name, case, model, gt, N, seed, T, ncut, ap, meta, mutate=None):
+    np.random.seed(seed)
+    data = model.generate_data(gt, N)
+    params = model.standard_init(data)
+    if mutate:
+        params = mutate(params)
+    an = LinearAnnealing(2)
+    an['T'] = T
+    an['Ncut_factor'] = ncut
+    an['anneal_prior'] = ap
+    params = model.check_params(params)
+    p0 = dict((k, np.copy(v)) for k, v in params.items())
+    data = model.select_Hprimes(params, data)
+    suff = model.E_step(an, params, data)
+    new = model.M_step(an, params, suff, data)
+    out = dict(model=name, meta=np.array(meta), T=T, Ncut_factor=ncut, anneal_prior=ap,
+               y=data['y'], W0=p0['W'], pi0=p0['pi'], sigma0=p0['sigma'],
+               candidates=np.asarray(data['candidates'], dtype=np.int64), logpj=suff['logpj'],
+               W_new=new['W'], pi_new=new['pi'], sigma_new=new['sigma'],
+               L=log.values.get('L', [np.nan])[-1] if 'Q' not in new or name in ('tsc', 'dsc') else np.nan,
+               Q=new.get('Q', np.nan), N_use=log.last('N_use'))
+    if name == 'dsc':
+        out['states'] = model.states
+    path = os.path.join(HERE, "%s_%s.npz" % (name, case))
+    np.savez_compressed(path, **out)
+    print("wrote", path, "pi_new", new['pi'], "sigma_new", new['sigma'], "L/Q", out['L'], out['Q'], "N_use", out['N_use'])
+
+
+def main():
+    from prosper.em.camodels.bsc_et import BSC_ET
+    from prosper.em.camodels.tsc_et import TSC_ET
+    from prosper.em.camodels.dsc_et import DSC_ET
+    from prosper.em.camodels.mca_et import MCA_ET
+    from prosper.em.camodels.mmca_et import MMCA_ET
+    gt10 = {'W': 10 * generate_bars_dict(10), 'pi': 0.2, 'sigma': 2.0}
+    cases = [('t1', 1.0, 0.0, False), ('t2cut', 2.0, 0.5, False), ('prior', 1.5, 0.3, True)]
+    for case, T, c, ap in cases:
+        run_case('bsc', case, BSC_ET(25, 10, 6, 3), gt10, 300, 1, T, c, ap, (25, 10, 6, 3))
+        run_case('mca', case, MCA_ET(25, 10, 6, 3), gt10, 300, 1, T, c, ap, (25, 10, 6, 3))
+        run_case('mmca', case, MMCA_ET(25, 10, 6, 3), gt10, 300, 1, T, c, ap, (25, 10, 6, 3))
+    gt12 = {'W': 10 * generate_bars_dict(12), 'pi': 0.125, 'sigma': 2.0}
+    gt12d = {'W': 10 * generate_bars_dict(12), 'pi': np.array([.06, .88, .06]), 'sigma': 2.0}
+    for case, T, c, ap in cases:
+        run_case('tsc', case, TSC_ET(36, 12, 6, 3), gt12, 200, 1, T, c, ap, (36, 12, 6, 3))
+        run_case('dsc', case, DSC_ET(36, 12, 6, 3, np.array([-1., 0., 1.])), gt12d, 200, 1, T, c, ap, (36, 12, 6, 3))
+    # a second binary shape with gamma=4 and H'=8 (more states than columns of singles)
+    gt16 = {'W': 10 * generate_bars_dict(16), 'pi': 0.125, 'sigma': 2.0}
+    run_case('bsc', 'h16', BSC_ET(64, 16, 8, 4), gt16, 150, 2, 1.2, 0.7, False, (64, 16, 8, 4))
+
+
+if __name__ == "__main__":
+    main()

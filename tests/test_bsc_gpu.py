@@ -1,0 +1,210 @@
+"""GPU parity tests of the BSC-ET hot path: CUDA (through the C ABI) vs golden vectors minted
+from the reference, vs the NumPy oracle on seeded inputs, plus size-independent properties."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from helpers import bsc_problem, rel_err, cand_mismatch_gap
+from oracle.bsc import BSC
+from oracle.common import DictAnneal
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+TOL = 1e-8          # float64 path; north_star asks for <= 1e-5 relative
+
+
+def model(D, H, Hp, g, **kw):
+    from prosper_b200.em.camodels.bsc_et import BSC_ET
+    assert torch.cuda.is_available(), "GPU tests need a B200"
+    return BSC_ET(D, H, Hp, g, **kw)
+
+
+def keep_log():
+    from prosper_b200.utils.datalog import dlog, Keep
+    return dlog, dlog.set_handler('*', Keep)
+
+
+def copy_params(p):
+    return dict((k, (np.copy(v) if isinstance(v, np.ndarray) else v)) for k, v in p.items())
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "bsc_*.npz"))),
+                         ids=lambda p: os.path.basename(p))
+def test_bsc_against_reference_golden(path):
+    g = np.load(path)
+    D, H, Hp, gam = (int(v) for v in g['meta'])
+    m = model(D, H, Hp, gam)
+    an = DictAnneal(T=float(g['T']), Ncut_factor=float(g['Ncut_factor']), anneal_prior=bool(g['anneal_prior']))
+    params = {'W': g['W0'].copy(), 'pi': float(g['pi0']), 'sigma': float(g['sigma0'])}
+    data = m.select_Hprimes(params, {'y': g['y'].copy()})
+    assert data['candidates'].dtype == np.int64
+    assert np.array_equal(data['candidates'], g['candidates'])
+    suff = m.E_step(an, params, data)
+    assert 'mu' in params                                   # bsc_et.py:145-149 side effect
+    assert suff['logpj'].shape == g['logpj'].shape
+    assert np.abs(suff['logpj'] - g['logpj']).max() < 1e-10 * np.abs(g['logpj']).max()
+    dlog, keep = keep_log()
+    try:
+        new = m.M_step(an, params, suff, data)
+        assert rel_err(new['W'], g['W_new']) < TOL
+        assert abs(new['pi'] - g['pi_new']) < TOL * g['pi_new']
+        assert abs(new['sigma'] - g['sigma_new']) < TOL * g['sigma_new']
+        assert abs(keep.last('L') - float(g['L'])) < TOL * abs(float(g['L']))
+        assert keep.last('N_use') == int(g['N_use'])
+        # fused path (what CAModel.step runs): nothing of size n*C is materialised
+        newf = m._fused_step(an, {'W': g['W0'].copy(), 'pi': float(g['pi0']), 'sigma': float(g['sigma0'])}, {'y': g['y'].copy()})
+        assert rel_err(newf['W'], g['W_new']) < TOL
+        assert abs(newf['pi'] - g['pi_new']) < TOL * g['pi_new']
+        assert abs(newf['sigma'] - g['sigma_new']) < TOL * g['sigma_new']
+        assert abs(keep.last('L') - float(g['L'])) < TOL * abs(float(g['L']))
+        assert keep.last('N_use') == int(g['N_use'])
+    finally:
+        dlog.remove_handler(keep)
+
+
+CASES = [
+    # D, H, H', gamma, N, seed, T, Ncut, anneal_prior
+    (25, 10, 6, 3, 1000, 1, 1.0, 0.0, False),
+    (25, 10, 6, 3, 1000, 1, 2.0, 1.0, False),
+    (100, 50, 8, 3, 2000, 2, 1.0, 0.0, False),
+    (100, 50, 8, 4, 2000, 2, 1.3, 1.0, True),
+    (31, 17, 5, 5, 333, 4, 1.1, 0.4, False),          # odd D and H, gamma == H'
+    (40, 12, 4, 1, 257, 6, 1.0, 0.0, False),          # gamma = 1: no multi-cause states at all
+    (64, 16, 16, 2, 100, 7, 1.0, 0.0, False),         # H' == H
+    (676, 1000, 12, 5, 192, 5, 1.0, 0.0, False),      # north-star shape, small N
+    (676, 1000, 12, 5, 192, 5, 1.2, 1.0, False),
+]
+
+
+@pytest.mark.parametrize("D,H,Hp,gam,N,seed,T,ncut,ap", CASES)
+def test_bsc_against_oracle(D, H, Hp, gam, N, seed, T, ncut, ap):
+    bars = (D == 25)
+    y, params, _ = bsc_problem(D, H, N, seed, bars=bars, pi=(0.2 if bars else None), sigma=(2.0 if bars else 1.0))
+    an = DictAnneal(T=T, Ncut_factor=ncut, anneal_prior=ap)
+    o = BSC(D, H, Hp, gam)
+    od = o.select_hprimes(copy_params(params), {'y': y.copy()})
+    p0 = copy_params(params)
+    oss = o.e_step(an, p0, od)
+    onew = o.m_step(an, p0, oss, od)
+
+    m = model(D, H, Hp, gam)
+    p1 = copy_params(params)
+    d = m.select_Hprimes(p1, {'y': y.copy()})
+    bad, gap = cand_mismatch_gap(od['_sim'], od['candidates'], d['candidates'])
+    assert bad == 0 or gap < 1e-12, (bad, gap)              # sets identical unless scores tie
+    d['candidates'] = od['candidates'].copy()               # line the columns up for the elementwise check
+    ss = m.E_step(an, p1, d)
+    assert np.abs(ss['logpj'] - oss['logpj']).max() < 1e-11 * np.abs(oss['logpj']).max()
+    dlog, keep = keep_log()
+    try:
+        new = m.M_step(an, p1, {'logpj': oss['logpj']}, d)
+        for got in (new, m._fused_step(an, copy_params(params), {'y': y.copy()})):
+            assert rel_err(got['W'], onew['W']) < TOL
+            assert abs(got['pi'] - onew['pi']) < TOL * onew['pi']
+            assert abs(got['sigma'] - onew['sigma']) < TOL * onew['sigma']
+            assert abs(keep.last('L') - o.log['L']) < TOL * abs(o.log['L'])
+            assert keep.last('N_use') == o.log['N_use']
+    finally:
+        dlog.remove_handler(keep)
+
+
+def test_bsc_trajectory_50_iterations_tracks_oracle():
+    """BASELINE configs[0]: bars test 5x5, H=10, H'=6, gamma=3, N=1000, 50 annealed EM iterations."""
+    from prosper_b200.em import EM
+    from prosper_b200.em.annealing import LinearAnnealing
+    D, H, Hp, gam, N = 25, 10, 6, 3, 1000
+    y, params, gt = bsc_problem(D, H, N, 1, bars=True, pi=0.2, sigma=2.0)
+    anneal = LinearAnnealing(50)
+    anneal['T'] = [(0, 2.), (.7, 1.)]
+    anneal['Ncut_factor'] = [(0, 0.), (2. / 3, 1.)]
+    anneal['anneal_prior'] = False
+    o = BSC(D, H, Hp, gam)
+    po = copy_params(params)
+    m = model(D, H, Hp, gam)
+    em = EM(model=m, anneal=anneal, data={'y': y.copy()}, lparams=copy_params(params))
+    worst = 0.0
+    while not anneal.finished:
+        an = DictAnneal(**anneal.as_dict())
+        po = o.step(an, po, {'y': y})
+        new = m.step(anneal, em.lparams, em.data)
+        anneal.next()
+        em.lparams = new
+        worst = max(worst, rel_err(new['W'], po['W']), abs(new['pi'] - po['pi']) / po['pi'],
+                    abs(new['sigma'] - po['sigma']) / po['sigma'])
+    assert worst < 1e-6, worst
+    # bars are recovered: every ground-truth bar is matched by some learned column
+    Wl, Wg = new['W'], gt['W']
+    err = np.abs(Wl[:, :, None] - Wg[:, None, :]).mean(axis=0)
+    assert (err.min(axis=0) < 1.0).all()
+    assert abs(new['sigma'] - 2.0) < 0.2 and abs(new['pi'] - 0.2) < 0.05
+
+
+def test_properties_at_scale():
+    """Size-independent properties at a size the oracle cannot reach (N = 40k, north-star shape):
+    permutation invariance over datapoints, chunking invariance, truncation count, select idempotence."""
+    from prosper_b200.em.camodels import Engine
+    D, H, Hp, gam, N = 676, 1000, 12, 5, 40000
+    dev = torch.device('cuda', 0)
+    g = torch.Generator(device=dev); g.manual_seed(11)
+    Wg = torch.randn(D, H, dtype=torch.float64, device=dev, generator=g)
+    Wg *= 10 / Wg.norm(dim=0, keepdim=True)
+    s = (torch.rand(N, H, device=dev, generator=g) < 2.0 / H).to(torch.float64)
+    y = s @ Wg.T + torch.randn(N, D, dtype=torch.float64, device=dev, generator=g)
+    W0 = (y.mean(0)[:, None] + 0.3 * torch.randn(D, H, dtype=torch.float64, device=dev, generator=g)).cpu().numpy()
+    params = {'W': W0, 'pi': 1. / H, 'sigma': 1.2}
+    an = DictAnneal(T=1.1, Ncut_factor=1.0, anneal_prior=False)
+    m = model(D, H, Hp, gam)
+    dlog, keep = keep_log()
+    try:
+        a = m._fused_step(an, copy_params(params), {'y': y})
+        L_a, nuse_a = keep.last('L'), keep.last('N_use')
+        perm = torch.randperm(N, device=dev, generator=g)
+        b = m._fused_step(an, copy_params(params), {'y': y[perm].contiguous()})
+        L_b, nuse_b = keep.last('L'), keep.last('N_use')
+        m2 = model(D, H, Hp, gam)
+        m2._engine = Engine(m2.model_kind, D, H, Hp, gam, chunk_rows=4096)      # 10 chunks instead of 3
+        c = m2._fused_step(an, copy_params(params), {'y': y})
+        L_c, nuse_c = keep.last('L'), keep.last('N_use')
+    finally:
+        dlog.remove_handler(keep)
+    for other, L_o, n_o in ((b, L_b, nuse_b), (c, L_c, nuse_c)):
+        assert rel_err(other['W'], a['W']) < 1e-9
+        assert abs(other['pi'] - a['pi']) < 1e-11 * a['pi'] and abs(other['sigma'] - a['sigma']) < 1e-11 * a['sigma']
+        assert abs(L_o - L_a) < 1e-11 * abs(L_a) and n_o == nuse_a
+    # truncation keeps at least the model-predicted number of datapoints (bsc_et.py:250-257, '>=' rule)
+    A, _ = m._AB(params['pi'])
+    target = int(N * (1 - (1 - A) * 1.0))
+    assert target <= nuse_a <= N
+    # select is deterministic and its output is a valid index set, best candidate last
+    c1 = m.select_Hprimes(copy_params(params), {'y': y})['candidates']
+    c2 = m.select_Hprimes(copy_params(params), {'y': y})['candidates']
+    assert np.array_equal(c1, c2) and c1.min() >= 0 and c1.max() < H
+    assert all(len(set(r)) == Hp for r in c1[:500].tolist())
+
+
+def test_edge_cases():
+    m = model(25, 10, 6, 3)
+    y, params, _ = bsc_problem(25, 10, 1, 3, bars=True, pi=0.2, sigma=2.0)
+    an = DictAnneal(T=1.0, Ncut_factor=0.0, anneal_prior=False)
+    o = BSC(25, 10, 6, 3)
+    want = o.step(an, copy_params(params), {'y': y.copy()})           # a single datapoint
+    got = m._fused_step(an, copy_params(params), {'y': y.copy()})
+    assert abs(got['sigma'] - want['sigma']) < TOL * want['sigma'] and abs(got['pi'] - want['pi']) < TOL * want['pi']
+    # wrong feature dimension is rejected like the reference's shape asserts
+    with pytest.raises(AssertionError):
+        m.select_Hprimes(copy_params(params), {'y': np.zeros((5, 24))})
+    # E-step before any candidates exist -> explicit error, not garbage
+    from prosper_b200._lib import PetError
+    m3 = model(25, 10, 6, 3)
+    m3._bind({'y': np.zeros((4, 25))})
+    with pytest.raises(PetError):
+        m3.engine.e_step(m3.engine.anneal(an), m3._params(copy_params(params)))
+    # invalid constructor arguments (camodels/__init__.py:90-91)
+    with pytest.raises(AssertionError):
+        model(25, 10, 11, 3)
+    with pytest.raises(AssertionError):
+        model(25, 10, 6, 7)
