@@ -291,7 +291,7 @@ def run_gpu(args):
         if dom in ('score_gemm', 'stats_gemm'):
             achieved = 2.0 * D * H * rows_per_launch / (avg_launch_ms / 1e3) / 1e12
             roof = {"kernel": "dgemm_kernel (FP64 DMMA, %s)" % dom, "bound": "tensor", "pipe": "fp64 mma.sync (no f64 tcgen05 kind exists)",
-                    "achieved": achieved, "peak": peak / 1e3, "unit": "TFLOP/s", "frac": achieved / (peak / 1e3),
+                    "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                     "peak_source": "cuBLAS DGEMM 8192^3 measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
                     "traffic": None}
         else:
@@ -305,7 +305,7 @@ def run_gpu(args):
                     "frac": achieved / hbm, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)", "traffic": None}
         roof["avg_launch_ms"] = avg_launch_ms
         roof["stage_ms_per_step"] = per_step
-        roof["whole_step_fp64_frac"] = (flops_per_dp() * N_TOTAL / world / (ms_max / args.steps / 1e3) / 1e9) / peak
+        roof["whole_step_fp64_frac"] = (flops_per_dp() * N_TOTAL / world / (ms_max / args.steps / 1e3) / 1e12) / peak
         n_cpu = int(os.environ.get("PET_CPU_SAMPLE", 256))
         cpu_vals, cores = cpu_port_throughput(n_cpu, 2)
         cpu = {"value": float(cpu_vals[-1]), "unit": "datapoints/s", "cores": cores, "kind": "port",

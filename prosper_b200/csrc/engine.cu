@@ -122,7 +122,7 @@ struct pet_engine {
     double *stage_logpj = nullptr; int64_t stage_logpj_doubles = 0;
     int64_t *stage_i64 = nullptr; int64_t stage_i64_count = 0;
     unsigned long long *ksel_state = nullptr;
-    unsigned long long *d_states = nullptr; unsigned int *d_entries = nullptr; double *d_wlut = nullptr;
+    unsigned long long *d_states = nullptr; unsigned short *d_entries = nullptr; int *d_first = nullptr, *d_single = nullptr;
 
     cudaStream_t copy_stream = nullptr;
     std::vector<cudaEvent_t> chunk_ready; bool upload_pending = false;
@@ -158,7 +158,7 @@ extern "C" void pet_destroy(pet_engine *e) {
     free_dev(e->YW); free_dev(e->Sbuf); free_dev(e->S2buf); free_dev(e->gemm_work);
     free_dev(e->solveA); free_dev(e->solveB); free_dev(e->solve_work); free_dev(e->s2sum);
     free_dev(e->stage_logpj); free_dev(e->stage_i64); free_dev(e->ksel_state);
-    free_dev(e->d_states); free_dev(e->d_entries); free_dev(e->d_wlut);
+    free_dev(e->d_states); free_dev(e->d_entries); free_dev(e->d_first); free_dev(e->d_single);
     for (auto ev : e->chunk_ready) cudaEventDestroy(ev);
     for (auto ev : e->timer.pool) cudaEventDestroy(ev);
     if (e->compute_done) cudaEventDestroy(e->compute_done);
@@ -243,7 +243,8 @@ extern "C" int pet_create(const pet_config *cfg, pet_engine **out) {
     g.C = (int)e->C;
     g.entries_per_lane = e->ss.entries_per_lane;
     g.n_out = e->ss.n_out;
-    if (gl_smem_bytes(g, 4) > 227 * 1024) {
+    g.n_g = e->ss.n_g;
+    if (gl_pick_warps(g) == 0) {
         delete e;
         set_error("H=%d with %lld states needs more shared memory than one SM has", e->H, (long long)e->ss.S);
         return PET_EINVAL;
@@ -253,11 +254,13 @@ extern "C" int pet_create(const pet_config *cfg, pet_engine **out) {
 #define TRYC(x) do { cudaError_t _c = (x); if (_c != cudaSuccess) { set_error("%s: %s", #x, cudaGetErrorString(_c)); pet_destroy(e); return PET_ECUDA; } } while (0)
     TRY(dev_alloc(&e->d_states, std::max<int64_t>(1, e->ss.S)));
     TRY(dev_alloc(&e->d_entries, (int64_t)e->ss.entries.size()));
-    TRY(dev_alloc(&e->d_wlut, (int64_t)e->ss.wlut.size()));
+    TRY(dev_alloc(&e->d_first, 32));
+    TRY(dev_alloc(&e->d_single, (int64_t)e->ss.single_idx.size()));
     if (e->ss.S) TRYC(cudaMemcpy(e->d_states, e->ss.records.data(), e->ss.S * 8, cudaMemcpyHostToDevice));
-    TRYC(cudaMemcpy(e->d_entries, e->ss.entries.data(), e->ss.entries.size() * 4, cudaMemcpyHostToDevice));
-    TRYC(cudaMemcpy(e->d_wlut, e->ss.wlut.data(), e->ss.wlut.size() * 8, cudaMemcpyHostToDevice));
-    g.states = e->d_states; g.entries = e->d_entries; g.wlut = e->d_wlut;
+    TRYC(cudaMemcpy(e->d_entries, e->ss.entries.data(), e->ss.entries.size() * 2, cudaMemcpyHostToDevice));
+    TRYC(cudaMemcpy(e->d_first, e->ss.first_out.data(), 32 * 4, cudaMemcpyHostToDevice));
+    TRYC(cudaMemcpy(e->d_single, e->ss.single_idx.data(), e->ss.single_idx.size() * 4, cudaMemcpyHostToDevice));
+    g.states = e->d_states; g.entries = e->d_entries; g.first_out = e->d_first; g.single_idx = e->d_single;
 
     // chunking: posterior / score buffers of ~128 MB each
     int64_t cr = cfg->chunk_rows > 0 ? cfg->chunk_rows : (int64_t(128) << 20) / (e->ldH * 8);

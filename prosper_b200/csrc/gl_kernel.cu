@@ -9,36 +9,50 @@
 // work per state (the reference does an S x H' x D product per datapoint, bsc_et.py:180-184).
 //
 // Phases (each cites what it replaces):
-//   1 top-H' preselection            bsc_et.py:110-112 / tsc_et.py:198-210 / dsc_et.py:398-408
+//   1 top-H' preselection, scores in registers   bsc_et.py:110-112 / tsc_et.py:198-210 / dsc_et.py:398-408
 //   2 gather YW[cand], G[cand,cand]
-//   3 log-joint of every column, running max   bsc_et.py:168-190 / tsc_et.py:337-355 / dsc_et.py:558-584
-//   4 exp / sum (log-sum-exp), sigma and prior statistics   bsc_et.py:271-272,362,395-415
-//   5 first and second posterior moments over the candidates (gather lists, no atomics)
-//   6 <s> row for the statistics GEMM, Wq scatter, per-datapoint outputs   bsc_et.py:349-366
+//   3 log-joint of every column, running max     bsc_et.py:168-190 / tsc_et.py:337-355 / dsc_et.py:558-584
+//   4 exp / sum (log-sum-exp), sigma statistic   bsc_et.py:271-272,362,395-415
+//   5 pair sums over the state space from a shared-memory gather table (16-bit state ids)
+//   6 first/second posterior moments, <s> row for the statistics GEMM, Wq scatter   bsc_et.py:349-366
 #include <math.h>
+
+#include <algorithm>
 
 #include "gl_kernel.cuh"
 
 namespace pet {
 
-constexpr int GL_WARPS = 4;
+constexpr int GL_MAX_WARPS = 8;
 constexpr double GL_EXP_CUTOFF = -100.0;   // exp(x) for x below this contributes < 4e-44 relative
-
-struct WarpSmem {
-    double *row;    // H   : YW row, later un-normalised <s>
-    double *qbuf;   // S   : squared errors, later un-normalised posteriors of the states
-    double *Gc;     // 16x16 gathered Gram block
-    double *ywc;    // 16  gathered scores
-    double *mom;    // n_out moment outputs
-    int *cand;      // 16
-    int *live;      // 16
-};
 
 static __host__ __device__ inline int r2(int x) { return (x + 1) & ~1; }
 
+struct SmemLayout {
+    int shared_doubles;   // state records + gather table + first_out
+    int off_ids, off_first;
+    int per_warp;         // doubles
+    int off_q, off_G, off_ywc, off_mom, off_P, off_cand;
+};
+
+static __host__ __device__ inline SmemLayout smem_layout(const GLStatic &s) {
+    SmemLayout L;
+    L.off_ids = r2(s.S);
+    L.off_first = L.off_ids + (s.entries_per_lane > 0 ? s.entries_per_lane : 4) * 8;   // epl*32 u16 = epl*8 doubles
+    L.shared_doubles = L.off_first + 16;
+    L.off_q = r2(s.H);
+    L.off_G = L.off_q + r2(s.S + 1);
+    L.off_ywc = L.off_G + PET_MAXHP * PET_MAXHP;
+    L.off_mom = L.off_ywc + PET_MAXHP;
+    L.off_P = L.off_mom + r2(s.n_out > 0 ? s.n_out : 1);
+    L.off_cand = L.off_P + r2(s.Hp * (s.n_cnt > 0 ? s.n_cnt : 1));
+    L.per_warp = L.off_cand + PET_MAXHP;     // cand[16] + live[16] ints
+    return L;
+}
+
 size_t gl_smem_bytes(const GLStatic &s, int warps) {
-    size_t per_warp = size_t(r2(s.H)) + r2(s.S) + PET_MAXHP * PET_MAXHP + PET_MAXHP + r2(s.n_out) + PET_MAXHP;
-    return (size_t(r2(s.S)) + per_warp * warps) * sizeof(double);
+    SmemLayout L = smem_layout(s);
+    return (size_t(L.shared_doubles) + size_t(L.per_warp) * warps) * sizeof(double);
 }
 
 __device__ __forceinline__ double combine(const GLIter &it, double prior, double q) {
@@ -86,55 +100,134 @@ __device__ __forceinline__ double state_prior(unsigned long long rec, const GLSt
     return pr;
 }
 
-// selection score of cause h (or signed/valued singleton) from the score row
-__device__ __forceinline__ double sel_score(const GLArgs &a, const double *row, int h, double yy) {
+// selection score of item i (a cause h, or for TSC a signed singleton (sign block, h))
+__device__ __forceinline__ double sel_score(const GLArgs &a, const double *row, int i, double yy) {
     const GLStatic &st = a.st;
     switch (st.select_mode) {
         case SEL_BSC:
-            return row[h] * a.invn[h];
+            return row[i] * a.invn[i];
         case SEL_NEGDIST:
-            return 2.0 * row[h] - a.wn2[h];
+            return 2.0 * row[i] - a.wn2[i];
         case SEL_GIVEN:
-            return -row[h];
-        default: {   // SEL_DSC: best valued singleton of this h
+            return -row[i];
+        case SEL_TSC: {   // -1 block first, then +1 (tsc_et.py:54-65); the log-prior is the same for all
+            int h = i % st.H;
+            double sg = (i < st.H) ? -1.0 : 1.0;
+            return a.it.pre1 * (yy + (a.wn2[h] - 2.0 * sg * row[h]));
+        }
+        default: {        // SEL_DSC: best valued singleton of this h
             double best = -INFINITY;
             for (int b = 0; b < st.n_blocks; ++b) {
                 double v = st.block_val[b];
-                double q = yy + v * (v * a.wn2[h] - 2.0 * row[h]);
-                double f = a.it.sel_prior[b] + a.it.pre1 * q;
-                best = fmax(best, f);
+                double q = yy + v * (v * a.wn2[i] - 2.0 * row[i]);
+                best = fmax(best, a.it.sel_prior[b] + a.it.pre1 * q);
             }
             return best;
         }
     }
 }
 
+__device__ __forceinline__ void warp_argmax(double &v, int &i) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        double ov = __shfl_xor_sync(0xffffffffu, v, o);
+        int oi = __shfl_xor_sync(0xffffffffu, i, o);
+        if ((ov > v) || (ov == v && oi > i)) { v = ov; i = oi; }
+    }
+}
+
+__device__ __forceinline__ void store_cand(const GLStatic &st, int *cand, int rnd, int item) {
+    const bool tsc = (st.select_mode == SEL_TSC);
+    const bool ascending = (st.select_mode == SEL_BSC) || tsc;
+    cand[ascending ? (st.Hp - 1 - rnd) : rnd] = tsc ? (item % st.H) : item;
+}
+
+// Top-H' with the scores of this lane's items held in registers (items <= 32*HC).
+// Order: value descending, ties -> larger item index first (same rule as the generic path).
+template <int HC>
+__device__ __noinline__ void select_regs(const GLArgs &a, const double *row, double yy, int items, int *cand) {
+    const int lane = threadIdx.x & 31;
+    double sc[HC];
+#pragma unroll
+    for (int k = 0; k < HC; ++k) {
+        int i = k * 32 + lane;
+        sc[k] = (i < items) ? sel_score(a, row, i, yy) : -INFINITY;
+        if (sc[k] != sc[k]) sc[k] = -INFINITY;       // NaN scores never win
+    }
+    for (int rnd = 0; rnd < a.st.Hp; ++rnd) {
+        double lm = -INFINITY;
+        int lk = 0;
+#pragma unroll
+        for (int k = 0; k < HC; ++k)
+            if (sc[k] >= lm) { lm = sc[k]; lk = k; }     // '>=': the larger item index wins ties
+        double bv = lm;
+        int bi = lk * 32 + lane;
+        warp_argmax(bv, bi);
+        if (bi < 0 || bi >= items) bi = 0;
+        if (lane == 0) store_cand(a.st, cand, rnd, bi);
+        if ((bi & 31) == lane) {
+            int wk = bi >> 5;
+#pragma unroll
+            for (int k = 0; k < HC; ++k)
+                if (k == wk) sc[k] = -INFINITY;
+        }
+    }
+}
+
+// generic path: any number of items, scores recomputed every round
+__device__ __noinline__ void select_generic(const GLArgs &a, const double *row, double yy, int items, int *cand) {
+    const int lane = threadIdx.x & 31;
+    double prev_v = INFINITY;
+    int prev_i = 0x7fffffff;
+    for (int rnd = 0; rnd < a.st.Hp; ++rnd) {
+        double best_v = -INFINITY;
+        int best_i = -1;
+        for (int i = lane; i < items; i += 32) {
+            double v = sel_score(a, row, i, yy);
+            bool below = (v < prev_v) || (v == prev_v && i < prev_i);
+            bool better = (v > best_v) || (v == best_v && i > best_i);
+            if (below && better) { best_v = v; best_i = i; }
+        }
+        warp_argmax(best_v, best_i);
+        if (best_i < 0) best_i = 0;
+        prev_v = best_v;
+        prev_i = best_i;
+        if (lane == 0) store_cand(a.st, cand, rnd, best_i);
+    }
+}
+
 template <int GMAX, bool BINARY>
-__global__ void __launch_bounds__(GL_WARPS * 32) gl_kernel(const GLArgs a) {
+__global__ void __launch_bounds__(GL_MAX_WARPS * 32) gl_kernel(const __grid_constant__ GLArgs a) {
     extern __shared__ __align__(16) double smem[];
     const GLStatic &st = a.st;
     const GLIter &it = a.it;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int H = st.H, Hp = st.Hp, S = st.S;
+    const SmemLayout L = smem_layout(st);
 
     unsigned long long *states_s = reinterpret_cast<unsigned long long *>(smem);
+    unsigned short *ids_s = reinterpret_cast<unsigned short *>(smem + L.off_ids);
+    int *first_s = reinterpret_cast<int *>(smem + L.off_first);
     for (int s = threadIdx.x; s < S; s += blockDim.x) states_s[s] = st.states[s];
-    const size_t per_warp = size_t(r2(H)) + r2(S) + PET_MAXHP * PET_MAXHP + PET_MAXHP + r2(st.n_out) + PET_MAXHP;
-    double *wbase = smem + r2(S) + per_warp * warp;
-    WarpSmem ws;
-    ws.row = wbase;
-    ws.qbuf = ws.row + r2(H);
-    ws.Gc = ws.qbuf + r2(S);
-    ws.ywc = ws.Gc + PET_MAXHP * PET_MAXHP;
-    ws.mom = ws.ywc + PET_MAXHP;
-    ws.cand = reinterpret_cast<int *>(ws.mom + r2(st.n_out));
-    ws.live = ws.cand + PET_MAXHP;
+    for (int i = threadIdx.x; i < st.entries_per_lane * 32; i += blockDim.x) ids_s[i] = st.entries[i];
+    if (threadIdx.x < 32) first_s[threadIdx.x] = st.first_out[threadIdx.x];
+    double *wbase = smem + L.shared_doubles + size_t(L.per_warp) * warp;
+    double *row = wbase;
+    double *qbuf = wbase + L.off_q;
+    double *Gc = wbase + L.off_G;
+    double *ywc = wbase + L.off_ywc;
+    double *mom = wbase + L.off_mom;
+    double *Pj = wbase + L.off_P;
+    int *cand_s = reinterpret_cast<int *>(wbase + L.off_cand);
+    int *live_s = cand_s + PET_MAXHP;
     __syncthreads();
 
     const bool do_stats = !(a.flags & (GLF_LSE_ONLY | GLF_SELECT_ONLY));
-    const int n_cnt = st.n_cnt;
-    const int base2 = Hp * n_cnt;                 // first off-diagonal second-moment output
+    const int n_cnt = st.n_cnt, n_g = st.n_g;
     const double cut = (a.flags & GLF_USE_CUT) ? *a.cut : 0.0;
+    const bool rd = (a.flags & GLF_READ_LOGPJ) != 0, wr = (a.flags & GLF_WRITE_LOGPJ) != 0;
+    const int col_states = st.has_null + st.n_blocks * H;
+    const int items = (st.select_mode == SEL_TSC) ? 2 * H : H;
 
     // per-warp running sums over its datapoints (lane 0 holds them)
     double acc_n = 0.0, acc_lse = 0.0, acc_sig = 0.0;
@@ -142,8 +235,8 @@ __global__ void __launch_bounds__(GL_WARPS * 32) gl_kernel(const GLArgs a) {
 #pragma unroll
     for (int v = 0; v < PET_MAXV; ++v) acc_cnt[v] = 0.0;
 
-    const int64_t wstride = int64_t(gridDim.x) * GL_WARPS;
-    for (int64_t r = int64_t(blockIdx.x) * GL_WARPS + warp; r < a.n_rows; r += wstride) {
+    const int64_t wstride = int64_t(gridDim.x) * nwarps;
+    for (int64_t r = int64_t(blockIdx.x) * nwarps + warp; r < a.n_rows; r += wstride) {
         const int64_t n = a.row0 + r;
         const double *yw = a.YW + r * st.ldH;
         const double yy = a.yy[n];
@@ -161,70 +254,38 @@ __global__ void __launch_bounds__(GL_WARPS * 32) gl_kernel(const GLArgs a) {
         }
 
         // ---- phase 0: score row into shared memory ---------------------------------
-        for (int h = lane; h < H; h += 32) ws.row[h] = yw[h];
+        for (int h = lane; h < H; h += 32) row[h] = yw[h];
         __syncwarp();
 
         // ---- phase 1: top-H' preselection -------------------------------------------
         if (a.flags & GLF_SELECT) {
-            const bool tsc = (st.select_mode == SEL_TSC);
-            const int items = tsc ? 2 * H : H;
-            double prev_v = INFINITY;
-            int prev_i = 0x7fffffff;
-            for (int rnd = 0; rnd < Hp; ++rnd) {
-                double best_v = -INFINITY;
-                int best_i = -1;
-                for (int i = lane; i < items; i += 32) {
-                    double v;
-                    if (tsc) {   // item = (sign block, h): -1 block first (tsc_et.py:54-65)
-                        int h = i % H;
-                        double sg = (i < H) ? -1.0 : 1.0;
-                        v = it.pre1 * (yy + (a.wn2[h] - 2.0 * sg * ws.row[h]));
-                    } else {
-                        v = sel_score(a, ws.row, i, yy);
-                    }
-                    bool below = (v < prev_v) || (v == prev_v && i < prev_i);
-                    bool better = (v > best_v) || (v == best_v && i > best_i);
-                    if (below && better) { best_v = v; best_i = i; }
-                }
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    double ov = __shfl_xor_sync(0xffffffffu, best_v, o);
-                    int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
-                    if ((ov > best_v) || (ov == best_v && oi > best_i)) { best_v = ov; best_i = oi; }
-                }
-                if (best_i < 0) best_i = 0;   // all-NaN row: keep indices valid
-                prev_v = best_v; prev_i = best_i;
-                if (lane == 0) {
-                    int h = tsc ? (best_i % H) : best_i;
-                    bool ascending = (st.select_mode == SEL_BSC) || tsc;
-                    ws.cand[ascending ? (Hp - 1 - rnd) : rnd] = h;
-                }
-            }
+            if (items <= 32) select_regs<1>(a, row, yy, items, cand_s);
+            else if (items <= 128) select_regs<4>(a, row, yy, items, cand_s);
+            else if (items <= 1024) select_regs<32>(a, row, yy, items, cand_s);
+            else select_generic(a, row, yy, items, cand_s);
             __syncwarp();
-            if (lane < Hp) a.cand[n * Hp + lane] = ws.cand[lane];
+            if (lane < Hp) a.cand[n * Hp + lane] = cand_s[lane];
         } else {
-            if (lane < Hp) ws.cand[lane] = a.cand[n * Hp + lane];
+            if (lane < Hp) cand_s[lane] = a.cand[n * Hp + lane];
             __syncwarp();
         }
         if (a.flags & GLF_SELECT_ONLY) continue;
 
         // ---- phase 2: gather scores and Gram block of the candidates ----------------
         if (lane < Hp) {
-            int c = ws.cand[lane];
-            ws.ywc[lane] = ws.row[c];
+            int c = cand_s[lane];
+            ywc[lane] = row[c];
             int lv = 1;
-            for (int j = lane + 1; j < Hp; ++j) lv &= (ws.cand[j] != c);   // numpy "last write wins"
-            ws.live[lane] = lv;
+            for (int j = lane + 1; j < Hp; ++j) lv &= (cand_s[j] != c);   // numpy "last write wins"
+            live_s[lane] = lv;
         }
         for (int idx = lane; idx < Hp * Hp; idx += 32) {
             int j = idx / Hp, k = idx % Hp;
-            ws.Gc[j * PET_MAXHP + k] = a.G[int64_t(ws.cand[j]) * st.ldH + ws.cand[k]];
+            Gc[j * PET_MAXHP + k] = a.G[int64_t(cand_s[j]) * st.ldH + cand_s[k]];
         }
         __syncwarp();
 
         double *logpj_row = a.logpj ? a.logpj + n * a.ld_logpj : nullptr;
-        const bool rd = (a.flags & GLF_READ_LOGPJ) != 0, wr = (a.flags & GLF_WRITE_LOGPJ) != 0;
-        const int col_states = st.has_null + st.n_blocks * H;
 
         // ---- phase 3: log-joints, running max ---------------------------------------
         double mx = -INFINITY;
@@ -240,17 +301,18 @@ __global__ void __launch_bounds__(GL_WARPS * 32) gl_kernel(const GLArgs a) {
                 double F;
                 if (rd) F = logpj_row[st.has_null + b * H + h];
                 else {
-                    double q = yy + v * (v * a.wn2[h] - 2.0 * ws.row[h]);
+                    double q = yy + v * (v * a.wn2[h] - 2.0 * row[h]);
                     F = combine(it, it.prior_block[b], q);
                     if (wr) logpj_row[st.has_null + b * H + h] = F;
                 }
                 mx = fmax(mx, F);
             }
         }
+#pragma unroll 2
         for (int s = lane; s < S; s += 32) {
             double q, prior;
-            eval_state<GMAX, BINARY>(states_s[s], st, it, ws.ywc, ws.Gc, yy, q, prior);
-            ws.qbuf[s] = q;
+            eval_state<GMAX, BINARY>(states_s[s], st, it, ywc, Gc, yy, q, prior);
+            qbuf[s] = q;
             double F;
             if (rd) F = logpj_row[col_states + s];
             else {
@@ -275,7 +337,7 @@ __global__ void __launch_bounds__(GL_WARPS * 32) gl_kernel(const GLArgs a) {
         }
         for (int h = lane; h < H; h += 32) {
             double snew = 0.0, s2new = 0.0;
-            const double ywh = ws.row[h], wn2h = (st.n_blocks > 0) ? a.wn2[h] : 0.0;
+            const double ywh = row[h], wn2h = (st.n_blocks > 0) ? a.wn2[h] : 0.0;
 #pragma unroll
             for (int b = 0; b < PET_MAXV; ++b) {
                 if (b < st.n_blocks) {
@@ -292,23 +354,21 @@ __global__ void __launch_bounds__(GL_WARPS * 32) gl_kernel(const GLArgs a) {
                 }
             }
             if (do_stats) {
-                ws.row[h] = snew;
-                if (a.S2) a.S2[r * st.ldH + h] = s2new;   // scaled below through a second pass
+                row[h] = snew;
+                if (a.S2) a.S2[r * st.ldH + h] = s2new;   // normalised in phase 6
             }
         }
+#pragma unroll 2
         for (int s = lane; s < S; s += 32) {
-            double q = ws.qbuf[s];
-            double F;
-            if (rd) F = logpj_row[col_states + s];
-            else {
-                F = combine(it, state_prior<GMAX>(states_s[s], st, it), q);
-            }
+            double q = qbuf[s];
+            double F = rd ? logpj_row[col_states + s] : combine(it, state_prior<GMAX>(states_s[s], st, it), q);
             double x = F - mx;
             double p = (x > GL_EXP_CUTOFF) ? exp(x) : 0.0;
             denom += p;
             sig += p * q;
-            ws.qbuf[s] = p;
+            qbuf[s] = p;
         }
+        if (lane == 0) qbuf[S] = 0.0;   // zero slot read by padding / dummy gather entries
         denom = warp_sum(denom);
         const double lse = mx + log(denom);
         if (lane == 0) a.lse[n] = lse;
@@ -318,33 +378,50 @@ __global__ void __launch_bounds__(GL_WARPS * 32) gl_kernel(const GLArgs a) {
         for (int v = 0; v < PET_MAXV; ++v) cntb[v] = warp_sum(cntb[v]);
         const double inv = 1.0 / denom;
 
-        // ---- phase 5: posterior moments over the candidates (gather lists) ----------
-        for (int o = lane; o < st.n_out; o += 32) ws.mom[o] = 0.0;
+        // ---- phase 5: pair sums from the shared-memory gather table -----------------
+        for (int o = lane; o < st.n_out; o += 32) mom[o] = 0.0;
         __syncwarp();
         {
-            int cur = -1;
+            int cur = first_s[lane];
             double acc = 0.0;
-            for (int t = 0; t < st.entries_per_lane; ++t) {
-                unsigned e = st.entries[t * 32 + lane];
-                if (e == 0xFFFFFFFFu) continue;
-                int o = int((e >> 16) & 0xFFu);
-                if (o != cur) {
-                    if (cur >= 0) atomicAdd(&ws.mom[cur], acc);
-                    cur = o;
-                    acc = 0.0;
+            const unsigned short *ids = ids_s + lane;
+            for (int t = 0; t < st.entries_per_lane; t += 4) {
+                unsigned e0 = ids[(t + 0) * 32], e1 = ids[(t + 1) * 32], e2 = ids[(t + 2) * 32], e3 = ids[(t + 3) * 32];
+                double p0 = qbuf[e0 & 0x7FFFu], p1 = qbuf[e1 & 0x7FFFu], p2 = qbuf[e2 & 0x7FFFu], p3 = qbuf[e3 & 0x7FFFu];
+                if (((e0 | e1 | e2 | e3) & 0x8000u) == 0) {
+                    acc += (p0 + p1) + (p2 + p3);
+                } else {
+                    acc += p0; if (e0 & 0x8000u) { atomicAdd(&mom[cur], acc); ++cur; acc = 0.0; }
+                    acc += p1; if (e1 & 0x8000u) { atomicAdd(&mom[cur], acc); ++cur; acc = 0.0; }
+                    acc += p2; if (e2 & 0x8000u) { atomicAdd(&mom[cur], acc); ++cur; acc = 0.0; }
+                    acc += p3; if (e3 & 0x8000u) { atomicAdd(&mom[cur], acc); ++cur; acc = 0.0; }
                 }
-                double p = ws.qbuf[e & 0xFFFFu];
-                acc += BINARY ? p : p * st.wlut[e >> 24];
             }
-            if (cur >= 0) atomicAdd(&ws.mom[cur], acc);
+            if (cur < st.n_out && acc != 0.0) atomicAdd(&mom[cur], acc);
         }
         __syncwarp();
 
-        // ---- phase 6: outputs --------------------------------------------------------
-        // 6a. <s_h> row: singles already in row[], add candidate marginals, normalise, store
+        // ---- phase 6: moments and outputs --------------------------------------------
+        // 6a. P[j][a] = posterior mass of (s_j = v_a):  singleton state + size-weighted pair sums
+        for (int idx = lane; idx < Hp * n_cnt; idx += 32) {
+            const int j = idx / n_cnt, av = idx % n_cnt;
+            const int sid = st.single_idx[idx];
+            double P = (sid >= 0) ? qbuf[sid] : 0.0;
+            for (int k = 0; k < Hp; ++k) {
+                if (k == j) continue;
+                const int lo = min(j, k), hi = max(j, k);
+                const int pair = lo * Hp - lo * (lo + 1) / 2 + (hi - lo - 1);
+                for (int bv = 0; bv < n_cnt; ++bv) {
+                    const int base = ((pair * n_cnt + (j < k ? av : bv)) * n_cnt + (j < k ? bv : av)) * n_g;
+                    for (int g = 0; g < n_g; ++g) P += mom[base + g] / double(g + 1);
+                }
+            }
+            Pj[idx] = P;
+        }
         if (st.n_blocks == 0)
-            for (int h = lane; h < H; h += 32) ws.row[h] = 0.0;
+            for (int h = lane; h < H; h += 32) row[h] = 0.0;
         __syncwarp();
+        // 6b. <s_h> row: singles already in row[], add candidate marginals, normalise, store
         double cnt_states[PET_MAXV];
 #pragma unroll
         for (int v = 0; v < PET_MAXV; ++v) cnt_states[v] = 0.0;
@@ -353,36 +430,43 @@ __global__ void __launch_bounds__(GL_WARPS * 32) gl_kernel(const GLArgs a) {
 #pragma unroll
             for (int v = 0; v < PET_MAXV; ++v)
                 if (v < n_cnt) {
-                    double P = ws.mom[lane * n_cnt + v];
+                    double P = Pj[lane * n_cnt + v];
                     m1 = fma(BINARY ? 1.0 : st.vals[v], P, m1);
                     cnt_states[v] = P;
                 }
-            if (ws.live[lane]) ws.row[ws.cand[lane]] += m1;
+            if (live_s[lane]) row[cand_s[lane]] += m1;
         }
         __syncwarp();
         for (int h = lane; h < st.ldH; h += 32) {
-            a.S[r * st.ldH + h] = (h < H) ? ws.row[h] * inv : 0.0;
+            a.S[r * st.ldH + h] = (h < H) ? row[h] * inv : 0.0;
             if (a.S2) a.S2[r * st.ldH + h] = (h < H) ? a.S2[r * st.ldH + h] * inv : 0.0;
         }
-        // 6b. second moments scattered into Wq (numpy fancy-index semantics for duplicates)
+        // 6c. second moments scattered into Wq (numpy fancy-index semantics for duplicates)
         for (int idx = lane; idx < Hp * Hp; idx += 32) {
-            int j = idx / Hp, k = idx % Hp;
-            if (!(ws.live[j] && ws.live[k])) continue;
-            double m2;
+            const int j = idx / Hp, k = idx % Hp;
+            if (!(live_s[j] && live_s[k])) continue;
+            double m2 = 0.0;
             if (j == k) {
                 if (st.diag_from_colsum) continue;
-                m2 = 0.0;
                 for (int v = 0; v < n_cnt; ++v) {
                     double vv = BINARY ? 1.0 : st.vals[v];
-                    m2 = fma(vv * vv, ws.mom[j * n_cnt + v], m2);
+                    m2 = fma(vv * vv, Pj[j * n_cnt + v], m2);
                 }
             } else {
-                int lo = min(j, k), hi = max(j, k);
-                m2 = ws.mom[base2 + lo * Hp - lo * (lo + 1) / 2 + (hi - lo - 1)];
+                const int lo = min(j, k), hi = max(j, k);
+                const int pair = lo * Hp - lo * (lo + 1) / 2 + (hi - lo - 1);
+                for (int av = 0; av < n_cnt; ++av)
+                    for (int bv = 0; bv < n_cnt; ++bv) {
+                        double w = BINARY ? 1.0 : st.vals[av] * st.vals[bv];
+                        const int base = ((pair * n_cnt + av) * n_cnt + bv) * n_g;
+                        double sacc = 0.0;
+                        for (int g = 0; g < n_g; ++g) sacc += mom[base + g];
+                        m2 = fma(w, sacc, m2);
+                    }
             }
-            if (m2 != 0.0) atomicAdd(&a.Wq[int64_t(ws.cand[j]) * st.ldH + ws.cand[k]], m2 * inv);
+            if (m2 != 0.0) atomicAdd(&a.Wq[int64_t(cand_s[j]) * st.ldH + cand_s[k]], m2 * inv);
         }
-        // 6c. scalar statistics
+        // 6d. scalar statistics
 #pragma unroll
         for (int v = 0; v < PET_MAXV; ++v) cnt_states[v] = warp_sum(cnt_states[v]);
         if (lane == 0) {
@@ -409,25 +493,35 @@ __global__ void __launch_bounds__(GL_WARPS * 32) gl_kernel(const GLArgs a) {
     }
 }
 
+// largest warp count whose shared memory fits one SM (0 = does not fit at all)
+int gl_pick_warps(const GLStatic &s) {
+    for (int w = GL_MAX_WARPS; w >= 1; --w)
+        if (gl_smem_bytes(s, w) <= 227 * 1024) return w;
+    return 0;
+}
+
 template <int GMAX, bool BINARY>
 static int launch_inst(const GLArgs &a, int sm_count, cudaStream_t stream) {
     auto kern = gl_kernel<GMAX, BINARY>;
-    size_t smem = gl_smem_bytes(a.st, GL_WARPS);
-    if (smem > 227 * 1024) {
-        set_error("posterior kernel needs %zu bytes of shared memory (H=%d, states=%d): unsupported size",
-                  smem, a.st.H, a.st.S);
+    const int warps = gl_pick_warps(a.st);
+    if (warps == 0) {
+        set_error("posterior kernel needs %zu bytes of shared memory per warp set (H=%d, states=%d): unsupported size",
+                  gl_smem_bytes(a.st, 1), a.st.H, a.st.S);
         return PET_EINVAL;
     }
+    const int use_warps = warps;
+    const size_t smem = gl_smem_bytes(a.st, use_warps);
     static size_t configured = 0;
     if (smem > configured) {
         PET_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
         configured = smem;
     }
     int per_sm = int(std::max<size_t>(1, std::min<size_t>(8, (227 * 1024) / (smem + 1024))));
-    int64_t want = ceil_div(a.n_rows, GL_WARPS);
+    per_sm = std::min(per_sm, std::max(1, 64 / use_warps));
+    int64_t want = ceil_div(a.n_rows, use_warps);
     int64_t grid = std::min<int64_t>(want, int64_t(sm_count) * per_sm);
     if (grid <= 0) return PET_OK;
-    kern<<<(unsigned)grid, GL_WARPS * 32, smem, stream>>>(a);
+    kern<<<(unsigned)grid, use_warps * 32, smem, stream>>>(a);
     PET_LAUNCH_CHECK();
     return PET_OK;
 }

@@ -41,10 +41,12 @@ struct GLStatic {                 // fixed per engine
     int select_mode;
     int diag_from_colsum;         // binary: Wq diagonal = column sums of <s> (not scattered)
     const unsigned long long *states;   // S records: 8 x (pos | vidx<<4), 0xFF = unused
-    const unsigned int *entries;  // moment gather lists, transposed [t][lane]
-    int entries_per_lane;
-    int n_out;                    // number of moment outputs (first + second moments)
-    const double *wlut;           // weight LUT for moment entries
+    const unsigned short *entries;   // pair-sum gather lists of state ids, transposed [t][lane]
+    int entries_per_lane;            // multiple of 4
+    int n_out;                       // pair-sum outputs: pairs * n_cnt^2 * n_g
+    int n_g;                         // state sizes 2..n_g+1 carry pairs
+    const int *first_out;            // [32] output of each lane's first entry
+    const int *single_idx;           // [Hp*n_cnt] in-table singleton state ids (TSC) or -1
 };
 
 struct GLIter {                   // per call
@@ -80,5 +82,6 @@ struct GLArgs {
 
 int launch_gl_kernel(const GLArgs &a, int gamma, bool binary, int sm_count, cudaStream_t st);
 size_t gl_smem_bytes(const GLStatic &s, int warps);
+int gl_pick_warps(const GLStatic &s);
 
 }  // namespace pet

@@ -189,6 +189,8 @@ def test_properties_at_scale():
 def test_edge_cases():
     m = model(25, 10, 6, 3)
     y, params, _ = bsc_problem(25, 10, 1, 3, bars=True, pi=0.2, sigma=2.0)
+    params['sigma'] = 2.5                                            # (std of one datapoint is 0)
+    params['W'] = params['W'] + np.random.RandomState(0).normal(size=(25, 10))
     an = DictAnneal(T=1.0, Ncut_factor=0.0, anneal_prior=False)
     o = BSC(25, 10, 6, 3)
     want = o.step(an, copy_params(params), {'y': y.copy()})           # a single datapoint
@@ -202,7 +204,7 @@ def test_edge_cases():
     m3 = model(25, 10, 6, 3)
     m3._bind({'y': np.zeros((4, 25))})
     with pytest.raises(PetError):
-        m3.engine.e_step(m3.engine.anneal(an), m3._params(copy_params(params)))
+        m3.engine.e_step(m3.engine.anneal(an), m3._pack_params(copy_params(params)))
     # invalid constructor arguments (camodels/__init__.py:90-91)
     with pytest.raises(AssertionError):
         model(25, 10, 11, 3)
