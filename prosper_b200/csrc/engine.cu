@@ -122,7 +122,8 @@ struct pet_engine {
     double *stage_logpj = nullptr; int64_t stage_logpj_doubles = 0;
     int64_t *stage_i64 = nullptr; int64_t stage_i64_count = 0;
     unsigned long long *ksel_state = nullptr;
-    unsigned long long *d_states = nullptr; unsigned short *d_entries = nullptr; int *d_first = nullptr, *d_single = nullptr;
+    unsigned long long *d_states = nullptr; unsigned short *d_entries = nullptr, *d_chunk = nullptr; unsigned int *d_direct = nullptr;
+    int *d_single = nullptr; double *d_state_prior = nullptr;
 
     cudaStream_t copy_stream = nullptr;
     std::vector<cudaEvent_t> chunk_ready; bool upload_pending = false;
@@ -158,7 +159,7 @@ extern "C" void pet_destroy(pet_engine *e) {
     free_dev(e->YW); free_dev(e->Sbuf); free_dev(e->S2buf); free_dev(e->gemm_work);
     free_dev(e->solveA); free_dev(e->solveB); free_dev(e->solve_work); free_dev(e->s2sum);
     free_dev(e->stage_logpj); free_dev(e->stage_i64); free_dev(e->ksel_state);
-    free_dev(e->d_states); free_dev(e->d_entries); free_dev(e->d_first); free_dev(e->d_single);
+    free_dev(e->d_states); free_dev(e->d_entries); free_dev(e->d_chunk); free_dev(e->d_direct); free_dev(e->d_single); free_dev(e->d_state_prior);
     for (auto ev : e->chunk_ready) cudaEventDestroy(ev);
     for (auto ev : e->timer.pool) cudaEventDestroy(ev);
     if (e->compute_done) cudaEventDestroy(e->compute_done);
@@ -234,14 +235,15 @@ extern "C" int pet_create(const pet_config *cfg, pet_engine **out) {
         }
         g.diag_from_colsum = 0;
     }
-    int rc = build_state_space(e->ss, e->Hp, rows, e->values, e->k0);
+    int rc = build_state_space(e->ss, e->Hp, rows, e->values, e->k0, e->binary);
     if (rc != PET_OK) { delete e; return rc; }
     g.H = e->H; g.Hp = e->Hp; g.S = (int)e->ss.S; g.ldH = (int)e->ldH;
     g.n_cnt = e->K - 1;
     { int v = 0; for (int k = 0; k < e->K; ++k) if (k != e->k0) g.vals[v++] = e->values[k]; }
     e->C = g.has_null + (int64_t)g.n_blocks * e->H + e->ss.S;
     g.C = (int)e->C;
-    g.entries_per_lane = e->ss.entries_per_lane;
+    g.n_chunks = e->ss.n_chunks; g.chunk_len = e->ss.chunk_len;
+    g.n_direct = (int)e->ss.direct.size();
     g.n_out = e->ss.n_out;
     g.n_g = e->ss.n_g;
     if (gl_pick_warps(g) == 0) {
@@ -254,13 +256,16 @@ extern "C" int pet_create(const pet_config *cfg, pet_engine **out) {
 #define TRYC(x) do { cudaError_t _c = (x); if (_c != cudaSuccess) { set_error("%s: %s", #x, cudaGetErrorString(_c)); pet_destroy(e); return PET_ECUDA; } } while (0)
     TRY(dev_alloc(&e->d_states, std::max<int64_t>(1, e->ss.S)));
     TRY(dev_alloc(&e->d_entries, (int64_t)e->ss.entries.size()));
-    TRY(dev_alloc(&e->d_first, 32));
+    TRY(dev_alloc(&e->d_chunk, (int64_t)e->ss.chunk_tab.size()));
+    TRY(dev_alloc(&e->d_direct, (int64_t)e->ss.direct.size()));
     TRY(dev_alloc(&e->d_single, (int64_t)e->ss.single_idx.size()));
+    TRY(dev_alloc(&e->d_state_prior, e->ss.S));
     if (e->ss.S) TRYC(cudaMemcpy(e->d_states, e->ss.records.data(), e->ss.S * 8, cudaMemcpyHostToDevice));
     TRYC(cudaMemcpy(e->d_entries, e->ss.entries.data(), e->ss.entries.size() * 2, cudaMemcpyHostToDevice));
-    TRYC(cudaMemcpy(e->d_first, e->ss.first_out.data(), 32 * 4, cudaMemcpyHostToDevice));
+    TRYC(cudaMemcpy(e->d_chunk, e->ss.chunk_tab.data(), e->ss.chunk_tab.size() * 2, cudaMemcpyHostToDevice));
+    if (!e->ss.direct.empty()) TRYC(cudaMemcpy(e->d_direct, e->ss.direct.data(), e->ss.direct.size() * 4, cudaMemcpyHostToDevice));
     TRYC(cudaMemcpy(e->d_single, e->ss.single_idx.data(), e->ss.single_idx.size() * 4, cudaMemcpyHostToDevice));
-    g.states = e->d_states; g.entries = e->d_entries; g.first_out = e->d_first; g.single_idx = e->d_single;
+    g.states = e->d_states; g.entries = e->d_entries; g.chunk_tab = e->d_chunk; g.direct = e->d_direct; g.single_idx = e->d_single;
 
     // chunking: posterior / score buffers of ~128 MB each
     int64_t cr = cfg->chunk_rows > 0 ? cfg->chunk_rows : (int64_t(128) << 20) / (e->ldH * 8);
@@ -480,6 +485,8 @@ static int sweep(pet_engine *e, const pet_anneal *a, const pet_params *p, int kf
     ga.flags = kflags;
     if (e->model == PET_MODEL_DSC) ga.flags |= (kflags & GLF_USE_CUT) ? GLF_CUT_STRICT : 0;
     ga.yy = e->yy; ga.wn2 = e->wn2; ga.invn = e->invn; ga.G = e->G;
+    ga.state_prior = e->d_state_prior;
+    PET_CHECK(launch_state_prior(ga.st, ga.it, e->d_state_prior, st));
     ga.cand = e->cand; ga.lse = e->lse; ga.cut = cut_dev;
     pet_stats_layout lay;
     pet_stats_layout_get(e, &lay);

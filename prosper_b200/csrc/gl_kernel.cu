@@ -28,23 +28,26 @@ constexpr double GL_EXP_CUTOFF = -100.0;   // exp(x) for x below this contribute
 
 static __host__ __device__ inline int r2(int x) { return (x + 1) & ~1; }
 
+constexpr int GS = PET_MAXHP + 1;          // stride of the gathered Gram block; row/col Hp is all zero
+
 struct SmemLayout {
-    int shared_doubles;   // state records + gather table + first_out
-    int off_ids, off_first;
+    int shared_doubles;   // state records + gather table + chunk table
+    int off_ids, off_chunk;
     int per_warp;         // doubles
-    int off_q, off_G, off_ywc, off_mom, off_P, off_cand;
+    int off_q, off_G, off_lin, off_mom, off_P, off_cand;
 };
 
 static __host__ __device__ inline SmemLayout smem_layout(const GLStatic &s) {
     SmemLayout L;
+    const int nch = s.n_chunks > 0 ? s.n_chunks : 1;
     L.off_ids = r2(s.S);
-    L.off_first = L.off_ids + (s.entries_per_lane > 0 ? s.entries_per_lane : 4) * 8;   // epl*32 u16 = epl*8 doubles
-    L.shared_doubles = L.off_first + 16;
+    L.off_chunk = L.off_ids + nch * s.chunk_len * 8;      // nch*CH*32 u16
+    L.shared_doubles = L.off_chunk + nch * 8;             // nch*32 u16
     L.off_q = r2(s.H);
     L.off_G = L.off_q + r2(s.S + 1);
-    L.off_ywc = L.off_G + PET_MAXHP * PET_MAXHP;
-    L.off_mom = L.off_ywc + PET_MAXHP;
-    L.off_P = L.off_mom + r2(s.n_out > 0 ? s.n_out : 1);
+    L.off_lin = L.off_G + r2(GS * GS);
+    L.off_mom = L.off_lin + r2(GS);
+    L.off_P = L.off_mom + r2(s.n_out + 1);
     L.off_cand = L.off_P + r2(s.Hp * (s.n_cnt > 0 ? s.n_cnt : 1));
     L.per_warp = L.off_cand + PET_MAXHP;     // cand[16] + live[16] ints
     return L;
@@ -55,49 +58,77 @@ size_t gl_smem_bytes(const GLStatic &s, int warps) {
     return (size_t(L.shared_doubles) + size_t(L.per_warp) * warps) * sizeof(double);
 }
 
+__constant__ double c_winv[8] = {1.0, 1.0 / 2, 1.0 / 3, 1.0 / 4, 1.0 / 5, 1.0 / 6, 1.0 / 7, 1.0 / 8};
+
 __device__ __forceinline__ double combine(const GLIter &it, double prior, double q) {
     return it.anneal_prior ? it.beta * (prior + it.pre1 * q) : prior + it.beta * (it.pre1 * q);
 }
 
-// squared error and log-prior of one multi-state record
+// squared error of one multi-state record.
+// BINARY: member bytes are positions; unused slots hold the dummy position Hp whose lin[] entry and
+// Gram row/column are zero, so there are no multiplies, selects or branches:
+//     q = yy + sum_m lin[p_m] + 2 sum_{m2<m} G[p_m][p_m2],   lin[p] = G[p][p] - 2 YW[c_p]
+// valued states (TSC/DSC): byte = pos | vidx<<4, 0xFF unused; lin[] holds YW[c_p].
 template <int GMAX, bool BINARY>
-__device__ __forceinline__ void eval_state(unsigned long long rec, const GLStatic &st, const GLIter &it,
-                                           const double *ywc, const double *Gc, double yy, double &q,
-                                           double &prior) {
-    int pos[GMAX];
-    double val[GMAX];
-    double pr = double(st.zbase) * it.lp0;
+__device__ __forceinline__ double eval_state(unsigned long long rec, const GLStatic &st, const double *lin,
+                                             const double *Gc, double yy) {
+    if (BINARY) {
+        int p[GMAX];
 #pragma unroll
-    for (int m = 0; m < GMAX; ++m) {
-        unsigned b = unsigned(rec >> (8 * m)) & 0xFFu;
-        bool ok = (b != 0xFFu);
-        pos[m] = ok ? int(b & 15u) : 0;
-        int vi = ok ? int(b >> 4) : 0;
-        val[m] = ok ? (BINARY ? 1.0 : st.vals[vi]) : 0.0;
-        pr += ok ? (it.lp[vi] - it.lp0) : 0.0;
+        for (int m = 0; m < GMAX; ++m) p[m] = int(unsigned(rec >> (8 * m)) & 0xFFu);
+        double a1 = yy, a2 = 0.0;
+#pragma unroll
+        for (int m = 0; m < GMAX; ++m) {
+            a1 += lin[p[m]];
+            const double *g = Gc + p[m] * GS;
+#pragma unroll
+            for (int m2 = 0; m2 < m; ++m2) a2 += g[p[m2]];
+        }
+        return fma(2.0, a2, a1);
+    } else {
+        int pos[GMAX];
+        double val[GMAX];
+#pragma unroll
+        for (int m = 0; m < GMAX; ++m) {
+            unsigned b = unsigned(rec >> (8 * m)) & 0xFFu;
+            bool ok = (b != 0xFFu);
+            pos[m] = ok ? int(b & 15u) : 0;
+            val[m] = ok ? st.vals[b >> 4] : 0.0;
+        }
+        double acc = yy;
+#pragma unroll
+        for (int m = 0; m < GMAX; ++m) {
+            double l = fma(val[m], Gc[pos[m] * GS + pos[m]], -2.0 * lin[pos[m]]);
+            double cross = 0.0;
+#pragma unroll
+            for (int m2 = 0; m2 < m; ++m2) cross = fma(val[m2], Gc[pos[m] * GS + pos[m2]], cross);
+            acc = fma(val[m], fma(2.0, cross, l), acc);
+        }
+        return acc;
     }
-    double acc = yy;
-#pragma unroll
-    for (int m = 0; m < GMAX; ++m) {
-        double lin = fma(val[m], Gc[pos[m] * PET_MAXHP + pos[m]], -2.0 * ywc[pos[m]]);
-        double cross = 0.0;
-#pragma unroll
-        for (int m2 = 0; m2 < m; ++m2) cross = fma(val[m2], Gc[pos[m] * PET_MAXHP + pos[m2]], cross);
-        acc = fma(val[m], fma(2.0, cross, lin), acc);
-    }
-    q = acc;
-    prior = pr;
 }
 
-template <int GMAX>
-__device__ __forceinline__ double state_prior(unsigned long long rec, const GLStatic &st, const GLIter &it) {
+// log-prior of every multi-state, once per iteration (it depends on pi only):
+//   BSC pil_bar*|s| (bsc_et.py:164); TSC sum_j log p(s_j) over H' entries (tsc_et.py:316-326);
+//   DSC state_abs . log pi with H - nnz zeros (dsc_et.py:525-527)
+__global__ void state_prior_kernel(GLStatic st, GLIter it, double *out) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= st.S) return;
+    unsigned long long rec = st.states[s];
+    const unsigned unused = (st.n_cnt == 1 && st.vals[0] == 1.0 && st.zbase == 0) ? unsigned(st.Hp) : 0xFFu;
     double pr = double(st.zbase) * it.lp0;
-#pragma unroll
-    for (int m = 0; m < GMAX; ++m) {
+    for (int m = 0; m < PET_MAXG; ++m) {
         unsigned b = unsigned(rec >> (8 * m)) & 0xFFu;
-        pr += (b != 0xFFu) ? (it.lp[b >> 4] - it.lp0) : 0.0;
+        if (b != unused && b != 0xFFu) pr += it.lp[(b >> 4) & 15u] - it.lp0;
     }
-    return pr;
+    out[s] = pr;
+}
+
+int launch_state_prior(const GLStatic &st, const GLIter &it, double *out, cudaStream_t stream) {
+    if (st.S <= 0) return PET_OK;
+    state_prior_kernel<<<(st.S + 127) / 128, 128, 0, stream>>>(st, it, out);
+    PET_LAUNCH_CHECK();
+    return PET_OK;
 }
 
 // selection score of item i (a cause h, or for TSC a signed singleton (sign block, h))
@@ -204,22 +235,26 @@ __global__ void __launch_bounds__(GL_MAX_WARPS * 32) gl_kernel(const __grid_cons
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     const int H = st.H, Hp = st.Hp, S = st.S;
     const SmemLayout L = smem_layout(st);
+    const int CH = st.chunk_len, NCH = st.n_chunks;
 
     unsigned long long *states_s = reinterpret_cast<unsigned long long *>(smem);
     unsigned short *ids_s = reinterpret_cast<unsigned short *>(smem + L.off_ids);
-    int *first_s = reinterpret_cast<int *>(smem + L.off_first);
+    unsigned short *chunk_s = reinterpret_cast<unsigned short *>(smem + L.off_chunk);
     for (int s = threadIdx.x; s < S; s += blockDim.x) states_s[s] = st.states[s];
-    for (int i = threadIdx.x; i < st.entries_per_lane * 32; i += blockDim.x) ids_s[i] = st.entries[i];
-    if (threadIdx.x < 32) first_s[threadIdx.x] = st.first_out[threadIdx.x];
+    for (int i = threadIdx.x; i < NCH * CH * 32; i += blockDim.x) ids_s[i] = st.entries[i];
+    for (int i = threadIdx.x; i < NCH * 32; i += blockDim.x) chunk_s[i] = st.chunk_tab[i];
     double *wbase = smem + L.shared_doubles + size_t(L.per_warp) * warp;
     double *row = wbase;
     double *qbuf = wbase + L.off_q;
     double *Gc = wbase + L.off_G;
-    double *ywc = wbase + L.off_ywc;
+    double *lin = wbase + L.off_lin;
     double *mom = wbase + L.off_mom;
     double *Pj = wbase + L.off_P;
     int *cand_s = reinterpret_cast<int *>(wbase + L.off_cand);
     int *live_s = cand_s + PET_MAXHP;
+    // zero row/column Hp of the Gram block and lin[Hp] once: the dummy position of unused member slots
+    for (int i = lane; i < GS * GS; i += 32) Gc[i] = 0.0;
+    for (int i = lane; i < GS; i += 32) lin[i] = 0.0;
     __syncthreads();
 
     const bool do_stats = !(a.flags & (GLF_LSE_ONLY | GLF_SELECT_ONLY));
@@ -272,16 +307,20 @@ __global__ void __launch_bounds__(GL_MAX_WARPS * 32) gl_kernel(const __grid_cons
         if (a.flags & GLF_SELECT_ONLY) continue;
 
         // ---- phase 2: gather scores and Gram block of the candidates ----------------
+        for (int idx = lane; idx < Hp * Hp; idx += 32) {
+            int j = idx / Hp, k = idx % Hp;
+            Gc[j * GS + k] = a.G[int64_t(cand_s[j]) * st.ldH + cand_s[k]];
+        }
         if (lane < Hp) {
             int c = cand_s[lane];
-            ywc[lane] = row[c];
             int lv = 1;
             for (int j = lane + 1; j < Hp; ++j) lv &= (cand_s[j] != c);   // numpy "last write wins"
             live_s[lane] = lv;
         }
-        for (int idx = lane; idx < Hp * Hp; idx += 32) {
-            int j = idx / Hp, k = idx % Hp;
-            Gc[j * PET_MAXHP + k] = a.G[int64_t(cand_s[j]) * st.ldH + cand_s[k]];
+        __syncwarp();
+        if (lane < Hp) {
+            double ywc = row[cand_s[lane]];
+            lin[lane] = BINARY ? fma(-2.0, ywc, Gc[lane * GS + lane]) : ywc;
         }
         __syncwarp();
 
@@ -310,13 +349,12 @@ __global__ void __launch_bounds__(GL_MAX_WARPS * 32) gl_kernel(const __grid_cons
         }
 #pragma unroll 2
         for (int s = lane; s < S; s += 32) {
-            double q, prior;
-            eval_state<GMAX, BINARY>(states_s[s], st, it, ywc, Gc, yy, q, prior);
+            double q = eval_state<GMAX, BINARY>(states_s[s], st, lin, Gc, yy);
             qbuf[s] = q;
             double F;
             if (rd) F = logpj_row[col_states + s];
             else {
-                F = combine(it, prior, q);
+                F = combine(it, a.state_prior[s], q);
                 if (wr) logpj_row[col_states + s] = F;
             }
             mx = fmax(mx, F);
@@ -361,43 +399,46 @@ __global__ void __launch_bounds__(GL_MAX_WARPS * 32) gl_kernel(const __grid_cons
 #pragma unroll 2
         for (int s = lane; s < S; s += 32) {
             double q = qbuf[s];
-            double F = rd ? logpj_row[col_states + s] : combine(it, state_prior<GMAX>(states_s[s], st, it), q);
+            double F = rd ? logpj_row[col_states + s] : combine(it, a.state_prior[s], q);
             double x = F - mx;
             double p = (x > GL_EXP_CUTOFF) ? exp(x) : 0.0;
             denom += p;
             sig += p * q;
             qbuf[s] = p;
         }
-        if (lane == 0) qbuf[S] = 0.0;   // zero slot read by padding / dummy gather entries
+        if (lane == 0) qbuf[S] = 0.0;   // zero slot read by padding entries of the gather table
         denom = warp_sum(denom);
         const double lse = mx + log(denom);
         if (lane == 0) a.lse[n] = lse;
         if (!do_stats) continue;
         sig = warp_sum(sig);
 #pragma unroll
-        for (int v = 0; v < PET_MAXV; ++v) cntb[v] = warp_sum(cntb[v]);
+        for (int v = 0; v < PET_MAXV; ++v)
+            if (v < st.n_blocks) cntb[v] = warp_sum(cntb[v]);
         const double inv = 1.0 / denom;
 
         // ---- phase 5: pair sums from the shared-memory gather table -----------------
-        for (int o = lane; o < st.n_out; o += 32) mom[o] = 0.0;
+        // every lane runs NCH chunks of CH ids; all chunks of an output belong to one lane
+        for (int o = lane; o <= st.n_out; o += 32) mom[o] = 0.0;
         __syncwarp();
+        for (int i = lane; i < st.n_direct; i += 32) {
+            unsigned d = st.direct[i];
+            mom[d >> 16] = qbuf[d & 0xFFFFu];
+        }
         {
-            int cur = first_s[lane];
             double acc = 0.0;
             const unsigned short *ids = ids_s + lane;
-            for (int t = 0; t < st.entries_per_lane; t += 4) {
-                unsigned e0 = ids[(t + 0) * 32], e1 = ids[(t + 1) * 32], e2 = ids[(t + 2) * 32], e3 = ids[(t + 3) * 32];
-                double p0 = qbuf[e0 & 0x7FFFu], p1 = qbuf[e1 & 0x7FFFu], p2 = qbuf[e2 & 0x7FFFu], p3 = qbuf[e3 & 0x7FFFu];
-                if (((e0 | e1 | e2 | e3) & 0x8000u) == 0) {
-                    acc += (p0 + p1) + (p2 + p3);
-                } else {
-                    acc += p0; if (e0 & 0x8000u) { atomicAdd(&mom[cur], acc); ++cur; acc = 0.0; }
-                    acc += p1; if (e1 & 0x8000u) { atomicAdd(&mom[cur], acc); ++cur; acc = 0.0; }
-                    acc += p2; if (e2 & 0x8000u) { atomicAdd(&mom[cur], acc); ++cur; acc = 0.0; }
-                    acc += p3; if (e3 & 0x8000u) { atomicAdd(&mom[cur], acc); ++cur; acc = 0.0; }
+            for (int c = 0; c < NCH; ++c) {
+                const unsigned co = chunk_s[c * 32 + lane];
+                double s0 = 0.0, s1 = 0.0;
+                for (int i = 0; i < CH; i += 4) {
+                    const unsigned short *e = ids + (c * CH + i) * 32;
+                    s0 += qbuf[e[0]] + qbuf[e[32]];
+                    s1 += qbuf[e[64]] + qbuf[e[96]];
                 }
+                acc += s0 + s1;
+                if (co & 0x8000u) { mom[co & 0x7FFFu] = acc; acc = 0.0; }
             }
-            if (cur < st.n_out && acc != 0.0) atomicAdd(&mom[cur], acc);
         }
         __syncwarp();
 
@@ -413,7 +454,7 @@ __global__ void __launch_bounds__(GL_MAX_WARPS * 32) gl_kernel(const __grid_cons
                 const int pair = lo * Hp - lo * (lo + 1) / 2 + (hi - lo - 1);
                 for (int bv = 0; bv < n_cnt; ++bv) {
                     const int base = ((pair * n_cnt + (j < k ? av : bv)) * n_cnt + (j < k ? bv : av)) * n_g;
-                    for (int g = 0; g < n_g; ++g) P += mom[base + g] / double(g + 1);
+                    for (int g = 0; g < n_g; ++g) P = fma(mom[base + g], c_winv[g], P);
                 }
             }
             Pj[idx] = P;
@@ -468,7 +509,8 @@ __global__ void __launch_bounds__(GL_MAX_WARPS * 32) gl_kernel(const __grid_cons
         }
         // 6d. scalar statistics
 #pragma unroll
-        for (int v = 0; v < PET_MAXV; ++v) cnt_states[v] = warp_sum(cnt_states[v]);
+        for (int v = 0; v < PET_MAXV; ++v)
+            if (v < n_cnt) cnt_states[v] = warp_sum(cnt_states[v]);
         if (lane == 0) {
             acc_n += 1.0;
             acc_lse += lse;

@@ -41,11 +41,13 @@ struct GLStatic {                 // fixed per engine
     int select_mode;
     int diag_from_colsum;         // binary: Wq diagonal = column sums of <s> (not scattered)
     const unsigned long long *states;   // S records: 8 x (pos | vidx<<4), 0xFF = unused
-    const unsigned short *entries;   // pair-sum gather lists of state ids, transposed [t][lane]
-    int entries_per_lane;            // multiple of 4
+    const unsigned short *entries;   // [(chunk*CH+i)*32 + lane] state ids of the pair-sum gather lists
+    const unsigned short *chunk_tab; // [chunk*32 + lane] output id | 0x8000 on the last chunk of an output
+    const unsigned int *direct;      // (output<<16 | state id) of single-entry lists
+    int n_direct;
+    int n_chunks, chunk_len;         // per lane; chunk_len is a multiple of 4
     int n_out;                       // pair-sum outputs: pairs * n_cnt^2 * n_g
     int n_g;                         // state sizes 2..n_g+1 carry pairs
-    const int *first_out;            // [32] output of each lane's first entry
     const int *single_idx;           // [Hp*n_cnt] in-table singleton state ids (TSC) or -1
 };
 
@@ -70,6 +72,7 @@ struct GLArgs {
     const double *wn2;            // (H,)  ||W_h||^2
     const double *invn;           // (H,)  1/||W_h||
     const double *G;              // (H, ldH) Gram matrix
+    const double *state_prior;    // (S,) log-prior of every multi-state for this iteration
     int *cand;                    // (n, Hp) global index
     double *logpj; int64_t ld_logpj;   // (n, C) global index (read or write)
     double *lse;                  // (n,) global index (written, or read when GLF_USE_CUT)
@@ -83,5 +86,6 @@ struct GLArgs {
 int launch_gl_kernel(const GLArgs &a, int gamma, bool binary, int sm_count, cudaStream_t st);
 size_t gl_smem_bytes(const GLStatic &s, int warps);
 int gl_pick_warps(const GLStatic &s);
+int launch_state_prior(const GLStatic &st, const GLIter &it, double *out, cudaStream_t stream);
 
 }  // namespace pet
