@@ -242,6 +242,17 @@ extern "C" int pet_create(const pet_config *cfg, pet_engine **out) {
     { int v = 0; for (int k = 0; k < e->K; ++k) if (k != e->k0) g.vals[v++] = e->values[k]; }
     e->C = g.has_null + (int64_t)g.n_blocks * e->H + e->ss.S;
     g.C = (int)e->C;
+    g.binary = e->binary ? 1 : 0;
+    for (int gsz = 0; gsz < PET_MAXG + 2; ++gsz) g.size_start[gsz] = (int)e->ss.S;
+    if (e->binary) {   // states are enumerated by size 2..gamma
+        int64_t idx = 0;
+        for (int gsz = 2; gsz <= e->gamma; ++gsz) {
+            g.size_start[gsz] = (int)idx;
+            double c = 1.0;
+            for (int t = 0; t < gsz; ++t) c = c * (e->Hp - t) / (t + 1);
+            idx += (int64_t)(c + 0.5);
+        }
+    }
     g.n_chunks = e->ss.n_chunks; g.chunk_len = e->ss.chunk_len;
     g.n_direct = (int)e->ss.direct.size();
     g.n_out = e->ss.n_out;

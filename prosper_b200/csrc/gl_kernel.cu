@@ -16,6 +16,7 @@
 //   5 pair sums over the state space from a shared-memory gather table (16-bit state ids)
 //   6 first/second posterior moments, <s> row for the statistics GEMM, Wq scatter   bsc_et.py:349-366
 #include <math.h>
+#include <stdlib.h>
 
 #include <algorithm>
 
@@ -59,6 +60,19 @@ size_t gl_smem_bytes(const GLStatic &s, int warps) {
 }
 
 __constant__ double c_winv[8] = {1.0, 1.0 / 2, 1.0 / 3, 1.0 / 4, 1.0 / 5, 1.0 / 6, 1.0 / 7, 1.0 / 8};
+
+// log-prior of multi-state s.  Binary spaces are enumerated by size (camodels/__init__.py:30-33), so
+// |s| follows from the index and nothing is loaded; valued spaces read the per-iteration table.
+template <bool BINARY>
+__device__ __forceinline__ double prior_of(const GLArgs &a, int s) {
+    if (BINARY) {
+        int n = 2;
+#pragma unroll
+        for (int g = 3; g <= PET_MAXG; ++g) n += (s >= a.st.size_start[g]) ? 1 : 0;
+        return a.it.lp[0] * double(n);
+    }
+    return a.state_prior[s];
+}
 
 __device__ __forceinline__ double combine(const GLIter &it, double prior, double q) {
     return it.anneal_prior ? it.beta * (prior + it.pre1 * q) : prior + it.beta * (it.pre1 * q);
@@ -115,7 +129,7 @@ __global__ void state_prior_kernel(GLStatic st, GLIter it, double *out) {
     int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= st.S) return;
     unsigned long long rec = st.states[s];
-    const unsigned unused = (st.n_cnt == 1 && st.vals[0] == 1.0 && st.zbase == 0) ? unsigned(st.Hp) : 0xFFu;
+    const unsigned unused = st.binary ? unsigned(st.Hp) : 0xFFu;
     double pr = double(st.zbase) * it.lp0;
     for (int m = 0; m < PET_MAXG; ++m) {
         unsigned b = unsigned(rec >> (8 * m)) & 0xFFu;
@@ -354,7 +368,7 @@ __global__ void __launch_bounds__(GL_MAX_WARPS * 32) gl_kernel(const __grid_cons
             double F;
             if (rd) F = logpj_row[col_states + s];
             else {
-                F = combine(it, a.state_prior[s], q);
+                F = combine(it, prior_of<BINARY>(a, s), q);
                 if (wr) logpj_row[col_states + s] = F;
             }
             mx = fmax(mx, F);
@@ -399,7 +413,7 @@ __global__ void __launch_bounds__(GL_MAX_WARPS * 32) gl_kernel(const __grid_cons
 #pragma unroll 2
         for (int s = lane; s < S; s += 32) {
             double q = qbuf[s];
-            double F = rd ? logpj_row[col_states + s] : combine(it, a.state_prior[s], q);
+            double F = rd ? logpj_row[col_states + s] : combine(it, prior_of<BINARY>(a, s), q);
             double x = F - mx;
             double p = (x > GL_EXP_CUTOFF) ? exp(x) : 0.0;
             denom += p;
@@ -537,7 +551,8 @@ __global__ void __launch_bounds__(GL_MAX_WARPS * 32) gl_kernel(const __grid_cons
 
 // largest warp count whose shared memory fits one SM (0 = does not fit at all)
 int gl_pick_warps(const GLStatic &s) {
-    for (int w = GL_MAX_WARPS; w >= 1; --w)
+    static int cap = []() { const char *e = getenv("PET_GL_WARPS"); int v = e ? atoi(e) : GL_MAX_WARPS; return v < 1 ? 1 : (v > GL_MAX_WARPS ? GL_MAX_WARPS : v); }();
+    for (int w = cap; w >= 1; --w)
         if (gl_smem_bytes(s, w) <= 227 * 1024) return w;
     return 0;
 }

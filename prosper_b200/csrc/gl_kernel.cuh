@@ -49,6 +49,8 @@ struct GLStatic {                 // fixed per engine
     int n_out;                       // pair-sum outputs: pairs * n_cnt^2 * n_g
     int n_g;                         // state sizes 2..n_g+1 carry pairs
     const int *single_idx;           // [Hp*n_cnt] in-table singleton state ids (TSC) or -1
+    int binary;                      // BSC-style state space: values {0,1}, states ordered by size
+    int size_start[PET_MAXG + 2];    // binary: index of the first state with g members (g = 2..gamma), then S
 };
 
 struct GLIter {                   // per call
