@@ -10,6 +10,7 @@
 
 #include "common.cuh"
 #include "gl_kernel.cuh"
+#include "mca_kernel.cuh"
 
 namespace pet {
 
@@ -119,6 +120,8 @@ struct pet_engine {
     double *gemm_work = nullptr; int64_t gemm_work_doubles = 0;
     double *solveA = nullptr, *solveB = nullptr, *solve_work = nullptr;
     double *s2sum = nullptr;
+    double *Wl = nullptr, *Wr = nullptr, *simbuf = nullptr; int64_t ldD = 0;   // MCA/MMCA tables
+    const double *Wsrc = nullptr; int64_t Wsrc_ld = 0;                          // W (D,H) on the device for this call
     double *stage_logpj = nullptr; int64_t stage_logpj_doubles = 0;
     int64_t *stage_i64 = nullptr; int64_t stage_i64_count = 0;
     unsigned long long *ksel_state = nullptr;
@@ -159,6 +162,7 @@ extern "C" void pet_destroy(pet_engine *e) {
     free_dev(e->YW); free_dev(e->Sbuf); free_dev(e->S2buf); free_dev(e->gemm_work);
     free_dev(e->solveA); free_dev(e->solveB); free_dev(e->solve_work); free_dev(e->s2sum);
     free_dev(e->stage_logpj); free_dev(e->stage_i64); free_dev(e->ksel_state);
+    free_dev(e->Wl); free_dev(e->Wr); free_dev(e->simbuf);
     free_dev(e->d_states); free_dev(e->d_entries); free_dev(e->d_chunk); free_dev(e->d_direct); free_dev(e->d_single); free_dev(e->d_state_prior);
     for (auto ev : e->chunk_ready) cudaEventDestroy(ev);
     for (auto ev : e->timer.pool) cudaEventDestroy(ev);
@@ -184,7 +188,8 @@ extern "C" int pet_create(const pet_config *cfg, pet_engine **out) {
         set_error("device %d is sm_%d%d; this library is built for sm_100a only", cfg->device, prop.major, prop.minor);
         return PET_EINVAL;
     }
-    if (cfg->model != PET_MODEL_BSC && cfg->model != PET_MODEL_TSC && cfg->model != PET_MODEL_DSC) {
+    if (cfg->model != PET_MODEL_BSC && cfg->model != PET_MODEL_TSC && cfg->model != PET_MODEL_DSC &&
+        cfg->model != PET_MODEL_MCA && cfg->model != PET_MODEL_MMCA) {
         set_error("model kind %d is not handled by this engine entry point", cfg->model);
         return PET_EINVAL;
     }
@@ -206,11 +211,13 @@ extern "C" int pet_create(const pet_config *cfg, pet_engine **out) {
     std::vector<std::vector<int>> rows;
     GLStatic &g = e->gls;
     memset(&g, 0, sizeof(g));
-    if (e->model == PET_MODEL_BSC) {
+    const bool maxmodel = (e->model == PET_MODEL_MCA || e->model == PET_MODEL_MMCA);
+    if (e->model == PET_MODEL_BSC || maxmodel) {
         e->values = {0.0, 1.0}; e->k0 = 0; e->K = 2; e->binary = true;
         enum_binary(e->Hp, e->gamma, rows);
         g.has_null = 1; g.n_blocks = 1; g.block_val[0] = 1.0; g.block_vidx[0] = 0;
-        g.zbase = 0; g.select_mode = SEL_BSC; g.diag_from_colsum = 1;
+        g.zbase = 0; g.diag_from_colsum = 1;
+        g.select_mode = (e->model == PET_MODEL_BSC) ? SEL_BSC : (e->model == PET_MODEL_MCA ? SEL_GIVEN : SEL_NEGDIST);
     } else {
         std::vector<double> vals;
         if (e->model == PET_MODEL_TSC) vals = {-1.0, 0.0, 1.0};
@@ -290,6 +297,11 @@ extern "C" int pet_create(const pet_config *cfg, pet_engine **out) {
     TRY(dev_alloc(&e->mu_dev, e->ldY));
     TRY(dev_alloc(&e->Sbuf, e->chunk_rows * e->ldH));
     if (e->model == PET_MODEL_DSC) { TRY(dev_alloc(&e->S2buf, e->chunk_rows * e->ldH)); TRY(dev_alloc(&e->s2sum, e->ldH)); }
+    if (maxmodel) {
+        e->ldD = round_up(e->D, 2);
+        TRY(dev_alloc(&e->Wl, (int64_t)e->H * e->ldD)); TRY(dev_alloc(&e->Wr, (int64_t)e->H * e->ldD));
+        if (e->model == PET_MODEL_MCA) TRY(dev_alloc(&e->simbuf, e->chunk_rows * e->ldH));
+    }
     {
         int splits = dgemm_mn_splits(e->D + 1, e->H, e->chunk_rows, e->sm_count);
         e->gemm_work_doubles = int64_t(splits) * (e->D + 1) * e->ldH;
@@ -396,6 +408,7 @@ static int load_W(pet_engine *e, const pet_params *p, cudaStream_t st) {
         PET_CUDA(cudaMemcpy2DAsync(e->Wtmp, e->ldH * 8, p->W, p->ldW * 8, size_t(e->H) * 8, e->D, cudaMemcpyHostToDevice, st));
         Wsrc = e->Wtmp; ldw = e->ldH;
     }
+    e->Wsrc = Wsrc; e->Wsrc_ld = ldw;
     PET_CHECK(launch_transpose_w(e->Wt, e->ldY, Wsrc, ldw, e->D, e->H, st));
     return PET_OK;
 }
@@ -482,7 +495,7 @@ static void mark_compute_done(pet_engine *e, cudaStream_t st) {
 enum { PASS_SELECT = 1, PASS_REUSE_SCORES = 2 };
 
 // One sweep over the shard.  kflags: GLF_* for the posterior kernel.
-static int sweep(pet_engine *e, const pet_anneal *a, const pet_params *p, int kflags, int pass_flags,
+static int sweep_gl(pet_engine *e, const pet_anneal *a, const pet_params *p, int kflags, int pass_flags,
                  const double *logpj_user, int64_t ld_logpj, bool logpj_is_output, const double *cut_dev,
                  double *stats_dev, cudaStream_t st) {
     if (e->n <= 0) { set_error("no data bound (pet_set_data)"); return PET_ESTATE; }
@@ -564,11 +577,136 @@ static int sweep(pet_engine *e, const pet_anneal *a, const pet_params *p, int kf
     return PET_OK;
 }
 
+
+// ---- MCA / MMCA -------------------------------------------------------------------------------
+static double mca_rho(const pet_engine *e, double T) {
+    if (e->model == PET_MODEL_MCA) return 1.0 / (1.0 - 1.0 / std::max(T, 1.05));          // mca_et.py:143-145
+    double rho = 1.0 / (1.0 - 1.0 / std::max(T, 1.20));                                     // mmca_et.py:163-165
+    return std::max(std::min(rho, 35.0), 1.0);
+}
+
+static int sweep_mca(pet_engine *e, const pet_anneal *a, const pet_params *p, int kflags, int pass_flags,
+                     const double *logpj_user, int64_t ld_logpj, bool logpj_is_output, const double *cut_dev,
+                     double *stats_dev, cudaStream_t st) {
+    if (e->n <= 0) { set_error("no data bound (pet_set_data)"); return PET_ESTATE; }
+    if (!(kflags & GLF_SELECT) && e->cand_state == 0) { set_error("no candidates: run select_Hprimes first"); return PET_ESTATE; }
+    if (!a || !(a->T > 0.0)) { set_error("annealing temperature T must be > 0"); return PET_EINVAL; }
+    if (!p || !(p->sigma > 0.0) || !p->pi_host) { set_error("bad model parameters"); return PET_EINVAL; }
+    const int mmca = (e->model == PET_MODEL_MMCA) ? 1 : 0;
+    const double rho = mca_rho(e, a->T);
+    const bool reuse = (pass_flags & PASS_REUSE_SCORES) && e->yw_all;
+    e->timer.begin(ST_PREPARE, st);
+    if (!reuse) PET_CHECK(load_W(e, p, st));
+    PET_CHECK(launch_mca_tables(e->Wt, e->ldY, e->H, e->D, rho, mmca, e->Wl, e->Wr, e->ldD, e->wn2, st));
+    e->timer.end(st);
+
+    GLArgs sel;                      // preselection reuses the top-H' code of the Gaussian-linear kernel
+    memset(&sel, 0, sizeof(sel));
+    sel.st = e->gls;
+    sel.it.beta = 1.0; sel.it.pre1 = -1.0;
+    sel.flags = GLF_SELECT | GLF_SELECT_ONLY;
+    sel.yy = e->yy; sel.wn2 = e->wn2; sel.invn = e->invn; sel.G = e->G; sel.cand = e->cand; sel.lse = e->lse;
+    sel.state_prior = e->d_state_prior;
+
+    MCAArgs m;
+    memset(&m, 0, sizeof(m));
+    m.mmca = mmca; m.D = e->D; m.H = e->H; m.Hp = e->Hp; m.S = (int)e->ss.S; m.C = (int)e->C; m.gamma = e->gamma;
+    m.ldH = (int)e->ldH; m.ldY = (int)e->ldY; m.ldD = (int)e->ldD; m.ldc = e->D | 1;    // odd stride: conflict-free rows
+    m.states = e->d_states;
+    m.rho = rho; m.beta = 1.0 / a->T; m.pre1 = -1.0 / 2.0 / p->sigma / p->sigma;
+    m.pil_bar = log(p->pi_host[0] / (1.0 - p->pi_host[0]));
+    m.flags = kflags & (GLF_WRITE_LOGPJ | GLF_READ_LOGPJ | GLF_LSE_ONLY | GLF_USE_CUT);
+    m.yy = e->yy; m.wn2 = e->wn2; m.Wl = e->Wl; m.Wr = e->Wr; m.cand = e->cand; m.lse = e->lse; m.cut = cut_dev;
+    pet_stats_layout lay;
+    pet_stats_layout_get(e, &lay);
+    const bool select_only = (kflags & GLF_SELECT_ONLY) != 0;
+    const bool do_stats = !(kflags & (GLF_LSE_ONLY | GLF_SELECT_ONLY));
+    if (do_stats) {
+        if (!stats_dev) { set_error("stats buffer is null"); return PET_EINVAL; }
+        PET_CUDA(cudaMemsetAsync(stats_dev, 0, lay.total * 8, st));
+        m.Wpm = stats_dev + lay.off_Wq;
+        m.Wqm = m.Wpm + (int64_t)e->H * e->ldD;
+        m.scalars = stats_dev + lay.off_scalars;
+    }
+    const bool user_logpj = (kflags & (GLF_READ_LOGPJ | GLF_WRITE_LOGPJ)) != 0;
+    const bool logpj_on_dev = user_logpj && is_device_ptr(logpj_user);
+    if (user_logpj && !logpj_on_dev) {
+        int64_t need = e->chunk_rows * e->C;
+        if (need > e->stage_logpj_doubles) {
+            cudaStreamSynchronize(st);
+            free_dev(e->stage_logpj); e->stage_logpj = nullptr; e->stage_logpj_doubles = 0;
+            PET_CHECK(dev_alloc(&e->stage_logpj, need));
+            e->stage_logpj_doubles = need;
+        }
+    }
+    const int64_t nchunks = ceil_div(e->n, e->chunk_rows);
+    for (int64_t c = 0; c < nchunks; ++c) {
+        const int64_t r0 = c * e->chunk_rows, rows = std::min(e->chunk_rows, e->n - r0);
+        PET_CHECK(ensure_chunk_inputs(e, c, r0, rows, st));
+        double *yw = e->yw_all ? e->YW + r0 * e->ldH : e->YW;
+        if (!reuse) {
+            e->timer.begin(ST_SCORE, st);
+            PET_CHECK(dgemm_kk(rows, e->H, e->D, e->Y + r0 * e->ldY, e->ldY, e->Wt, e->ldY, yw, e->ldH, 1.0, 0, st));
+            e->timer.end(st);
+        }
+        if (kflags & GLF_SELECT) {
+            e->timer.begin(ST_POST, st);
+            sel.n_rows = rows; sel.row0 = r0;
+            if (mmca) sel.YW = yw;                       // smallest ||W_h - y||^2  (mmca_et.py:118)
+            else {                                       // smallest sum_d max(W_hd - y_d, 0)  (mca_et.py:105-106)
+                PET_CHECK(launch_mca_sim(e->Y + r0 * e->ldY, e->ldY, rows, e->Wsrc, e->Wsrc_ld, e->D, e->H, e->simbuf, e->ldH, st));
+                sel.YW = e->simbuf;
+            }
+            PET_CHECK(launch_gl_kernel(sel, e->gamma, true, e->sm_count, st));
+            e->timer.end(st);
+        }
+        if (select_only) continue;
+        m.n_rows = rows; m.row0 = r0; m.Y = e->Y + r0 * e->ldY; m.YW = yw; m.Spost = e->Sbuf;
+        if (user_logpj) {
+            if (logpj_on_dev) { m.logpj = const_cast<double *>(logpj_user); m.ld_logpj = ld_logpj; }
+            else {
+                m.logpj = e->stage_logpj - r0 * e->C; m.ld_logpj = e->C;
+                if (!logpj_is_output)
+                    PET_CUDA(cudaMemcpy2DAsync(e->stage_logpj, e->C * 8, logpj_user + r0 * ld_logpj, ld_logpj * 8,
+                                               size_t(e->C) * 8, rows, cudaMemcpyHostToDevice, st));
+            }
+        }
+        e->timer.begin(ST_POST, st);
+        PET_CHECK(launch_mca_kernel(m, e->sm_count, st));
+        e->timer.end(st);
+        if (user_logpj && !logpj_on_dev && logpj_is_output)
+            PET_CUDA(cudaMemcpy2DAsync(const_cast<double *>(logpj_user) + r0 * ld_logpj, ld_logpj * 8, e->stage_logpj,
+                                       e->C * 8, size_t(e->C) * 8, rows, cudaMemcpyDeviceToHost, st));
+        if (do_stats) {
+            e->timer.begin(ST_STATS, st);
+            PET_CHECK(dgemm_mn(e->D + 1, e->H, rows, e->Y + r0 * e->ldY, e->ldY, e->Sbuf, e->ldH,
+                               stats_dev + lay.off_Wp, e->ldH, 1, e->gemm_work, e->gemm_work_doubles, e->sm_count, st));
+            e->timer.end(st);
+        }
+    }
+    e->yy_valid = true;
+    if (kflags & GLF_SELECT) e->cand_state = 1;
+    mark_compute_done(e, st);
+    return PET_OK;
+}
+
+
+static int sweep(pet_engine *e, const pet_anneal *a, const pet_params *p, int kflags, int pass_flags,
+                 const double *logpj_user, int64_t ld_logpj, bool logpj_is_output, const double *cut_dev,
+                 double *stats_dev, cudaStream_t st) {
+    if (e->model == PET_MODEL_MCA || e->model == PET_MODEL_MMCA)
+        return sweep_mca(e, a, p, kflags, pass_flags, logpj_user, ld_logpj, logpj_is_output, cut_dev, stats_dev, st);
+    return sweep_gl(e, a, p, kflags, pass_flags, logpj_user, ld_logpj, logpj_is_output, cut_dev, stats_dev, st);
+}
+
 extern "C" int pet_stats_layout_get(const pet_engine *e, pet_stats_layout *out) {
     if (!e || !out) { set_error("pet_stats_layout_get: null argument"); return PET_EINVAL; }
     memset(out, 0, sizeof(*out));
     out->off_Wp = 0; out->rows_Wp = e->D + 1; out->cols_Wp = e->H; out->ld_Wp = e->ldH;
     out->off_Wq = out->rows_Wp * out->ld_Wp; out->rows_Wq = e->H; out->cols_Wq = e->H; out->ld_Wq = e->ldH;
+    if (e->model == PET_MODEL_MCA || e->model == PET_MODEL_MMCA) {   // two (H,D) blocks: multi-cause Wp then Wq
+        out->rows_Wq = 2 * (int64_t)e->H; out->cols_Wq = e->D; out->ld_Wq = e->ldD;
+    }
     out->off_scalars = out->off_Wq + out->rows_Wq * out->ld_Wq;
     out->n_scalars = 16;
     out->total = out->off_scalars + out->n_scalars;
@@ -674,6 +812,19 @@ extern "C" int pet_m_step_solve(pet_engine *e, const pet_params *p, const double
     PET_CUDA(cudaSetDevice(e->device));
     pet_stats_layout lay;
     pet_stats_layout_get(e, &lay);
+    if (e->model == PET_MODEL_MCA || e->model == PET_MODEL_MMCA) {
+        // element-wise update; needs the OLD W (inertia term / W^2 factors): Wt still holds it
+        e->timer.begin(ST_SOLVE, st);
+        const double *Wpm = stats_dev + lay.off_Wq, *Wqm = Wpm + (int64_t)e->H * e->ldD;
+        PET_CHECK(launch_mca_update(stats_dev + lay.off_Wp, e->ldH, Wpm, Wqm, e->ldD, e->Wt, e->ldY, e->D, e->H,
+                                    e->model == PET_MODEL_MMCA, 1e-4, e->solveB, e->ldH, st));
+        e->timer.end(st);
+        cudaMemcpyKind kind2 = is_device_ptr(W_new) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+        PET_CUDA(cudaMemcpy2DAsync(W_new, size_t(e->H) * 8, e->solveB, e->ldH * 8, size_t(e->H) * 8, e->D, kind2, st));
+        PET_CUDA(cudaStreamSynchronize(st));
+        if (info_host) info_host[0] = 0;
+        return PET_OK;
+    }
     e->timer.begin(ST_SOLVE, st);
     PET_CUDA(cudaMemcpyAsync(e->solveA, stats_dev + lay.off_Wq, (int64_t)e->H * e->ldH * 8, cudaMemcpyDeviceToDevice, st));
     PET_CUDA(cudaMemcpyAsync(e->solveB, stats_dev + lay.off_Wp, (int64_t)e->D * e->ldH * 8, cudaMemcpyDeviceToDevice, st));

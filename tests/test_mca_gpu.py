@@ -1,0 +1,108 @@
+"""GPU parity tests of MCA-ET and MMCA-ET (rho-norm superposition: D-loop per state)."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from helpers import bars_dict, rel_err
+from oracle.common import DictAnneal
+from oracle.mca import MCA, MMCA
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+TOL = 1e-8
+
+
+def cp(p):
+    return dict((k, (np.copy(v) if isinstance(v, np.ndarray) else v)) for k, v in p.items())
+
+
+def make(name, D, H, Hp, g):
+    assert torch.cuda.is_available(), "GPU tests need a B200"
+    if name == 'mca':
+        from prosper_b200.em.camodels.mca_et import MCA_ET
+        return MCA_ET(D, H, Hp, g), MCA(D, H, Hp, g)
+    from prosper_b200.em.camodels.mmca_et import MMCA_ET
+    return MMCA_ET(D, H, Hp, g), MMCA(D, H, Hp, g)
+
+
+def check_all(m, o, an, params, y, golden=None):
+    from prosper_b200.utils.datalog import dlog, Keep
+    po = o.check_params(cp(params))
+    od = o.select_hprimes(po, {'y': y.copy()})
+    oss = o.e_step(an, po, od)
+    onew = o.m_step(an, po, oss, od)
+    if golden is not None:
+        assert np.array_equal(od['candidates'], golden['candidates'])
+        assert rel_err(onew['W'], golden['W_new']) < 1e-9 and abs(onew['Q'] - float(golden['Q'])) < 1e-9 * abs(float(golden['Q']))
+    p1 = m.check_params(cp(params))
+    assert np.array_equal(p1['W'], po['W'])
+    d = m.select_Hprimes(p1, {'y': y.copy()})
+    same_rows = (d['candidates'] == od['candidates']).all(axis=1)
+    assert same_rows.mean() > 0.99, same_rows.mean()
+    d['candidates'] = od['candidates'].copy()
+    ss = m.E_step(an, p1, d)
+    assert ss['logpj'].shape == oss['logpj'].shape
+    assert np.abs(ss['logpj'] - oss['logpj']).max() < 1e-10 * np.abs(oss['logpj']).max()
+    keep = dlog.set_handler('*', Keep)
+    try:
+        outs = [m.M_step(an, p1, {'logpj': oss['logpj']}, d)]
+        if same_rows.all():
+            outs.append(m._fused_step(an, m.check_params(cp(params)), {'y': y.copy()}))
+        for got in outs:
+            assert rel_err(got['W'], onew['W']) < TOL
+            assert abs(got['pi'] - onew['pi']) < TOL * onew['pi']
+            assert abs(got['sigma'] - onew['sigma']) < TOL * onew['sigma']
+            assert abs(got['Q'] - onew['Q']) < TOL * abs(onew['Q'])
+            assert keep.last('N_use') == o.log['N_use']
+    finally:
+        dlog.remove_handler(keep)
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "mca_*.npz")) + glob.glob(os.path.join(GOLDEN, "mmca_*.npz"))),
+                         ids=lambda p: os.path.basename(p))
+def test_against_reference_golden(path):
+    g = np.load(path)
+    D, H, Hp, gam = (int(v) for v in g['meta'])
+    m, o = make(str(g['model']), D, H, Hp, gam)
+    an = DictAnneal(T=float(g['T']), Ncut_factor=float(g['Ncut_factor']), anneal_prior=bool(g['anneal_prior']))
+    params = {'W': g['W0'].copy(), 'pi': float(g['pi0']), 'sigma': float(g['sigma0'])}
+    check_all(m, o, an, params, g['y'], golden=g)
+
+
+def synth(name, D, H, N, seed):
+    rng = np.random.RandomState(seed)
+    Wgt = 10 * bars_dict(H) if D == (H // 2) ** 2 else np.abs(rng.standard_normal((D, H))) * 4
+    if name == 'mmca':
+        Wgt = Wgt * (1 - 2 * rng.randint(2, size=(1, H)))
+    s = rng.random_sample((N, H)) < 2.0 / H
+    y = np.zeros((N, D))
+    for n in range(N):
+        t0 = s[n, :, None] * Wgt.T
+        idx = np.argmax(np.abs(t0), axis=0)
+        y[n] = t0[idx, np.arange(D)]
+    y += 1.5 * rng.standard_normal((N, D))
+    W0 = y.mean(0)[:, None] + rng.normal(scale=0.7, size=(D, H))
+    return y, {'W': W0, 'pi': 1.5 / H, 'sigma': 2.0}
+
+
+CASES = [
+    ('mca', 25, 10, 6, 3, 2000, 1, 1.0, 0.0),        # BASELINE configs[1] shape (N=2000)
+    ('mca', 25, 10, 6, 3, 2000, 1, 4.0, 0.0),        # start of its annealing schedule
+    ('mca', 25, 10, 6, 3, 700, 2, 2.0, 0.7),
+    ('mca', 31, 9, 5, 2, 301, 3, 1.3, 1.0),
+    ('mca', 40, 12, 4, 1, 200, 4, 1.0, 0.0),
+    ('mmca', 25, 10, 6, 3, 2000, 1, 1.0, 0.0),
+    ('mmca', 25, 10, 6, 3, 700, 2, 3.0, 0.7),
+    ('mmca', 31, 9, 5, 2, 301, 3, 1.1, 1.0),
+    ('mmca', 64, 16, 8, 4, 150, 5, 1.5, 0.5),
+]
+
+
+@pytest.mark.parametrize("name,D,H,Hp,gam,N,seed,T,ncut", CASES)
+def test_against_oracle(name, D, H, Hp, gam, N, seed, T, ncut):
+    m, o = make(name, D, H, Hp, gam)
+    y, params = synth(name, D, H, N, seed)
+    check_all(m, o, DictAnneal(T=T, Ncut_factor=ncut, anneal_prior=False), params, y)

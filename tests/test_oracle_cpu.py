@@ -25,6 +25,12 @@ def _oracle_for(name, meta):
     if name == 'dsc':
         from oracle.dsc import DSC
         return DSC(*meta)
+    if name == 'mca':
+        from oracle.mca import MCA
+        return MCA(*meta)
+    if name == 'mmca':
+        from oracle.mca import MMCA
+        return MMCA(*meta)
     raise KeyError(name)
 
 
@@ -37,8 +43,6 @@ def test_oracle_matches_reference_golden(path):
     """Every stage of the oracle reproduces what the unmodified reference produced."""
     g = np.load(path, allow_pickle=False)
     name = str(g['model'])
-    if name not in ('bsc', 'tsc', 'dsc'):
-        pytest.skip("oracle for %s not built yet" % name)
     o = _oracle_for(name, tuple(int(v) for v in g['meta']))
     an = DictAnneal(T=float(g['T']), Ncut_factor=float(g['Ncut_factor']), anneal_prior=bool(g['anneal_prior']))
     params = {'W': g['W0'].copy(), 'pi': (g['pi0'].copy() if g['pi0'].ndim else float(g['pi0'])), 'sigma': float(g['sigma0'])}
@@ -51,7 +55,10 @@ def test_oracle_matches_reference_golden(path):
     assert rel_err(new['W'], g['W_new']) < 1e-9
     assert rel_err(new['pi'], g['pi_new']) < 1e-10
     assert rel_err(new['sigma'], g['sigma_new']) < 1e-10
-    assert abs(o.log['L'] - float(g['L'])) < 1e-9 * abs(float(g['L']))
+    if name in ('mca', 'mmca'):
+        assert abs(new['Q'] - float(g['Q'])) < 1e-9 * abs(float(g['Q']))
+    else:
+        assert abs(o.log['L'] - float(g['L'])) < 1e-9 * abs(float(g['L']))
     assert o.log['N_use'] == int(g['N_use'])
 
 
