@@ -75,5 +75,51 @@ def main():
     run_case('bsc', 'h16', BSC_ET(64, 16, 8, 4), gt16, 150, 2, 1.2, 0.7, False, (64, 16, 8, 4))
 
 
+def run_gsc(case, D, H, Hp, gam, stype, N, seed, T):
+    """GSC returns moment tensors instead of logpj and mutates its inputs (gsc_et.py:572-573,584-718)."""
+    from prosper.em.camodels.gsc_et import GSC
+    np.random.seed(seed)
+    model = GSC(D, H, Hp, gam, sigma_sq_type=stype)
+    sig = {'scalar': 1.0, 'diagonal': np.ones(D), 'full': np.eye(D)}[stype]
+    gt = {'W': 10 * generate_bars_dict(H), 'pi': 0.2 * np.ones(H), 'mu': np.ones(H), 'psi_sq': np.eye(H), 'sigma_sq': sig}
+    data = model.generate_data(gt, N)
+    params = model.standard_init(data)
+    an = LinearAnnealing(2)
+    an['T'] = T
+    if stype == 'full':      # standard_init's 'full' matrix is non-symmetric (broadcasting slip, gsc_et.py:85):
+        v = np.diag(params['sigma_sq']).copy()       # use a proper symmetric positive-definite one instead
+        u = np.random.randn(D) * 0.5
+        params['sigma_sq'] = np.diag(v) + np.outer(u, u)
+    params = model.check_params(params)
+    p0 = dict((k, np.copy(v)) for k, v in params.items())
+    y0 = data['y'].copy()
+    data = model.select_Hprimes(params, data)
+    cand = np.zeros((N, model.Hprime), dtype=np.int64)
+    for cl in data['data_clusters'].values():
+        cand[cl['ind']] = cl['hprimes'][None, :]
+    suff = model.E_step(an, params, data)
+    y_after = data['y'].copy()
+    new = model.M_step(an, params, suff, data)
+    out = dict(model='gsc', meta=np.array((D, H, Hp, gam)), sigma_sq_type=stype, T=T, y=y0, y_after=y_after,
+               candidates=cand, candidates_after=np.asarray(data['candidates']),
+               W0=p0['W'], pi0=p0['pi'], mu0=p0['mu'], psi_sq0=p0['psi_sq'], sigma_sq0=p0['sigma_sq'],
+               xpt_s=suff['xpt_s'], xpt_ss=suff['xpt_ss'], xpt_sz=suff['xpt_sz'], xpt_szsz=suff['xpt_szsz'],
+               W_new=new['W'], pi_new=new['pi'], mu_new=new['mu'], psi_sq_new=new['psi_sq'], sigma_sq_new=new['sigma_sq'])
+    path = os.path.join(HERE, "gsc_%s.npz" % case)
+    np.savez_compressed(path, **out)
+    print("wrote", path, "pi_new[:3]", new['pi'][:3], "sigma_sq_new", np.ravel(new['sigma_sq'])[:2], "W sum", new['W'].sum())
+
+
+def main_gsc():
+    run_gsc('scalar_t1', 25, 10, 6, 3, 'scalar', 120, 1, 1.0)
+    run_gsc('scalar_t2', 25, 10, 6, 3, 'scalar', 120, 1, 2.0)
+    run_gsc('diag_t1', 25, 10, 5, 2, 'diagonal', 100, 2, 1.3)
+    run_gsc('full_t1', 16, 8, 4, 2, 'full', 80, 3, 1.0)
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == 'gsc':
+        main_gsc()
+    else:
+        main()
+        main_gsc()

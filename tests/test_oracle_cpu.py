@@ -35,7 +35,7 @@ def _oracle_for(name, meta):
 
 
 def golden_files():
-    return sorted(glob.glob(os.path.join(GOLDEN, "*.npz")))
+    return sorted(p for p in glob.glob(os.path.join(GOLDEN, "*.npz")) if not os.path.basename(p).startswith("gsc_"))
 
 
 @pytest.mark.parametrize("path", golden_files(), ids=[os.path.basename(p) for p in golden_files()])
@@ -162,3 +162,25 @@ def test_product_never_imports_oracle():
             if f.endswith(".py"):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "gsc_*.npz"))), ids=lambda p: os.path.basename(p))
+def test_gsc_oracle_matches_reference_golden(path):
+    """GSC returns posterior moment tensors and mutates its inputs; every piece is compared."""
+    from oracle.gsc import GSC
+    g = np.load(path)
+    D, H, Hp, gam = (int(v) for v in g['meta'])
+    o = GSC(D, H, Hp, gam, sigma_sq_type=str(g['sigma_sq_type']))
+    an = DictAnneal(T=float(g['T']))
+    s2 = g['sigma_sq0']
+    params = {'W': g['W0'].copy(), 'pi': g['pi0'].copy(), 'mu': g['mu0'].copy(), 'psi_sq': g['psi_sq0'].copy(),
+              'sigma_sq': (float(s2) if s2.ndim == 0 else s2.copy())}
+    data = o.select_hprimes(params, {'y': g['y'].copy()})
+    assert np.array_equal(data['candidates'], g['candidates'])
+    suff = o.e_step(an, params, data)
+    assert np.array_equal(data['y'], g['y_after']) and np.array_equal(data['candidates'], g['candidates_after'])
+    for k in ('xpt_s', 'xpt_ss', 'xpt_sz', 'xpt_szsz'):
+        assert np.abs(suff[k] - g[k]).max() < 1e-9 * max(1.0, np.abs(g[k]).max()), k
+    new = o.m_step(an, params, suff, data)
+    for k in ('W', 'pi', 'mu', 'psi_sq', 'sigma_sq'):
+        assert rel_err(new[k], g[k + '_new']) < 1e-8, k
