@@ -166,6 +166,49 @@ int  pet_stats_layout_get(const pet_engine *e, pet_stats_layout *out);
 int  pet_m_step_solve(pet_engine *e, const pet_params *p, const double *stats_dev,
                       double *W_new_dev, int32_t *info_host, void *stream);
 
+/* ---- GSC (gsc_et.py): spike-and-slab model with its own parameter set and statistics --------- */
+/* model_params of GSC: W (D,H), pi (H,), mu (H,), psi_sq (H,H), sigma_sq scalar / (D,) / (D,D)
+ * (gsc_et.py:60-110).  sigma_sq_type: 0 'scalar', 1 'diagonal', 2 'full' (2 is rejected: not built). */
+typedef struct pet_gsc_params {
+    const double *W;            /* (D,H) host or device                                    */
+    int64_t ldW;
+    const double *pi_host;      /* (H,)                                                    */
+    const double *mu_host;      /* (H,)                                                    */
+    const double *psi_sq_host;  /* (H,H) row-major                                         */
+    const double *sigma_sq_host;/* 1 or D values                                           */
+    int32_t sigma_sq_type;
+} pet_gsc_params;
+
+/* Packed statistics of GSC.M_step (gsc_et.py:608-620,662-671,683-713), all-reduced as ONE buffer. */
+typedef struct pet_gsc_layout {
+    int64_t total, ld;
+    int64_t off_A;        /* (D+1, H): Y^T.<sz>; row D = sum_n <sz>                        */
+    int64_t off_Mssz;     /* (H,H): sum_n <s> (x) <sz>                                     */
+    int64_t off_Mout;     /* (H,H): sum_n <sz> (x) <sz>                                    */
+    int64_t off_ss;       /* (H,H): sum_n <s s^T>, off-diagonal part (diagonal = sum_s)    */
+    int64_t off_szsz;     /* (H,H): sum_n <sz sz^T>, multi-cause part                      */
+    int64_t off_sum_s;    /* (H,)                                                          */
+    int64_t off_sum_sz2;  /* (H,): singleton part of the diagonal of sum_n <sz sz^T>       */
+    int64_t off_ysq;      /* (D,): sum_n y_nd^2                                            */
+    int64_t off_scalars;  /* [0] = datapoints of this rank                                 */
+} pet_gsc_layout;
+int  pet_gsc_layout_get(const pet_engine *e, pet_gsc_layout *out);
+
+/* GSC.select_Hprimes (gsc_et.py:721-749): top-H' singleton marginal scores, sorted ascending.
+ * cand_out (n,Hprime) int64, host or device, may be NULL. */
+int  pet_gsc_select(pet_engine *e, const pet_gsc_params *p, int64_t *cand_out, void *stream);
+/* GSC.E_step (gsc_et.py:401-580): dense posterior moments, written at row dst_rows[n] (the
+ * reference returns them grouped by candidate set; NULL = identity).  Device outputs:
+ * xpt_s, xpt_sz (n,H); xpt_ss, xpt_szsz (n,H,H). */
+int  pet_gsc_e_step(pet_engine *e, const pet_anneal *a, const pet_gsc_params *p, const int64_t *dst_rows,
+                    double *xpt_s_dev, double *xpt_ss_dev, double *xpt_sz_dev, double *xpt_szsz_dev, void *stream);
+/* Fused select (flags & PET_PASS_SELECT) + E-step + local statistics; nothing of size n*H*H is
+ * materialised.  stats_dev: pet_gsc_layout.total doubles, overwritten. */
+int  pet_gsc_stats(pet_engine *e, const pet_anneal *a, const pet_gsc_params *p, int32_t flags,
+                   double *stats_dev, void *stream);
+/* out[c] += sum_r M[r][c] (used by the compat GSC M-step on caller-supplied moment tensors) */
+int  pet_colsum(int64_t rows, int64_t cols, const double *M_dev, int64_t ld, double *out_dev, void *stream);
+
 /* ---- building blocks exported for tests / benchmarks ------------------------------ */
 /* C(M,N) = A.B with both operands K-contiguous: A(M,K) lda, B(N,K) ldb (FP64 tensor-core
  * tiles).  Device pointers, 16-byte aligned, even lda/ldb. */

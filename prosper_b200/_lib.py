@@ -44,6 +44,16 @@ class StatsLayout(C.Structure):
                 ("off_scalars", C.c_int64), ("n_scalars", C.c_int64)]
 
 
+class GSCParams(C.Structure):
+    _fields_ = [("W", C.c_void_p), ("ldW", C.c_int64), ("pi_host", c_double_p), ("mu_host", c_double_p),
+                ("psi_sq_host", c_double_p), ("sigma_sq_host", c_double_p), ("sigma_sq_type", C.c_int32)]
+
+
+class GSCLayout(C.Structure):
+    _fields_ = [(n, C.c_int64) for n in ("total", "ld", "off_A", "off_Mssz", "off_Mout", "off_ss", "off_szsz",
+                                        "off_sum_s", "off_sum_sz2", "off_ysq", "off_scalars")]
+
+
 # every symbol the header declares: name -> (restype, argtypes)
 SIGNATURES = {
     "pet_abi_version": (C.c_int, []),
@@ -67,6 +77,12 @@ SIGNATURES = {
     "pet_stats_layout_get": (C.c_int, [C.c_void_p, C.POINTER(StatsLayout)]),
     "pet_m_step_solve": (C.c_int, [C.c_void_p, C.POINTER(Params), C.c_void_p, C.c_void_p,
                                    C.POINTER(C.c_int32), C.c_void_p]),
+    "pet_gsc_layout_get": (C.c_int, [C.c_void_p, C.POINTER(GSCLayout)]),
+    "pet_gsc_select": (C.c_int, [C.c_void_p, C.POINTER(GSCParams), C.c_void_p, C.c_void_p]),
+    "pet_gsc_e_step": (C.c_int, [C.c_void_p, C.POINTER(Anneal), C.POINTER(GSCParams), C.c_void_p, C.c_void_p,
+                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "pet_gsc_stats": (C.c_int, [C.c_void_p, C.POINTER(Anneal), C.POINTER(GSCParams), C.c_int32, C.c_void_p, C.c_void_p]),
+    "pet_colsum": (C.c_int, [C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "pet_dgemm_kk": (C.c_int, [C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
                                C.c_void_p, C.c_int64, C.c_double, C.c_double, C.c_void_p]),
     "pet_dgemm_mn": (C.c_int, [C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,

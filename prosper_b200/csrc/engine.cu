@@ -11,6 +11,7 @@
 #include "common.cuh"
 #include "gl_kernel.cuh"
 #include "mca_kernel.cuh"
+#include "gsc_kernel.cuh"
 
 namespace pet {
 
@@ -46,6 +47,7 @@ int launch_cand_to_i64(int64_t *out, const int *in, int64_t count, cudaStream_t 
 int launch_cand_from_i64(int *out, const int64_t *in, int64_t count, int H, cudaStream_t st);
 int launch_add_diag(double *Wq, int64_t ld, const double *colsum, int H, cudaStream_t st);
 int launch_colsum(double *out, const double *M, int64_t ld, int64_t rows, int cols, cudaStream_t st);
+int launch_colsumsq(double *out, const double *M, int64_t ld, int64_t rows, int cols, cudaStream_t st);
 
 #include "statespace.cpp.inc"
 
@@ -121,6 +123,8 @@ struct pet_engine {
     double *solveA = nullptr, *solveB = nullptr, *solve_work = nullptr;
     double *s2sum = nullptr;
     double *Wl = nullptr, *Wr = nullptr, *simbuf = nullptr; int64_t ldD = 0;   // MCA/MMCA tables
+    double *Wt2 = nullptr, *gsc_tab = nullptr, *psi_dev = nullptr, *bdiag = nullptr, *XSZ = nullptr, *SZ2 = nullptr, *yyw = nullptr;   // GSC
+    int64_t *dst_dev = nullptr; int64_t dst_cap = 0;
     const double *Wsrc = nullptr; int64_t Wsrc_ld = 0;                          // W (D,H) on the device for this call
     double *stage_logpj = nullptr; int64_t stage_logpj_doubles = 0;
     int64_t *stage_i64 = nullptr; int64_t stage_i64_count = 0;
@@ -163,6 +167,7 @@ extern "C" void pet_destroy(pet_engine *e) {
     free_dev(e->solveA); free_dev(e->solveB); free_dev(e->solve_work); free_dev(e->s2sum);
     free_dev(e->stage_logpj); free_dev(e->stage_i64); free_dev(e->ksel_state);
     free_dev(e->Wl); free_dev(e->Wr); free_dev(e->simbuf);
+    free_dev(e->Wt2); free_dev(e->gsc_tab); free_dev(e->psi_dev); free_dev(e->bdiag); free_dev(e->XSZ); free_dev(e->SZ2); free_dev(e->yyw); free_dev(e->dst_dev);
     free_dev(e->d_states); free_dev(e->d_entries); free_dev(e->d_chunk); free_dev(e->d_direct); free_dev(e->d_single); free_dev(e->d_state_prior);
     for (auto ev : e->chunk_ready) cudaEventDestroy(ev);
     for (auto ev : e->timer.pool) cudaEventDestroy(ev);
@@ -189,7 +194,7 @@ extern "C" int pet_create(const pet_config *cfg, pet_engine **out) {
         return PET_EINVAL;
     }
     if (cfg->model != PET_MODEL_BSC && cfg->model != PET_MODEL_TSC && cfg->model != PET_MODEL_DSC &&
-        cfg->model != PET_MODEL_MCA && cfg->model != PET_MODEL_MMCA) {
+        cfg->model != PET_MODEL_MCA && cfg->model != PET_MODEL_MMCA && cfg->model != PET_MODEL_GSC) {
         set_error("model kind %d is not handled by this engine entry point", cfg->model);
         return PET_EINVAL;
     }
@@ -212,7 +217,7 @@ extern "C" int pet_create(const pet_config *cfg, pet_engine **out) {
     GLStatic &g = e->gls;
     memset(&g, 0, sizeof(g));
     const bool maxmodel = (e->model == PET_MODEL_MCA || e->model == PET_MODEL_MMCA);
-    if (e->model == PET_MODEL_BSC || maxmodel) {
+    if (e->model == PET_MODEL_BSC || maxmodel || e->model == PET_MODEL_GSC) {
         e->values = {0.0, 1.0}; e->k0 = 0; e->K = 2; e->binary = true;
         enum_binary(e->Hp, e->gamma, rows);
         g.has_null = 1; g.n_blocks = 1; g.block_val[0] = 1.0; g.block_vidx[0] = 0;
@@ -297,6 +302,16 @@ extern "C" int pet_create(const pet_config *cfg, pet_engine **out) {
     TRY(dev_alloc(&e->mu_dev, e->ldY));
     TRY(dev_alloc(&e->Sbuf, e->chunk_rows * e->ldH));
     if (e->model == PET_MODEL_DSC) { TRY(dev_alloc(&e->S2buf, e->chunk_rows * e->ldH)); TRY(dev_alloc(&e->s2sum, e->ldH)); }
+    if (e->model == PET_MODEL_GSC) {
+        TRY(dev_alloc(&e->Wt2, e->ldH * e->ldY));
+        TRY(dev_alloc(&e->gsc_tab, 8 * e->ldH));          // g, ilam, lcdet, logit, mu, pi, (spare)
+        TRY(dev_alloc(&e->psi_dev, e->ldH * e->ldH));
+        TRY(dev_alloc(&e->bdiag, e->ldY));
+        TRY(dev_alloc(&e->XSZ, e->chunk_rows * e->ldH));
+        TRY(dev_alloc(&e->SZ2, e->chunk_rows * e->ldH));
+        TRYC(cudaMemset(e->Wt2, 0, e->ldH * e->ldY * 8));
+        TRYC(cudaMemset(e->psi_dev, 0, e->ldH * e->ldH * 8));
+    }
     if (maxmodel) {
         e->ldD = round_up(e->D, 2);
         TRY(dev_alloc(&e->Wl, (int64_t)e->H * e->ldD)); TRY(dev_alloc(&e->Wr, (int64_t)e->H * e->ldD));
@@ -306,6 +321,11 @@ extern "C" int pet_create(const pet_config *cfg, pet_engine **out) {
         int splits = dgemm_mn_splits(e->D + 1, e->H, e->chunk_rows, e->sm_count);
         e->gemm_work_doubles = int64_t(splits) * (e->D + 1) * e->ldH;
         TRY(dev_alloc(&e->gemm_work, e->gemm_work_doubles));
+    }
+    if (e->model == PET_MODEL_GSC) {
+        int sp = dgemm_mn_splits(e->H, e->H, e->chunk_rows, e->sm_count);
+        int64_t need = int64_t(sp) * e->H * e->ldH;
+        if (need > e->gemm_work_doubles) { free_dev(e->gemm_work); e->gemm_work = nullptr; TRY(dev_alloc(&e->gemm_work, need)); e->gemm_work_doubles = need; }
     }
     TRY(dev_alloc(&e->solveA, (int64_t)e->H * e->ldH));
     TRY(dev_alloc(&e->solveB, (int64_t)e->D * e->ldH));
@@ -354,6 +374,7 @@ static int ensure_rows(pet_engine *e, int64_t n) {
     PET_CHECK(dev_alloc(&e->yy, n));
     PET_CHECK(dev_alloc(&e->cand, n * e->Hp));
     PET_CHECK(dev_alloc(&e->lse, n));
+    if (e->model == PET_MODEL_GSC) { free_dev(e->yyw); e->yyw = nullptr; PET_CHECK(dev_alloc(&e->yyw, n)); }
     // cache the whole score matrix when it is affordable (lets the truncated M-step skip the
     // second score GEMM); otherwise one chunk
     size_t free_b = 0, total_b = 0;
@@ -839,6 +860,177 @@ extern "C" int pet_m_step_solve(pet_engine *e, const pet_params *p, const double
     PET_CUDA(cudaStreamSynchronize(st));
     if (info_host) info_host[0] = (int32_t)scal[1];
     return PET_OK;
+}
+
+
+// ---- GSC (spike-and-slab) ----------------------------------------------------------------------
+extern "C" int pet_gsc_layout_get(const pet_engine *e, pet_gsc_layout *out) {
+    if (!e || !out) { set_error("pet_gsc_layout_get: null argument"); return PET_EINVAL; }
+    const int64_t H = e->H, ld = e->ldH;
+    out->ld = ld;
+    out->off_A = 0;                                   // (D+1, H): Y^T <sz>, row D = sum_n <sz>
+    out->off_Mssz = (e->D + 1) * ld;                  // (H,H)  sum_n <s> (x) <sz>
+    out->off_Mout = out->off_Mssz + H * ld;           // (H,H)  sum_n <sz> (x) <sz>
+    out->off_ss = out->off_Mout + H * ld;             // (H,H)  sum_n <s s^T>, off-diagonal part
+    out->off_szsz = out->off_ss + H * ld;             // (H,H)  sum_n <sz sz^T>, multi-cause part
+    out->off_sum_s = out->off_szsz + H * ld;          // (H,)   sum_n <s>     (= diagonal of sum <s s^T>)
+    out->off_sum_sz2 = out->off_sum_s + ld;           // (H,)   singleton part of diag sum <sz sz^T>
+    out->off_ysq = out->off_sum_sz2 + ld;             // (D,)   sum_n y_nd^2
+    out->off_scalars = out->off_ysq + e->ldY;         // [0] = datapoints
+    out->total = out->off_scalars + 8;
+    return PET_OK;
+}
+
+static int prepare_gsc(pet_engine *e, const pet_gsc_params *p, cudaStream_t st) {
+    if (!p || !p->W || !p->pi_host || !p->mu_host || !p->psi_sq_host || !p->sigma_sq_host) { set_error("bad GSC parameters"); return PET_EINVAL; }
+    if (p->sigma_sq_type == 2) { set_error("sigma_sq_type 'full' is not built on the device yet (use 'scalar' or 'diagonal')"); return PET_EINVAL; }
+    e->timer.begin(ST_PREPARE, st);
+    pet_params pw;
+    memset(&pw, 0, sizeof(pw));
+    pw.W = p->W; pw.ldW = p->ldW; pw.pi_host = p->pi_host; pw.n_pi = e->H;
+    PET_CHECK(load_W(e, &pw, st));
+    // inverse noise variances: B = Sigma^-1 (gsc_et.py:415-423)
+    std::vector<double> host((size_t)std::max<int64_t>(e->ldY, 8 * e->ldH), 0.0);
+    double bscalar = 0.0;
+    const double *bdiag = nullptr;
+    if (p->sigma_sq_type == 1) {
+        for (int d = 0; d < e->D; ++d) host[d] = 1.0 / p->sigma_sq_host[d];
+        PET_CUDA(cudaMemcpyAsync(e->bdiag, host.data(), e->D * 8, cudaMemcpyHostToDevice, st));
+        PET_CUDA(cudaStreamSynchronize(st));
+        bdiag = e->bdiag;
+    } else bscalar = 1.0 / p->sigma_sq_host[0];
+    PET_CHECK(launch_scale_rows(e->Wt2, e->Wt, e->ldY, e->H, e->D, bdiag, bscalar, st));
+    PET_CHECK(dgemm_kk(e->H, e->H, e->D, e->Wt, e->ldY, e->Wt2, e->ldY, e->G, e->ldH, 1.0, 0, st));   // W^T Sigma^-1 W
+    // psi_sq (H,H), pi, mu to the device
+    PET_CUDA(cudaMemcpy2DAsync(e->psi_dev, e->ldH * 8, p->psi_sq_host, size_t(e->H) * 8, size_t(e->H) * 8, e->H, cudaMemcpyHostToDevice, st));
+    double *tab = e->gsc_tab;
+    PET_CUDA(cudaMemcpyAsync(tab + 4 * e->ldH, p->mu_host, e->H * 8, cudaMemcpyHostToDevice, st));
+    PET_CUDA(cudaMemcpyAsync(tab + 5 * e->ldH, p->pi_host, e->H * 8, cudaMemcpyHostToDevice, st));
+    PET_CUDA(cudaStreamSynchronize(st));       // the host vectors may be temporaries of the caller
+    PET_CHECK(launch_gsc_tables(e->G, e->ldH, e->psi_dev, e->ldH, tab + 5 * e->ldH, tab + 4 * e->ldH, e->H, tab, tab + e->ldH,
+                                tab + 2 * e->ldH, tab + 3 * e->ldH, st));
+    e->timer.end(st);
+    // y^T Sigma^-1 y for every datapoint (sigma changes every iteration)
+    const int64_t nchunks = ceil_div(e->n, e->chunk_rows);
+    for (int64_t c = 0; c < nchunks; ++c) {
+        const int64_t r0 = c * e->chunk_rows, rows = std::min(e->chunk_rows, e->n - r0);
+        PET_CHECK(ensure_chunk_inputs(e, c, r0, rows, st));
+        PET_CHECK(launch_weighted_rownorm(e->Y + r0 * e->ldY, e->ldY, rows, e->D, bdiag, bscalar, e->yyw + r0, st));
+    }
+    e->yy_valid = true;
+    return PET_OK;
+}
+
+// flags: GSCF_*.  Dense outputs are device pointers (n,H) / (n,H,H); dst maps datapoint -> output row.
+static int sweep_gsc(pet_engine *e, const pet_anneal *a, const pet_gsc_params *p, int flags, const int64_t *dst_dev,
+                     double *xs, double *xss, double *xsz, double *xszsz, double *stats_dev, cudaStream_t st) {
+    if (e->n <= 0) { set_error("no data bound (pet_set_data)"); return PET_ESTATE; }
+    if (!(flags & GSCF_SELECT) && e->cand_state == 0) { set_error("no candidates: run select_Hprimes first"); return PET_ESTATE; }
+    if (!a || !(a->T > 0.0)) { set_error("annealing temperature T must be > 0"); return PET_EINVAL; }
+    PET_CHECK(prepare_gsc(e, p, st));
+    GSCArgs g;
+    memset(&g, 0, sizeof(g));
+    g.st = e->gls;
+    double *tab = e->gsc_tab;
+    g.tb.g = tab; g.tb.ilam = tab + e->ldH; g.tb.lcdet = tab + 2 * e->ldH; g.tb.logit = tab + 3 * e->ldH; g.tb.mu = tab + 4 * e->ldH;
+    g.flags = flags;
+    g.beta = 1.0 / a->T;
+    g.yyw = e->yyw; g.G = e->G; g.psi = e->psi_dev; g.cand = e->cand;
+    g.dst = dst_dev; g.xpt_s = xs; g.xpt_ss = xss; g.xpt_sz = xsz; g.xpt_szsz = xszsz;
+    pet_gsc_layout lay;
+    pet_gsc_layout_get(e, &lay);
+    if (flags & GSCF_STATS) {
+        if (!stats_dev) { set_error("stats buffer is null"); return PET_EINVAL; }
+        PET_CUDA(cudaMemsetAsync(stats_dev, 0, lay.total * 8, st));
+        g.sum_ss = stats_dev + lay.off_ss; g.sum_szsz = stats_dev + lay.off_szsz;
+    }
+    const int64_t nchunks = ceil_div(e->n, e->chunk_rows);
+    for (int64_t c = 0; c < nchunks; ++c) {
+        const int64_t r0 = c * e->chunk_rows, rows = std::min(e->chunk_rows, e->n - r0);
+        double *yw = e->yw_all ? e->YW + r0 * e->ldH : e->YW;
+        e->timer.begin(ST_SCORE, st);
+        PET_CHECK(dgemm_kk(rows, e->H, e->D, e->Y + r0 * e->ldY, e->ldY, e->Wt2, e->ldY, yw, e->ldH, 1.0, 0, st));
+        e->timer.end(st);
+        g.n_rows = rows; g.row0 = r0; g.YW = yw; g.XS = e->Sbuf; g.XSZ = e->XSZ; g.SZ2 = e->SZ2;
+        e->timer.begin(ST_POST, st);
+        PET_CHECK(launch_gsc_kernel(g, e->gamma, e->sm_count, st));
+        e->timer.end(st);
+        if (flags & GSCF_STATS) {
+            e->timer.begin(ST_STATS, st);
+            const double *Yc = e->Y + r0 * e->ldY;
+            PET_CHECK(dgemm_mn(e->D + 1, e->H, rows, Yc, e->ldY, e->XSZ, e->ldH, stats_dev + lay.off_A, e->ldH, 1,
+                               e->gemm_work, e->gemm_work_doubles, e->sm_count, st));          // gsc_et.py:613-620
+            PET_CHECK(dgemm_mn(e->H, e->H, rows, e->Sbuf, e->ldH, e->XSZ, e->ldH, stats_dev + lay.off_Mssz, e->ldH, 1,
+                               e->gemm_work, e->gemm_work_doubles, e->sm_count, st));          // :665
+            PET_CHECK(dgemm_mn(e->H, e->H, rows, e->XSZ, e->ldH, e->XSZ, e->ldH, stats_dev + lay.off_Mout, e->ldH, 1,
+                               e->gemm_work, e->gemm_work_doubles, e->sm_count, st));          // :683,:697,:711
+            PET_CHECK(launch_colsum(stats_dev + lay.off_sum_s, e->Sbuf, e->ldH, rows, e->H, st));
+            PET_CHECK(launch_colsum(stats_dev + lay.off_sum_sz2, e->SZ2, e->ldH, rows, e->H, st));
+            PET_CHECK(launch_colsumsq(stats_dev + lay.off_ysq, Yc, e->ldY, rows, e->D, st));
+            e->timer.end(st);
+        }
+    }
+    if (flags & GSCF_STATS) {
+        double nloc = (double)e->n;
+        PET_CUDA(cudaMemcpyAsync(stats_dev + lay.off_scalars, &nloc, 8, cudaMemcpyHostToDevice, st));
+        PET_CUDA(cudaStreamSynchronize(st));
+    }
+    if (flags & GSCF_SELECT) e->cand_state = 1;
+    mark_compute_done(e, st);
+    return PET_OK;
+}
+
+static int copy_cand_out(pet_engine *e, int64_t *cand_out, cudaStream_t st) {
+    int64_t count = e->n * e->Hp;
+    if (is_device_ptr(cand_out)) return launch_cand_to_i64(cand_out, e->cand, count, st);
+    if (count > e->stage_i64_count) {
+        cudaStreamSynchronize(st);
+        free_dev(e->stage_i64); e->stage_i64 = nullptr; e->stage_i64_count = 0;
+        PET_CHECK(dev_alloc(&e->stage_i64, count));
+        e->stage_i64_count = count;
+    }
+    PET_CHECK(launch_cand_to_i64(e->stage_i64, e->cand, count, st));
+    PET_CUDA(cudaMemcpyAsync(cand_out, e->stage_i64, count * 8, cudaMemcpyDeviceToHost, st));
+    PET_CUDA(cudaStreamSynchronize(st));
+    return PET_OK;
+}
+
+extern "C" int pet_gsc_select(pet_engine *e, const pet_gsc_params *p, int64_t *cand_out, void *stream) {
+    if (!e || e->model != PET_MODEL_GSC) { set_error("pet_gsc_select: not a GSC engine"); return PET_EINVAL; }
+    cudaStream_t st = (cudaStream_t)stream;
+    PET_CUDA(cudaSetDevice(e->device));
+    pet_anneal a{1.0, 0.0, 0};
+    PET_CHECK(sweep_gsc(e, &a, p, GSCF_SELECT | GSCF_SELECT_ONLY, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, st));
+    if (cand_out) PET_CHECK(copy_cand_out(e, cand_out, st));
+    return PET_OK;
+}
+
+extern "C" int pet_gsc_e_step(pet_engine *e, const pet_anneal *a, const pet_gsc_params *p, const int64_t *dst_rows,
+                              double *xpt_s_dev, double *xpt_ss_dev, double *xpt_sz_dev, double *xpt_szsz_dev, void *stream) {
+    if (!e || e->model != PET_MODEL_GSC || !xpt_s_dev || !xpt_ss_dev || !xpt_sz_dev || !xpt_szsz_dev) { set_error("pet_gsc_e_step: bad arguments"); return PET_EINVAL; }
+    cudaStream_t st = (cudaStream_t)stream;
+    PET_CUDA(cudaSetDevice(e->device));
+    const int64_t *dst = dst_rows;
+    if (dst_rows && !is_device_ptr(dst_rows)) {
+        if (e->n > e->dst_cap) { cudaStreamSynchronize(st); free_dev(e->dst_dev); e->dst_dev = nullptr; PET_CHECK(dev_alloc(&e->dst_dev, e->n)); e->dst_cap = e->n; }
+        PET_CUDA(cudaMemcpyAsync(e->dst_dev, dst_rows, e->n * 8, cudaMemcpyHostToDevice, st));
+        PET_CUDA(cudaStreamSynchronize(st));
+        dst = e->dst_dev;
+    }
+    return sweep_gsc(e, a, p, GSCF_DENSE, dst, xpt_s_dev, xpt_ss_dev, xpt_sz_dev, xpt_szsz_dev, nullptr, st);
+}
+
+extern "C" int pet_gsc_stats(pet_engine *e, const pet_anneal *a, const pet_gsc_params *p, int32_t flags, double *stats_dev,
+                             void *stream) {
+    if (!e || e->model != PET_MODEL_GSC || !stats_dev) { set_error("pet_gsc_stats: bad arguments"); return PET_EINVAL; }
+    cudaStream_t st = (cudaStream_t)stream;
+    PET_CUDA(cudaSetDevice(e->device));
+    return sweep_gsc(e, a, p, GSCF_STATS | ((flags & PASS_SELECT) ? GSCF_SELECT : 0), nullptr, nullptr, nullptr, nullptr, nullptr, stats_dev, st);
+}
+
+extern "C" int pet_colsum(int64_t rows, int64_t cols, const double *M_dev, int64_t ld, double *out_dev, void *stream) {
+    if (!M_dev || !out_dev || cols > ld) { set_error("pet_colsum: bad arguments"); return PET_EINVAL; }
+    return launch_colsum(out_dev, M_dev, ld, rows, (int)cols, (cudaStream_t)stream);
 }
 
 // ---- exported building blocks ------------------------------------------------------------

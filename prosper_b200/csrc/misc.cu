@@ -77,6 +77,15 @@ __global__ void colsum_kernel(double *out, const double *M, int64_t ld, int64_t 
     for (int64_t r = r0; r < r1; ++r) s += M[r * ld + c];
     atomicAdd(&out[c], s);
 }
+// out[c] += sum_r M[r][c]^2   (GSC sigma update: sum_n y_nd^2, gsc_et.py:696,710)
+__global__ void colsumsq_kernel(double *out, const double *M, int64_t ld, int64_t rows, int cols) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= cols) return;
+    int64_t r0 = int64_t(blockIdx.y) * 256, r1 = (rows < r0 + 256) ? rows : r0 + 256;
+    double s = 0.0;
+    for (int64_t r = r0; r < r1; ++r) { double v = M[r * ld + c]; s = fma(v, v, s); }
+    atomicAdd(&out[c], s);
+}
 __global__ void add_diag_from_vec_kernel(double *Wq, int64_t ld, const double *v, int H) {
     int h = blockIdx.x * blockDim.x + threadIdx.x;
     if (h < H) Wq[int64_t(h) * ld + h] += v[h];
@@ -187,6 +196,13 @@ int launch_cand_from_i64(int *out, const int64_t *in, int64_t count, int H, cuda
 }
 int launch_add_diag(double *Wq, int64_t ld, const double *colsum, int H, cudaStream_t st) {
     add_diag_kernel<<<(unsigned)ceil_div(H, 256), 256, 0, st>>>(Wq, ld, colsum, H);
+    PET_LAUNCH_CHECK();
+    return PET_OK;
+}
+int launch_colsumsq(double *out, const double *M, int64_t ld, int64_t rows, int cols, cudaStream_t st) {
+    if (rows <= 0) return PET_OK;
+    dim3 g((unsigned)ceil_div(cols, 128), (unsigned)ceil_div(rows, 256));
+    colsumsq_kernel<<<g, 128, 0, st>>>(out, M, ld, rows, cols);
     PET_LAUNCH_CHECK();
     return PET_OK;
 }
