@@ -1,0 +1,106 @@
+"""CPU tests of the N>1 host logic with a world_size-2 gloo process group: the mpi4py-style
+communicator, stride_data sharding, allsort, and that a 2-rank run reproduces the 1-rank result
+(oracle models driven through the same communicator interface the CUDA models use)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+class _OracleComm(object):
+    """Adapter: what oracle models call (allreduce, allsort) on top of prosper_b200's TorchComm."""
+
+    def __init__(self, comm):
+        from prosper_b200.utils import parallel
+        self.comm, self.parallel = comm, parallel
+        self.rank, self.size = comm.rank, comm.size
+
+    def allreduce(self, x):
+        return self.comm.allreduce(x)
+
+    def allsort(self, a):
+        return self.parallel.allsort(a, comm=self.comm)
+
+
+def _worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from prosper_b200.utils import parallel
+    from helpers import bsc_problem
+    from oracle.bsc import BSC
+    from oracle.common import DictAnneal
+    comm = parallel.default_comm()
+    res = {}
+    assert comm.rank == rank and comm.size == world
+    # scalar / array reductions, broadcast
+    res['sum_int'] = comm.allreduce(rank + 1)
+    res['sum_float'] = comm.allreduce(0.5 * (rank + 1))
+    res['sum_arr'] = comm.allreduce(np.arange(4, dtype=np.float64) * (rank + 1))
+    res['max'] = comm.allreduce_max(10 + rank)
+    res['bcast'] = comm.bcast({'a': rank}, root=0)
+    t = torch.full((3,), float(rank + 1), dtype=torch.float64)
+    res['tensor'] = comm.allreduce_tensor_(t).numpy().copy()
+    # uneven shards (N=11 over 2 ranks -> 6 + 5, parallel.py:67-84)
+    N = 11
+    first, last = parallel.stride_data(N, comm=comm)
+    res['range'] = (first, last)
+    allv = np.random.RandomState(0).standard_normal(N)
+    res['allsort'] = parallel.allsort(allv[first:last], comm=comm)
+    res['allmean'] = parallel.allmean(allv[first:last, None] * np.ones((1, 3)), axis=0, comm=comm)
+    # a sharded EM step equals the single-rank step on the concatenated data
+    y, params, _ = bsc_problem(25, 10, 301, 1, bars=True, pi=0.2, sigma=2.0)
+    f, l = parallel.stride_data(y.shape[0], comm=comm)
+    an = DictAnneal(T=1.5, Ncut_factor=0.6, anneal_prior=False)
+    m = BSC(25, 10, 6, 3, comm=_OracleComm(comm))
+    new = m.step(an, dict(params), {'y': y[f:l].copy()})
+    res['W'], res['pi'], res['sigma'], res['L'], res['N_use'] = new['W'], new['pi'], new['sigma'], m.log['L'], m.log['N_use']
+    np.save(os.path.join(out_dir, "rank%d.npy" % rank), np.array([res], dtype=object), allow_pickle=True)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_world_size_2_gloo(tmp_path):
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from helpers import bsc_problem, rel_err
+    from oracle.bsc import BSC
+    from oracle.common import DictAnneal
+    port = _free_port()
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    r = [np.load(os.path.join(str(tmp_path), "rank%d.npy" % i), allow_pickle=True)[0] for i in range(2)]
+    for i in range(2):
+        assert r[i]['sum_int'] == 3 and r[i]['sum_float'] == 1.5 and r[i]['max'] == 11
+        assert np.array_equal(r[i]['sum_arr'], np.arange(4) * 3.0)
+        assert r[i]['bcast'] == {'a': 0}
+        assert np.array_equal(r[i]['tensor'], np.full(3, 3.0))
+    assert r[0]['range'] == (0, 6) and r[1]['range'] == (6, 11)
+    allv = np.random.RandomState(0).standard_normal(11)
+    for i in range(2):
+        assert np.array_equal(r[i]['allsort'], np.sort(allv))
+        assert np.allclose(r[i]['allmean'], allv.mean())
+    # 2-rank EM step == 1-rank EM step
+    y, params, _ = bsc_problem(25, 10, 301, 1, bars=True, pi=0.2, sigma=2.0)
+    an = DictAnneal(T=1.5, Ncut_factor=0.6, anneal_prior=False)
+    m = BSC(25, 10, 6, 3)
+    want = m.step(an, dict(params), {'y': y.copy()})
+    for i in range(2):
+        assert rel_err(r[i]['W'], want['W']) < 1e-10
+        assert abs(r[i]['pi'] - want['pi']) < 1e-12 and abs(r[i]['sigma'] - want['sigma']) < 1e-12
+        assert abs(r[i]['L'] - m.log['L']) < 1e-10 and r[i]['N_use'] == m.log['N_use']
