@@ -8,6 +8,7 @@
 // row/column of Wq is zero.  B is held transposed, (D,H), so X = W_new comes out directly
 // in the reference's (D,H) layout and every rank-k update is a K-contiguous DMMA GEMM.
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -19,7 +20,7 @@ int dgemm_kk(int64_t M, int64_t N, int64_t K, const double *A, int64_t lda, cons
 constexpr int NB = 64;
 
 // scal[0] = max diagonal, scal[1] = dropped-pivot counter
-__global__ void maxdiag_kernel(const double *A, int64_t lda, int n, double *scal) {
+__global__ void maxdiag_kernel(const double *A, int64_t lda, int n, double *scal, double tol_scale) {
     __shared__ double red[32];
     double m = 0.0;
     for (int i = threadIdx.x; i < n; i += blockDim.x) m = fmax(m, fabs(A[int64_t(i) * lda + i]));
@@ -29,7 +30,7 @@ __global__ void maxdiag_kernel(const double *A, int64_t lda, int n, double *scal
     if (threadIdx.x < 32) {
         m = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.0;
         m = warp_max(m);
-        if (threadIdx.x == 0) { scal[0] = m; scal[1] = 0.0; }
+        if (threadIdx.x == 0) { scal[0] = m; scal[1] = 0.0; scal[2] = tol_scale; }
     }
 }
 
@@ -39,7 +40,9 @@ __global__ void __launch_bounds__(256) potrf_block_kernel(double *A, int64_t lda
                                                           double *invd, double *scal) {
     __shared__ double T[NB][NB + 1];
     __shared__ double s_inv;
-    const double tol = scal[0] * double(n) * 2.220446049250313e-16;
+    // LAPACK gelsd with rcond < 0 (what bsc_et.py:377-380 passes on NumPy 2.x) keeps singular values above
+    // eps * sigma_max with eps = 2^-53; the largest diagonal entry stands in for sigma_max here
+    const double tol = scal[0] * scal[2];
     for (int idx = threadIdx.x; idx < nb * nb; idx += blockDim.x) {
         int r = idx / nb, c = idx % nb;
         T[r][c] = (c <= r) ? A[int64_t(j0 + r) * lda + j0 + c] : 0.0;
@@ -161,7 +164,8 @@ int spd_solve_right(int64_t n64, int64_t m, double *A, int64_t lda, double *B, i
     double *Lt = work;
     double *invd = work + n64 * lda;
     double *scal = invd + round_up(n64, 2);
-    maxdiag_kernel<<<1, 256, 0, st>>>(A, lda, n, scal);
+    static double tol_scale = []() { const char *e = getenv("PET_PIVOT_TOL"); return e ? atof(e) : 1.1102230246251565e-16; }();
+    maxdiag_kernel<<<1, 256, 0, st>>>(A, lda, n, scal, tol_scale);
     PET_LAUNCH_CHECK();
     // ---- factor ----
     for (int j0 = 0; j0 < n; j0 += NB) {
@@ -212,6 +216,6 @@ int spd_solve_right(int64_t n64, int64_t m, double *A, int64_t lda, double *B, i
     return PET_OK;
 }
 
-int64_t spd_solve_work_doubles(int64_t n, int64_t lda) { return n * lda + round_up(n, 2) + 2; }
+int64_t spd_solve_work_doubles(int64_t n, int64_t lda) { return n * lda + round_up(n, 2) + 4; }
 
 }  // namespace pet

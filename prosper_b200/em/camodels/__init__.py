@@ -158,6 +158,22 @@ class Engine(object):
         _lib.check(self.lib.pet_m_step_solve(self.h, C.byref(p), _ptr(stats), _ptr(W_new), C.byref(info), self.stream()))
         return W_new, int(info.value)
 
+    def solve_rank_deficient(self, stats, rcond, add_colsum_diag):
+        """Minimum-norm solution X = Wp^T . pinv(Wq) for a numerically singular Wq (dead units, N < H).
+
+        np.linalg.lstsq / pinv (bsc_et.py:380, tsc_et.py:493) cut singular values below rcond * sigma_max;
+        a Cholesky with dropped pivots only agrees with that when the null space is axis-aligned.  This rare,
+        data-independent O(H^3) case goes through a symmetric eigendecomposition on the device."""
+        lay, H, D = self.layout, self.H, self.D
+        Wq = stats[lay.off_Wq:lay.off_Wq + H * lay.ld_Wq].reshape(H, lay.ld_Wq)[:, :H].clone()
+        A = stats[lay.off_Wp:lay.off_Wp + (D + 1) * lay.ld_Wp].reshape(D + 1, lay.ld_Wp)[:, :H]
+        if add_colsum_diag:
+            Wq += torch.diag(A[D])
+        lam, V = torch.linalg.eigh(0.5 * (Wq + Wq.T))
+        keep = lam.abs() > rcond * lam.abs().max()
+        Vk = V[:, keep]
+        return (A[:D] @ Vk) / lam[keep] @ Vk.T
+
     def scalars(self, stats):
         lay = self.layout
         return stats[lay.off_scalars:lay.off_scalars + lay.n_scalars].cpu().numpy()

@@ -14,6 +14,9 @@ from ...utils.datalog import dlog
 
 
 class GaussianLinearET(CAModel):
+    # singular-value cutoff of the reference's solver: lstsq(rcond=-1) -> LAPACK machine epsilon 2^-53 on NumPy 2.x
+    # (bsc_et.py:377-380, dsc_et.py:732-735); TSC overrides with pinv's default 1e-15 (tsc_et.py:493)
+    _solve_rcond = 1.1102230246251565e-16
 
     # -- hooks ----------------------------------------------------------------------------------
     def _pack_params(self, model_params):
@@ -75,6 +78,8 @@ class GaussianLinearET(CAModel):
         dlog.append('L', L)
         if 'W' in self.to_learn:
             W_dev, self.last_dropped_pivots = eng.solve(p, stats)
+            if self.last_dropped_pivots > 0:      # singular Wq: reproduce lstsq/pinv's minimum-norm answer
+                W_dev = eng.solve_rank_deficient(stats, self._solve_rcond, self.model_kind == _lib.MODEL_BSC)
             W_new = W_dev.cpu().numpy()
         else:
             W_new = model_params['W']

@@ -25,6 +25,7 @@ def generate_state_matrix(Hprime, gamma, H, states):
 
 class TSC_ET(GaussianLinearET):
     model_kind = _lib.MODEL_TSC
+    _solve_rcond = 1e-15          # np.linalg.pinv default (tsc_et.py:493)
 
     def __init__(self, D, H, Hprime, gamma, to_learn=['W', 'pi', 'sigma'], comm=None):
         Model.__init__(self, comm)

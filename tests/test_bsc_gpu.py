@@ -196,6 +196,15 @@ def test_edge_cases():
     want = o.step(an, copy_params(params), {'y': y.copy()})           # a single datapoint
     got = m._fused_step(an, copy_params(params), {'y': y.copy()})
     assert abs(got['sigma'] - want['sigma']) < TOL * want['sigma'] and abs(got['pi'] - want['pi']) < TOL * want['pi']
+    # a dead unit (never a candidate, singleton posterior underflows to exactly 0) leaves a zero row/column in Wq:
+    # np.linalg.lstsq returns the minimum-norm answer (zero column of W), and so must the device path
+    y2, p2, _ = bsc_problem(25, 10, 400, 5, bars=True, pi=0.2, sigma=2.0)
+    p2['W'][:, 3] = 1e3
+    want2 = BSC(25, 10, 6, 3).step(an, copy_params(p2), {'y': y2.copy()})
+    m2 = model(25, 10, 6, 3)
+    got2 = m2._fused_step(an, copy_params(p2), {'y': y2.copy()})
+    assert m2.last_dropped_pivots == 1 and np.abs(got2['W'][:, 3]).max() < 1e-10 and np.abs(want2['W'][:, 3]).max() < 1e-10
+    assert rel_err(got2['W'], want2['W']) < TOL and abs(got2['pi'] - want2['pi']) < TOL * want2['pi']
     # wrong feature dimension is rejected like the reference's shape asserts
     with pytest.raises(AssertionError):
         m.select_Hprimes(copy_params(params), {'y': np.zeros((5, 24))})
