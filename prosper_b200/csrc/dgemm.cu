@@ -12,6 +12,9 @@
 // mma.sync.m8n8k4.f64 (DMMA).  Operands are staged global->shared with 16-byte cp.async
 // in a 3-stage ring; shared tiles are padded (+4 doubles per row) so that the per-lane
 // 8-byte fragment loads of a half-warp hit 16 distinct double-banks.
+#include <math.h>
+#include <stdlib.h>
+
 #include <algorithm>
 
 #include "common.cuh"
@@ -75,8 +78,8 @@ __device__ __forceinline__ void load_tile(double *s, const double *g, int64_t ld
     }
 }
 
-template <bool KK, int BM, int BN, int BK, int WARPS_M, int WARPS_N, int STAGES>
-__global__ void __launch_bounds__(WARPS_M *WARPS_N * 32)
+template <bool KK, int BM, int BN, int BK, int WARPS_M, int WARPS_N, int STAGES, int MINB>
+__global__ void __launch_bounds__(WARPS_M *WARPS_N * 32, MINB)
 dgemm_kernel(GemmArgs g) {
     using Cfg = GemmCfg<KK, BM, BN, BK, WARPS_M, WARPS_N, STAGES>;
     extern __shared__ __align__(16) double smem[];
@@ -210,10 +213,10 @@ __global__ void splitk_reduce_kernel(double *out, const double *part, int64_t M,
     }
 }
 
-template <bool KK, int BM, int BN, int BK, int WARPS_M, int WARPS_N, int STAGES>
+template <bool KK, int BM, int BN, int BK, int WARPS_M, int WARPS_N, int STAGES, int MINB = 1>
 static int launch_gemm(const GemmArgs &g, int splits, cudaStream_t st) {
     using Cfg = GemmCfg<KK, BM, BN, BK, WARPS_M, WARPS_N, STAGES>;
-    auto kern = dgemm_kernel<KK, BM, BN, BK, WARPS_M, WARPS_N, STAGES>;
+    auto kern = dgemm_kernel<KK, BM, BN, BK, WARPS_M, WARPS_N, STAGES, MINB>;
     static bool configured = false;   // per instantiation; attribute is per-device but we use one device per process
     if (!configured) {
         PET_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(Cfg::SMEM)));
@@ -229,6 +232,11 @@ static int launch_gemm(const GemmArgs &g, int splits, cudaStream_t st) {
 
 static bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
+static int env_int(const char *name, int dflt) {
+    const char *e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
+
 int dgemm_kk(int64_t M, int64_t N, int64_t K, const double *A, int64_t lda, const double *B,
              int64_t ldb, double *C, int64_t ldc, double alpha, int accumulate, cudaStream_t st) {
     if (M <= 0 || N <= 0) return PET_OK;
@@ -237,20 +245,46 @@ int dgemm_kk(int64_t M, int64_t N, int64_t K, const double *A, int64_t lda, cons
         return PET_EINVAL;
     }
     GemmArgs g{M, N, K, A, lda, B, ldb, C, ldc, alpha, accumulate, 0, 0};
-    if (M * N >= int64_t(128) * 128 * 64 && N > 64)
-        return launch_gemm<true, 128, 128, 16, 2, 4, 3>(g, 1, st);
+    static const int variant = env_int("PET_GEMM_KK", 1);
+    if (M * N >= int64_t(128) * 128 * 64 && N > 64) {
+        switch (variant) {
+            case 0: return launch_gemm<true, 128, 128, 16, 2, 4, 3>(g, 1, st);
+            case 2: return launch_gemm<true, 128, 64, 32, 2, 2, 2, 2>(g, 1, st);
+            case 3: return launch_gemm<true, 128, 128, 16, 2, 4, 4>(g, 1, st);
+            default: return launch_gemm<true, 128, 64, 16, 2, 2, 3, 2>(g, 1, st);   // two CTAs per SM hide each other's prologue/epilogue
+        }
+    }
     return launch_gemm<true, 64, 64, 16, 2, 2, 3>(g, 1, st);
 }
 
-// how many K-splits the MN kernel uses for a given problem (also sizes the workspace)
+static int mn_variant() {
+    static const int v = env_int("PET_GEMM_MN", 1);
+    return v;
+}
+// tile height (rows of C = M) the MN kernel uses for a problem: 136 = 17 fragments fits D+1 = 677 -> 680 exactly
+static int64_t mn_tile_m(int64_t M, int64_t N) {
+    if (!(M > 64 && N > 64)) return 64;
+    if (mn_variant() == 0) return 128;
+    int64_t w128 = ceil_div(M, 128) * 128, w136 = ceil_div(M, 136) * 136;
+    return (w136 < w128) ? 136 : 128;
+}
+
+// how many K-splits the MN kernel uses for a given problem (also sizes the workspace): fill whole waves
 int dgemm_mn_splits(int64_t M, int64_t N, int64_t K, int sm_count) {
     bool big = (M > 64 && N > 64);
-    int64_t bm = big ? 128 : 64;
-    int64_t tiles = ceil_div(M, bm) * ceil_div(N, bm);
-    int64_t want = ceil_div(int64_t(3) * sm_count, tiles);          // ~3 waves
-    int64_t max_by_k = std::max<int64_t>(1, K / 256);               // >= 256 rows per split
-    int64_t s = std::min(want, max_by_k);
-    return int(std::max<int64_t>(1, std::min<int64_t>(s, 64)));
+    int64_t bm = mn_tile_m(M, N), bn = (big && !(bm == 136 && mn_variant() == 2)) ? 128 : 64;
+    int64_t tiles = ceil_div(M, bm) * ceil_div(N, bn);
+    int64_t max_by_k = std::max<int64_t>(1, K / 512);               // >= 512 rows per split
+    int best = 1;
+    double best_score = -1.0;
+    for (int64_t s = 1; s <= std::min<int64_t>(max_by_k, 64); ++s) {
+        int64_t ctas = tiles * s;
+        double waves = double(ctas) / sm_count;
+        double eff = waves / ceil(waves);                           // wave quantisation
+        double score = eff - 0.01 * s - (waves < 1.5 ? 0.5 : 0.0);  // prefer few splits, at least ~2 waves
+        if (score > best_score) { best_score = score; best = int(s); }
+    }
+    return best;
 }
 
 int dgemm_mn(int64_t M, int64_t N, int64_t K, const double *A, int64_t lda, const double *B,
@@ -265,15 +299,19 @@ int dgemm_mn(int64_t M, int64_t N, int64_t K, const double *A, int64_t lda, cons
     int64_t stride = M * ldc;
     if (splits > 1 && (work == nullptr || work_doubles < stride * splits)) splits = 1;
     int64_t kps = round_up(ceil_div(std::max<int64_t>(K, 1), splits), 16);
-    bool big = (M > 64 && N > 64);
+    const int64_t bm = mn_tile_m(M, N);
+    auto launch = [&](const GemmArgs &g, int sp) -> int {
+        if (bm == 64) return launch_gemm<false, 64, 64, 16, 2, 2, 3>(g, sp, st);
+        if (bm == 136 && mn_variant() == 2) return launch_gemm<false, 136, 64, 16, 1, 4, 3, 2>(g, sp, st);
+        if (bm == 136) return launch_gemm<false, 136, 128, 16, 1, 8, 3>(g, sp, st);
+        return launch_gemm<false, 128, 128, 16, 2, 4, 3>(g, sp, st);
+    };
     if (splits == 1) {
         GemmArgs g{M, N, K, A, lda, B, ldb, C, ldc, 1.0, accumulate, kps, 0};
-        return big ? launch_gemm<false, 128, 128, 16, 2, 4, 3>(g, 1, st)
-                   : launch_gemm<false, 64, 64, 16, 2, 2, 3>(g, 1, st);
+        return launch(g, 1);
     }
     GemmArgs g{M, N, K, A, lda, B, ldb, work, ldc, 1.0, 0, kps, stride};
-    PET_CHECK((big ? launch_gemm<false, 128, 128, 16, 2, 4, 3>(g, splits, st)
-                   : launch_gemm<false, 64, 64, 16, 2, 2, 3>(g, splits, st)));
+    PET_CHECK(launch(g, splits));
     int threads = 256;
     int64_t blocks = ceil_div(M * ((N + 1) / 2), threads);
     splitk_reduce_kernel<<<(unsigned)blocks, threads, 0, st>>>(C, work, M, N, ldc, splits, stride, accumulate);

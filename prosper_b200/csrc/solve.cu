@@ -34,18 +34,21 @@ __global__ void maxdiag_kernel(const double *A, int64_t lda, int n, double *scal
     }
 }
 
-// Unblocked Cholesky of the nb x nb diagonal block at (j0,j0); writes L (lower, zero upper)
-// and invd[j0+c] = 1/L_cc (0 for dropped pivots).
+// Unblocked Cholesky of the nb x nb diagonal block at (j0,j0); writes L (lower, zero upper) back, and the
+// inverse of the triangular block both plain and transposed (NB x NB, ld NB) so that every triangular solve of
+// the blocked algorithm becomes a DMMA GEMM:   x . L_jj^T = r  <=>  x = r . inv(L_jj)^T .
+// A pivot below tol is dropped: its row/column of L and of inv(L) are zero (minimum-norm behaviour for dead units).
 __global__ void __launch_bounds__(256) potrf_block_kernel(double *A, int64_t lda, int j0, int nb, int n,
-                                                          double *invd, double *scal) {
-    __shared__ double T[NB][NB + 1];
-    __shared__ double s_inv;
-    // LAPACK gelsd with rcond < 0 (what bsc_et.py:377-380 passes on NumPy 2.x) keeps singular values above
-    // eps * sigma_max with eps = 2^-53; the largest diagonal entry stands in for sigma_max here
+                                                          double *invd, double *scal, double *Linv, double *LinvT) {
+    extern __shared__ __align__(16) double potrf_smem[];
+    double (*T)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(potrf_smem);
+    double (*X)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(potrf_smem + NB * (NB + 1));
+    double *dinv = potrf_smem + 2 * NB * (NB + 1);
+    const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;      // 64 x 4
     const double tol = scal[0] * scal[2];
-    for (int idx = threadIdx.x; idx < nb * nb; idx += blockDim.x) {
-        int r = idx / nb, c = idx % nb;
-        T[r][c] = (c <= r) ? A[int64_t(j0 + r) * lda + j0 + c] : 0.0;
+    for (int r = ty; r < NB; r += 4) {
+        T[r][tx] = (r < nb && tx < nb && tx <= r) ? A[int64_t(j0 + r) * lda + j0 + tx] : 0.0;
+        X[r][tx] = 0.0;
     }
     __syncthreads();
     for (int c = 0; c < nb; ++c) {
@@ -54,76 +57,42 @@ __global__ void __launch_bounds__(256) potrf_block_kernel(double *A, int64_t lda
             if (d > tol) {
                 double l = sqrt(d);
                 T[c][c] = l;
-                s_inv = 1.0 / l;
+                dinv[c] = 1.0 / l;
             } else {
                 T[c][c] = 0.0;
-                s_inv = 0.0;
+                dinv[c] = 0.0;
                 atomicAdd(&scal[1], 1.0);
             }
-            invd[j0 + c] = s_inv;
+            invd[j0 + c] = dinv[c];
         }
         __syncthreads();
-        const double inv = s_inv;
-        for (int r = c + 1 + threadIdx.x; r < nb; r += blockDim.x) T[r][c] *= inv;
+        const double inv = dinv[c];
+        if (ty == 0 && tx > c && tx < nb) T[tx][c] *= inv;
         __syncthreads();
         // trailing update of the lower triangle: T[r][cc] -= L[r][c] * L[cc][c], c < cc <= r
-        int rem = nb - c - 1;
-        for (int idx = threadIdx.x; idx < rem * rem; idx += blockDim.x) {
-            int r = c + 1 + idx / rem, cc = c + 1 + idx % rem;
-            if (cc <= r) T[r][cc] -= T[r][c] * T[cc][c];
+        const int cc = c + 1 + tx;
+        if (cc < nb) {
+            const double lcc = T[cc][c];
+            for (int r = c + 1 + ty; r < nb; r += 4)
+                if (cc <= r) T[r][cc] -= T[r][c] * lcc;
         }
         __syncthreads();
     }
-    for (int idx = threadIdx.x; idx < nb * nb; idx += blockDim.x) {
-        int r = idx / nb, c = idx % nb;
-        A[int64_t(j0 + r) * lda + j0 + c] = T[r][c];
-    }
-}
-
-// Row-wise triangular solves against the nb x nb diagonal block L_jj (at (j0,j0) of L):
-//   forward  (backward=0): x . L_jj^T = r   ->  x_c = (r_c - sum_{t<c} x_t L[c][t]) * invd[c]
-//   backward (backward=1): x . L_jj   = r   ->  x_c = (r_c - sum_{t>c} x_t L[t][c]) * invd[c]
-// applied in place to rows [0,m) of R (ldr), columns [j0, j0+nb).
-__global__ void __launch_bounds__(NB) trsm_rows_kernel(double *R, int64_t ldr, int64_t m, const double *L,
-                                                        int64_t ldl, int j0, int nb, const double *invd,
-                                                        int backward) {
-    extern __shared__ __align__(16) double trsm_smem[];
-    double (*Ls)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(trsm_smem);
-    double (*Xs)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(trsm_smem + NB * (NB + 1));
-    double *inv_s = trsm_smem + 2 * NB * (NB + 1);
-    for (int idx = threadIdx.x; idx < nb * nb; idx += blockDim.x) {
-        int r = idx / nb, c = idx % nb;
-        Ls[r][c] = L[int64_t(j0 + r) * ldl + j0 + c];
-    }
-    if (threadIdx.x < nb) inv_s[threadIdx.x] = invd[j0 + threadIdx.x];
-    const int64_t row0 = int64_t(blockIdx.x) * NB;
-    const int rows = (m - row0 < NB) ? int(m - row0) : NB;
-    // coalesced load of the row slab
-    for (int idx = threadIdx.x; idx < rows * nb; idx += blockDim.x) {
-        int r = idx / nb, c = idx % nb;
-        Xs[r][c] = R[(row0 + r) * ldr + j0 + c];
-    }
-    __syncthreads();
-    const int r = threadIdx.x;
-    if (r < rows) {
-        if (!backward) {
-            for (int c = 0; c < nb; ++c) {
-                double s = Xs[r][c];
-                for (int t = 0; t < c; ++t) s = fma(-Xs[r][t], Ls[c][t], s);
-                Xs[r][c] = s * inv_s[c];
-            }
-        } else {
-            for (int c = nb - 1; c >= 0; --c) {
-                double s = Xs[r][c];
-                for (int t = c + 1; t < nb; ++t) s = fma(-Xs[r][t], Ls[t][c], s);
-                Xs[r][c] = s * inv_s[c];
-            }
+    // inverse of the lower-triangular block, one column per thread (forward substitution on unit vectors)
+    if (threadIdx.x < nb) {
+        const int c = threadIdx.x;
+        X[c][c] = dinv[c];
+        for (int r = c + 1; r < nb; ++r) {
+            double sacc = 0.0;
+            for (int t = c; t < r; ++t) sacc = fma(T[r][t], X[t][c], sacc);
+            X[r][c] = -sacc * dinv[r];
         }
     }
     __syncthreads();
-    for (int idx = threadIdx.x; idx < rows * nb; idx += blockDim.x) {
-        int rr = idx / nb, c = idx % nb;
-        R[(row0 + rr) * ldr + j0 + c] = Xs[rr][c];
+    for (int r = ty; r < NB; r += 4) {
+        if (r < nb && tx < nb) A[int64_t(j0 + r) * lda + j0 + tx] = T[r][tx];
+        Linv[r * NB + tx] = X[r][tx];
+        LinvT[r * NB + tx] = X[tx][r];
     }
 }
 
@@ -151,37 +120,39 @@ __global__ void zero_upper_kernel(double *A, int64_t lda, int n) {
 }
 
 // A (n,n) lda : overwritten by L.  B (m,n) ldb : overwritten by X with X.A = B.
-// work: n*lda doubles (L^T) + n (invd) + 2 (scalars).
+// work: n*lda (L^T) + n (invd) + 4 (scalars) + 2 * nblocks * NB*NB (inverse diagonal blocks, plain and transposed).
 int spd_solve_right(int64_t n64, int64_t m, double *A, int64_t lda, double *B, int64_t ldb, double *work,
                     cudaStream_t st) {
     const int n = int(n64);
-    constexpr size_t TRSM_SMEM = (2 * NB * (NB + 1) + NB) * sizeof(double);
-    static bool configured = false;
-    if (!configured) {
-        PET_CUDA(cudaFuncSetAttribute(trsm_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(TRSM_SMEM)));
-        configured = true;
-    }
+    const int nblk = (n + NB - 1) / NB;
+    static double tol_scale = []() { const char *e = getenv("PET_PIVOT_TOL"); return e ? atof(e) : 1.1102230246251565e-16; }();
     double *Lt = work;
     double *invd = work + n64 * lda;
     double *scal = invd + round_up(n64, 2);
-    static double tol_scale = []() { const char *e = getenv("PET_PIVOT_TOL"); return e ? atof(e) : 1.1102230246251565e-16; }();
+    double *Linv = scal + 4;
+    double *LinvT = Linv + int64_t(nblk) * NB * NB;
+    constexpr size_t POTRF_SMEM = (2 * NB * (NB + 1) + NB) * sizeof(double);
+    static bool configured = false;
+    if (!configured) {
+        PET_CUDA(cudaFuncSetAttribute(potrf_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(POTRF_SMEM)));
+        configured = true;
+    }
     maxdiag_kernel<<<1, 256, 0, st>>>(A, lda, n, scal, tol_scale);
     PET_LAUNCH_CHECK();
     // ---- factor ----
-    for (int j0 = 0; j0 < n; j0 += NB) {
+    for (int j0 = 0, jb = 0; j0 < n; j0 += NB, ++jb) {
         int nb = std::min(NB, n - j0);
-        potrf_block_kernel<<<1, 256, 0, st>>>(A, lda, j0, nb, n, invd, scal);
+        double *Li = Linv + int64_t(jb) * NB * NB;
+        potrf_block_kernel<<<1, 256, POTRF_SMEM, st>>>(A, lda, j0, nb, n, invd, scal, Li, LinvT + int64_t(jb) * NB * NB);
         PET_LAUNCH_CHECK();
         int j1 = j0 + nb;
         if (j1 < n) {
             int64_t rows = n - j1;
-            // panel: L[j1:, j0:j1] = A[j1:, j0:j1] . L_jj^{-T}
-            trsm_rows_kernel<<<(unsigned)ceil_div(rows, NB), NB, TRSM_SMEM, st>>>(A + int64_t(j1) * lda, lda, rows, A,
-                                                                         lda, j0, nb, invd, 0);
-            PET_LAUNCH_CHECK();
+            double *panel = A + int64_t(j1) * lda + j0;
+            // panel: L[j1:, j0:j1] = A[j1:, j0:j1] . inv(L_jj)^T   (in place: one column tile, rows are CTA-private)
+            PET_CHECK(dgemm_kk(rows, nb, nb, panel, lda, Li, NB, panel, lda, 1.0, 0, st));
             // trailing: A[j1:, j1:] -= L[j1:, j0:j1] . L[j1:, j0:j1]^T
-            PET_CHECK(dgemm_kk(rows, rows, nb, A + int64_t(j1) * lda + j0, lda, A + int64_t(j1) * lda + j0,
-                               lda, A + int64_t(j1) * lda + j1, lda, -1.0, 1, st));
+            PET_CHECK(dgemm_kk(rows, rows, nb, panel, lda, panel, lda, A + int64_t(j1) * lda + j1, lda, -1.0, 1, st));
         }
     }
     {
@@ -193,29 +164,28 @@ int spd_solve_right(int64_t n64, int64_t m, double *A, int64_t lda, double *B, i
         PET_LAUNCH_CHECK();
     }
     if (m <= 0) return PET_OK;
-    const unsigned row_blocks = (unsigned)ceil_div(m, NB);
     // ---- Z . L^T = B, column blocks ascending ----
-    for (int j0 = 0; j0 < n; j0 += NB) {
+    for (int j0 = 0, jb = 0; j0 < n; j0 += NB, ++jb) {
         int nb = std::min(NB, n - j0);
         if (j0 > 0)
             PET_CHECK(dgemm_kk(m, nb, j0, B, ldb, A + int64_t(j0) * lda, lda, B + j0, ldb, -1.0, 1, st));
-        trsm_rows_kernel<<<row_blocks, NB, TRSM_SMEM, st>>>(B, ldb, m, A, lda, j0, nb, invd, 0);
-        PET_LAUNCH_CHECK();
+        PET_CHECK(dgemm_kk(m, nb, nb, B + j0, ldb, Linv + int64_t(jb) * NB * NB, NB, B + j0, ldb, 1.0, 0, st));
     }
     // ---- X . L = Z, column blocks descending ----
-    int last = ((n - 1) / NB) * NB;
-    for (int j0 = last; j0 >= 0; j0 -= NB) {
+    for (int jb = nblk - 1; jb >= 0; --jb) {
+        int j0 = jb * NB;
         int nb = std::min(NB, n - j0);
         int j1 = j0 + nb;
         if (j1 < n)
             PET_CHECK(dgemm_kk(m, nb, n - j1, B + j1, ldb, Lt + int64_t(j0) * lda + j1, lda, B + j0, ldb, -1.0,
                                1, st));
-        trsm_rows_kernel<<<row_blocks, NB, TRSM_SMEM, st>>>(B, ldb, m, A, lda, j0, nb, invd, 1);
-        PET_LAUNCH_CHECK();
+        PET_CHECK(dgemm_kk(m, nb, nb, B + j0, ldb, LinvT + int64_t(jb) * NB * NB, NB, B + j0, ldb, 1.0, 0, st));
     }
     return PET_OK;
 }
 
-int64_t spd_solve_work_doubles(int64_t n, int64_t lda) { return n * lda + round_up(n, 2) + 4; }
+int64_t spd_solve_work_doubles(int64_t n, int64_t lda) {
+    return n * lda + round_up(n, 2) + 4 + 2 * ceil_div(n, NB) * NB * NB;
+}
 
 }  // namespace pet
