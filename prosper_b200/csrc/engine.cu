@@ -112,6 +112,7 @@ struct pet_engine {
     // device-resident shard
     double *Y = nullptr; int64_t n = 0, n_cap = 0;
     double *yy = nullptr; int *cand = nullptr; double *lse = nullptr;
+    double *rs = nullptr, *ywc = nullptr, *scl = nullptr;      // per-datapoint records exchanged by the posterior kernels
     bool yy_valid = false; int cand_state = 0;
     std::vector<double> mu_applied;
 
@@ -161,7 +162,7 @@ extern "C" void pet_destroy(pet_engine *e) {
     if (!e) return;
     cudaSetDevice(e->device);
     cudaDeviceSynchronize();
-    free_dev(e->Y); free_dev(e->yy); free_dev(e->cand); free_dev(e->lse);
+    free_dev(e->Y); free_dev(e->yy); free_dev(e->cand); free_dev(e->lse); free_dev(e->rs); free_dev(e->ywc); free_dev(e->scl);
     free_dev(e->Wt); free_dev(e->G); free_dev(e->wn2); free_dev(e->invn); free_dev(e->Wtmp); free_dev(e->mu_dev);
     free_dev(e->YW); free_dev(e->Sbuf); free_dev(e->S2buf); free_dev(e->gemm_work);
     free_dev(e->solveA); free_dev(e->solveB); free_dev(e->solve_work); free_dev(e->s2sum);
@@ -368,12 +369,17 @@ static int ensure_rows(pet_engine *e, int64_t n) {
     if (n <= e->n_cap) return PET_OK;
     cudaDeviceSynchronize();
     free_dev(e->Y); free_dev(e->yy); free_dev(e->cand); free_dev(e->lse); free_dev(e->YW);
+    free_dev(e->rs); free_dev(e->ywc); free_dev(e->scl);
     e->Y = nullptr; e->yy = nullptr; e->cand = nullptr; e->lse = nullptr; e->YW = nullptr;
+    e->rs = nullptr; e->ywc = nullptr; e->scl = nullptr;
     e->n_cap = 0;
     PET_CHECK(dev_alloc(&e->Y, n * e->ldY));
     PET_CHECK(dev_alloc(&e->yy, n));
     PET_CHECK(dev_alloc(&e->cand, n * e->Hp));
     PET_CHECK(dev_alloc(&e->lse, n));
+    PET_CHECK(dev_alloc(&e->rs, n * (4 + PET_MAXV)));
+    PET_CHECK(dev_alloc(&e->ywc, n * e->Hp));
+    PET_CHECK(dev_alloc(&e->scl, n * (1 + PET_MAXHP)));
     if (e->model == PET_MODEL_GSC) { free_dev(e->yyw); e->yyw = nullptr; PET_CHECK(dev_alloc(&e->yyw, n)); }
     // cache the whole score matrix when it is affordable (lets the truncated M-step skip the
     // second score GEMM); otherwise one chunk
@@ -533,6 +539,7 @@ static int sweep_gl(pet_engine *e, const pet_anneal *a, const pet_params *p, int
     ga.state_prior = e->d_state_prior;
     PET_CHECK(launch_state_prior(ga.st, ga.it, e->d_state_prior, st));
     ga.cand = e->cand; ga.lse = e->lse; ga.cut = cut_dev;
+    ga.rs = e->rs; ga.ywc = e->ywc; ga.scl = e->scl;
     pet_stats_layout lay;
     pet_stats_layout_get(e, &lay);
     const bool do_stats = !(kflags & (GLF_LSE_ONLY | GLF_SELECT_ONLY));
@@ -628,6 +635,7 @@ static int sweep_mca(pet_engine *e, const pet_anneal *a, const pet_params *p, in
     sel.flags = GLF_SELECT | GLF_SELECT_ONLY;
     sel.yy = e->yy; sel.wn2 = e->wn2; sel.invn = e->invn; sel.G = e->G; sel.cand = e->cand; sel.lse = e->lse;
     sel.state_prior = e->d_state_prior;
+    sel.rs = e->rs; sel.ywc = e->ywc; sel.scl = e->scl;
 
     MCAArgs m;
     memset(&m, 0, sizeof(m));

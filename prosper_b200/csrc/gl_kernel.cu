@@ -24,39 +24,43 @@
 
 namespace pet {
 
-constexpr int GL_MAX_WARPS = 8;
+constexpr int GL_MAX_GROUPS = 8;           // datapoints in flight per CTA of the state kernel (2 warps each)
+constexpr int ROW_WARPS = 8;               // warps per CTA of the row kernel
 constexpr double GL_EXP_CUTOFF = -100.0;   // exp(x) for x below this contributes < 4e-44 relative
 
 static __host__ __device__ inline int r2(int x) { return (x + 1) & ~1; }
 
 constexpr int GS = PET_MAXHP + 1;          // stride of the gathered Gram block; row/col Hp is all zero
 
+constexpr int GRP_LANES = 64;              // two warps work on one datapoint in the state kernel
+
 struct SmemLayout {
     int shared_doubles;   // state records + gather table + chunk table
     int off_ids, off_chunk;
-    int per_warp;         // doubles
-    int off_q, off_G, off_lin, off_mom, off_P, off_cand;
+    int per_dp;           // doubles per datapoint group
+    int off_G, off_lin, off_mom, off_P, off_red, off_cand;
 };
 
 static __host__ __device__ inline SmemLayout smem_layout(const GLStatic &s) {
     SmemLayout L;
     const int nch = s.n_chunks > 0 ? s.n_chunks : 1;
     L.off_ids = r2(s.S);
-    L.off_chunk = L.off_ids + nch * s.chunk_len * 8;      // nch*CH*32 u16
-    L.shared_doubles = L.off_chunk + nch * 8;             // nch*32 u16
-    L.off_q = r2(s.H);
-    L.off_G = L.off_q + r2(s.S + 1);
+    L.off_chunk = L.off_ids + nch * s.chunk_len * (GRP_LANES / 4);   // nch*CH*64 u16
+    L.shared_doubles = L.off_chunk + nch * (GRP_LANES / 4);          // nch*64 u16
+    L.off_G = r2(s.S + 1);                                           // qbuf first
     L.off_lin = L.off_G + r2(GS * GS);
     L.off_mom = L.off_lin + r2(GS);
     L.off_P = L.off_mom + r2(s.n_out + 1);
-    L.off_cand = L.off_P + r2(s.Hp * (s.n_cnt > 0 ? s.n_cnt : 1));
-    L.per_warp = L.off_cand + PET_MAXHP;     // cand[16] + live[16] ints
+    L.off_red = L.off_P + r2(s.Hp * (s.n_cnt > 0 ? s.n_cnt : 1));
+    L.off_cand = L.off_red + 16;
+    L.per_dp = L.off_cand + PET_MAXHP;     // cand[16] + live[16] ints
     return L;
 }
 
-size_t gl_smem_bytes(const GLStatic &s, int warps) {
+// bytes of the state kernel with `groups` datapoints in flight per CTA
+size_t gl_smem_bytes(const GLStatic &s, int groups) {
     SmemLayout L = smem_layout(s);
-    return (size_t(L.shared_doubles) + size_t(L.per_warp) * warps) * sizeof(double);
+    return (size_t(L.shared_doubles) + size_t(L.per_dp) * groups) * sizeof(double);
 }
 
 __constant__ double c_winv[8] = {1.0, 1.0 / 2, 1.0 / 3, 1.0 / 4, 1.0 / 5, 1.0 / 6, 1.0 / 7, 1.0 / 8};
@@ -241,72 +245,35 @@ __device__ __noinline__ void select_generic(const GLArgs &a, const double *row, 
     }
 }
 
-template <int GMAX, bool BINARY>
-__global__ void __launch_bounds__(GL_MAX_WARPS * 32) gl_kernel(const __grid_constant__ GLArgs a) {
+// =================================================================================================
+// Kernel A -- row kernel: everything that is a function of the H-long score row.  One warp per
+// datapoint, the row in shared memory, selection scores in registers, no state-space tables, so it
+// runs at high occupancy.  Produces: candidates, their scores, the un-normalised singleton posteriors
+// (written to the <s> row, relative to the singleton max m1) and the per-datapoint partial sums.
+//   rs[n] = { m1, Z1, sig1, -, cnt1[0..5] }
+// =================================================================================================
+constexpr int RS = 4 + PET_MAXV;
+
+__global__ void __launch_bounds__(ROW_WARPS * 32, 2) gl_row_kernel(const __grid_constant__ GLArgs a) {
     extern __shared__ __align__(16) double smem[];
     const GLStatic &st = a.st;
     const GLIter &it = a.it;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    const int H = st.H, Hp = st.Hp, S = st.S;
-    const SmemLayout L = smem_layout(st);
-    const int CH = st.chunk_len, NCH = st.n_chunks;
-
-    unsigned long long *states_s = reinterpret_cast<unsigned long long *>(smem);
-    unsigned short *ids_s = reinterpret_cast<unsigned short *>(smem + L.off_ids);
-    unsigned short *chunk_s = reinterpret_cast<unsigned short *>(smem + L.off_chunk);
-    for (int s = threadIdx.x; s < S; s += blockDim.x) states_s[s] = st.states[s];
-    for (int i = threadIdx.x; i < NCH * CH * 32; i += blockDim.x) ids_s[i] = st.entries[i];
-    for (int i = threadIdx.x; i < NCH * 32; i += blockDim.x) chunk_s[i] = st.chunk_tab[i];
-    double *wbase = smem + L.shared_doubles + size_t(L.per_warp) * warp;
-    double *row = wbase;
-    double *qbuf = wbase + L.off_q;
-    double *Gc = wbase + L.off_G;
-    double *lin = wbase + L.off_lin;
-    double *mom = wbase + L.off_mom;
-    double *Pj = wbase + L.off_P;
-    int *cand_s = reinterpret_cast<int *>(wbase + L.off_cand);
-    int *live_s = cand_s + PET_MAXHP;
-    // zero row/column Hp of the Gram block and lin[Hp] once: the dummy position of unused member slots
-    for (int i = lane; i < GS * GS; i += 32) Gc[i] = 0.0;
-    for (int i = lane; i < GS; i += 32) lin[i] = 0.0;
-    __syncthreads();
-
-    const bool do_stats = !(a.flags & (GLF_LSE_ONLY | GLF_SELECT_ONLY));
-    const int n_cnt = st.n_cnt, n_g = st.n_g;
-    const double cut = (a.flags & GLF_USE_CUT) ? *a.cut : 0.0;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int H = st.H, Hp = st.Hp;
+    double *row = smem + size_t(r2(H) + PET_MAXHP) * warp;
+    int *cand_s = reinterpret_cast<int *>(row + r2(H));
     const bool rd = (a.flags & GLF_READ_LOGPJ) != 0, wr = (a.flags & GLF_WRITE_LOGPJ) != 0;
-    const int col_states = st.has_null + st.n_blocks * H;
+    const bool do_stats = !(a.flags & (GLF_LSE_ONLY | GLF_SELECT_ONLY));
     const int items = (st.select_mode == SEL_TSC) ? 2 * H : H;
 
-    // per-warp running sums over its datapoints (lane 0 holds them)
-    double acc_n = 0.0, acc_lse = 0.0, acc_sig = 0.0;
-    double acc_cnt[PET_MAXV];
-#pragma unroll
-    for (int v = 0; v < PET_MAXV; ++v) acc_cnt[v] = 0.0;
-
-    const int64_t wstride = int64_t(gridDim.x) * nwarps;
-    for (int64_t r = int64_t(blockIdx.x) * nwarps + warp; r < a.n_rows; r += wstride) {
+    const int64_t wstride = int64_t(gridDim.x) * ROW_WARPS;
+    for (int64_t r = int64_t(blockIdx.x) * ROW_WARPS + warp; r < a.n_rows; r += wstride) {
         const int64_t n = a.row0 + r;
         const double *yw = a.YW + r * st.ldH;
         const double yy = a.yy[n];
-
-        if ((a.flags & GLF_USE_CUT) && do_stats) {
-            double l = a.lse[n];
-            bool keep = (a.flags & GLF_CUT_STRICT) ? (l > cut) : (l >= cut);
-            if (!keep) {   // truncated away: contributes nothing (bsc_et.py:254-257)
-                for (int h = lane; h < st.ldH; h += 32) {
-                    a.S[r * st.ldH + h] = 0.0;
-                    if (a.S2) a.S2[r * st.ldH + h] = 0.0;
-                }
-                continue;
-            }
-        }
-
-        // ---- phase 0: score row into shared memory ---------------------------------
         for (int h = lane; h < H; h += 32) row[h] = yw[h];
         __syncwarp();
-
-        // ---- phase 1: top-H' preselection -------------------------------------------
+        // ---- top-H' preselection ---------------------------------------------------------------
         if (a.flags & GLF_SELECT) {
             if (items <= 32) select_regs<1>(a, row, yy, items, cand_s);
             else if (items <= 128) select_regs<4>(a, row, yy, items, cand_s);
@@ -318,35 +285,16 @@ __global__ void __launch_bounds__(GL_MAX_WARPS * 32) gl_kernel(const __grid_cons
             if (lane < Hp) cand_s[lane] = a.cand[n * Hp + lane];
             __syncwarp();
         }
-        if (a.flags & GLF_SELECT_ONLY) continue;
+        if (a.flags & GLF_SELECT_ONLY) { __syncwarp(); continue; }
+        if (lane < Hp) a.ywc[n * Hp + lane] = row[cand_s[lane]];
 
-        // ---- phase 2: gather scores and Gram block of the candidates ----------------
-        for (int idx = lane; idx < Hp * Hp; idx += 32) {
-            int j = idx / Hp, k = idx % Hp;
-            Gc[j * GS + k] = a.G[int64_t(cand_s[j]) * st.ldH + cand_s[k]];
-        }
-        if (lane < Hp) {
-            int c = cand_s[lane];
-            int lv = 1;
-            for (int j = lane + 1; j < Hp; ++j) lv &= (cand_s[j] != c);   // numpy "last write wins"
-            live_s[lane] = lv;
-        }
-        __syncwarp();
-        if (lane < Hp) {
-            double ywc = row[cand_s[lane]];
-            lin[lane] = BINARY ? fma(-2.0, ywc, Gc[lane * GS + lane]) : ywc;
-        }
-        __syncwarp();
-
+        // ---- null state and all-H singleton blocks: log-joints and their max ------------------------
         double *logpj_row = a.logpj ? a.logpj + n * a.ld_logpj : nullptr;
-
-        // ---- phase 3: log-joints, running max ---------------------------------------
-        double mx = -INFINITY;
-        double F0 = 0.0;
+        double m1 = -INFINITY, F0 = 0.0;
         if (st.has_null) {
             F0 = rd ? logpj_row[0] : combine(it, it.prior_null, yy);
             if (wr && lane == 0) logpj_row[0] = F0;
-            mx = F0;
+            m1 = F0;
         }
         for (int b = 0; b < st.n_blocks; ++b) {
             const double v = st.block_val[b];
@@ -358,11 +306,166 @@ __global__ void __launch_bounds__(GL_MAX_WARPS * 32) gl_kernel(const __grid_cons
                     F = combine(it, it.prior_block[b], q);
                     if (wr) logpj_row[st.has_null + b * H + h] = F;
                 }
-                mx = fmax(mx, F);
+                m1 = fmax(m1, F);
             }
         }
+        m1 = warp_max(m1);
+        if (wr && (a.flags & GLF_LSE_ONLY)) { __syncwarp(); continue; }      // compat E_step: logpj only
+
+        // ---- exp relative to m1, partial sums, un-normalised <s> row --------------------------------
+        double Z1 = 0.0, sig1 = 0.0;
+        double cntb[PET_MAXV];
+#pragma unroll
+        for (int v = 0; v < PET_MAXV; ++v) cntb[v] = 0.0;
+        if (st.has_null && lane == 0) {
+            double x = F0 - m1;
+            double p = (x > GL_EXP_CUTOFF) ? exp(x) : 0.0;
+            Z1 += p;
+            sig1 += p * yy;
+        }
+        for (int h = lane; h < st.ldH; h += 32) {
+            double snew = 0.0, s2new = 0.0;
+            if (h < H) {
+                const double ywh = row[h], wn2h = (st.n_blocks > 0) ? a.wn2[h] : 0.0;
+#pragma unroll
+                for (int b = 0; b < PET_MAXV; ++b) {
+                    if (b < st.n_blocks) {
+                        const double v = st.block_val[b];
+                        double q = yy + v * (v * wn2h - 2.0 * ywh);
+                        double F = rd ? logpj_row[st.has_null + b * H + h] : combine(it, it.prior_block[b], q);
+                        double x = F - m1;
+                        double p = (x > GL_EXP_CUTOFF) ? exp(x) : 0.0;
+                        Z1 += p;
+                        sig1 += p * q;
+                        cntb[b] += p;
+                        snew = fma(p, v, snew);
+                        s2new = fma(p, v * v, s2new);
+                    }
+                }
+            }
+            if (do_stats) {
+                a.S[r * st.ldH + h] = snew;              // scaled by exp(m1 - m)/Z in the scale kernel
+                if (a.S2) a.S2[r * st.ldH + h] = s2new;
+            }
+        }
+        Z1 = warp_sum(Z1);
+        sig1 = warp_sum(sig1);
+#pragma unroll
+        for (int v = 0; v < PET_MAXV; ++v)
+            if (v < st.n_blocks) cntb[v] = warp_sum(cntb[v]);
+        if (lane == 0) {
+            double *rs = a.rs + n * RS;
+            rs[0] = m1; rs[1] = Z1; rs[2] = sig1;
+#pragma unroll
+            for (int v = 0; v < PET_MAXV; ++v) rs[4 + v] = cntb[v];
+        }
+        __syncwarp();
+    }
+}
+
+// =================================================================================================
+// Kernel B -- state kernel: the truncated multi-cause state space of one datapoint, TWO warps per
+// datapoint (the shared-memory footprint is per datapoint, so more lanes per datapoint is what hides
+// latency).  Combines with the row kernel's partial sums by log-sum-exp merging:
+//   m = max(m1, m2),  Z = Z1 e^(m1-m) + Z2,  lse = m + log Z.
+// =================================================================================================
+__device__ __forceinline__ void grp_sync(int gid) { asm volatile("bar.sync %0, 64;" ::"r"(gid + 1) : "memory"); }
+
+__device__ __forceinline__ double grp_max(double v, double *red, int gid, int wig) {
+    v = warp_max(v);
+    grp_sync(gid);
+    if ((threadIdx.x & 31) == 0) red[wig] = v;
+    grp_sync(gid);
+    return fmax(red[0], red[1]);
+}
+__device__ __forceinline__ double grp_sum(double v, double *red, int gid, int wig) {
+    v = warp_sum(v);
+    grp_sync(gid);
+    if ((threadIdx.x & 31) == 0) red[wig] = v;
+    grp_sync(gid);
+    return red[0] + red[1];
+}
+
+template <int GMAX, bool BINARY>
+__global__ void __launch_bounds__(GL_MAX_GROUPS * GRP_LANES) gl_state_kernel(const __grid_constant__ GLArgs a) {
+    extern __shared__ __align__(16) double smem[];
+    const GLStatic &st = a.st;
+    const GLIter &it = a.it;
+    const int ngroups = blockDim.x / GRP_LANES;
+    const int gid = threadIdx.x / GRP_LANES, l64 = threadIdx.x % GRP_LANES, wig = l64 >> 5;
+    const int Hp = st.Hp, S = st.S, H = st.H;
+    const SmemLayout L = smem_layout(st);
+    const int CH = st.chunk_len, NCH = st.n_chunks;
+
+    unsigned long long *states_s = reinterpret_cast<unsigned long long *>(smem);
+    unsigned short *ids_s = reinterpret_cast<unsigned short *>(smem + L.off_ids);
+    unsigned short *chunk_s = reinterpret_cast<unsigned short *>(smem + L.off_chunk);
+    for (int s = threadIdx.x; s < S; s += blockDim.x) states_s[s] = st.states[s];
+    for (int i = threadIdx.x; i < NCH * CH * GRP_LANES; i += blockDim.x) ids_s[i] = st.entries[i];
+    for (int i = threadIdx.x; i < NCH * GRP_LANES; i += blockDim.x) chunk_s[i] = st.chunk_tab[i];
+    double *gb = smem + L.shared_doubles + size_t(L.per_dp) * gid;
+    double *qbuf = gb;
+    double *Gc = gb + L.off_G;
+    double *lin = gb + L.off_lin;
+    double *mom = gb + L.off_mom;
+    double *Pj = gb + L.off_P;
+    double *red = gb + L.off_red;
+    int *cand_s = reinterpret_cast<int *>(gb + L.off_cand);
+    int *live_s = cand_s + PET_MAXHP;
+    for (int i = l64; i < GS * GS; i += GRP_LANES) Gc[i] = 0.0;       // row/column Hp stay zero: dummy position
+    for (int i = l64; i < GS; i += GRP_LANES) lin[i] = 0.0;
+    __syncthreads();
+
+    const bool do_stats = !(a.flags & (GLF_LSE_ONLY | GLF_SELECT_ONLY));
+    const int n_cnt = st.n_cnt, n_g = st.n_g;
+    const double cut = (a.flags & GLF_USE_CUT) ? *a.cut : 0.0;
+    const bool rd = (a.flags & GLF_READ_LOGPJ) != 0, wr = (a.flags & GLF_WRITE_LOGPJ) != 0;
+    const int col_states = st.has_null + st.n_blocks * H;
+
+    double acc_n = 0.0, acc_lse = 0.0, acc_sig = 0.0;      // lane 0 of each group accumulates
+    double acc_cnt[PET_MAXV];
+#pragma unroll
+    for (int v = 0; v < PET_MAXV; ++v) acc_cnt[v] = 0.0;
+
+    const int64_t gstride = int64_t(gridDim.x) * ngroups;
+    for (int64_t r = int64_t(blockIdx.x) * ngroups + gid; r < a.n_rows; r += gstride) {
+        const int64_t n = a.row0 + r;
+        const double yy = a.yy[n];
+        double *scl = a.scl + n * (1 + PET_MAXHP);
+        if ((a.flags & GLF_USE_CUT) && do_stats) {
+            double l = a.lse[n];
+            bool keep = (a.flags & GLF_CUT_STRICT) ? (l > cut) : (l >= cut);
+            if (!keep) {   // truncated away: contributes nothing (bsc_et.py:254-257)
+                if (l64 <= Hp) scl[l64] = 0.0;
+                continue;
+            }
+        }
+        // ---- gather ------------------------------------------------------------------------------
+        grp_sync(gid);
+        if (l64 < Hp) cand_s[l64] = a.cand[n * Hp + l64];
+        grp_sync(gid);
+        for (int idx = l64; idx < Hp * Hp; idx += GRP_LANES) {
+            int j = idx / Hp, k = idx % Hp;
+            Gc[j * GS + k] = a.G[int64_t(cand_s[j]) * st.ldH + cand_s[k]];
+        }
+        if (l64 < Hp) {
+            int c = cand_s[l64];
+            int lv = 1;
+            for (int j = l64 + 1; j < Hp; ++j) lv &= (cand_s[j] != c);   // numpy "last write wins"
+            live_s[l64] = lv;
+        }
+        grp_sync(gid);
+        if (l64 < Hp) {
+            double ywc = a.ywc[n * Hp + l64];
+            lin[l64] = BINARY ? fma(-2.0, ywc, Gc[l64 * GS + l64]) : ywc;
+        }
+        grp_sync(gid);
+
+        double *logpj_row = a.logpj ? a.logpj + n * a.ld_logpj : nullptr;
+        // ---- log-joints of the multi-cause states, max ------------------------------------------------
+        double m2 = -INFINITY;
 #pragma unroll 2
-        for (int s = lane; s < S; s += 32) {
+        for (int s = l64; s < S; s += GRP_LANES) {
             double q = eval_state<GMAX, BINARY>(states_s[s], st, lin, Gc, yy);
             qbuf[s] = q;
             double F;
@@ -371,94 +474,62 @@ __global__ void __launch_bounds__(GL_MAX_WARPS * 32) gl_kernel(const __grid_cons
                 F = combine(it, prior_of<BINARY>(a, s), q);
                 if (wr) logpj_row[col_states + s] = F;
             }
-            mx = fmax(mx, F);
+            m2 = fmax(m2, F);
         }
-        mx = warp_max(mx);
         if (wr && (a.flags & GLF_LSE_ONLY)) continue;   // compat E_step: logpj only
-
-        // ---- phase 4: exp, denominators, scalar statistics --------------------------
-        double denom = 0.0, sig = 0.0;
-        double cntb[PET_MAXV];
-#pragma unroll
-        for (int v = 0; v < PET_MAXV; ++v) cntb[v] = 0.0;
-        if (st.has_null && lane == 0) {
-            double x = F0 - mx;
-            double p = (x > GL_EXP_CUTOFF) ? exp(x) : 0.0;
-            denom += p;
-            sig += p * yy;
-        }
-        for (int h = lane; h < H; h += 32) {
-            double snew = 0.0, s2new = 0.0;
-            const double ywh = row[h], wn2h = (st.n_blocks > 0) ? a.wn2[h] : 0.0;
-#pragma unroll
-            for (int b = 0; b < PET_MAXV; ++b) {
-                if (b < st.n_blocks) {
-                    const double v = st.block_val[b];
-                    double q = yy + v * (v * wn2h - 2.0 * ywh);
-                    double F = rd ? logpj_row[st.has_null + b * H + h] : combine(it, it.prior_block[b], q);
-                    double x = F - mx;
-                    double p = (x > GL_EXP_CUTOFF) ? exp(x) : 0.0;
-                    denom += p;
-                    sig += p * q;
-                    cntb[b] += p;
-                    snew = fma(p, v, snew);
-                    s2new = fma(p, v * v, s2new);
-                }
-            }
-            if (do_stats) {
-                row[h] = snew;
-                if (a.S2) a.S2[r * st.ldH + h] = s2new;   // normalised in phase 6
-            }
-        }
+        m2 = grp_max(m2, red, gid, wig);
+        const double *rs = a.rs + n * RS;
+        const double m1 = rs[0];
+        const double mx = fmax(m1, m2);
+        // ---- exp, merge with the singleton partial sums -------------------------------------------------
+        double Z2 = 0.0, sig2 = 0.0;
 #pragma unroll 2
-        for (int s = lane; s < S; s += 32) {
+        for (int s = l64; s < S; s += GRP_LANES) {
             double q = qbuf[s];
             double F = rd ? logpj_row[col_states + s] : combine(it, prior_of<BINARY>(a, s), q);
             double x = F - mx;
             double p = (x > GL_EXP_CUTOFF) ? exp(x) : 0.0;
-            denom += p;
-            sig += p * q;
+            Z2 += p;
+            sig2 += p * q;
             qbuf[s] = p;
         }
-        if (lane == 0) qbuf[S] = 0.0;   // zero slot read by padding entries of the gather table
-        denom = warp_sum(denom);
-        const double lse = mx + log(denom);
-        if (lane == 0) a.lse[n] = lse;
+        if (l64 == 0) qbuf[S] = 0.0;   // zero slot read by padding entries of the gather table
+        Z2 = grp_sum(Z2, red, gid, wig);
+        const double e1 = (m1 == -INFINITY) ? 0.0 : exp(m1 - mx);
+        const double Z = fma(rs[1], e1, Z2);
+        const double lse = mx + log(Z);
+        if (l64 == 0) a.lse[n] = lse;
         if (!do_stats) continue;
-        sig = warp_sum(sig);
-#pragma unroll
-        for (int v = 0; v < PET_MAXV; ++v)
-            if (v < st.n_blocks) cntb[v] = warp_sum(cntb[v]);
-        const double inv = 1.0 / denom;
+        sig2 = grp_sum(sig2, red, gid, wig);
+        const double inv = 1.0 / Z;
 
-        // ---- phase 5: pair sums from the shared-memory gather table -----------------
-        // every lane runs NCH chunks of CH ids; all chunks of an output belong to one lane
-        for (int o = lane; o <= st.n_out; o += 32) mom[o] = 0.0;
-        __syncwarp();
-        for (int i = lane; i < st.n_direct; i += 32) {
+        // ---- pair sums from the shared-memory gather table (64 lanes, exclusive owners) ---------------
+        for (int o = l64; o <= st.n_out; o += GRP_LANES) mom[o] = 0.0;
+        grp_sync(gid);
+        for (int i = l64; i < st.n_direct; i += GRP_LANES) {
             unsigned d = st.direct[i];
             mom[d >> 16] = qbuf[d & 0xFFFFu];
         }
         {
             double acc = 0.0;
-            const unsigned short *ids = ids_s + lane;
+            const unsigned short *ids = ids_s + l64;
             for (int c = 0; c < NCH; ++c) {
-                const unsigned co = chunk_s[c * 32 + lane];
+                const unsigned co = chunk_s[c * GRP_LANES + l64];
                 double s0 = 0.0, s1 = 0.0;
                 for (int i = 0; i < CH; i += 4) {
-                    const unsigned short *e = ids + (c * CH + i) * 32;
-                    s0 += qbuf[e[0]] + qbuf[e[32]];
-                    s1 += qbuf[e[64]] + qbuf[e[96]];
+                    const unsigned short *e = ids + (c * CH + i) * GRP_LANES;
+                    s0 += qbuf[e[0]] + qbuf[e[GRP_LANES]];
+                    s1 += qbuf[e[2 * GRP_LANES]] + qbuf[e[3 * GRP_LANES]];
                 }
                 acc += s0 + s1;
                 if (co & 0x8000u) { mom[co & 0x7FFFu] = acc; acc = 0.0; }
             }
         }
-        __syncwarp();
+        grp_sync(gid);
 
-        // ---- phase 6: moments and outputs --------------------------------------------
-        // 6a. P[j][a] = posterior mass of (s_j = v_a):  singleton state + size-weighted pair sums
-        for (int idx = lane; idx < Hp * n_cnt; idx += 32) {
+        // ---- moments -------------------------------------------------------------------------------
+        // P[j][a] = posterior mass of (s_j = v_a): singleton state + size-weighted pair sums
+        for (int idx = l64; idx < Hp * n_cnt; idx += GRP_LANES) {
             const int j = idx / n_cnt, av = idx % n_cnt;
             const int sid = st.single_idx[idx];
             double P = (sid >= 0) ? qbuf[sid] : 0.0;
@@ -473,39 +544,33 @@ __global__ void __launch_bounds__(GL_MAX_WARPS * 32) gl_kernel(const __grid_cons
             }
             Pj[idx] = P;
         }
-        if (st.n_blocks == 0)
-            for (int h = lane; h < H; h += 32) row[h] = 0.0;
-        __syncwarp();
-        // 6b. <s_h> row: singles already in row[], add candidate marginals, normalise, store
+        grp_sync(gid);
+        // scale of the singleton row and the candidate marginals for the scale kernel
         double cnt_states[PET_MAXV];
 #pragma unroll
         for (int v = 0; v < PET_MAXV; ++v) cnt_states[v] = 0.0;
-        if (lane < Hp) {
-            double m1 = 0.0;
+        if (l64 == 0) scl[0] = e1 * inv;
+        if (l64 < Hp) {
+            double m1j = 0.0;
 #pragma unroll
             for (int v = 0; v < PET_MAXV; ++v)
                 if (v < n_cnt) {
-                    double P = Pj[lane * n_cnt + v];
-                    m1 = fma(BINARY ? 1.0 : st.vals[v], P, m1);
+                    double P = Pj[l64 * n_cnt + v];
+                    m1j = fma(BINARY ? 1.0 : st.vals[v], P, m1j);
                     cnt_states[v] = P;
                 }
-            if (live_s[lane]) row[cand_s[lane]] += m1;
+            scl[1 + l64] = live_s[l64] ? m1j * inv : 0.0;
         }
-        __syncwarp();
-        for (int h = lane; h < st.ldH; h += 32) {
-            a.S[r * st.ldH + h] = (h < H) ? row[h] * inv : 0.0;
-            if (a.S2) a.S2[r * st.ldH + h] = (h < H) ? a.S2[r * st.ldH + h] * inv : 0.0;
-        }
-        // 6c. second moments scattered into Wq (numpy fancy-index semantics for duplicates)
-        for (int idx = lane; idx < Hp * Hp; idx += 32) {
+        // second moments scattered into Wq (numpy fancy-index semantics for duplicates)
+        for (int idx = l64; idx < Hp * Hp; idx += GRP_LANES) {
             const int j = idx / Hp, k = idx % Hp;
             if (!(live_s[j] && live_s[k])) continue;
-            double m2 = 0.0;
+            double m2v = 0.0;
             if (j == k) {
                 if (st.diag_from_colsum) continue;
                 for (int v = 0; v < n_cnt; ++v) {
                     double vv = BINARY ? 1.0 : st.vals[v];
-                    m2 = fma(vv * vv, Pj[j * n_cnt + v], m2);
+                    m2v = fma(vv * vv, Pj[j * n_cnt + v], m2v);
                 }
             } else {
                 const int lo = min(j, k), hi = max(j, k);
@@ -516,32 +581,32 @@ __global__ void __launch_bounds__(GL_MAX_WARPS * 32) gl_kernel(const __grid_cons
                         const int base = ((pair * n_cnt + av) * n_cnt + bv) * n_g;
                         double sacc = 0.0;
                         for (int g = 0; g < n_g; ++g) sacc += mom[base + g];
-                        m2 = fma(w, sacc, m2);
+                        m2v = fma(w, sacc, m2v);
                     }
             }
-            if (m2 != 0.0) atomicAdd(&a.Wq[int64_t(cand_s[j]) * st.ldH + cand_s[k]], m2 * inv);
+            if (m2v != 0.0) atomicAdd(&a.Wq[int64_t(cand_s[j]) * st.ldH + cand_s[k]], m2v * inv);
         }
-        // 6d. scalar statistics
+        // scalar statistics (only warp 0 of the group holds candidate lanes)
+        if (wig == 0) {
 #pragma unroll
-        for (int v = 0; v < PET_MAXV; ++v)
-            if (v < n_cnt) cnt_states[v] = warp_sum(cnt_states[v]);
-        if (lane == 0) {
-            acc_n += 1.0;
-            acc_lse += lse;
-            acc_sig += sig * inv;
+            for (int v = 0; v < PET_MAXV; ++v)
+                if (v < n_cnt) cnt_states[v] = warp_sum(cnt_states[v]);
+            if (l64 == 0) {
+                acc_n += 1.0;
+                acc_lse += lse;
+                acc_sig += fma(rs[2], e1, sig2) * inv;
 #pragma unroll
-            for (int v = 0; v < PET_MAXV; ++v) {
-                double c = cnt_states[v];
+                for (int v = 0; v < PET_MAXV; ++v) {
+                    double c = cnt_states[v];
 #pragma unroll
-                for (int b = 0; b < PET_MAXV; ++b)
-                    if (b < st.n_blocks && st.block_vidx[b] == v) c += cntb[b];
-                acc_cnt[v] += c * inv;
+                    for (int b = 0; b < PET_MAXV; ++b)
+                        if (b < st.n_blocks && st.block_vidx[b] == v) c = fma(rs[4 + b], e1, c);
+                    acc_cnt[v] += c * inv;
+                }
             }
         }
-        __syncwarp();
     }
-
-    if (do_stats && lane == 0) {
+    if (do_stats && l64 == 0) {
         atomicAdd(&a.scalars[0], acc_n);
         atomicAdd(&a.scalars[1], acc_lse);
         atomicAdd(&a.scalars[2], acc_sig);
@@ -549,48 +614,95 @@ __global__ void __launch_bounds__(GL_MAX_WARPS * 32) gl_kernel(const __grid_cons
     }
 }
 
-// largest warp count whose shared memory fits one SM (0 = does not fit at all)
+// =================================================================================================
+// Kernel C -- scale kernel: <s>[n,:] = singles[n,:] * e^(m1-m)/Z  (+ candidate marginals).
+// =================================================================================================
+__global__ void __launch_bounds__(256) gl_scale_kernel(const __grid_constant__ GLArgs a) {
+    const GLStatic &st = a.st;
+    const int lane = threadIdx.x & 31;
+    const int64_t r = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    if (r >= a.n_rows) return;
+    const int64_t n = a.row0 + r;
+    const double *scl = a.scl + n * (1 + PET_MAXHP);
+    const double sc = scl[0];
+    double *Srow = a.S + r * st.ldH;
+    for (int h = lane; h < st.ldH; h += 32) {
+        Srow[h] *= sc;
+        if (a.S2) a.S2[r * st.ldH + h] *= sc;
+    }
+    __syncwarp();
+    if (lane < st.Hp) {
+        double mj = scl[1 + lane];
+        if (mj != 0.0) Srow[a.cand[n * st.Hp + lane]] += mj;      // non-live duplicates carry 0 and do not write
+    }
+}
+
+// datapoint groups per CTA of the state kernel whose shared memory fits one SM (0 = does not fit at all)
 int gl_pick_warps(const GLStatic &s) {
-    static int cap = []() { const char *e = getenv("PET_GL_WARPS"); int v = e ? atoi(e) : GL_MAX_WARPS; return v < 1 ? 1 : (v > GL_MAX_WARPS ? GL_MAX_WARPS : v); }();
+    static int cap = []() { const char *e = getenv("PET_GL_GROUPS"); int v = e ? atoi(e) : GL_MAX_GROUPS; return v < 1 ? 1 : (v > GL_MAX_GROUPS ? GL_MAX_GROUPS : v); }();
     for (int w = cap; w >= 1; --w)
         if (gl_smem_bytes(s, w) <= 227 * 1024) return w;
     return 0;
 }
 
 template <int GMAX, bool BINARY>
-static int launch_inst(const GLArgs &a, int sm_count, cudaStream_t stream) {
-    auto kern = gl_kernel<GMAX, BINARY>;
-    const int warps = gl_pick_warps(a.st);
-    if (warps == 0) {
-        set_error("posterior kernel needs %zu bytes of shared memory per warp set (H=%d, states=%d): unsupported size",
-                  gl_smem_bytes(a.st, 1), a.st.H, a.st.S);
+static int launch_state(const GLArgs &a, int sm_count, cudaStream_t stream) {
+    auto kern = gl_state_kernel<GMAX, BINARY>;
+    const int groups = gl_pick_warps(a.st);
+    if (groups == 0) {
+        set_error("state kernel needs %zu bytes of shared memory per datapoint (H'=%d, states=%d): unsupported size",
+                  gl_smem_bytes(a.st, 1), a.st.Hp, a.st.S);
         return PET_EINVAL;
     }
-    const int use_warps = warps;
-    const size_t smem = gl_smem_bytes(a.st, use_warps);
+    const size_t smem = gl_smem_bytes(a.st, groups);
     static size_t configured = 0;
     if (smem > configured) {
         PET_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
         configured = smem;
     }
-    int per_sm = int(std::max<size_t>(1, std::min<size_t>(8, (227 * 1024) / (smem + 1024))));
-    per_sm = std::min(per_sm, std::max(1, 64 / use_warps));
-    int64_t want = ceil_div(a.n_rows, use_warps);
+    int per_sm = int(std::max<size_t>(1, std::min<size_t>(4, (227 * 1024) / (smem + 1024))));
+    per_sm = std::min(per_sm, std::max(1, 32 / (2 * groups)));
+    int64_t want = ceil_div(a.n_rows, groups);
     int64_t grid = std::min<int64_t>(want, int64_t(sm_count) * per_sm);
     if (grid <= 0) return PET_OK;
-    kern<<<(unsigned)grid, use_warps * 32, smem, stream>>>(a);
+    kern<<<(unsigned)grid, groups * GRP_LANES, smem, stream>>>(a);
     PET_LAUNCH_CHECK();
     return PET_OK;
 }
 
+// One pass of the posterior pipeline over a chunk: row kernel -> state kernel -> scale kernel.
 int launch_gl_kernel(const GLArgs &a, int gamma, bool binary, int sm_count, cudaStream_t stream) {
-    if (binary) {
-        if (gamma <= 3) return launch_inst<3, true>(a, sm_count, stream);
-        if (gamma <= 5) return launch_inst<5, true>(a, sm_count, stream);
-        return launch_inst<8, true>(a, sm_count, stream);
+    if (a.n_rows <= 0) return PET_OK;
+    {
+        const size_t smem = size_t(r2(a.st.H) + PET_MAXHP) * ROW_WARPS * sizeof(double);
+        if (smem > 227 * 1024) {
+            set_error("row kernel needs %zu bytes of shared memory (H=%d): unsupported size", smem, a.st.H);
+            return PET_EINVAL;
+        }
+        static size_t configured = 0;
+        if (smem > configured) {
+            PET_CUDA(cudaFuncSetAttribute(gl_row_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+            configured = smem;
+        }
+        int per_sm = int(std::max<size_t>(1, std::min<size_t>(2, (227 * 1024) / (smem + 1024))));
+        int64_t grid = std::min<int64_t>(ceil_div(a.n_rows, ROW_WARPS), int64_t(sm_count) * per_sm);
+        gl_row_kernel<<<(unsigned)grid, ROW_WARPS * 32, smem, stream>>>(a);
+        PET_LAUNCH_CHECK();
     }
-    if (gamma <= 4) return launch_inst<4, false>(a, sm_count, stream);
-    return launch_inst<8, false>(a, sm_count, stream);
+    if (a.flags & GLF_SELECT_ONLY) return PET_OK;
+    if (binary) {
+        if (gamma <= 3) PET_CHECK((launch_state<3, true>(a, sm_count, stream)));
+        else if (gamma <= 5) PET_CHECK((launch_state<5, true>(a, sm_count, stream)));
+        else PET_CHECK((launch_state<8, true>(a, sm_count, stream)));
+    } else {
+        if (gamma <= 4) PET_CHECK((launch_state<4, false>(a, sm_count, stream)));
+        else PET_CHECK((launch_state<8, false>(a, sm_count, stream)));
+    }
+    if (!(a.flags & (GLF_LSE_ONLY | GLF_SELECT_ONLY))) {
+        gl_scale_kernel<<<(unsigned)ceil_div(a.n_rows * 32, 256), 256, 0, stream>>>(a);
+        PET_LAUNCH_CHECK();
+    }
+    return PET_OK;
 }
 
 }  // namespace pet

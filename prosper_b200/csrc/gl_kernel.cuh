@@ -83,6 +83,9 @@ struct GLArgs {
     double *S2;                   // (n_rows, ldH) second moments of the singleton blocks (DSC) or NULL
     double *Wq;                   // (H, ldH) atomic scatter target
     double *scalars;              // [0]=n_used [1]=sum lse [2]=sigma stat [3..]=counts
+    double *rs;                   // (n, 4+PET_MAXV) row-kernel partial sums {m1, Z1, sig1, -, cnt1[..]}, global index
+    double *ywc;                  // (n, Hp) scores of the candidates, global index
+    double *scl;                  // (n, 1+PET_MAXHP) {scale of the singleton row, candidate marginals}, global index
 };
 
 int launch_gl_kernel(const GLArgs &a, int gamma, bool binary, int sm_count, cudaStream_t st);
