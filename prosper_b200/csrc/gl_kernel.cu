@@ -33,6 +33,7 @@ static __host__ __device__ inline int r2(int x) { return (x + 1) & ~1; }
 constexpr int GS = PET_MAXHP + 1;          // stride of the gathered Gram block; row/col Hp is all zero
 
 constexpr int GRP_LANES = 64;              // two warps work on one datapoint in the state kernel
+constexpr int GL_CHUNK = 8;                // entries per gather chunk (fixed: the inner loop is fully unrolled)
 
 struct SmemLayout {
     int shared_doubles;   // state records + gather table + chunk table
@@ -66,15 +67,26 @@ size_t gl_smem_bytes(const GLStatic &s, int groups) {
 __constant__ double c_winv[8] = {1.0, 1.0 / 2, 1.0 / 3, 1.0 / 4, 1.0 / 5, 1.0 / 6, 1.0 / 7, 1.0 / 8};
 
 // log-prior of multi-state s.  Binary spaces are enumerated by size (camodels/__init__.py:30-33), so
-// |s| follows from the index and nothing is loaded; valued spaces read the per-iteration table.
-template <bool BINARY>
-__device__ __forceinline__ double prior_of(const GLArgs &a, int s) {
-    if (BINARY) {
+// |s| follows from the index (size boundaries held in registers) and nothing is loaded; valued spaces
+// read the per-iteration table.
+template <int GMAX>
+struct SizeBounds {
+    int b[GMAX + 1];
+    __device__ __forceinline__ void load(const GLStatic &st) {
+#pragma unroll
+        for (int g = 3; g <= GMAX; ++g) b[g] = st.size_start[g];
+    }
+    __device__ __forceinline__ int members(int s) const {
         int n = 2;
 #pragma unroll
-        for (int g = 3; g <= PET_MAXG; ++g) n += (s >= a.st.size_start[g]) ? 1 : 0;
-        return a.it.lp[0] * double(n);
+        for (int g = 3; g <= GMAX; ++g) n += (s >= b[g]) ? 1 : 0;
+        return n;
     }
+};
+
+template <int GMAX, bool BINARY>
+__device__ __forceinline__ double prior_of(const GLArgs &a, const SizeBounds<GMAX> &sb, int s) {
+    if (BINARY) return a.it.lp[0] * double(sb.members(s));
     return a.state_prior[s];
 }
 
@@ -395,7 +407,7 @@ __global__ void __launch_bounds__(GL_MAX_GROUPS * GRP_LANES) gl_state_kernel(con
     const int gid = threadIdx.x / GRP_LANES, l64 = threadIdx.x % GRP_LANES, wig = l64 >> 5;
     const int Hp = st.Hp, S = st.S, H = st.H;
     const SmemLayout L = smem_layout(st);
-    const int CH = st.chunk_len, NCH = st.n_chunks;
+    const int CH = GL_CHUNK, NCH = st.n_chunks;
 
     unsigned long long *states_s = reinterpret_cast<unsigned long long *>(smem);
     unsigned short *ids_s = reinterpret_cast<unsigned short *>(smem + L.off_ids);
@@ -421,6 +433,8 @@ __global__ void __launch_bounds__(GL_MAX_GROUPS * GRP_LANES) gl_state_kernel(con
     const double cut = (a.flags & GLF_USE_CUT) ? *a.cut : 0.0;
     const bool rd = (a.flags & GLF_READ_LOGPJ) != 0, wr = (a.flags & GLF_WRITE_LOGPJ) != 0;
     const int col_states = st.has_null + st.n_blocks * H;
+    SizeBounds<GMAX> sb;
+    sb.load(st);
 
     double acc_n = 0.0, acc_lse = 0.0, acc_sig = 0.0;      // lane 0 of each group accumulates
     double acc_cnt[PET_MAXV];
@@ -471,7 +485,7 @@ __global__ void __launch_bounds__(GL_MAX_GROUPS * GRP_LANES) gl_state_kernel(con
             double F;
             if (rd) F = logpj_row[col_states + s];
             else {
-                F = combine(it, prior_of<BINARY>(a, s), q);
+                F = combine(it, prior_of<GMAX, BINARY>(a, sb, s), q);
                 if (wr) logpj_row[col_states + s] = F;
             }
             m2 = fmax(m2, F);
@@ -486,7 +500,7 @@ __global__ void __launch_bounds__(GL_MAX_GROUPS * GRP_LANES) gl_state_kernel(con
 #pragma unroll 2
         for (int s = l64; s < S; s += GRP_LANES) {
             double q = qbuf[s];
-            double F = rd ? logpj_row[col_states + s] : combine(it, prior_of<BINARY>(a, s), q);
+            double F = rd ? logpj_row[col_states + s] : combine(it, prior_of<GMAX, BINARY>(a, sb, s), q);
             double x = F - mx;
             double p = (x > GL_EXP_CUTOFF) ? exp(x) : 0.0;
             Z2 += p;
@@ -512,16 +526,15 @@ __global__ void __launch_bounds__(GL_MAX_GROUPS * GRP_LANES) gl_state_kernel(con
         }
         {
             double acc = 0.0;
-            const unsigned short *ids = ids_s + l64;
-            for (int c = 0; c < NCH; ++c) {
-                const unsigned co = chunk_s[c * GRP_LANES + l64];
-                double s0 = 0.0, s1 = 0.0;
-                for (int i = 0; i < CH; i += 4) {
-                    const unsigned short *e = ids + (c * CH + i) * GRP_LANES;
-                    s0 += qbuf[e[0]] + qbuf[e[GRP_LANES]];
-                    s1 += qbuf[e[2 * GRP_LANES]] + qbuf[e[3 * GRP_LANES]];
-                }
-                acc += s0 + s1;
+            const unsigned short *e = ids_s + l64;            // [(chunk*8 + i)*64 + lane]
+            const unsigned short *ct = chunk_s + l64;
+            for (int c = 0; c < NCH; ++c, e += GL_CHUNK * GRP_LANES, ct += GRP_LANES) {
+                double s0 = qbuf[e[0]] + qbuf[e[GRP_LANES]];
+                double s1 = qbuf[e[2 * GRP_LANES]] + qbuf[e[3 * GRP_LANES]];
+                double s2 = qbuf[e[4 * GRP_LANES]] + qbuf[e[5 * GRP_LANES]];
+                double s3 = qbuf[e[6 * GRP_LANES]] + qbuf[e[7 * GRP_LANES]];
+                acc += (s0 + s1) + (s2 + s3);
+                const unsigned co = *ct;
                 if (co & 0x8000u) { mom[co & 0x7FFFu] = acc; acc = 0.0; }
             }
         }
