@@ -284,13 +284,15 @@ def run_gpu(args):
     if rank == 0:
         peak = measure_fp64_peak(dev)
         per_step = dict((k, v['ms'] / args.steps) for k, v in stages.items())
-        dom = max(('score_gemm', 'posterior', 'stats_gemm'), key=lambda k: per_step[k])
+        kernels = ('score_gemm', 'stats_gemm', 'state_kernel', 'row_kernel')
+        dom = max(kernels, key=lambda k: per_step[k])
         spans = max(1, stages[dom]['spans'])
         avg_launch_ms = stages[dom]['ms'] / spans
         rows_per_launch = n_local * args.steps / spans
         if dom in ('score_gemm', 'stats_gemm'):
+            # both GEMM stages are the same kernel template (dgemm_kernel); algorithmic work 2*D*H flop per datapoint each
             achieved = 2.0 * D * H * rows_per_launch / (avg_launch_ms / 1e3) / 1e12
-            roof = {"kernel": "dgemm_kernel (FP64 DMMA, %s)" % dom, "bound": "tensor", "pipe": "fp64 mma.sync (no f64 tcgen05 kind exists)",
+            roof = {"kernel": "dgemm_kernel (FP64 DMMA, %s)" % dom, "bound": "tensor", "pipe": "fp64 mma.sync m8n8k4 (tcgen05 has no f64 kind)",
                     "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                     "peak_source": "cuBLAS DGEMM 8192^3 measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
                     "traffic": None}
@@ -301,7 +303,7 @@ def run_gpu(args):
             except Exception:
                 pass
             achieved = 2.0 * 8 * H * rows_per_launch / (avg_launch_ms / 1e3) / 1e9
-            roof = {"kernel": "gl_kernel (posterior)", "bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s",
+            roof = {"kernel": "gl_%s (posterior)" % dom, "bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s",
                     "frac": achieved / hbm, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)", "traffic": None}
         roof["avg_launch_ms"] = avg_launch_ms
         roof["stage_ms_per_step"] = per_step

@@ -230,10 +230,11 @@ int  pet_spd_solve_right(int64_t n, int64_t m, double *A_dev, int64_t lda,
 int64_t pet_spd_solve_work_doubles(int64_t n, int64_t lda);   /* size of work_dev */
 
 /* Device time per stage since pet_enable_timing(e,1), measured with CUDA events on the
- * caller's stream around every launch group: out[0..5] = total ms of [0]=prepare
- * (transpose+Gram) [1]=score GEMM [2]=posterior kernel [3]=statistics GEMM [4]=solve
- * [5]=kth-largest; out[6..11] = how many spans each total sums.  Synchronises. */
-int  pet_stage_times_ms(pet_engine *e, double *out_host12);
+ * caller's stream around every launch group: out[0..7] = total ms of [0]=prepare
+ * (transpose+Gram) [1]=score GEMM [2]=state kernel (or the whole posterior kernel for
+ * MCA/MMCA/GSC) [3]=statistics GEMM [4]=solve [5]=kth-largest [6]=row kernel [7]=scale kernel;
+ * out[8..15] = how many spans each total sums.  Synchronises. */
+int  pet_stage_times_ms(pet_engine *e, double *out_host16);
 int  pet_enable_timing(pet_engine *e, int32_t on);
 /* number of kernels launched by the engine since creation (bench.py's gpu_launches) */
 int64_t pet_launch_count(const pet_engine *e);

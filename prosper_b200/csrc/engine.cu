@@ -57,7 +57,7 @@ static bool is_device_ptr(const void *p) {
     return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
 }
 
-enum Stage { ST_PREPARE = 0, ST_SCORE, ST_POST, ST_STATS, ST_SOLVE, ST_KSEL, ST_COUNT };
+enum Stage { ST_PREPARE = 0, ST_SCORE, ST_POST, ST_STATS, ST_SOLVE, ST_KSEL, ST_ROW, ST_SCALE, ST_COUNT };
 
 struct StageTimer {
     bool on = false;
@@ -65,8 +65,8 @@ struct StageTimer {
     size_t used = 0;
     struct Span { int stage; cudaEvent_t a, b; };
     std::vector<Span> spans;
-    double totals[ST_COUNT] = {0, 0, 0, 0, 0, 0};
-    int counts[ST_COUNT] = {0, 0, 0, 0, 0, 0};
+    double totals[ST_COUNT] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int counts[ST_COUNT] = {0, 0, 0, 0, 0, 0, 0, 0};
     cudaEvent_t get() {
         if (used == pool.size()) { cudaEvent_t e; cudaEventCreate(&e); pool.push_back(e); }
         return pool[used++];
@@ -582,8 +582,14 @@ static int sweep_gl(pet_engine *e, const pet_anneal *a, const pet_params *p, int
                                                size_t(e->C) * 8, rows, cudaMemcpyHostToDevice, st));
             }
         }
+        e->timer.begin(ST_ROW, st);
+        PET_CHECK(launch_gl_row(ga, e->sm_count, st));
+        e->timer.end(st);
         e->timer.begin(ST_POST, st);
-        PET_CHECK(launch_gl_kernel(ga, e->gamma, e->binary, e->sm_count, st));
+        PET_CHECK(launch_gl_state(ga, e->gamma, e->binary, e->sm_count, st));
+        e->timer.end(st);
+        e->timer.begin(ST_SCALE, st);
+        PET_CHECK(launch_gl_scale(ga, st));
         e->timer.end(st);
         if (user_logpj && !logpj_on_dev && logpj_is_output)
             PET_CUDA(cudaMemcpy2DAsync(const_cast<double *>(logpj_user) + r0 * ld_logpj, ld_logpj * 8, e->stage_logpj,

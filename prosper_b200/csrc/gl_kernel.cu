@@ -683,39 +683,48 @@ static int launch_state(const GLArgs &a, int sm_count, cudaStream_t stream) {
     return PET_OK;
 }
 
-// One pass of the posterior pipeline over a chunk: row kernel -> state kernel -> scale kernel.
-int launch_gl_kernel(const GLArgs &a, int gamma, bool binary, int sm_count, cudaStream_t stream) {
+// The posterior pipeline over a chunk is: row kernel -> state kernel -> scale kernel.
+int launch_gl_row(const GLArgs &a, int sm_count, cudaStream_t stream) {
     if (a.n_rows <= 0) return PET_OK;
-    {
-        const size_t smem = size_t(r2(a.st.H) + PET_MAXHP) * ROW_WARPS * sizeof(double);
-        if (smem > 227 * 1024) {
-            set_error("row kernel needs %zu bytes of shared memory (H=%d): unsupported size", smem, a.st.H);
-            return PET_EINVAL;
-        }
-        static size_t configured = 0;
-        if (smem > configured) {
-            PET_CUDA(cudaFuncSetAttribute(gl_row_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-            configured = smem;
-        }
-        int per_sm = int(std::max<size_t>(1, std::min<size_t>(2, (227 * 1024) / (smem + 1024))));
-        int64_t grid = std::min<int64_t>(ceil_div(a.n_rows, ROW_WARPS), int64_t(sm_count) * per_sm);
-        gl_row_kernel<<<(unsigned)grid, ROW_WARPS * 32, smem, stream>>>(a);
-        PET_LAUNCH_CHECK();
+    const size_t smem = size_t(r2(a.st.H) + PET_MAXHP) * ROW_WARPS * sizeof(double);
+    if (smem > 227 * 1024) {
+        set_error("row kernel needs %zu bytes of shared memory (H=%d): unsupported size", smem, a.st.H);
+        return PET_EINVAL;
     }
-    if (a.flags & GLF_SELECT_ONLY) return PET_OK;
-    if (binary) {
-        if (gamma <= 3) PET_CHECK((launch_state<3, true>(a, sm_count, stream)));
-        else if (gamma <= 5) PET_CHECK((launch_state<5, true>(a, sm_count, stream)));
-        else PET_CHECK((launch_state<8, true>(a, sm_count, stream)));
-    } else {
-        if (gamma <= 4) PET_CHECK((launch_state<4, false>(a, sm_count, stream)));
-        else PET_CHECK((launch_state<8, false>(a, sm_count, stream)));
+    static size_t configured = 0;
+    if (smem > configured) {
+        PET_CUDA(cudaFuncSetAttribute(gl_row_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        configured = smem;
     }
-    if (!(a.flags & (GLF_LSE_ONLY | GLF_SELECT_ONLY))) {
-        gl_scale_kernel<<<(unsigned)ceil_div(a.n_rows * 32, 256), 256, 0, stream>>>(a);
-        PET_LAUNCH_CHECK();
-    }
+    int per_sm = int(std::max<size_t>(1, std::min<size_t>(2, (227 * 1024) / (smem + 1024))));
+    int64_t grid = std::min<int64_t>(ceil_div(a.n_rows, ROW_WARPS), int64_t(sm_count) * per_sm);
+    gl_row_kernel<<<(unsigned)grid, ROW_WARPS * 32, smem, stream>>>(a);
+    PET_LAUNCH_CHECK();
     return PET_OK;
+}
+
+int launch_gl_state(const GLArgs &a, int gamma, bool binary, int sm_count, cudaStream_t stream) {
+    if (a.n_rows <= 0 || (a.flags & GLF_SELECT_ONLY)) return PET_OK;
+    if (binary) {
+        if (gamma <= 3) return launch_state<3, true>(a, sm_count, stream);
+        if (gamma <= 5) return launch_state<5, true>(a, sm_count, stream);
+        return launch_state<8, true>(a, sm_count, stream);
+    }
+    if (gamma <= 4) return launch_state<4, false>(a, sm_count, stream);
+    return launch_state<8, false>(a, sm_count, stream);
+}
+
+int launch_gl_scale(const GLArgs &a, cudaStream_t stream) {
+    if (a.n_rows <= 0 || (a.flags & (GLF_LSE_ONLY | GLF_SELECT_ONLY))) return PET_OK;
+    gl_scale_kernel<<<(unsigned)ceil_div(a.n_rows * 32, 256), 256, 0, stream>>>(a);
+    PET_LAUNCH_CHECK();
+    return PET_OK;
+}
+
+int launch_gl_kernel(const GLArgs &a, int gamma, bool binary, int sm_count, cudaStream_t stream) {
+    PET_CHECK(launch_gl_row(a, sm_count, stream));
+    PET_CHECK(launch_gl_state(a, gamma, binary, sm_count, stream));
+    return launch_gl_scale(a, stream);
 }
 
 }  // namespace pet

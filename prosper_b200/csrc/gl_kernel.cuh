@@ -89,6 +89,9 @@ struct GLArgs {
 };
 
 int launch_gl_kernel(const GLArgs &a, int gamma, bool binary, int sm_count, cudaStream_t st);
+int launch_gl_row(const GLArgs &a, int sm_count, cudaStream_t st);
+int launch_gl_state(const GLArgs &a, int gamma, bool binary, int sm_count, cudaStream_t st);
+int launch_gl_scale(const GLArgs &a, cudaStream_t st);
 size_t gl_smem_bytes(const GLStatic &s, int warps);
 int gl_pick_warps(const GLStatic &s);
 int launch_state_prior(const GLStatic &st, const GLIter &it, double *out, cudaStream_t stream);

@@ -182,10 +182,10 @@ class Engine(object):
         _lib.check(self.lib.pet_enable_timing(self.h, 1 if on else 0))
 
     def stage_times(self):
-        out = (C.c_double * 12)()
+        out = (C.c_double * 16)()
         _lib.check(self.lib.pet_stage_times_ms(self.h, out))
-        names = ['prepare', 'score_gemm', 'posterior', 'stats_gemm', 'solve', 'kth']
-        return dict((nm, {'ms': out[i], 'spans': int(out[6 + i])}) for i, nm in enumerate(names))
+        names = ['prepare', 'score_gemm', 'state_kernel', 'stats_gemm', 'solve', 'kth', 'row_kernel', 'scale_kernel']
+        return dict((nm, {'ms': out[i], 'spans': int(out[8 + i])}) for i, nm in enumerate(names))
 
     def launch_count(self):
         return int(self.lib.pet_launch_count(self.h))
