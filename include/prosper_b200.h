@@ -221,6 +221,14 @@ int  pet_dgemm_mn(int64_t M, int64_t N, int64_t K, const double *A_dev, int64_t 
                   const double *B_dev, int64_t ldb, double *C_dev, int64_t ldc,
                   int32_t accumulate, double *workspace_dev, int64_t workspace_doubles,
                   void *stream);
+/* C(M,N) = A.B^T as pet_dgemm_kk (alpha 1, beta 0), computed on the INT8 tcgen05 tensor
+ * cores by error-free slicing of both operands into `nslices` (6 or 7) int8 slices with
+ * exact int32 accumulation in TMEM (Ozaki scheme; 7 slices: |err| <= ~1e-13 max|C|).
+ * Slices both operands, then runs the GEMM `repeat` times (>= 1; for benchmarks).
+ * Synchronises the stream. */
+int  pet_ozaki_gemm_kk(int64_t M, int64_t N, int64_t K, const double *A_dev, int64_t lda,
+                       const double *B_dev, int64_t ldb, double *C_dev, int64_t ldc,
+                       int32_t nslices, int32_t repeat, void *stream);
 /* Solve X.A = B for X with A (n,n) symmetric positive semi-definite (pivots below
  * tol are dropped, giving the minimum-norm behaviour of lstsq for dead units).
  * A is overwritten by its Cholesky factor; B (m,n) overwritten by X. Synchronises. */

@@ -87,6 +87,8 @@ SIGNATURES = {
                                C.c_void_p, C.c_int64, C.c_double, C.c_double, C.c_void_p]),
     "pet_dgemm_mn": (C.c_int, [C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
                                C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p]),
+    "pet_ozaki_gemm_kk": (C.c_int, [C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
+                                    C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p]),
     "pet_spd_solve_right": (C.c_int, [C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
                                       C.c_void_p, C.POINTER(C.c_int32), C.c_void_p]),
     "pet_spd_solve_work_doubles": (C.c_int64, [C.c_int64, C.c_int64]),

@@ -1,0 +1,408 @@
+// FP64-accurate score GEMM on the 5th-generation tensor cores (tcgen05 + TMEM + TMA).
+//
+// tcgen05 has no f64 kind, and the FP64 DMMA pipe caps the path at ~35 TFLOP/s.  This kernel computes
+//     C(M,N) = A(M,K) . B(N,K)^T          (both K-contiguous, float64 in / float64 out)
+// with INT8 tensor-core MMAs by error-free slicing (Ozaki scheme):
+//   * every row of A and of B is scaled by a power of two and cut into NS signed 7-bit slices
+//     (first slice 6 bits), a_mk = 2^eA[m] * sum_i 2^-(6+7i) A_i[m,k],  |A_i| <= 64;
+//   * slice products A_i . B_j^T are accumulated EXACTLY in int32 (|sum| <= (t+1) K 2^12 < 2^31),
+//     all pairs with i + j = t into the same TMEM accumulator, one accumulator per t = 0..NS-1;
+//   * the epilogue converts the NS accumulators to float64, weights them by 2^-(12+7t) and the row /
+//     column scales (all exact powers of two) and adds them up: the only rounding is that final sum and
+//     the truncation of pairs with i + j >= NS  (NS = 7: |error| <= ~5e-14 * max|C|, measured in tests).
+// One CTA computes a 128 x 64 tile; per 64-byte K block all NS slices of A and B are staged once by TMA
+// (SWIZZLE_64B) and reused by the NS(NS+1)/2 pair MMAs, so shared memory / L2 traffic is per slice, not
+// per pair.  Warp roles: 0 = TMA producer, 1 = MMA issuer (one elected lane), 2 = TMEM allocator,
+// 4..7 = epilogue (tcgen05.ld -> FP64 accumulate in registers -> global).
+#include <cuda.h>
+#include <math.h>
+
+#include "common.cuh"
+
+namespace pet {
+
+namespace oz {
+constexpr int BM = 128, BN = 64, KB = 64;          // tile rows, tile cols, bytes (= int8 elements) of K per stage
+constexpr int UMMA_K = 32;                         // K of one kind::i8 MMA
+constexpr int THREADS = 256;
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+// K-major SWIZZLE_64B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address >> 4,
+// LBO = 1, SBO = 8 rows * 64 B = 512 B, version 1 (Blackwell), layout type 4 (SWIZZLE_64B)
+__device__ __forceinline__ uint64_t make_desc(const void *smem_ptr) {
+    uint64_t addr = smem_u32(smem_ptr);
+    return ((addr & 0x3FFFFull) >> 4) | (1ull << 16) | (uint64_t(512 >> 4) << 32) | (1ull << 46) | (4ull << 61);
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor) for kind::i8: D = S32 (2 << 4), A = B = signed int8 (1 << 7,
+// 1 << 10), both K-major, N >> 3 at bit 17, M >> 4 at bit 24: make_idesc_n below
+__device__ __forceinline__ void mma_i8(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(0u)
+        : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, int32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+
+struct Args {
+    int64_t M, N;
+    int kblocks;                 // K padded / 64
+    int splits, kb_per_split;    // split-K: unit (tile, split) covers k blocks [split * kb_per_split, ...)
+    int accumulate;              // epilogue: C += result instead of C = result
+    const double *sA, *sB;       // row scales 2^eA[m], 2^eB[n]
+    double *C;
+    int64_t ldc, split_stride;   // split s writes C + s * split_stride
+};
+
+__device__ __forceinline__ uint32_t make_idesc_n(int n) {
+    return (2u << 4) | (1u << 7) | (1u << 10) | (uint32_t(n >> 3) << 17) | (uint32_t(BM >> 4) << 24);
+}
+
+template <int NS, int STAGES>
+__global__ void __launch_bounds__(THREADS, 1) gemm_kernel(const __grid_constant__ CUtensorMap mapA,
+                                                          const __grid_constant__ CUtensorMap mapB, const Args a) {
+    constexpr int A_SLICE = BM * KB, B_SLICE = BN * KB;                 // bytes per slice tile
+    constexpr int STAGE_BYTES = NS * (A_SLICE + B_SLICE);
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + STAGES * STAGE_BYTES);
+    uint64_t *full = bars, *empty = bars + STAGES, *tmem_full = bars + 2 * STAGES, *tmem_empty = bars + 2 * STAGES + 1;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * STAGES + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(tmem_full, 1);
+        mbar_init(tmem_empty, 4);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int64_t tiles_n = (a.N + BN - 1) / BN, tiles_m = (a.M + BM - 1) / BM;
+    const int64_t tiles = tiles_m * tiles_n, units = tiles * a.splits;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int64_t u = blockIdx.x; u < units; u += gridDim.x) {
+                const int64_t tile = u % tiles;
+                const int split = int(u / tiles);
+                const int m0 = int(tile / tiles_n) * BM, n0 = int(tile % tiles_n) * BN;
+                const int kb0 = split * a.kb_per_split, kb1 = min(kb0 + a.kb_per_split, a.kblocks);
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    mbar_expect_tx(&full[stage], STAGE_BYTES);
+                    uint8_t *sa = smem + stage * STAGE_BYTES, *sb = sa + NS * A_SLICE;
+#pragma unroll
+                    for (int i = 0; i < NS; ++i) {
+                        tma_load_3d(sa + i * A_SLICE, &mapA, &full[stage], kb * KB, m0, i);
+                        tma_load_3d(sb + i * B_SLICE, &mapB, &full[stage], kb * KB, n0, i);
+                    }
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        // A_i multiplies the stacked B slices 0 .. NS-1-i (consecutive 64-row tiles in shared memory) in one or two
+        // wide MMAs whose N columns land on the consecutive accumulators t = i .. NS-1.
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0, tphase = 0;
+            for (int64_t u = blockIdx.x; u < units; u += gridDim.x) {
+                const int split = int(u / tiles);
+                const int kb0 = split * a.kb_per_split, kb1 = min(kb0 + a.kb_per_split, a.kblocks);
+                mbar_wait(tmem_empty, tphase ^ 1);           // epilogue has drained the accumulators
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    mbar_wait(&full[stage], phase);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint8_t *sa = smem + stage * STAGE_BYTES, *sb = sa + NS * A_SLICE;
+#pragma unroll
+                    for (int kk = 0; kk < KB / UMMA_K; ++kk) {
+#pragma unroll
+                        for (int i = 0; i < NS; ++i) {
+                            const uint64_t da = make_desc(sa + i * A_SLICE + kk * UMMA_K);
+                            const uint32_t acc = (i != 0 || kb != kb0 || kk != 0) ? 1u : 0u;
+                            constexpr int MAXJ = 256 / BN;                       // B slices per MMA (N <= 256)
+#pragma unroll
+                            for (int j0 = 0; j0 < NS - i; j0 += MAXJ) {
+                                const int cnt = (NS - i - j0 < MAXJ) ? NS - i - j0 : MAXJ;
+                                const uint64_t db = make_desc(sb + j0 * B_SLICE + kk * UMMA_K);
+                                mma_i8(tmem_base + (i + j0) * BN, da, db, make_idesc_n(cnt * BN), acc);
+                            }
+                        }
+                    }
+                    mma_commit(&empty[stage]);               // frees the smem stage when these MMAs retire
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                mma_commit(tmem_full);                       // accumulators complete
+                tphase ^= 1;
+            }
+        }
+    } else if (warp >= 4) {
+        // ===== epilogue: TMEM -> exact int64 combination -> FP64 -> global =====
+        // sum_t v_t 2^-(12+7t) = 2^-33 (hi + lo 2^-(7 (NS-4))),  hi = sum_{t<4} v_t 2^(7(3-t)) (< 2^53, exact in FP64),
+        // lo = sum_{t>=4} v_t 2^(7(NS-1-t))
+        const int q = warp & 3;                              // TMEM lane quadrant of this warp
+        uint32_t tphase = 0;
+        const double w_hi = __longlong_as_double((long long)(1023 - 33) << 52);
+        const double w_lo = __longlong_as_double((long long)(1023 - 7 * (NS - 4)) << 52);
+        for (int64_t u = blockIdx.x; u < units; u += gridDim.x) {
+            const int64_t tile = u % tiles;
+            const int split = int(u / tiles);
+            const int64_t m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
+            mbar_wait(tmem_full, tphase);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const int64_t row = m0 + q * 32 + lane;
+            const double sa = (row < a.M) ? a.sA[row] * w_hi : 0.0;
+            double *crow = a.C + split * a.split_stride + row * a.ldc + n0;
+#pragma unroll 1
+            for (int half = 0; half < 2; ++half) {
+                const uint32_t tcol = tmem_base + (uint32_t(q * 32) << 16) + half * 32;
+                long long hi[32], lo[32];
+                {
+                    int32_t v0[32], v1[32], v2[32], v3[32];
+                    tmem_ld32(tcol + 0 * BN, v0);
+                    tmem_ld32(tcol + 1 * BN, v1);
+                    tmem_ld32(tcol + 2 * BN, v2);
+                    tmem_ld32(tcol + 3 * BN, v3);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                    for (int c = 0; c < 32; ++c)
+                        hi[c] = ((long long)v0[c] << 21) + ((long long)v1[c] << 14) + ((long long)v2[c] << 7) + (long long)v3[c];
+                }
+                {
+                    int32_t v4[32], v5[32], v6[32];
+                    tmem_ld32(tcol + 4 * BN, v4);
+                    tmem_ld32(tcol + 5 * BN, v5);
+                    if (NS == 7) tmem_ld32(tcol + 6 * BN, v6);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                    for (int c = 0; c < 32; ++c)
+                        lo[c] = (NS == 7) ? ((long long)v4[c] << 14) + ((long long)v5[c] << 7) + (long long)v6[c]
+                                          : ((long long)v4[c] << 7) + (long long)v5[c];
+                }
+                if (half == 1) {                             // all TMEM reads of this tile are done
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(tmem_empty);
+                }
+                if (row < a.M) {
+                    const int64_t nb = n0 + half * 32;
+                    double *cp = crow + half * 32;
+#pragma unroll
+                    for (int c = 0; c < 32; c += 2) {
+                        double o0 = fma(double(lo[c]), w_lo, double(hi[c])) * sa;
+                        double o1 = fma(double(lo[c + 1]), w_lo, double(hi[c + 1])) * sa;
+                        if (nb + c + 1 < a.N) {
+                            o0 *= a.sB[nb + c]; o1 *= a.sB[nb + c + 1];
+                            double2 *dst = reinterpret_cast<double2 *>(cp + c);
+                            if (a.accumulate) { double2 old = *dst; o0 += old.x; o1 += old.y; }
+                            *dst = make_double2(o0, o1);
+                        } else if (nb + c < a.N) {
+                            o0 *= a.sB[nb + c];
+                            if (a.accumulate) o0 += cp[c];
+                            cp[c] = o0;
+                        }
+                    }
+                }
+            }
+            tphase ^= 1;
+        }
+    }
+    __syncthreads();
+    if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+}
+
+// One warp per row: power-of-two scale and NS int8 slices (first slice 6 bits + sign, the rest 7 bits + sign,
+// round to nearest so every slice is in [-64, 64]).  out: [NS][rows][Kp] int8, zero padded in k.
+__global__ void slice_rows_kernel(const double *X, int64_t ldx, int64_t rows, int K, int Kp, int ns, int8_t *out,
+                                  double *scale) {
+    const int64_t row = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const double *x = X + row * ldx;
+    double mx = 0.0;
+    for (int k = lane; k < K; k += 32) mx = fmax(mx, fabs(x[k]));
+    mx = warp_max(mx);
+    int e = 0;
+    if (mx > 0.0) frexp(mx, &e);                   // mx = m * 2^e, m in [0.5, 1)  ->  |x| / 2^e < 1
+    if (lane == 0) scale[row] = ldexp(1.0, e);
+    const double s0 = ldexp(64.0, -e);
+    const int64_t slice_stride = rows * int64_t(Kp);
+    for (int k = lane; k < Kp; k += 32) {
+        double r = (k < K) ? x[k] * s0 : 0.0;
+        int8_t *o = out + row * int64_t(Kp) + k;
+        for (int t = 0; t < ns; ++t) {
+            double v = rint(r);
+            o[t * slice_stride] = (int8_t)v;
+            r = (r - v) * 128.0;
+        }
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// slices: [ns][rows][Kp] int8
+static int make_map(CUtensorMap *map, const int8_t *slices, int64_t rows, int Kp, int ns, int box_rows) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return PET_ECUDA; }
+    cuuint64_t dims[3] = {(cuuint64_t)Kp, (cuuint64_t)rows, (cuuint64_t)ns};
+    cuuint64_t strides[2] = {(cuuint64_t)Kp, (cuuint64_t)Kp * (cuuint64_t)rows};
+    cuuint32_t box[3] = {(cuuint32_t)KB, (cuuint32_t)box_rows, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<int8_t *>(slices), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", int(r)); return PET_ECUDA; }
+    return PET_OK;
+}
+}  // namespace oz
+
+int ozaki_kp(int K) { return int(round_up(K, oz::KB)); }
+
+int ozaki_slice_rows(const double *X, int64_t ldx, int64_t rows, int K, int ns, int8_t *out, double *scale, cudaStream_t st) {
+    if (rows <= 0) return PET_OK;
+    oz::slice_rows_kernel<<<(unsigned)ceil_div(rows * 32, 256), 256, 0, st>>>(X, ldx, rows, K, ozaki_kp(K), ns, out, scale);
+    PET_LAUNCH_CHECK();
+    return PET_OK;
+}
+
+// C(M,N) (+)= A . B^T from pre-sliced operands (slice rows Kp bytes apart, Kp a multiple of 64).  ns in {6, 7}.
+// splits > 1: split s covers an equal share of the K blocks and writes C + s * split_stride.
+int ozaki_gemm(int64_t M, int64_t N, int Kp, int ns, const int8_t *Asl, const double *sA, const int8_t *Bsl, const double *sB,
+               double *C, int64_t ldc, int splits, int64_t split_stride, bool accumulate, int sm_count, cudaStream_t st) {
+    if (M <= 0 || N <= 0) return PET_OK;
+    if ((ldc & 1) || (split_stride & 1) || (reinterpret_cast<uintptr_t>(C) & 15)) {
+        set_error("ozaki_gemm: C must be 16-byte aligned with even ldc");
+        return PET_EINVAL;
+    }
+    if (Kp <= 0 || Kp % oz::KB) { set_error("ozaki_gemm: padded K must be a positive multiple of %d", oz::KB); return PET_EINVAL; }
+    const int kblocks = Kp / oz::KB;
+    if (splits < 1) splits = 1;
+    if (splits > kblocks) splits = kblocks;
+    const int kbs = int(ceil_div(kblocks, splits));
+    splits = int(ceil_div(kblocks, kbs));                  // no empty split
+    if (int64_t(kbs) * oz::KB * ns * 4096 >= (int64_t(1) << 31)) {
+        set_error("ozaki_gemm: %d K elements per split overflow the int32 accumulators", kbs * oz::KB);
+        return PET_EINVAL;
+    }
+    CUtensorMap mapA, mapB;
+    PET_CHECK(oz::make_map(&mapA, Asl, M, Kp, ns, oz::BM));
+    PET_CHECK(oz::make_map(&mapB, Bsl, N, Kp, ns, oz::BN));
+    oz::Args a{M, N, kblocks, splits, kbs, accumulate ? 1 : 0, sA, sB, C, ldc, split_stride};
+    const int64_t units = ceil_div(M, oz::BM) * ceil_div(N, oz::BN) * splits;
+    const unsigned grid = (unsigned)std::min<int64_t>(units, sm_count);
+    if (ns == 7) {
+        constexpr int ST = 2;
+        const size_t smem = size_t(ST) * 7 * (oz::BM + oz::BN) * oz::KB + 1024 + 256;
+        static bool cfg = false;
+        if (!cfg) { PET_CUDA(cudaFuncSetAttribute(oz::gemm_kernel<7, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem))); cfg = true; }
+        oz::gemm_kernel<7, ST><<<grid, oz::THREADS, smem, st>>>(mapA, mapB, a);
+    } else if (ns == 6) {
+        constexpr int ST = 3;
+        const size_t smem = size_t(ST) * 6 * (oz::BM + oz::BN) * oz::KB + 1024 + 256;
+        static bool cfg = false;
+        if (!cfg) { PET_CUDA(cudaFuncSetAttribute(oz::gemm_kernel<6, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem))); cfg = true; }
+        oz::gemm_kernel<6, ST><<<grid, oz::THREADS, smem, st>>>(mapA, mapB, a);
+    } else {
+        set_error("ozaki_gemm: ns must be 6 or 7");
+        return PET_EINVAL;
+    }
+    PET_LAUNCH_CHECK();
+    return PET_OK;
+}
+
+}  // namespace pet
+
+// Test / benchmark entry: slices both operands (workspace from cudaMalloc) and multiplies.
+extern "C" int pet_ozaki_gemm_kk(int64_t M, int64_t N, int64_t K, const double *A_dev, int64_t lda, const double *B_dev,
+                                 int64_t ldb, double *C_dev, int64_t ldc, int32_t nslices, int32_t repeat, void *stream) {
+    using namespace pet;
+    cudaStream_t st = (cudaStream_t)stream;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int Kp = ozaki_kp((int)K);
+    int8_t *As = nullptr, *Bs = nullptr;
+    double *sA = nullptr, *sB = nullptr;
+    PET_CUDA(cudaMalloc(&As, size_t(nslices) * M * Kp));
+    PET_CUDA(cudaMalloc(&Bs, size_t(nslices) * N * Kp));
+    PET_CUDA(cudaMalloc(&sA, M * 8));
+    PET_CUDA(cudaMalloc(&sB, N * 8));
+    int rc = ozaki_slice_rows(A_dev, lda, M, (int)K, nslices, As, sA, st);
+    if (rc == PET_OK) rc = ozaki_slice_rows(B_dev, ldb, N, (int)K, nslices, Bs, sB, st);
+    for (int r = 0; rc == PET_OK && r < (repeat > 0 ? repeat : 1); ++r)
+        rc = ozaki_gemm(M, N, Kp, nslices, As, sA, Bs, sB, C_dev, ldc, 1, 0, false, sms, st);
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (rc == PET_OK && e != cudaSuccess) { set_error("ozaki gemm failed: %s", cudaGetErrorString(e)); rc = PET_ECUDA; }
+    cudaFree(As); cudaFree(Bs); cudaFree(sA); cudaFree(sB);
+    return rc;
+}
