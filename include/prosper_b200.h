@@ -229,6 +229,13 @@ int  pet_dgemm_mn(int64_t M, int64_t N, int64_t K, const double *A_dev, int64_t 
 int  pet_ozaki_gemm_kk(int64_t M, int64_t N, int64_t K, const double *A_dev, int64_t lda,
                        const double *B_dev, int64_t ldb, double *C_dev, int64_t ldc,
                        int32_t nslices, int32_t repeat, void *stream);
+/* Same arithmetic for C(M,N) = A^T.B with A (K,M) lda, B (K,N) ldb (reduction over rows,
+ * as pet_dgemm_mn): column-wise slicing with a transposing store, split-K inside. */
+int  pet_ozaki_gemm_mn(int64_t M, int64_t N, int64_t K, const double *A_dev, int64_t lda,
+                       const double *B_dev, int64_t ldb, double *C_dev, int64_t ldc,
+                       int32_t nslices, int32_t repeat, void *stream);
+/* milliseconds per product of the last pet_ozaki_gemm_* call (events around the repeat loop) */
+double pet_ozaki_last_ms(void);
 /* Solve X.A = B for X with A (n,n) symmetric positive semi-definite (pivots below
  * tol are dropped, giving the minimum-norm behaviour of lstsq for dead units).
  * A is overwritten by its Cholesky factor; B (m,n) overwritten by X. Synchronises. */

@@ -89,6 +89,9 @@ SIGNATURES = {
                                C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p]),
     "pet_ozaki_gemm_kk": (C.c_int, [C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
                                     C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p]),
+    "pet_ozaki_gemm_mn": (C.c_int, [C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
+                                    C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p]),
+    "pet_ozaki_last_ms": (C.c_double, []),
     "pet_spd_solve_right": (C.c_int, [C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
                                       C.c_void_p, C.POINTER(C.c_int32), C.c_void_p]),
     "pet_spd_solve_work_doubles": (C.c_int64, [C.c_int64, C.c_int64]),

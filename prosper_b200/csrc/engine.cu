@@ -3,6 +3,7 @@
 // -> (all-reduce by the caller) -> solve.   See include/prosper_b200.h for the contract.
 #include <math.h>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -12,6 +13,7 @@
 #include "gl_kernel.cuh"
 #include "mca_kernel.cuh"
 #include "gsc_kernel.cuh"
+#include "ozaki.cuh"
 
 namespace pet {
 
@@ -133,6 +135,12 @@ struct pet_engine {
     unsigned long long *d_states = nullptr; unsigned short *d_entries = nullptr, *d_chunk = nullptr; unsigned int *d_direct = nullptr;
     int *d_single = nullptr; double *d_state_prior = nullptr;
 
+    // int8-sliced operands of the two large GEMMs (ozaki.cu); oz_on = buffers present and the path selected
+    bool oz_want = false, oz_on = false; int oz_ns = 7, oz_kpd = 0, oz_splits = 1; int64_t oz_rows = 0;
+    int8_t *ozY = nullptr, *ozYT = nullptr, *ozW = nullptr, *ozS = nullptr;
+    double *ozYs = nullptr, *ozYTs = nullptr, *ozWs = nullptr, *ozSs = nullptr, *oz_slabs = nullptr;
+    unsigned long long *oz_colmax = nullptr;
+
     cudaStream_t copy_stream = nullptr;
     std::vector<cudaEvent_t> chunk_ready; bool upload_pending = false;
     cudaEvent_t compute_done = nullptr; bool compute_done_valid = false;
@@ -169,6 +177,8 @@ extern "C" void pet_destroy(pet_engine *e) {
     free_dev(e->stage_logpj); free_dev(e->stage_i64); free_dev(e->ksel_state);
     free_dev(e->Wl); free_dev(e->Wr); free_dev(e->simbuf);
     free_dev(e->Wt2); free_dev(e->gsc_tab); free_dev(e->psi_dev); free_dev(e->bdiag); free_dev(e->XSZ); free_dev(e->SZ2); free_dev(e->yyw); free_dev(e->dst_dev);
+    free_dev(e->ozY); free_dev(e->ozYT); free_dev(e->ozW); free_dev(e->ozS); free_dev(e->ozYs); free_dev(e->ozYTs);
+    free_dev(e->ozWs); free_dev(e->ozSs); free_dev(e->oz_slabs); free_dev(e->oz_colmax);
     free_dev(e->d_states); free_dev(e->d_entries); free_dev(e->d_chunk); free_dev(e->d_direct); free_dev(e->d_single); free_dev(e->d_state_prior);
     for (auto ev : e->chunk_ready) cudaEventDestroy(ev);
     for (auto ev : e->timer.pool) cudaEventDestroy(ev);
@@ -328,6 +338,22 @@ extern "C" int pet_create(const pet_config *cfg, pet_engine **out) {
         int64_t need = int64_t(sp) * e->H * e->ldH;
         if (need > e->gemm_work_doubles) { free_dev(e->gemm_work); e->gemm_work = nullptr; TRY(dev_alloc(&e->gemm_work, need)); e->gemm_work_doubles = need; }
     }
+    if (e->model == PET_MODEL_BSC || e->model == PET_MODEL_TSC || e->model == PET_MODEL_DSC) {
+        // score and statistics GEMMs on the int8 tensor cores (PET_OZAKI=0 keeps the FP64 DMMA kernels)
+        const char *env = getenv("PET_OZAKI"), *envs = getenv("PET_OZAKI_SLICES");
+        e->oz_want = !(env && atoi(env) == 0);
+        e->oz_ns = (envs && atoi(envs) == 6) ? 6 : 7;
+        if (e->oz_want) {
+            e->oz_kpd = ozaki_kp(e->D);
+            e->oz_splits = ozaki_splits(e->D + 1, e->H, ozaki_kp(e->chunk_rows), e->sm_count);
+            TRY(dev_alloc(&e->ozW, (int64_t)e->oz_ns * e->H * e->oz_kpd));
+            TRY(dev_alloc(&e->ozWs, e->ldH));
+            TRY(dev_alloc(&e->ozS, (int64_t)e->oz_ns * e->H * e->chunk_rows));
+            TRY(dev_alloc(&e->ozSs, e->ldH));
+            TRY(dev_alloc(&e->oz_colmax, std::max<int64_t>(e->ldH, e->ldY)));
+            TRY(dev_alloc(&e->oz_slabs, (int64_t)e->oz_splits * (e->D + 1) * e->ldH));
+        }
+    }
     TRY(dev_alloc(&e->solveA, (int64_t)e->H * e->ldH));
     TRY(dev_alloc(&e->solveB, (int64_t)e->D * e->ldH));
     TRY(dev_alloc(&e->solve_work, spd_solve_work_doubles(e->H, e->ldH)));
@@ -390,6 +416,25 @@ static int ensure_rows(pet_engine *e, int64_t n) {
     e->yw_rows = e->yw_all ? n : std::min<int64_t>(n, e->chunk_rows);
     PET_CHECK(dev_alloc(&e->YW, e->yw_rows * e->ldH));
     e->n_cap = n;
+    free_dev(e->ozY); free_dev(e->ozYT); free_dev(e->ozYs); free_dev(e->ozYTs);
+    e->ozY = e->ozYT = nullptr; e->ozYs = e->ozYTs = nullptr;
+    e->oz_on = false;
+    if (e->oz_want) {
+        // row slices (score GEMM) and per-chunk transposed column slices (statistics GEMM) of the shard;
+        // without room for them the FP64 kernels take over
+        const int64_t nchunks = ceil_div(n, e->chunk_rows);
+        const int64_t b1 = (int64_t)e->oz_ns * n * e->oz_kpd, b2 = (int64_t)e->oz_ns * nchunks * (e->D + 1) * e->chunk_rows;
+        cudaMemGetInfo(&free_b, &total_b);
+        if (b1 + b2 + (int64_t(1) << 30) < (int64_t)free_b &&
+            dev_alloc(&e->ozY, b1) == PET_OK && dev_alloc(&e->ozYT, b2) == PET_OK &&
+            dev_alloc(&e->ozYs, n) == PET_OK && dev_alloc(&e->ozYTs, nchunks * e->ldY) == PET_OK) {
+            e->oz_on = true;
+            e->oz_rows = n;
+        } else {
+            free_dev(e->ozY); free_dev(e->ozYT); free_dev(e->ozYs); free_dev(e->ozYTs);
+            e->ozY = e->ozYT = nullptr; e->ozYs = e->ozYTs = nullptr;
+        }
+    }
     return PET_OK;
 }
 
@@ -471,6 +516,8 @@ static int prepare(pet_engine *e, const pet_params *p, cudaStream_t st) {
     // G = W^T W  (H,H); its diagonal gives ||W_h||^2 (bsc_et.py:111 recomputes this per datapoint)
     PET_CHECK(dgemm_kk(e->H, e->H, e->D, e->Wt, e->ldY, e->Wt, e->ldY, e->G, e->ldH, 1.0, 0, st));
     PET_CHECK(launch_gram_diag(e->G, e->ldH, e->H, e->wn2, e->invn, st));
+    if (e->oz_on)
+        PET_CHECK(ozaki_slice_rows(e->Wt, e->ldY, e->H, e->D, e->oz_ns, e->ozW, (int64_t)e->H * e->oz_kpd, e->ozWs, st));
     e->timer.end(st);
     return PET_OK;
 }
@@ -510,7 +557,16 @@ static int fill_iter(const pet_engine *e, const pet_anneal *a, const pet_params 
 
 static int ensure_chunk_inputs(pet_engine *e, int64_t c, int64_t r0, int64_t rows, cudaStream_t st) {
     if (e->upload_pending) PET_CUDA(cudaStreamWaitEvent(st, e->chunk_ready[c], 0));
-    if (!e->yy_valid) PET_CHECK(launch_rownorm_pad(e->Y + r0 * e->ldY, e->ldY, rows, e->D, e->yy + r0, st));
+    if (!e->yy_valid) {
+        PET_CHECK(launch_rownorm_pad(e->Y + r0 * e->ldY, e->ldY, rows, e->D, e->yy + r0, st));
+        if (e->oz_on) {
+            PET_CHECK(ozaki_slice_rows(e->Y + r0 * e->ldY, e->ldY, rows, e->D, e->oz_ns, e->ozY + r0 * e->oz_kpd,
+                                       e->oz_rows * e->oz_kpd, e->ozYs + r0, st));
+            const int64_t plane = (int64_t)(e->D + 1) * e->chunk_rows;
+            PET_CHECK(ozaki_slice_cols(e->Y + r0 * e->ldY, e->ldY, rows, e->D + 1, e->oz_ns, e->oz_colmax,
+                                       e->ozYT + c * e->oz_ns * plane, e->chunk_rows, plane, e->ozYTs + c * e->ldY, st));
+        }
+    }
     return PET_OK;
 }
 
@@ -549,6 +605,7 @@ static int sweep_gl(pet_engine *e, const pet_anneal *a, const pet_params *p, int
         ga.Wq = stats_dev + lay.off_Wq;
         ga.scalars = stats_dev + lay.off_scalars;
         if (e->S2buf) PET_CUDA(cudaMemsetAsync(e->s2sum, 0, e->ldH * 8, st));
+        if (e->oz_on) PET_CUDA(cudaMemsetAsync(e->oz_slabs, 0, (int64_t)e->oz_splits * (e->D + 1) * e->ldH * 8, st));
     }
     const bool user_logpj = (kflags & (GLF_READ_LOGPJ | GLF_WRITE_LOGPJ)) != 0;
     const bool logpj_on_dev = user_logpj && is_device_ptr(logpj_user);
@@ -568,7 +625,13 @@ static int sweep_gl(pet_engine *e, const pet_anneal *a, const pet_params *p, int
         double *yw = e->yw_all ? e->YW + r0 * e->ldH : e->YW;
         if (!reuse) {
             e->timer.begin(ST_SCORE, st);
-            PET_CHECK(dgemm_kk(rows, e->H, e->D, e->Y + r0 * e->ldY, e->ldY, e->Wt, e->ldY, yw, e->ldH, 1.0, 0, st));
+            if (e->oz_on) {
+                const OzOperand oy{e->ozY + r0 * e->oz_kpd, e->oz_kpd, e->oz_rows * e->oz_kpd, e->ozYs + r0};
+                const OzOperand ow{e->ozW, e->oz_kpd, (int64_t)e->H * e->oz_kpd, e->ozWs};
+                PET_CHECK(ozaki_gemm(rows, e->H, e->oz_kpd, e->oz_ns, oy, ow, yw, e->ldH, 1, 0, false, e->sm_count, st));
+            } else {
+                PET_CHECK(dgemm_kk(rows, e->H, e->D, e->Y + r0 * e->ldY, e->ldY, e->Wt, e->ldY, yw, e->ldH, 1.0, 0, st));
+            }
             e->timer.end(st);
         }
         ga.n_rows = rows; ga.row0 = r0; ga.YW = yw; ga.S = e->Sbuf; ga.S2 = e->S2buf;
@@ -597,14 +660,26 @@ static int sweep_gl(pet_engine *e, const pet_anneal *a, const pet_params *p, int
         if (do_stats) {
             e->timer.begin(ST_STATS, st);
             // Wp^T (D+1, H) += Y_chunk^T . <S>_chunk ; row D (all-ones column of Y) = sum_n <s>
-            PET_CHECK(dgemm_mn(e->D + 1, e->H, rows, e->Y + r0 * e->ldY, e->ldY, e->Sbuf, e->ldH,
-                               stats_dev + lay.off_Wp, e->ldH, 1, e->gemm_work, e->gemm_work_doubles, e->sm_count, st));
+            if (e->oz_on) {
+                const int64_t plane = (int64_t)(e->D + 1) * e->chunk_rows, wp = (int64_t)(e->D + 1) * e->ldH;
+                PET_CHECK(ozaki_slice_cols(e->Sbuf, e->ldH, rows, e->H, e->oz_ns, e->oz_colmax, e->ozS, e->chunk_rows,
+                                           (int64_t)e->H * e->chunk_rows, e->ozSs, st));
+                const OzOperand oy{e->ozYT + c * e->oz_ns * plane, e->chunk_rows, plane, e->ozYTs + c * e->ldY};
+                const OzOperand os{e->ozS, e->chunk_rows, (int64_t)e->H * e->chunk_rows, e->ozSs};
+                PET_CHECK(ozaki_gemm(e->D + 1, e->H, ozaki_kp(rows), e->oz_ns, oy, os, e->oz_slabs, e->ldH, e->oz_splits, wp,
+                                     true, e->sm_count, st));
+            } else {
+                PET_CHECK(dgemm_mn(e->D + 1, e->H, rows, e->Y + r0 * e->ldY, e->ldY, e->Sbuf, e->ldH,
+                                   stats_dev + lay.off_Wp, e->ldH, 1, e->gemm_work, e->gemm_work_doubles, e->sm_count, st));
+            }
             if (e->S2buf) PET_CHECK(launch_colsum(e->s2sum, e->S2buf, e->ldH, rows, e->H, st));
             e->timer.end(st);
         }
     }
     e->yy_valid = true;
     if (kflags & GLF_SELECT) e->cand_state = 1;
+    if (do_stats && e->oz_on)   // Wp^T = sum of the split-K slabs
+        PET_CHECK(ozaki_add_slabs(stats_dev + lay.off_Wp, e->oz_slabs, (int64_t)(e->D + 1) * e->ldH, e->oz_splits, st));
     if (do_stats && e->S2buf)   // DSC: singleton second moments onto the diagonal (dsc_et.py:701)
         PET_CHECK(launch_add_diag(stats_dev + lay.off_Wq, e->ldH, e->s2sum, e->H, st));
     mark_compute_done(e, st);

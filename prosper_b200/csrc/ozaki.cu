@@ -17,7 +17,10 @@
 #include <cuda.h>
 #include <math.h>
 
+#include <algorithm>
+
 #include "common.cuh"
+#include "ozaki.cuh"
 
 namespace pet {
 
@@ -270,7 +273,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_kernel(const __grid_constant_
 // One warp per row: power-of-two scale and NS int8 slices (first slice 6 bits + sign, the rest 7 bits + sign,
 // round to nearest so every slice is in [-64, 64]).  out: [NS][rows][Kp] int8, zero padded in k.
 __global__ void slice_rows_kernel(const double *X, int64_t ldx, int64_t rows, int K, int Kp, int ns, int8_t *out,
-                                  double *scale) {
+                                  int64_t slice_stride, double *scale) {
     const int64_t row = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (row >= rows) return;
@@ -282,7 +285,6 @@ __global__ void slice_rows_kernel(const double *X, int64_t ldx, int64_t rows, in
     if (mx > 0.0) frexp(mx, &e);                   // mx = m * 2^e, m in [0.5, 1)  ->  |x| / 2^e < 1
     if (lane == 0) scale[row] = ldexp(1.0, e);
     const double s0 = ldexp(64.0, -e);
-    const int64_t slice_stride = rows * int64_t(Kp);
     for (int k = lane; k < Kp; k += 32) {
         double r = (k < K) ? x[k] * s0 : 0.0;
         int8_t *o = out + row * int64_t(Kp) + k;
@@ -310,12 +312,17 @@ static EncodeTiledFn get_encode() {
     return fn;
 }
 
-// slices: [ns][rows][Kp] int8
-static int make_map(CUtensorMap *map, const int8_t *slices, int64_t rows, int Kp, int ns, int box_rows) {
+// slices: ns planes of (rows, Kp) int8, rows `row_stride` bytes apart, planes `slice_stride` bytes apart
+static int make_map(CUtensorMap *map, const int8_t *slices, int64_t rows, int Kp, int64_t row_stride, int64_t slice_stride,
+                    int ns, int box_rows) {
     EncodeTiledFn enc = get_encode();
     if (!enc) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return PET_ECUDA; }
+    if ((row_stride & 15) || (slice_stride & 15) || (reinterpret_cast<uintptr_t>(slices) & 15)) {
+        set_error("ozaki_gemm: slice planes must be 16-byte aligned");
+        return PET_EINVAL;
+    }
     cuuint64_t dims[3] = {(cuuint64_t)Kp, (cuuint64_t)rows, (cuuint64_t)ns};
-    cuuint64_t strides[2] = {(cuuint64_t)Kp, (cuuint64_t)Kp * (cuuint64_t)rows};
+    cuuint64_t strides[2] = {(cuuint64_t)row_stride, (cuuint64_t)slice_stride};
     cuuint32_t box[3] = {(cuuint32_t)KB, (cuuint32_t)box_rows, 1};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<int8_t *>(slices), dims, strides, box, estr,
@@ -324,21 +331,129 @@ static int make_map(CUtensorMap *map, const int8_t *slices, int64_t rows, int Kp
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", int(r)); return PET_ECUDA; }
     return PET_OK;
 }
+
+// ---- column-wise slicing with a transposing store (operands whose reduction runs over ROWS) -------------------
+// max |X[r][c]| over r, as the bit pattern of a non-negative double (monotonic under integer max)
+__global__ void col_absmax_kernel(const double *X, int64_t ldx, int64_t rows, int cols, unsigned long long *out) {
+    __shared__ double red[8][33];
+    const int c = blockIdx.x * 32 + threadIdx.x;
+    const int64_t r_per = (rows + gridDim.y - 1) / gridDim.y;
+    const int64_t r0 = blockIdx.y * r_per, r1 = min(rows, r0 + r_per);
+    double m = 0.0;
+    if (c < cols)
+        for (int64_t r = r0 + threadIdx.y; r < r1; r += 8) m = fmax(m, fabs(X[r * ldx + c]));
+    red[threadIdx.y][threadIdx.x] = m;
+    __syncthreads();
+    if (threadIdx.y == 0 && c < cols) {
+        for (int j = 1; j < 8; ++j) m = fmax(m, red[j][threadIdx.x]);
+        atomicMax(out + c, (unsigned long long)__double_as_longlong(m));
+    }
+}
+
+// X (rows, cols) -> out[t][c][r] int8 for r < Kp (zero for r >= rows), column scale 2^e from the column maximum.
+// CTA tile: 128 rows x 32 columns, staged through shared memory so that both sides are coalesced.
+constexpr int SC_R = 128, SC_C = 32, SC_PITCH = SC_R + 4;
+__global__ void __launch_bounds__(256) slice_cols_kernel(const double *X, int64_t ldx, int64_t rows, int cols, int Kp,
+                                                         const unsigned long long *colmax, int ns, int8_t *out,
+                                                         int64_t row_stride, int64_t slice_stride, double *scale) {
+    extern __shared__ int8_t tile[];                  // [ns][SC_C][SC_PITCH]
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int c = blockIdx.x * SC_C + tx;
+    const int64_t r0 = int64_t(blockIdx.y) * SC_R;
+    double s0 = 0.0;
+    if (c < cols) {
+        const double mx = __longlong_as_double((long long)colmax[c]);
+        int e = 0;
+        if (mx > 0.0) frexp(mx, &e);
+        s0 = ldexp(64.0, -e);
+        if (blockIdx.y == 0 && ty == 0) scale[c] = ldexp(1.0, e);
+    }
+    for (int j = ty; j < SC_R; j += 8) {
+        const int64_t r = r0 + j;
+        double v = (c < cols && r < rows) ? X[r * ldx + c] * s0 : 0.0;
+        for (int t = 0; t < ns; ++t) {
+            double q = rint(v);
+            tile[(t * SC_C + tx) * SC_PITCH + j] = (int8_t)q;
+            v = (v - q) * 128.0;
+        }
+    }
+    __syncthreads();
+    // one warp stores one (slice, column) row of 128 bytes per step
+    const int n_rows_out = ns * SC_C;
+    for (int ro = ty; ro < n_rows_out; ro += 8) {
+        const int t = ro / SC_C, cc = ro % SC_C;
+        const int col = blockIdx.x * SC_C + cc;
+        const int64_t r = r0 + tx * 4;
+        if (col < cols && r < Kp) {
+            const int32_t w = *reinterpret_cast<const int32_t *>(&tile[(t * SC_C + cc) * SC_PITCH + tx * 4]);
+            *reinterpret_cast<int32_t *>(out + t * slice_stride + col * row_stride + r) = w;
+        }
+    }
+}
+
+__global__ void add_slabs_kernel(double *dst, const double *slabs, int64_t count, int n_slabs) {
+    const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    double v = dst[i];
+    for (int s = 0; s < n_slabs; ++s) v += slabs[s * count + i];
+    dst[i] = v;
+}
 }  // namespace oz
 
-int ozaki_kp(int K) { return int(round_up(K, oz::KB)); }
+int ozaki_kp(int64_t K) { return int(round_up(K, oz::KB)); }
 
-int ozaki_slice_rows(const double *X, int64_t ldx, int64_t rows, int K, int ns, int8_t *out, double *scale, cudaStream_t st) {
+// split-K factor for an (M, N, Kp) product: whole waves of (tile, split) units, each unit paying a fixed epilogue
+int ozaki_splits(int64_t M, int64_t N, int Kp, int sm_count) {
+    const int64_t tiles = ceil_div(M, oz::BM) * ceil_div(N, oz::BN);
+    const int kblocks = Kp / oz::KB;
+    int best = 1;
+    double best_cost = 1e300;
+    for (int s = 1; s <= 16 && s <= kblocks; ++s) {
+        const int kbs = int(ceil_div(kblocks, s));
+        if (kbs < 16 && s > 1) break;
+        const double waves = double(ceil_div(tiles * ceil_div(kblocks, kbs), sm_count));
+        const double cost = waves * (kbs + 3.0);
+        if (cost < best_cost * 0.999) { best_cost = cost; best = s; }
+    }
+    return best;
+}
+
+// X (rows, cols) row-major -> transposed slices out[t][c][r] with per-column scales (colmax: cols scratch words)
+int ozaki_slice_cols(const double *X, int64_t ldx, int64_t rows, int cols, int ns, unsigned long long *colmax, int8_t *out,
+                     int64_t row_stride, int64_t slice_stride, double *scale, cudaStream_t st) {
+    if (rows <= 0 || cols <= 0) return PET_OK;
+    const int Kp = ozaki_kp(rows);
+    PET_CUDA(cudaMemsetAsync(colmax, 0, size_t(cols) * 8, st));
+    dim3 g1((unsigned)ceil_div(cols, 32), (unsigned)std::min<int64_t>(ceil_div(rows, 256), 64));
+    oz::col_absmax_kernel<<<g1, dim3(32, 8), 0, st>>>(X, ldx, rows, cols, colmax);
+    PET_LAUNCH_CHECK();
+    dim3 g2((unsigned)ceil_div(cols, oz::SC_C), (unsigned)ceil_div(Kp, oz::SC_R));
+    const size_t smem = size_t(ns) * oz::SC_C * oz::SC_PITCH;
+    oz::slice_cols_kernel<<<g2, 256, smem, st>>>(X, ldx, rows, cols, Kp, colmax, ns, out, row_stride, slice_stride, scale);
+    PET_LAUNCH_CHECK();
+    return PET_OK;
+}
+
+int ozaki_add_slabs(double *dst, const double *slabs, int64_t count, int n_slabs, cudaStream_t st) {
+    if (n_slabs <= 0 || count <= 0) return PET_OK;
+    oz::add_slabs_kernel<<<(unsigned)ceil_div(count, 256), 256, 0, st>>>(dst, slabs, count, n_slabs);
+    PET_LAUNCH_CHECK();
+    return PET_OK;
+}
+
+// X (rows, K) row-major -> slices out[t][r][k] (rows Kp bytes apart, planes slice_stride bytes apart), per-row scales
+int ozaki_slice_rows(const double *X, int64_t ldx, int64_t rows, int K, int ns, int8_t *out, int64_t slice_stride, double *scale,
+                     cudaStream_t st) {
     if (rows <= 0) return PET_OK;
-    oz::slice_rows_kernel<<<(unsigned)ceil_div(rows * 32, 256), 256, 0, st>>>(X, ldx, rows, K, ozaki_kp(K), ns, out, scale);
+    oz::slice_rows_kernel<<<(unsigned)ceil_div(rows * 32, 256), 256, 0, st>>>(X, ldx, rows, K, ozaki_kp(K), ns, out, slice_stride, scale);
     PET_LAUNCH_CHECK();
     return PET_OK;
 }
 
 // C(M,N) (+)= A . B^T from pre-sliced operands (slice rows Kp bytes apart, Kp a multiple of 64).  ns in {6, 7}.
 // splits > 1: split s covers an equal share of the K blocks and writes C + s * split_stride.
-int ozaki_gemm(int64_t M, int64_t N, int Kp, int ns, const int8_t *Asl, const double *sA, const int8_t *Bsl, const double *sB,
-               double *C, int64_t ldc, int splits, int64_t split_stride, bool accumulate, int sm_count, cudaStream_t st) {
+int ozaki_gemm(int64_t M, int64_t N, int Kp, int ns, const OzOperand &A, const OzOperand &B, double *C, int64_t ldc, int splits,
+               int64_t split_stride, bool accumulate, int sm_count, cudaStream_t st) {
     if (M <= 0 || N <= 0) return PET_OK;
     if ((ldc & 1) || (split_stride & 1) || (reinterpret_cast<uintptr_t>(C) & 15)) {
         set_error("ozaki_gemm: C must be 16-byte aligned with even ldc");
@@ -355,9 +470,9 @@ int ozaki_gemm(int64_t M, int64_t N, int Kp, int ns, const int8_t *Asl, const do
         return PET_EINVAL;
     }
     CUtensorMap mapA, mapB;
-    PET_CHECK(oz::make_map(&mapA, Asl, M, Kp, ns, oz::BM));
-    PET_CHECK(oz::make_map(&mapB, Bsl, N, Kp, ns, oz::BN));
-    oz::Args a{M, N, kblocks, splits, kbs, accumulate ? 1 : 0, sA, sB, C, ldc, split_stride};
+    PET_CHECK(oz::make_map(&mapA, A.slices, M, Kp, A.row_stride, A.slice_stride, ns, oz::BM));
+    PET_CHECK(oz::make_map(&mapB, B.slices, N, Kp, B.row_stride, B.slice_stride, ns, oz::BN));
+    oz::Args a{M, N, kblocks, splits, kbs, accumulate ? 1 : 0, A.scale, B.scale, C, ldc, split_stride};
     const int64_t units = ceil_div(M, oz::BM) * ceil_div(N, oz::BN) * splits;
     const unsigned grid = (unsigned)std::min<int64_t>(units, sm_count);
     if (ns == 7) {
@@ -382,6 +497,10 @@ int ozaki_gemm(int64_t M, int64_t N, int Kp, int ns, const int8_t *Asl, const do
 
 }  // namespace pet
 
+static double g_oz_last_ms = 0.0;
+/* milliseconds per product of the last pet_ozaki_gemm_* call (CUDA events around the `repeat` loop, slicing excluded) */
+extern "C" double pet_ozaki_last_ms(void) { return g_oz_last_ms; }
+
 // Test / benchmark entry: slices both operands (workspace from cudaMalloc) and multiplies.
 extern "C" int pet_ozaki_gemm_kk(int64_t M, int64_t N, int64_t K, const double *A_dev, int64_t lda, const double *B_dev,
                                  int64_t ldb, double *C_dev, int64_t ldc, int32_t nslices, int32_t repeat, void *stream) {
@@ -397,12 +516,62 @@ extern "C" int pet_ozaki_gemm_kk(int64_t M, int64_t N, int64_t K, const double *
     PET_CUDA(cudaMalloc(&Bs, size_t(nslices) * N * Kp));
     PET_CUDA(cudaMalloc(&sA, M * 8));
     PET_CUDA(cudaMalloc(&sB, N * 8));
-    int rc = ozaki_slice_rows(A_dev, lda, M, (int)K, nslices, As, sA, st);
-    if (rc == PET_OK) rc = ozaki_slice_rows(B_dev, ldb, N, (int)K, nslices, Bs, sB, st);
+    int rc = ozaki_slice_rows(A_dev, lda, M, (int)K, nslices, As, M * int64_t(Kp), sA, st);
+    if (rc == PET_OK) rc = ozaki_slice_rows(B_dev, ldb, N, (int)K, nslices, Bs, N * int64_t(Kp), sB, st);
+    const OzOperand opA{As, Kp, M * int64_t(Kp), sA}, opB{Bs, Kp, N * int64_t(Kp), sB};
+    cudaEvent_t ev0, ev1;
+    cudaEventCreate(&ev0); cudaEventCreate(&ev1);
+    cudaEventRecord(ev0, st);
     for (int r = 0; rc == PET_OK && r < (repeat > 0 ? repeat : 1); ++r)
-        rc = ozaki_gemm(M, N, Kp, nslices, As, sA, Bs, sB, C_dev, ldc, 1, 0, false, sms, st);
+        rc = ozaki_gemm(M, N, Kp, nslices, opA, opB, C_dev, ldc, 1, 0, false, sms, st);
+    cudaEventRecord(ev1, st);
     cudaError_t e = cudaStreamSynchronize(st);
+    float ms = 0.f;
+    if (e == cudaSuccess) { cudaEventElapsedTime(&ms, ev0, ev1); g_oz_last_ms = ms / (repeat > 0 ? repeat : 1); }
+    cudaEventDestroy(ev0); cudaEventDestroy(ev1);
     if (rc == PET_OK && e != cudaSuccess) { set_error("ozaki gemm failed: %s", cudaGetErrorString(e)); rc = PET_ECUDA; }
     cudaFree(As); cudaFree(Bs); cudaFree(sA); cudaFree(sB);
+    return rc;
+}
+
+// Test / benchmark entry for operands whose reduction runs over rows: C(M,N) = A^T . B, A (K,M) lda, B (K,N) ldb.
+extern "C" int pet_ozaki_gemm_mn(int64_t M, int64_t N, int64_t K, const double *A_dev, int64_t lda, const double *B_dev,
+                                 int64_t ldb, double *C_dev, int64_t ldc, int32_t nslices, int32_t repeat, void *stream) {
+    using namespace pet;
+    cudaStream_t st = (cudaStream_t)stream;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int Kp = ozaki_kp(K);
+    const int splits = ozaki_splits(M, N, Kp, sms);
+    int8_t *As = nullptr, *Bs = nullptr;
+    double *sA = nullptr, *sB = nullptr, *slabs = nullptr;
+    unsigned long long *cm = nullptr;
+    PET_CUDA(cudaMalloc(&As, size_t(nslices) * M * Kp));
+    PET_CUDA(cudaMalloc(&Bs, size_t(nslices) * N * Kp));
+    PET_CUDA(cudaMalloc(&sA, M * 8));
+    PET_CUDA(cudaMalloc(&sB, N * 8));
+    PET_CUDA(cudaMalloc(&cm, std::max(M, N) * 8));
+    PET_CUDA(cudaMalloc(&slabs, size_t(splits) * M * ldc * 8));
+    int rc = ozaki_slice_cols(A_dev, lda, K, (int)M, nslices, cm, As, Kp, M * int64_t(Kp), sA, st);
+    if (rc == PET_OK) rc = ozaki_slice_cols(B_dev, ldb, K, (int)N, nslices, cm, Bs, Kp, N * int64_t(Kp), sB, st);
+    const OzOperand opA{As, Kp, M * int64_t(Kp), sA}, opB{Bs, Kp, N * int64_t(Kp), sB};
+    cudaEvent_t ev0, ev1;
+    cudaEventCreate(&ev0); cudaEventCreate(&ev1);
+    cudaEventRecord(ev0, st);
+    for (int r = 0; rc == PET_OK && r < (repeat > 0 ? repeat : 1); ++r) {
+        rc = ozaki_gemm(M, N, Kp, nslices, opA, opB, slabs, ldc, splits, M * ldc, false, sms, st);
+        if (rc == PET_OK) {
+            cudaMemcpyAsync(C_dev, slabs, size_t(M) * ldc * 8, cudaMemcpyDeviceToDevice, st);
+            rc = ozaki_add_slabs(C_dev, slabs + M * ldc, M * ldc, splits - 1, st);
+        }
+    }
+    cudaEventRecord(ev1, st);
+    cudaError_t e = cudaStreamSynchronize(st);
+    float ms = 0.f;
+    if (e == cudaSuccess) { cudaEventElapsedTime(&ms, ev0, ev1); g_oz_last_ms = ms / (repeat > 0 ? repeat : 1); }
+    cudaEventDestroy(ev0); cudaEventDestroy(ev1);
+    if (rc == PET_OK && e != cudaSuccess) { set_error("ozaki gemm failed: %s", cudaGetErrorString(e)); rc = PET_ECUDA; }
+    cudaFree(As); cudaFree(Bs); cudaFree(sA); cudaFree(sB); cudaFree(cm); cudaFree(slabs);
     return rc;
 }

@@ -30,12 +30,33 @@ for (M, N, K) in shapes:
             int(torch.isnan(Cc[:, :N]).sum())), flush=True)
     if M >= 16384:
         for ns in (6, 7):
-            reps = 100
-            lib.pet_ozaki_gemm_kk(M, N, K, P(A), ld, P(B), ld, P(Cc), ldc, ns, 1, st)
-            torch.cuda.synchronize(); t0 = time.perf_counter()
-            lib.pet_ozaki_gemm_kk(M, N, K, P(A), ld, P(B), ld, P(Cc), ldc, ns, 1, st)
-            torch.cuda.synchronize(); t1 = time.perf_counter()
-            lib.pet_ozaki_gemm_kk(M, N, K, P(A), ld, P(B), ld, P(Cc), ldc, ns, 1 + reps, st)
-            torch.cuda.synchronize(); t2 = time.perf_counter()
-            ms = ((t2 - t1) - (t1 - t0)) * 1e3 / reps
+            lib.pet_ozaki_gemm_kk(M, N, K, P(A), ld, P(B), ld, P(Cc), ldc, ns, 50, st)
+            ms = lib.pet_ozaki_last_ms()
             print("  ns=%d gemm only %.3f ms -> %.1f effective FP64 TFLOP/s" % (ns, ms, 2.0 * M * N * K / ms / 1e9))
+
+# ---- reduction over rows (statistics shape) --------------------------------------------------------------
+shapes = [(5, 3, 7), (100, 70, 300), (677, 1000, 1000), (677, 1000, 16384), (677, 1000, 16001)]
+for (M, N, K) in shapes:
+    lda, ldb, ldc = (M + 1) // 2 * 2, (N + 1) // 2 * 2, (N + 1) // 2 * 2
+    A = torch.randn(K, lda, dtype=torch.float64, device=dev) * torch.exp(2 * torch.randn(1, lda, dtype=torch.float64, device=dev))
+    B = torch.rand(K, ldb, dtype=torch.float64, device=dev) * torch.exp(4 * torch.randn(1, ldb, dtype=torch.float64, device=dev))
+    ref = A[:, :M].T @ B[:, :N]
+    bound = (A[:, :M].abs().amax(0)[:, None] * B[:, :N].abs().amax(0)[None, :]) * K
+    for ns in (6, 7):
+        Cc = torch.full((M, ldc), float('nan'), dtype=torch.float64, device=dev)
+        rc = lib.pet_ozaki_gemm_mn(M, N, K, P(A), lda, P(B), ldb, P(Cc), ldc, ns, 1, st)
+        if rc != 0:
+            print("ERR", lib.pet_last_error()); sys.exit(1)
+        err = (Cc[:, :N] - ref).abs()
+        print("MN %dx%dx%d ns=%d max abs err %.2e  rel to max|C| %.2e  rel to K*amax*bmax %.2e nan %d" % (
+            M, N, K, ns, float(err.max()), float(err.max() / ref.abs().max()), float((err / bound).max()),
+            int(torch.isnan(Cc[:, :N]).sum())), flush=True)
+    if K >= 16384:
+        for ns in (6, 7):
+            torch.cuda.synchronize(); t0 = time.perf_counter()
+            lib.pet_ozaki_gemm_mn(M, N, K, P(A), lda, P(B), ldb, P(Cc), ldc, ns, 1, st)
+            torch.cuda.synchronize(); t1 = time.perf_counter()
+            lib.pet_ozaki_gemm_mn(M, N, K, P(A), lda, P(B), ldb, P(Cc), ldc, ns, 50, st)
+            ms = lib.pet_ozaki_last_ms()
+            print("  ns=%d gemm+reduce %.3f ms -> %.1f effective FP64 TFLOP/s (slicing both operands once: %.3f ms)" % (
+                ns, ms, 2.0 * M * N * K / ms / 1e9, (t1 - t0) * 1e3 - ms))
