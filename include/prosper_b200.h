@@ -107,9 +107,12 @@ int  pet_state_matrix(const pet_engine *e, double *out_host);
 
 /* ---- data ------------------------------------------------------------------------ */
 /* Bind my_data['y'] (n,D).  The engine keeps its own padded device copy (ld rounded up,
- * one extra all-ones column used by the statistics GEMM).  With a host pointer the copy is
- * issued chunk-wise on an internal copy stream and overlaps the compute of earlier chunks;
- * nothing blocks the caller. */
+ * one extra all-ones column used by the statistics GEMM).  With a host pointer (pinned for
+ * full speed) nothing blocks the caller: the shard is uploaded chunk-wise on an internal
+ * copy stream, a few chunks AHEAD of the first pass that consumes it, so the upload
+ * overlaps that pass -- `y` must therefore stay valid and unchanged until the first
+ * operator call after pet_set_data has completed.  Contiguous sources (ld == D) travel as
+ * 1-D copies through staging slots and are padded on the device. */
 int  pet_set_data(pet_engine *e, const double *y, int64_t n, int64_t ld, void *stream);
 int64_t pet_num_data(const pet_engine *e);
 

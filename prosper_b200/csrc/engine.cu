@@ -44,7 +44,7 @@ int kth_largest(const double *vals, int64_t n, int64_t k, double *out, unsigned 
 int launch_transpose_w(double *Wt, int64_t ldk, const double *W, int64_t ldw, int D, int H, cudaStream_t st);
 int launch_gram_diag(const double *G, int64_t ldg, int H, double *wn2, double *invn, cudaStream_t st);
 int launch_subtract_mu(double *Y, int64_t ldy, int64_t n, int D, const double *mu, cudaStream_t st);
-int launch_rownorm_pad(double *Y, int64_t ldy, int64_t n, int D, double *yy, cudaStream_t st);
+int launch_rownorm_pad(const double *src, int64_t ld_src, double *Y, int64_t ldy, int64_t n, int D, double *yy, cudaStream_t st);
 int launch_cand_to_i64(int64_t *out, const int *in, int64_t count, cudaStream_t st);
 int launch_cand_from_i64(int *out, const int64_t *in, int64_t count, int H, cudaStream_t st);
 int launch_add_diag(double *Wq, int64_t ld, const double *colsum, int H, cudaStream_t st);
@@ -143,6 +143,11 @@ struct pet_engine {
 
     cudaStream_t copy_stream = nullptr;
     std::vector<cudaEvent_t> chunk_ready; bool upload_pending = false;
+    // host shards are uploaded lazily, a few chunks ahead of the sweep that consumes them (so that the small
+    // per-iteration uploads are not queued behind the whole shard on the copy engine); contiguous sources go
+    // through 1-D copies into staging slots (pitched 2-D DMA is ~35% slower) and are expanded on the device
+    const double *up_src = nullptr; int64_t up_ld = 0, up_copied = 0, up_expanded = 0; bool up_staged = false;
+    double *up_slot[3] = {nullptr, nullptr, nullptr}; cudaEvent_t up_free[3] = {nullptr, nullptr, nullptr};
     cudaEvent_t compute_done = nullptr; bool compute_done_valid = false;
     StageTimer timer;
     int64_t launches0 = 0;
@@ -181,6 +186,7 @@ extern "C" void pet_destroy(pet_engine *e) {
     free_dev(e->ozWs); free_dev(e->ozSs); free_dev(e->oz_slabs); free_dev(e->oz_colmax);
     free_dev(e->d_states); free_dev(e->d_entries); free_dev(e->d_chunk); free_dev(e->d_direct); free_dev(e->d_single); free_dev(e->d_state_prior);
     for (auto ev : e->chunk_ready) cudaEventDestroy(ev);
+    for (int i = 0; i < 3; ++i) { free_dev(e->up_slot[i]); if (e->up_free[i]) cudaEventDestroy(e->up_free[i]); }
     for (auto ev : e->timer.pool) cudaEventDestroy(ev);
     if (e->compute_done) cudaEventDestroy(e->compute_done);
     if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
@@ -453,18 +459,25 @@ extern "C" int pet_set_data(pet_engine *e, const double *y, int64_t n, int64_t l
         PET_CUDA(cudaMemcpy2DAsync(e->Y, e->ldY * 8, y, ld * 8, size_t(e->D) * 8, n, cudaMemcpyDeviceToDevice, st));
         e->upload_pending = false;
     } else {
-        // the copy stream must not overwrite Y while earlier kernels still read it
+        // the copy stream must not overwrite Y / the staging slots while earlier kernels still read them
         if (e->compute_done_valid) PET_CUDA(cudaStreamWaitEvent(e->copy_stream, e->compute_done, 0));
         while ((int64_t)e->chunk_ready.size() < nchunks) {
             cudaEvent_t ev;
             PET_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
             e->chunk_ready.push_back(ev);
         }
-        for (int64_t c = 0; c < nchunks; ++c) {
-            int64_t r0 = c * e->chunk_rows, rows = std::min(e->chunk_rows, n - r0);
-            PET_CUDA(cudaMemcpy2DAsync(e->Y + r0 * e->ldY, e->ldY * 8, y + r0 * ld, ld * 8, size_t(e->D) * 8, rows,
-                                       cudaMemcpyHostToDevice, e->copy_stream));
-            PET_CUDA(cudaEventRecord(e->chunk_ready[c], e->copy_stream));
+        e->up_src = y; e->up_ld = ld; e->up_copied = 0; e->up_expanded = 0;
+        e->up_staged = (ld == e->D) && nchunks > 1;
+        if (e->up_staged && !e->up_slot[0]) {
+            for (int i = 0; i < 3 && e->up_staged; ++i) {
+                if (dev_alloc(&e->up_slot[i], e->chunk_rows * e->D) != PET_OK ||
+                    cudaEventCreateWithFlags(&e->up_free[i], cudaEventDisableTiming) != cudaSuccess) {
+                    cudaGetLastError();
+                    e->up_staged = false;          // no room for staging: direct pitched copies
+                }
+            }
+            if (!e->up_staged)
+                for (int i = 0; i < 3; ++i) { free_dev(e->up_slot[i]); e->up_slot[i] = nullptr; }
         }
         e->upload_pending = true;
     }
@@ -485,6 +498,8 @@ static int load_W(pet_engine *e, const pet_params *p, cudaStream_t st) {
     return PET_OK;
 }
 
+static int flush_upload(pet_engine *e, cudaStream_t st);
+
 static int apply_mu(pet_engine *e, const pet_params *p, cudaStream_t st) {
     // BSC only: y - mu (bsc_et.py:169,335,396).  The shard is stored shifted by the mu in force.
     std::vector<double> mu(e->D, 0.0);
@@ -498,9 +513,7 @@ static int apply_mu(pet_engine *e, const pet_params *p, cudaStream_t st) {
     std::vector<double> delta(e->D);
     for (int d = 0; d < e->D; ++d) { delta[d] = mu[d] - e->mu_applied[d]; same &= (delta[d] == 0.0); }
     if (same) return PET_OK;
-    if (e->upload_pending) {   // all chunks must have landed before shifting in place
-        PET_CUDA(cudaStreamWaitEvent(st, e->chunk_ready[ceil_div(e->n, e->chunk_rows) - 1], 0));
-    }
+    PET_CHECK(flush_upload(e, st));   // all chunks must have landed before shifting in place
     PET_CUDA(cudaMemcpyAsync(e->mu_dev, delta.data(), e->D * 8, cudaMemcpyHostToDevice, st));
     PET_CUDA(cudaStreamSynchronize(st));
     PET_CHECK(launch_subtract_mu(e->Y, e->ldY, e->n, e->D, e->mu_dev, st));
@@ -555,10 +568,48 @@ static int fill_iter(const pet_engine *e, const pet_anneal *a, const pet_params 
     return PET_OK;
 }
 
+// make chunk k of a pending host upload resident (stream-ordered on st); chunks are taken in order
+static int upload_chunk(pet_engine *e, int64_t k, cudaStream_t st, bool *fresh) {
+    const int64_t nchunks = ceil_div(e->n, e->chunk_rows);
+    const int LOOKAHEAD = 2;
+    while (e->up_copied < std::min<int64_t>(nchunks, k + 1 + LOOKAHEAD)) {
+        const int64_t j = e->up_copied, r0 = j * e->chunk_rows, rows = std::min(e->chunk_rows, e->n - r0);
+        if (e->up_staged) {
+            const int slot = int(j % 3);
+            if (j >= 3) PET_CUDA(cudaStreamWaitEvent(e->copy_stream, e->up_free[slot], 0));
+            PET_CUDA(cudaMemcpyAsync(e->up_slot[slot], e->up_src + r0 * e->up_ld, size_t(rows) * e->D * 8, cudaMemcpyHostToDevice,
+                                     e->copy_stream));
+        } else {
+            PET_CUDA(cudaMemcpy2DAsync(e->Y + r0 * e->ldY, e->ldY * 8, e->up_src + r0 * e->up_ld, e->up_ld * 8, size_t(e->D) * 8,
+                                       rows, cudaMemcpyHostToDevice, e->copy_stream));
+        }
+        PET_CUDA(cudaEventRecord(e->chunk_ready[j], e->copy_stream));
+        e->up_copied++;
+    }
+    PET_CUDA(cudaStreamWaitEvent(st, e->chunk_ready[k], 0));
+    if (e->up_staged) {
+        const int64_t r0 = k * e->chunk_rows, rows = std::min(e->chunk_rows, e->n - r0);
+        const int slot = int(k % 3);
+        PET_CHECK(launch_rownorm_pad(e->up_slot[slot], e->D, e->Y + r0 * e->ldY, e->ldY, rows, e->D, e->yy + r0, st));
+        PET_CUDA(cudaEventRecord(e->up_free[slot], st));
+        if (fresh) *fresh = true;
+    }
+    e->up_expanded = k + 1;
+    if (e->up_expanded >= nchunks) e->upload_pending = false;
+    return PET_OK;
+}
+
+static int flush_upload(pet_engine *e, cudaStream_t st) {
+    const int64_t nchunks = ceil_div(e->n, e->chunk_rows);
+    while (e->upload_pending && e->up_expanded < nchunks) PET_CHECK(upload_chunk(e, e->up_expanded, st, nullptr));
+    return PET_OK;
+}
+
 static int ensure_chunk_inputs(pet_engine *e, int64_t c, int64_t r0, int64_t rows, cudaStream_t st) {
-    if (e->upload_pending) PET_CUDA(cudaStreamWaitEvent(st, e->chunk_ready[c], 0));
+    bool fresh = false;          // yy and the padding columns were just written by the staged expansion
+    while (e->upload_pending && e->up_expanded <= c) PET_CHECK(upload_chunk(e, e->up_expanded, st, &fresh));
     if (!e->yy_valid) {
-        PET_CHECK(launch_rownorm_pad(e->Y + r0 * e->ldY, e->ldY, rows, e->D, e->yy + r0, st));
+        if (!fresh) PET_CHECK(launch_rownorm_pad(e->Y + r0 * e->ldY, e->ldY, e->Y + r0 * e->ldY, e->ldY, rows, e->D, e->yy + r0, st));
         if (e->oz_on) {
             PET_CHECK(ozaki_slice_rows(e->Y + r0 * e->ldY, e->ldY, rows, e->D, e->oz_ns, e->ozY + r0 * e->oz_kpd,
                                        e->oz_rows * e->oz_kpd, e->ozYs + r0, st));

@@ -38,13 +38,19 @@ __global__ void subtract_mu_kernel(double *Y, int64_t ldy, int64_t n, int D, con
 }
 
 // one warp per row: yy[n] = ||y_n||^2, and the engine's layout columns: Y[n][D] = 1, rest 0
-__global__ void rownorm_pad_kernel(double *Y, int64_t ldy, int64_t n, int D, double *yy) {
+// src != Y: the rows are first copied from a (contiguous) upload staging buffer
+__global__ void rownorm_pad_kernel(const double *src, int64_t ld_src, double *Y, int64_t ldy, int64_t n, int D, double *yy) {
     int64_t row = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     int lane = threadIdx.x & 31;
     if (row >= n) return;
     double *y = Y + row * ldy;
+    const double *x = src + row * ld_src;
     double s = 0.0;
-    for (int d = lane; d < D; d += 32) s = fma(y[d], y[d], s);
+    for (int d = lane; d < D; d += 32) {
+        const double v = x[d];
+        if (x != y) y[d] = v;
+        s = fma(v, v, s);
+    }
     s = warp_sum(s);
     if (lane == 0) yy[row] = s;
     for (int d = D + lane; d < ldy; d += 32) y[d] = (d == D) ? 1.0 : 0.0;
@@ -176,9 +182,9 @@ int launch_subtract_mu(double *Y, int64_t ldy, int64_t n, int D, const double *m
     PET_LAUNCH_CHECK();
     return PET_OK;
 }
-int launch_rownorm_pad(double *Y, int64_t ldy, int64_t n, int D, double *yy, cudaStream_t st) {
+int launch_rownorm_pad(const double *src, int64_t ld_src, double *Y, int64_t ldy, int64_t n, int D, double *yy, cudaStream_t st) {
     if (n <= 0) return PET_OK;
-    rownorm_pad_kernel<<<(unsigned)ceil_div(n * 32, 256), 256, 0, st>>>(Y, ldy, n, D, yy);
+    rownorm_pad_kernel<<<(unsigned)ceil_div(n * 32, 256), 256, 0, st>>>(src, ld_src, Y, ldy, n, D, yy);
     PET_LAUNCH_CHECK();
     return PET_OK;
 }
