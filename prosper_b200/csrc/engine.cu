@@ -7,6 +7,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <map>
 #include <vector>
 
 #include "common.cuh"
@@ -132,7 +133,7 @@ struct pet_engine {
     double *stage_logpj = nullptr; int64_t stage_logpj_doubles = 0;
     int64_t *stage_i64 = nullptr; int64_t stage_i64_count = 0;
     unsigned long long *ksel_state = nullptr;
-    unsigned long long *d_states = nullptr; unsigned short *d_entries = nullptr, *d_chunk = nullptr; unsigned int *d_direct = nullptr;
+    unsigned long long *d_states = nullptr, *d_inc = nullptr; unsigned short *d_entries = nullptr, *d_chunk = nullptr; unsigned int *d_direct = nullptr;
     int *d_single = nullptr; double *d_state_prior = nullptr;
 
     // int8-sliced operands of the two large GEMMs (ozaki.cu); oz_on = buffers present and the path selected
@@ -184,7 +185,7 @@ extern "C" void pet_destroy(pet_engine *e) {
     free_dev(e->Wt2); free_dev(e->gsc_tab); free_dev(e->psi_dev); free_dev(e->bdiag); free_dev(e->XSZ); free_dev(e->SZ2); free_dev(e->yyw); free_dev(e->dst_dev);
     free_dev(e->ozY); free_dev(e->ozYT); free_dev(e->ozW); free_dev(e->ozS); free_dev(e->ozYs); free_dev(e->ozYTs);
     free_dev(e->ozWs); free_dev(e->ozSs); free_dev(e->oz_slabs); free_dev(e->oz_colmax);
-    free_dev(e->d_states); free_dev(e->d_entries); free_dev(e->d_chunk); free_dev(e->d_direct); free_dev(e->d_single); free_dev(e->d_state_prior);
+    free_dev(e->d_inc); free_dev(e->d_states); free_dev(e->d_entries); free_dev(e->d_chunk); free_dev(e->d_direct); free_dev(e->d_single); free_dev(e->d_state_prior);
     for (auto ev : e->chunk_ready) cudaEventDestroy(ev);
     for (int i = 0; i < 3; ++i) { free_dev(e->up_slot[i]); if (e->up_free[i]) cudaEventDestroy(e->up_free[i]); }
     for (auto ev : e->timer.pool) cudaEventDestroy(ev);
@@ -305,10 +306,17 @@ extern "C" int pet_create(const pet_config *cfg, pet_engine **out) {
     TRYC(cudaMemcpy(e->d_chunk, e->ss.chunk_tab.data(), e->ss.chunk_tab.size() * 2, cudaMemcpyHostToDevice));
     if (!e->ss.direct.empty()) TRYC(cudaMemcpy(e->d_direct, e->ss.direct.data(), e->ss.direct.size() * 4, cudaMemcpyHostToDevice));
     TRYC(cudaMemcpy(e->d_single, e->ss.single_idx.data(), e->ss.single_idx.size() * 4, cudaMemcpyHostToDevice));
+    g.inc_states = nullptr;
+    if (!e->ss.inc_records.empty() && !getenv("PET_GL_NO_INC")) {
+        TRY(dev_alloc(&e->d_inc, e->ss.S));
+        TRYC(cudaMemcpy(e->d_inc, e->ss.inc_records.data(), e->ss.S * 8, cudaMemcpyHostToDevice));
+        g.inc_states = e->d_inc;
+    }
     g.states = e->d_states; g.entries = e->d_entries; g.chunk_tab = e->d_chunk; g.direct = e->d_direct; g.single_idx = e->d_single;
 
     // chunking: posterior / score buffers of ~128 MB each
     int64_t cr = cfg->chunk_rows > 0 ? cfg->chunk_rows : (int64_t(128) << 20) / (e->ldH * 8);
+    if (const char *env = getenv("PET_CHUNK_ROWS")) { if (atoll(env) > 0) cr = atoll(env); }
     cr = std::max<int64_t>(128, std::min<int64_t>(cr, 1 << 20));
     e->chunk_rows = round_up(cr, 128);
 

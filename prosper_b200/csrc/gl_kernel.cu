@@ -48,7 +48,7 @@ static __host__ __device__ inline SmemLayout smem_layout(const GLStatic &s) {
     L.off_ids = r2(s.S);
     L.off_chunk = L.off_ids + nch * s.chunk_len * (GRP_LANES / 4);   // nch*CH*64 u16
     L.shared_doubles = L.off_chunk + nch * (GRP_LANES / 4);          // nch*64 u16
-    L.off_G = r2(s.S + 1);                                           // qbuf first
+    L.off_G = r2(s.S + 1 + PET_MAXHP);                               // qbuf first: states, zero slot, singletons
     L.off_lin = L.off_G + r2(GS * GS);
     L.off_mom = L.off_lin + r2(GS);
     L.off_P = L.off_mom + r2(s.n_out + 1);
@@ -412,7 +412,8 @@ __global__ void __launch_bounds__(GL_MAX_GROUPS * GRP_LANES) gl_state_kernel(con
     unsigned long long *states_s = reinterpret_cast<unsigned long long *>(smem);
     unsigned short *ids_s = reinterpret_cast<unsigned short *>(smem + L.off_ids);
     unsigned short *chunk_s = reinterpret_cast<unsigned short *>(smem + L.off_chunk);
-    for (int s = threadIdx.x; s < S; s += blockDim.x) states_s[s] = st.states[s];
+    const bool inc = BINARY && GMAX <= 5 && st.inc_states != nullptr;
+    for (int s = threadIdx.x; s < S; s += blockDim.x) states_s[s] = inc ? st.inc_states[s] : st.states[s];
     for (int i = threadIdx.x; i < NCH * CH * GRP_LANES; i += blockDim.x) ids_s[i] = st.entries[i];
     for (int i = threadIdx.x; i < NCH * GRP_LANES; i += blockDim.x) chunk_s[i] = st.chunk_tab[i];
     double *gb = smem + L.shared_doubles + size_t(L.per_dp) * gid;
@@ -478,17 +479,47 @@ __global__ void __launch_bounds__(GL_MAX_GROUPS * GRP_LANES) gl_state_kernel(con
         double *logpj_row = a.logpj ? a.logpj + n * a.ld_logpj : nullptr;
         // ---- log-joints of the multi-cause states, max ------------------------------------------------
         double m2 = -INFINITY;
-#pragma unroll 2
-        for (int s = l64; s < S; s += GRP_LANES) {
-            double q = eval_state<GMAX, BINARY>(states_s[s], st, lin, Gc, yy);
-            qbuf[s] = q;
-            double F;
-            if (rd) F = logpj_row[col_states + s];
-            else {
-                F = combine(it, prior_of<GMAX, BINARY>(a, sb, s), q);
-                if (wr) logpj_row[col_states + s] = F;
+        if (inc) {
+            // size by size: q(s) = q(s without its largest member e) + lin[e] + 2 sum_i G[i][e]; the shorter state
+            // was evaluated one level earlier (singletons: yy + lin[j], kept behind the zero slot)
+            if (l64 < Hp) qbuf[S + 1 + l64] = yy + lin[l64];
+            grp_sync(gid);
+#pragma unroll
+            for (int g = 2; g <= GMAX; ++g) {
+                const int s_end = (g < GMAX) ? st.size_start[g + 1] : S;
+                const double pr = it.lp[0] * double(g);
+                for (int s = st.size_start[g] + l64; s < s_end; s += GRP_LANES) {
+                    const unsigned long long rec = states_s[s];
+                    const int e = int(unsigned(rec) & 0xFFu);
+                    const double *ge = Gc + e;
+                    double cross = 0.0;
+#pragma unroll
+                    for (int m = 1; m < GMAX; ++m) cross += ge[int(unsigned(rec >> (8 * m)) & 0xFFu) * GS];
+                    const double q = fma(2.0, cross, qbuf[int(rec >> 48)] + lin[e]);
+                    qbuf[s] = q;
+                    double F;
+                    if (rd) F = logpj_row[col_states + s];
+                    else {
+                        F = combine(it, pr, q);
+                        if (wr) logpj_row[col_states + s] = F;
+                    }
+                    m2 = fmax(m2, F);
+                }
+                if (g < GMAX) grp_sync(gid);
             }
-            m2 = fmax(m2, F);
+        } else {
+#pragma unroll 2
+            for (int s = l64; s < S; s += GRP_LANES) {
+                double q = eval_state<GMAX, BINARY>(states_s[s], st, lin, Gc, yy);
+                qbuf[s] = q;
+                double F;
+                if (rd) F = logpj_row[col_states + s];
+                else {
+                    F = combine(it, prior_of<GMAX, BINARY>(a, sb, s), q);
+                    if (wr) logpj_row[col_states + s] = F;
+                }
+                m2 = fmax(m2, F);
+            }
         }
         if (wr && (a.flags & GLF_LSE_ONLY)) continue;   // compat E_step: logpj only
         m2 = grp_max(m2, red, gid, wig);

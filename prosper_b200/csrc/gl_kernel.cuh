@@ -41,6 +41,7 @@ struct GLStatic {                 // fixed per engine
     int select_mode;
     int diag_from_colsum;         // binary: Wq diagonal = column sums of <s> (not scattered)
     const unsigned long long *states;   // S records: 8 x (pos | vidx<<4), 0xFF = unused
+    const unsigned long long *inc_states;   // binary, <= 5 members: incremental records (statespace.cpp.inc) or null
     const unsigned short *entries;   // [(chunk*CH+i)*32 + lane] state ids of the pair-sum gather lists
     const unsigned short *chunk_tab; // [chunk*32 + lane] output id | 0x8000 on the last chunk of an output
     const unsigned int *direct;      // (output<<16 | state id) of single-entry lists
