@@ -331,7 +331,7 @@ __global__ void __launch_bounds__(ROW_WARPS * 32, 2) gl_row_kernel(const __grid_
         for (int v = 0; v < PET_MAXV; ++v) cntb[v] = 0.0;
         if (st.has_null && lane == 0) {
             double x = F0 - m1;
-            double p = (x > GL_EXP_CUTOFF) ? exp(x) : 0.0;
+            double p = (x > GL_EXP_CUTOFF) ? exp_nonpos(x) : 0.0;
             Z1 += p;
             sig1 += p * yy;
         }
@@ -346,7 +346,7 @@ __global__ void __launch_bounds__(ROW_WARPS * 32, 2) gl_row_kernel(const __grid_
                         double q = yy + v * (v * wn2h - 2.0 * ywh);
                         double F = rd ? logpj_row[st.has_null + b * H + h] : combine(it, it.prior_block[b], q);
                         double x = F - m1;
-                        double p = (x > GL_EXP_CUTOFF) ? exp(x) : 0.0;
+                        double p = (x > GL_EXP_CUTOFF) ? exp_nonpos(x) : 0.0;
                         Z1 += p;
                         sig1 += p * q;
                         cntb[b] += p;
@@ -370,6 +370,137 @@ __global__ void __launch_bounds__(ROW_WARPS * 32, 2) gl_row_kernel(const __grid_
             rs[0] = m1; rs[1] = Z1; rs[2] = sig1;
 #pragma unroll
             for (int v = 0; v < PET_MAXV; ++v) rs[4 + v] = cntb[v];
+        }
+        __syncwarp();
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
+// Row kernel, fast path for the binary single-block layout [null | h = 0..H-1 | states] with H <= 1024,
+// no logpj I/O and no second-moment row (BSC): same results as gl_row_kernel, ~1/3 of the instructions.
+//   * selection: every lane keeps the best two of its 32 scores; a round is three warp REDUX.MAX over the
+//     order-preserving integer image of the score (value, then item index: larger index wins ties, the
+//     rule of the generic path) and a pop from the winning lane; a lane that has given both of its
+//     entries rebuilds them from its registers (taken items masked)
+//   * one latent value (1.0): no per-block loops
+// -------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long order_key(double v) {
+    const long long b = __double_as_longlong(v);
+    return (unsigned long long)(b ^ ((b >> 63) | (long long)0x8000000000000000ull));
+}
+
+template <int HC>
+__device__ __forceinline__ void top2_of(const double (&sc)[HC], unsigned taken, double &v1, int &k1, double &v2, int &k2) {
+    v1 = v2 = -INFINITY;
+    k1 = k2 = 0;
+#pragma unroll
+    for (int k = 0; k < HC; ++k) {
+        const double s = ((taken >> k) & 1u) ? -INFINITY : sc[k];
+        const bool b1 = s >= v1, b2 = s >= v2;            // '>=': the later (larger) item index wins ties
+        v2 = b1 ? v1 : (b2 ? s : v2);
+        k2 = b1 ? k1 : (b2 ? k : k2);
+        v1 = b1 ? s : v1;
+        k1 = b1 ? k : k1;
+    }
+}
+
+__global__ void __launch_bounds__(ROW_WARPS * 32, 2) gl_row_fast_kernel(const __grid_constant__ GLArgs a) {
+    extern __shared__ __align__(16) double smem[];
+    constexpr int HC = 32;
+    const GLStatic &st = a.st;
+    const GLIter &it = a.it;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int H = st.H, Hp = st.Hp;
+    double *row = smem + size_t(r2(H) + PET_MAXHP) * warp;
+    int *cand_s = reinterpret_cast<int *>(row + r2(H));
+    const bool do_stats = !(a.flags & (GLF_LSE_ONLY | GLF_SELECT_ONLY));
+    const double pb = it.prior_block[0];
+
+    const int64_t wstride = int64_t(gridDim.x) * ROW_WARPS;
+    for (int64_t r = int64_t(blockIdx.x) * ROW_WARPS + warp; r < a.n_rows; r += wstride) {
+        const int64_t n = a.row0 + r;
+        const double *yw = a.YW + r * st.ldH;
+        const double yy = a.yy[n];
+        double sc[HC];
+        double m1 = -INFINITY;
+        // ---- one pass over the score row: shared copy, selection scores, singleton log-joints' maximum ----
+#pragma unroll
+        for (int k = 0; k < HC; ++k) {
+            const int h = k * 32 + lane;
+            if (h < H) {
+                const double v = yw[h];
+                row[h] = v;
+                double s = (st.select_mode == SEL_BSC) ? v * a.invn[h]
+                         : (st.select_mode == SEL_NEGDIST) ? 2.0 * v - a.wn2[h] : -v;
+                s += 0.0;                                  // -0.0 ties with +0.0, as in a floating-point compare
+                sc[k] = (s != s) ? -INFINITY : s;          // NaN scores never win
+                m1 = fmax(m1, combine(it, pb, yy + (a.wn2[h] - 2.0 * v)));
+            } else {
+                sc[k] = -INFINITY;
+            }
+        }
+        __syncwarp();
+        if (a.flags & GLF_SELECT) {
+            unsigned taken = 0;
+            double v1, v2;
+            int k1, k2, left = 2;
+            top2_of<HC>(sc, taken, v1, k1, v2, k2);
+            for (int rnd = 0; rnd < Hp; ++rnd) {
+                const unsigned long long key = order_key(v1);
+                const unsigned hi = unsigned(key >> 32), lo = unsigned(key);
+                const unsigned mhi = __reduce_max_sync(0xffffffffu, hi);
+                const unsigned mlo = __reduce_max_sync(0xffffffffu, hi == mhi ? lo : 0u);
+                const unsigned mine = (hi == mhi && lo == mlo) ? unsigned(k1 * 32 + lane) + 1u : 0u;
+                int bi = int(__reduce_max_sync(0xffffffffu, mine)) - 1;
+                if (bi < 0 || bi >= H) bi = 0;
+                if (lane == 0) store_cand(st, cand_s, rnd, bi);          // BSC: ascending by score (bsc_et.py:113)
+                if ((bi & 31) == lane && (bi >> 5) == k1 && mine != 0u) {
+                    taken |= 1u << k1;
+                    v1 = v2; k1 = k2; v2 = -INFINITY;
+                    --left;
+                }
+                if (__any_sync(0xffffffffu, left == 0)) {                 // rare: a lane ran out of prepared entries
+                    if (left == 0) { top2_of<HC>(sc, taken, v1, k1, v2, k2); left = 2; }
+                }
+            }
+            __syncwarp();
+            if (lane < Hp) a.cand[n * Hp + lane] = cand_s[lane];
+        } else {
+            if (lane < Hp) cand_s[lane] = a.cand[n * Hp + lane];
+            __syncwarp();
+        }
+        if (a.flags & GLF_SELECT_ONLY) { __syncwarp(); continue; }
+        if (lane < Hp) a.ywc[n * Hp + lane] = row[cand_s[lane]];
+
+        const double F0 = combine(it, it.prior_null, yy);
+        m1 = warp_max(fmax(m1, F0));
+        double Z1 = 0.0, sig1 = 0.0, cnt = 0.0;
+        if (lane == 0) {
+            const double x = F0 - m1;
+            const double p = (x > GL_EXP_CUTOFF) ? exp_nonpos(x) : 0.0;
+            Z1 += p;
+            sig1 += p * yy;
+        }
+        double *Srow = a.S + r * st.ldH;
+#pragma unroll 4
+        for (int h = lane; h < st.ldH; h += 32) {
+            double p = 0.0;
+            if (h < H) {
+                const double q = yy + (a.wn2[h] - 2.0 * row[h]);
+                const double x = combine(it, pb, q) - m1;
+                p = (x > GL_EXP_CUTOFF) ? exp_nonpos(x) : 0.0;
+                Z1 += p;
+                sig1 = fma(p, q, sig1);
+                cnt += p;
+            }
+            if (do_stats) Srow[h] = p;                       // scaled by exp(m1 - m)/Z in the scale kernel
+        }
+        Z1 = warp_sum(Z1);
+        sig1 = warp_sum(sig1);
+        cnt = warp_sum(cnt);
+        if (lane == 0) {
+            double *rs = a.rs + n * RS;
+            rs[0] = m1; rs[1] = Z1; rs[2] = sig1; rs[4] = cnt;
         }
         __syncwarp();
     }
@@ -528,15 +659,33 @@ __global__ void __launch_bounds__(GL_MAX_GROUPS * GRP_LANES) gl_state_kernel(con
         const double mx = fmax(m1, m2);
         // ---- exp, merge with the singleton partial sums -------------------------------------------------
         double Z2 = 0.0, sig2 = 0.0;
+        if (inc) {
+#pragma unroll
+            for (int g = 2; g <= GMAX; ++g) {                 // by size: the log-prior is a constant of the level
+                const int s_end = (g < GMAX) ? st.size_start[g + 1] : S;
+                const double pr = it.lp[0] * double(g);
 #pragma unroll 2
-        for (int s = l64; s < S; s += GRP_LANES) {
-            double q = qbuf[s];
-            double F = rd ? logpj_row[col_states + s] : combine(it, prior_of<GMAX, BINARY>(a, sb, s), q);
-            double x = F - mx;
-            double p = (x > GL_EXP_CUTOFF) ? exp(x) : 0.0;
-            Z2 += p;
-            sig2 += p * q;
-            qbuf[s] = p;
+                for (int s = st.size_start[g] + l64; s < s_end; s += GRP_LANES) {
+                    double q = qbuf[s];
+                    double F = rd ? logpj_row[col_states + s] : combine(it, pr, q);
+                    double x = F - mx;
+                    double p = (x > GL_EXP_CUTOFF) ? exp_nonpos(x) : 0.0;
+                    Z2 += p;
+                    sig2 += p * q;
+                    qbuf[s] = p;
+                }
+            }
+        } else {
+#pragma unroll 2
+            for (int s = l64; s < S; s += GRP_LANES) {
+                double q = qbuf[s];
+                double F = rd ? logpj_row[col_states + s] : combine(it, prior_of<GMAX, BINARY>(a, sb, s), q);
+                double x = F - mx;
+                double p = (x > GL_EXP_CUTOFF) ? exp_nonpos(x) : 0.0;
+                Z2 += p;
+                sig2 += p * q;
+                qbuf[s] = p;
+            }
         }
         if (l64 == 0) qbuf[S] = 0.0;   // zero slot read by padding entries of the gather table
         Z2 = grp_sum(Z2, red, gid, wig);
@@ -729,6 +878,20 @@ int launch_gl_row(const GLArgs &a, int sm_count, cudaStream_t stream) {
     }
     int per_sm = int(std::max<size_t>(1, std::min<size_t>(2, (227 * 1024) / (smem + 1024))));
     int64_t grid = std::min<int64_t>(ceil_div(a.n_rows, ROW_WARPS), int64_t(sm_count) * per_sm);
+    static const bool no_fast = getenv("PET_GL_NO_FAST_ROW") != nullptr;
+    const bool fast = !no_fast && a.st.n_blocks == 1 && a.st.block_val[0] == 1.0 && a.st.has_null && a.st.H <= 1024 &&
+                      !a.S2 && !(a.flags & (GLF_READ_LOGPJ | GLF_WRITE_LOGPJ)) &&
+                      (a.st.select_mode == SEL_BSC || a.st.select_mode == SEL_NEGDIST || a.st.select_mode == SEL_GIVEN);
+    if (fast) {
+        static size_t configured_fast = 0;
+        if (smem > configured_fast) {
+            PET_CUDA(cudaFuncSetAttribute(gl_row_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+            configured_fast = smem;
+        }
+        gl_row_fast_kernel<<<(unsigned)grid, ROW_WARPS * 32, smem, stream>>>(a);
+        PET_LAUNCH_CHECK();
+        return PET_OK;
+    }
     gl_row_kernel<<<(unsigned)grid, ROW_WARPS * 32, smem, stream>>>(a);
     PET_LAUNCH_CHECK();
     return PET_OK;
