@@ -249,6 +249,7 @@ def run_gpu(args):
     ms = e0.elapsed_time(e1)
     launches = eng.launch_count() - launches0
     stages = eng.stage_times()
+    gemm_slices = eng.gemm_path()
     eng.enable_timing(False)
     clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
@@ -284,27 +285,48 @@ def run_gpu(args):
     if rank == 0:
         peak = measure_fp64_peak(dev)
         per_step = dict((k, v['ms'] / args.steps) for k, v in stages.items())
-        kernels = ('score_gemm', 'stats_gemm', 'state_kernel', 'row_kernel')
-        dom = max(kernels, key=lambda k: per_step[k])
-        spans = max(1, stages[dom]['spans'])
-        avg_launch_ms = stages[dom]['ms'] / spans
-        rows_per_launch = n_local * args.steps / spans
-        if dom in ('score_gemm', 'stats_gemm'):
-            # both GEMM stages are the same kernel template (dgemm_kernel); algorithmic work 2*D*H flop per datapoint each
+        ns = gemm_slices
+        # kernels by total time: both GEMM stages run the same kernel template
+        kernel_ms = {'gemm': per_step['score_gemm'] + per_step['stats_gemm'], 'state_kernel': per_step['state_kernel'],
+                     'row_kernel': per_step['row_kernel']}
+        dom = max(kernel_ms, key=lambda k: kernel_ms[k])
+        hbm, bf16 = 6527.5, 1590.5
+        peak_src = "fallback (B200_PROFILING.md)"
+        try:
+            mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+            hbm, bf16 = mp["hbm_gbs"], mp["bf16_tflops_sustained"]
+            peak_src = "MEASURED_PEAKS.json"
+        except Exception:
+            pass
+        if dom == 'gemm':
+            spans = max(1, stages['score_gemm']['spans'] + stages['stats_gemm']['spans'])
+            avg_launch_ms = (stages['score_gemm']['ms'] + stages['stats_gemm']['ms']) / spans
+            rows_per_launch = 2.0 * n_local * args.steps / spans
+            # algorithmic work: 2*D*H flop per datapoint per GEMM, whatever pipe executes it
             achieved = 2.0 * D * H * rows_per_launch / (avg_launch_ms / 1e3) / 1e12
-            roof = {"kernel": "dgemm_kernel (FP64 DMMA, %s)" % dom, "bound": "tensor", "pipe": "fp64 mma.sync m8n8k4 (tcgen05 has no f64 kind)",
-                    "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                    "peak_source": "cuBLAS DGEMM 8192^3 measured in this run (MEASURED_PEAKS.json has no FP64 entry)",
-                    "traffic": None}
+            if ns > 0:
+                pairs = ns * (ns + 1) // 2
+                int8_peak = 2.0 * bf16            # kind::i8 issues at twice the bf16 rate on B200 (4.5 vs 2.25 PFLOP/s nominal)
+                roof = {"kernel": "oz::gemm_kernel<%d> (score + statistics GEMM)" % ns, "bound": "tensor",
+                        "pipe": "tcgen05.mma kind::i8 + TMEM: %d int8 slice products per FP64 product" % pairs,
+                        "achieved": achieved, "peak": int8_peak / pairs, "unit": "TFLOP/s", "frac": achieved * pairs / int8_peak,
+                        "pipe_achieved_tops": achieved * pairs, "pipe_peak_tops": int8_peak,
+                        "peak_source": "2 x %s bf16_tflops_sustained (int8 dense rate), divided by the %d slice products; "
+                                       "cuBLAS DGEMM measured in this run: %.1f TFLOP/s" % (peak_src, pairs, peak),
+                        "traffic": None}
+            else:
+                roof = {"kernel": "dgemm_kernel (FP64 DMMA, score + statistics GEMM)", "bound": "tensor",
+                        "pipe": "fp64 mma.sync m8n8k4", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                        "frac": achieved / peak, "peak_source": "cuBLAS DGEMM 8192^3 measured in this run", "traffic": None}
         else:
-            hbm = 6527.5
-            try:
-                hbm = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
-            except Exception:
-                pass
+            spans = max(1, stages[dom]['spans'])
+            avg_launch_ms = stages[dom]['ms'] / spans
+            rows_per_launch = n_local * args.steps / spans
+            # posterior kernels: algorithmic traffic = the score row in, the <s> row out (2 * 8 * H bytes per datapoint);
+            # they are bound by shared-memory / issue latency, so the HBM fraction is low by construction
             achieved = 2.0 * 8 * H * rows_per_launch / (avg_launch_ms / 1e3) / 1e9
             roof = {"kernel": "gl_%s (posterior)" % dom, "bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s",
-                    "frac": achieved / hbm, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)", "traffic": None}
+                    "frac": achieved / hbm, "peak_source": peak_src + " hbm_gbs", "traffic": None}
         roof["avg_launch_ms"] = avg_launch_ms
         roof["stage_ms_per_step"] = per_step
         roof["whole_step_fp64_frac"] = (flops_per_dp() * N_TOTAL / world / (ms_max / args.steps / 1e3) / 1e12) / peak

@@ -248,11 +248,16 @@ int  pet_spd_solve_right(int64_t n, int64_t m, double *A_dev, int64_t lda,
 int64_t pet_spd_solve_work_doubles(int64_t n, int64_t lda);   /* size of work_dev */
 
 /* Device time per stage since pet_enable_timing(e,1), measured with CUDA events on the
- * caller's stream around every launch group: out[0..7] = total ms of [0]=prepare
- * (transpose+Gram) [1]=score GEMM [2]=state kernel (or the whole posterior kernel for
- * MCA/MMCA/GSC) [3]=statistics GEMM [4]=solve [5]=kth-largest [6]=row kernel [7]=scale kernel;
- * out[8..15] = how many spans each total sums.  Synchronises. */
-int  pet_stage_times_ms(pet_engine *e, double *out_host16);
+ * caller's stream around every launch group: out[0..PET_N_STAGES-1] = total ms of
+ * [0]=prepare (transpose+Gram+slicing of W) [1]=score GEMM [2]=state kernel (or the whole
+ * posterior kernel for MCA/MMCA/GSC) [3]=statistics GEMM [4]=solve [5]=kth-largest
+ * [6]=row kernel [7]=scale kernel [8]=int8 slicing of <s> for the statistics GEMM [9]=spare;
+ * out[PET_N_STAGES..2*PET_N_STAGES-1] = how many spans each total sums.  Synchronises. */
+#define PET_N_STAGES 10
+/* which kernels run the score / statistics GEMMs for the bound shard: 0 = FP64 DMMA
+ * (dgemm.cu), n > 0 = int8 tcgen05 with n slices per operand (ozaki.cu) */
+int32_t pet_gemm_path(const pet_engine *e);
+int  pet_stage_times_ms(pet_engine *e, double *out_host);
 int  pet_enable_timing(pet_engine *e, int32_t on);
 /* number of kernels launched by the engine since creation (bench.py's gpu_launches) */
 int64_t pet_launch_count(const pet_engine *e);

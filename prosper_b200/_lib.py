@@ -14,6 +14,7 @@ c_int64_p = C.POINTER(C.c_int64)
 MODEL_BSC, MODEL_MCA, MODEL_MMCA, MODEL_TSC, MODEL_DSC, MODEL_GSC = range(6)
 PASS_SELECT = 1
 PASS_REUSE_SCORES = 2
+N_STAGES = 10          # PET_N_STAGES
 
 
 class PetError(RuntimeError):
@@ -95,6 +96,7 @@ SIGNATURES = {
     "pet_spd_solve_right": (C.c_int, [C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
                                       C.c_void_p, C.POINTER(C.c_int32), C.c_void_p]),
     "pet_spd_solve_work_doubles": (C.c_int64, [C.c_int64, C.c_int64]),
+    "pet_gemm_path": (C.c_int32, [C.c_void_p]),
     "pet_stage_times_ms": (C.c_int, [C.c_void_p, c_double_p]),
     "pet_enable_timing": (C.c_int, [C.c_void_p, C.c_int32]),
     "pet_launch_count": (C.c_int64, [C.c_void_p]),

@@ -60,7 +60,8 @@ static bool is_device_ptr(const void *p) {
     return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
 }
 
-enum Stage { ST_PREPARE = 0, ST_SCORE, ST_POST, ST_STATS, ST_SOLVE, ST_KSEL, ST_ROW, ST_SCALE, ST_COUNT };
+enum Stage { ST_PREPARE = 0, ST_SCORE, ST_POST, ST_STATS, ST_SOLVE, ST_KSEL, ST_ROW, ST_SCALE, ST_SLICE, ST_SPARE, ST_COUNT };
+static_assert(ST_COUNT == PET_N_STAGES, "stage table");
 
 struct StageTimer {
     bool on = false;
@@ -68,8 +69,8 @@ struct StageTimer {
     size_t used = 0;
     struct Span { int stage; cudaEvent_t a, b; };
     std::vector<Span> spans;
-    double totals[ST_COUNT] = {0, 0, 0, 0, 0, 0, 0, 0};
-    int counts[ST_COUNT] = {0, 0, 0, 0, 0, 0, 0, 0};
+    double totals[ST_COUNT] = {};
+    int counts[ST_COUNT] = {};
     cudaEvent_t get() {
         if (used == pool.size()) { cudaEvent_t e; cudaEventCreate(&e); pool.push_back(e); }
         return pool[used++];
@@ -391,6 +392,7 @@ extern "C" int pet_state_matrix(const pet_engine *e, double *out_host) {
     memcpy(out_host, e->ss.matrix.data(), e->ss.matrix.size() * sizeof(double));
     return PET_OK;
 }
+extern "C" int32_t pet_gemm_path(const pet_engine *e) { return (e && e->oz_on) ? e->oz_ns : 0; }
 extern "C" int pet_enable_timing(pet_engine *e, int32_t on) {
     if (!e) return PET_EINVAL;
     e->timer.reset();
@@ -721,8 +723,12 @@ static int sweep_gl(pet_engine *e, const pet_anneal *a, const pet_params *p, int
             // Wp^T (D+1, H) += Y_chunk^T . <S>_chunk ; row D (all-ones column of Y) = sum_n <s>
             if (e->oz_on) {
                 const int64_t plane = (int64_t)(e->D + 1) * e->chunk_rows, wp = (int64_t)(e->D + 1) * e->ldH;
+                e->timer.end(st);
+                e->timer.begin(ST_SLICE, st);
                 PET_CHECK(ozaki_slice_cols(e->Sbuf, e->ldH, rows, e->H, e->oz_ns, e->oz_colmax, e->ozS, e->chunk_rows,
                                            (int64_t)e->H * e->chunk_rows, e->ozSs, st));
+                e->timer.end(st);
+                e->timer.begin(ST_STATS, st);
                 const OzOperand oy{e->ozYT + c * e->oz_ns * plane, e->chunk_rows, plane, e->ozYTs + c * e->ldY};
                 const OzOperand os{e->ozS, e->chunk_rows, (int64_t)e->H * e->chunk_rows, e->ozSs};
                 PET_CHECK(ozaki_gemm(e->D + 1, e->H, ozaki_kp(rows), e->oz_ns, oy, os, e->oz_slabs, e->ldH, e->oz_splits, wp,

@@ -404,7 +404,7 @@ __device__ __forceinline__ void top2_of(const double (&sc)[HC], unsigned taken, 
     }
 }
 
-__global__ void __launch_bounds__(ROW_WARPS * 32, 2) gl_row_fast_kernel(const __grid_constant__ GLArgs a) {
+__global__ void __launch_bounds__(ROW_WARPS * 32, 3) gl_row_fast_kernel(const __grid_constant__ GLArgs a) {
     extern __shared__ __align__(16) double smem[];
     constexpr int HC = 32;
     const GLStatic &st = a.st;
@@ -883,6 +883,8 @@ int launch_gl_row(const GLArgs &a, int sm_count, cudaStream_t stream) {
                       !a.S2 && !(a.flags & (GLF_READ_LOGPJ | GLF_WRITE_LOGPJ)) &&
                       (a.st.select_mode == SEL_BSC || a.st.select_mode == SEL_NEGDIST || a.st.select_mode == SEL_GIVEN);
     if (fast) {
+        per_sm = int(std::max<size_t>(1, std::min<size_t>(3, (227 * 1024) / (smem + 1024))));
+        grid = std::min<int64_t>(ceil_div(a.n_rows, ROW_WARPS), int64_t(sm_count) * per_sm);
         static size_t configured_fast = 0;
         if (smem > configured_fast) {
             PET_CUDA(cudaFuncSetAttribute(gl_row_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));

@@ -182,10 +182,16 @@ class Engine(object):
         _lib.check(self.lib.pet_enable_timing(self.h, 1 if on else 0))
 
     def stage_times(self):
-        out = (C.c_double * 16)()
+        ns = _lib.N_STAGES
+        out = (C.c_double * (2 * ns))()
         _lib.check(self.lib.pet_stage_times_ms(self.h, out))
-        names = ['prepare', 'score_gemm', 'state_kernel', 'stats_gemm', 'solve', 'kth', 'row_kernel', 'scale_kernel']
-        return dict((nm, {'ms': out[i], 'spans': int(out[8 + i])}) for i, nm in enumerate(names))
+        names = ['prepare', 'score_gemm', 'state_kernel', 'stats_gemm', 'solve', 'kth', 'row_kernel', 'scale_kernel',
+                 'slice_kernels']
+        return dict((nm, {'ms': out[i], 'spans': int(out[ns + i])}) for i, nm in enumerate(names))
+
+    def gemm_path(self):
+        """0 = FP64 DMMA kernels, n > 0 = int8 tcgen05 kernels with n slices per operand."""
+        return int(self.lib.pet_gemm_path(self.h))
 
     def launch_count(self):
         return int(self.lib.pet_launch_count(self.h))
