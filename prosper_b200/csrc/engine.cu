@@ -624,7 +624,7 @@ static int ensure_chunk_inputs(pet_engine *e, int64_t c, int64_t r0, int64_t row
             PET_CHECK(ozaki_slice_rows(e->Y + r0 * e->ldY, e->ldY, rows, e->D, e->oz_ns, e->ozY + r0 * e->oz_kpd,
                                        e->oz_rows * e->oz_kpd, e->ozYs + r0, st));
             const int64_t plane = (int64_t)(e->D + 1) * e->chunk_rows;
-            PET_CHECK(ozaki_slice_cols(e->Y + r0 * e->ldY, e->ldY, rows, e->D + 1, e->oz_ns, e->oz_colmax,
+            PET_CHECK(ozaki_slice_cols(e->Y + r0 * e->ldY, e->ldY, rows, e->D + 1, e->oz_ns, e->oz_colmax, false,
                                        e->ozYT + c * e->oz_ns * plane, e->chunk_rows, plane, e->ozYTs + c * e->ldY, st));
         }
     }
@@ -725,8 +725,8 @@ static int sweep_gl(pet_engine *e, const pet_anneal *a, const pet_params *p, int
                 const int64_t plane = (int64_t)(e->D + 1) * e->chunk_rows, wp = (int64_t)(e->D + 1) * e->ldH;
                 e->timer.end(st);
                 e->timer.begin(ST_SLICE, st);
-                PET_CHECK(ozaki_slice_cols(e->Sbuf, e->ldH, rows, e->H, e->oz_ns, e->oz_colmax, e->ozS, e->chunk_rows,
-                                           (int64_t)e->H * e->chunk_rows, e->ozSs, st));
+                PET_CHECK(ozaki_slice_cols(e->Sbuf, e->ldH, rows, e->H, e->oz_ns, e->oz_colmax, false, e->ozS,
+                                           e->chunk_rows, (int64_t)e->H * e->chunk_rows, e->ozSs, st));
                 e->timer.end(st);
                 e->timer.begin(ST_STATS, st);
                 const OzOperand oy{e->ozYT + c * e->oz_ns * plane, e->chunk_rows, plane, e->ozYTs + c * e->ldY};

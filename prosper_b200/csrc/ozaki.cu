@@ -357,6 +357,7 @@ __global__ void __launch_bounds__(256) slice_cols_kernel(const double *X, int64_
                                                          const unsigned long long *colmax, int ns, int8_t *out,
                                                          int64_t row_stride, int64_t slice_stride, double *scale) {
     extern __shared__ int8_t tile[];                  // [ns][SC_C][SC_PITCH]
+    int32_t *tile32 = reinterpret_cast<int32_t *>(tile);
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int c = blockIdx.x * SC_C + tx;
     const int64_t r0 = int64_t(blockIdx.y) * SC_R;
@@ -368,13 +369,24 @@ __global__ void __launch_bounds__(256) slice_cols_kernel(const double *X, int64_
         s0 = ldexp(64.0, -e);
         if (blockIdx.y == 0 && ty == 0) scale[c] = ldexp(1.0, e);
     }
-    for (int j = ty; j < SC_R; j += 8) {
-        const int64_t r = r0 + j;
-        double v = (c < cols && r < rows) ? X[r * ldx + c] * s0 : 0.0;
+    // thread (tx, ty): column c, the 16 consecutive rows r0 + 16 ty ...; four rows pack into one shared word per slice
+    double v[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const int64_t r = r0 + ty * 16 + i;
+        v[i] = (c < cols && r < rows) ? X[r * ldx + c] * s0 : 0.0;
+    }
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
         for (int t = 0; t < ns; ++t) {
-            double q = rint(v);
-            tile[(t * SC_C + tx) * SC_PITCH + j] = (int8_t)q;
-            v = (v - q) * 128.0;
+            uint32_t w = 0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const double q = rint(v[4 * g + i]);
+                w |= (uint32_t(int(q)) & 0xFFu) << (8 * i);
+                v[4 * g + i] = (v[4 * g + i] - q) * 128.0;
+            }
+            tile32[((t * SC_C + tx) * SC_PITCH) / 4 + ty * 4 + g] = int32_t(w);
         }
     }
     __syncthreads();
@@ -384,10 +396,8 @@ __global__ void __launch_bounds__(256) slice_cols_kernel(const double *X, int64_
         const int t = ro / SC_C, cc = ro % SC_C;
         const int col = blockIdx.x * SC_C + cc;
         const int64_t r = r0 + tx * 4;
-        if (col < cols && r < Kp) {
-            const int32_t w = *reinterpret_cast<const int32_t *>(&tile[(t * SC_C + cc) * SC_PITCH + tx * 4]);
-            *reinterpret_cast<int32_t *>(out + t * slice_stride + col * row_stride + r) = w;
-        }
+        if (col < cols && r < Kp)
+            *reinterpret_cast<int32_t *>(out + t * slice_stride + col * row_stride + r) = tile32[((t * SC_C + cc) * SC_PITCH) / 4 + tx];
     }
 }
 
@@ -419,14 +429,17 @@ int ozaki_splits(int64_t M, int64_t N, int Kp, int sm_count) {
 }
 
 // X (rows, cols) row-major -> transposed slices out[t][c][r] with per-column scales (colmax: cols scratch words)
-int ozaki_slice_cols(const double *X, int64_t ldx, int64_t rows, int cols, int ns, unsigned long long *colmax, int8_t *out,
-                     int64_t row_stride, int64_t slice_stride, double *scale, cudaStream_t st) {
+// have_colmax: colmax already holds (an upper bound of) the column maxima, e.g. from the scale kernel
+int ozaki_slice_cols(const double *X, int64_t ldx, int64_t rows, int cols, int ns, unsigned long long *colmax, bool have_colmax,
+                     int8_t *out, int64_t row_stride, int64_t slice_stride, double *scale, cudaStream_t st) {
     if (rows <= 0 || cols <= 0) return PET_OK;
     const int Kp = ozaki_kp(rows);
-    PET_CUDA(cudaMemsetAsync(colmax, 0, size_t(cols) * 8, st));
-    dim3 g1((unsigned)ceil_div(cols, 32), (unsigned)std::min<int64_t>(ceil_div(rows, 256), 64));
-    oz::col_absmax_kernel<<<g1, dim3(32, 8), 0, st>>>(X, ldx, rows, cols, colmax);
-    PET_LAUNCH_CHECK();
+    if (!have_colmax) {
+        PET_CUDA(cudaMemsetAsync(colmax, 0, size_t(cols) * 8, st));
+        dim3 g1((unsigned)ceil_div(cols, 32), (unsigned)std::min<int64_t>(ceil_div(rows, 256), 64));
+        oz::col_absmax_kernel<<<g1, dim3(32, 8), 0, st>>>(X, ldx, rows, cols, colmax);
+        PET_LAUNCH_CHECK();
+    }
     dim3 g2((unsigned)ceil_div(cols, oz::SC_C), (unsigned)ceil_div(Kp, oz::SC_R));
     const size_t smem = size_t(ns) * oz::SC_C * oz::SC_PITCH;
     oz::slice_cols_kernel<<<g2, 256, smem, st>>>(X, ldx, rows, cols, Kp, colmax, ns, out, row_stride, slice_stride, scale);
@@ -553,8 +566,8 @@ extern "C" int pet_ozaki_gemm_mn(int64_t M, int64_t N, int64_t K, const double *
     PET_CUDA(cudaMalloc(&sB, N * 8));
     PET_CUDA(cudaMalloc(&cm, std::max(M, N) * 8));
     PET_CUDA(cudaMalloc(&slabs, size_t(splits) * M * ldc * 8));
-    int rc = ozaki_slice_cols(A_dev, lda, K, (int)M, nslices, cm, As, Kp, M * int64_t(Kp), sA, st);
-    if (rc == PET_OK) rc = ozaki_slice_cols(B_dev, ldb, K, (int)N, nslices, cm, Bs, Kp, N * int64_t(Kp), sB, st);
+    int rc = ozaki_slice_cols(A_dev, lda, K, (int)M, nslices, cm, false, As, Kp, M * int64_t(Kp), sA, st);
+    if (rc == PET_OK) rc = ozaki_slice_cols(B_dev, ldb, K, (int)N, nslices, cm, false, Bs, Kp, N * int64_t(Kp), sB, st);
     const OzOperand opA{As, Kp, M * int64_t(Kp), sA}, opB{Bs, Kp, N * int64_t(Kp), sB};
     cudaEvent_t ev0, ev1;
     cudaEventCreate(&ev0); cudaEventCreate(&ev1);

@@ -105,3 +105,58 @@ def test_kth_largest_bit_exact(dev, n, k):
         v[21] = 0.0
     got = eng.kth_largest(torch.as_tensor(v).to(dev), k).cpu().numpy()[0]
     assert got == np.sort(v)[-k]
+
+
+# ---- FP64-accurate GEMMs on the int8 tcgen05 tensor cores (ozaki.cu) -----------------------------------
+# Error model: every operand row is cut into ns signed 7-bit slices relative to its largest entry, slice
+# products are exact, so |C - AB^T| <= ~K * 2^-(7 ns - 4) * rowmax(A) * rowmax(B); the tolerances below are
+# that bound (worst case K = 1; for long dot products the error is ~100x smaller, 7 slices ~ FP64 rounding).
+OZ_TOL = {6: 2e-12, 7: 2e-14}
+
+
+@pytest.mark.parametrize("ns", [6, 7])
+@pytest.mark.parametrize("M,N,K", [(1, 1, 1), (128, 64, 64), (300, 100, 70), (33, 7, 5), (1000, 1000, 676), (4099, 1000, 676)])
+def test_ozaki_gemm_kk_matches_fp64_matmul(lib, dev, M, N, K, ns):
+    lda = (K + 1) // 2 * 2
+    ldc = (N + 1) // 2 * 2
+    g = torch.Generator(device=dev); g.manual_seed(M * 7 + N)
+    A = torch.randn(M, lda, dtype=torch.float64, device=dev, generator=g)
+    A *= torch.exp(3 * torch.randn(M, 1, dtype=torch.float64, device=dev, generator=g))       # row scales over ~5 decades
+    B = torch.randn(N, lda, dtype=torch.float64, device=dev, generator=g)
+    Cm = torch.full((M, ldc), 3.0, dtype=torch.float64, device=dev)
+    assert lib.pet_ozaki_gemm_kk(M, N, K, P(A), lda, P(B), lda, P(Cm), ldc, ns, 1, stream()) == 0
+    ref = A[:, :K] @ B[:, :K].T
+    bound = K * A[:, :K].abs().amax(1, keepdim=True) * B[:, :K].abs().amax(1)[None, :]
+    assert float(((Cm[:, :N] - ref).abs() / bound).max()) < OZ_TOL[ns]
+    assert bool((Cm[:, N:] == 3.0).all())                       # padding untouched
+
+
+@pytest.mark.parametrize("ns", [6, 7])
+@pytest.mark.parametrize("M,N,K", [(5, 3, 7), (26, 10, 1000), (65, 17, 300), (677, 1000, 5000), (677, 1000, 16001)])
+def test_ozaki_gemm_mn_matches_fp64_matmul(lib, dev, M, N, K, ns):
+    lda, ldb = (M + 1) // 2 * 2, (N + 1) // 2 * 2
+    g = torch.Generator(device=dev); g.manual_seed(K)
+    A = torch.randn(K, lda, dtype=torch.float64, device=dev, generator=g)
+    B = torch.rand(K, ldb, dtype=torch.float64, device=dev, generator=g)                      # posterior-like, in [0, 1)
+    B *= torch.exp(4 * torch.randn(1, ldb, dtype=torch.float64, device=dev, generator=g))     # column scales
+    Cm = torch.zeros((M, ldb), dtype=torch.float64, device=dev)
+    assert lib.pet_ozaki_gemm_mn(M, N, K, P(A), lda, P(B), ldb, P(Cm), ldb, ns, 1, stream()) == 0
+    ref = A[:, :M].T @ B[:, :N]
+    bound = K * A[:, :M].abs().amax(0)[:, None] * B[:, :N].abs().amax(0)[None, :]
+    assert float(((Cm[:, :N] - ref).abs() / bound).max()) < OZ_TOL[ns]
+
+
+def test_ozaki_gemm_is_deterministic_and_exact_on_integers(lib, dev):
+    """Small integers are represented exactly by the slices, so the product is exact; two runs agree bit for bit."""
+    M, N, K = 257, 129, 200
+    g = torch.Generator(device=dev); g.manual_seed(5)
+    A = torch.randint(-60, 61, (M, K), device=dev, generator=g).to(torch.float64)
+    B = torch.randint(-60, 61, (N, K), device=dev, generator=g).to(torch.float64)
+    ldc = N + 1
+    outs = []
+    for _ in range(2):
+        Cm = torch.zeros((M, ldc), dtype=torch.float64, device=dev)
+        assert lib.pet_ozaki_gemm_kk(M, N, K, P(A), K, P(B), K, P(Cm), ldc, 7, 1, stream()) == 0
+        outs.append(Cm[:, :N].clone())
+    assert torch.equal(outs[0], outs[1])
+    assert torch.equal(outs[0], A @ B.T)
