@@ -130,6 +130,16 @@ int  pet_set_candidates(pet_engine *e, const int64_t *cand, void *stream);
 int  pet_e_step(pet_engine *e, const pet_anneal *a, const pet_params *p,
                 double *logpj_out, int64_t ld_logpj, void *stream);
 
+/* CAModel.inference (camodels/__init__.py:255-375) on the device, for one E-step's logpj (n,C)
+ * in device memory: per datapoint the K most probable columns (idx_out (n,topK) int32, value
+ * descending) with p_out (n,topK) = normalised log-posterior if logprob, else
+ * exp(logpj - rowmax) exactly as the reference returns it (:309,:324), and -- binary layout
+ * [null | singletons | states] only, m_out_dev may be NULL -- m_out (n,H) = marginal
+ * LOG-probability of every cause (:336-342; the caller exponentiates, :371).  Needs bound data and candidates. */
+int  pet_posterior_topk(pet_engine *e, const double *logpj_dev, int64_t ld_logpj, int32_t topK,
+                        int32_t logprob, int32_t *idx_out_dev, double *p_out_dev,
+                        double *m_out_dev, void *stream);
+
 /* First half of M_step: per-datapoint log-denominators log sum_c exp(logpj) used by the
  * truncation rule (bsc_et.py:222,247-258) and by L (bsc_et.py:265).  `logpj` NULL = evaluate
  * the E-step on the fly (fused path, nothing of size n*C is materialised).

@@ -15,6 +15,7 @@ MODEL_BSC, MODEL_MCA, MODEL_MMCA, MODEL_TSC, MODEL_DSC, MODEL_GSC = range(6)
 PASS_SELECT = 1
 PASS_REUSE_SCORES = 2
 N_STAGES = 10          # PET_N_STAGES
+MAX_HPRIME, MAX_GAMMA = 16, 8     # engine limits (gl_kernel.cuh)
 
 
 class PetError(RuntimeError):
@@ -69,6 +70,8 @@ SIGNATURES = {
     "pet_select_hprimes": (C.c_int, [C.c_void_p, C.POINTER(Params), C.c_void_p, C.c_void_p]),
     "pet_set_candidates": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "pet_e_step": (C.c_int, [C.c_void_p, C.POINTER(Anneal), C.POINTER(Params), C.c_void_p, C.c_int64, C.c_void_p]),
+    "pet_posterior_topk": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
+                                     C.c_void_p, C.c_void_p]),
     "pet_log_denominators": (C.c_int, [C.c_void_p, C.POINTER(Anneal), C.POINTER(Params), C.c_void_p, C.c_int64,
                                        C.c_int32, C.c_void_p, C.c_void_p]),
     "pet_log_denominators_ptr": (C.c_void_p, [C.c_void_p]),

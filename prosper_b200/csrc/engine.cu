@@ -52,6 +52,9 @@ int launch_add_diag(double *Wq, int64_t ld, const double *colsum, int H, cudaStr
 int launch_colsum(double *out, const double *M, int64_t ld, int64_t rows, int cols, cudaStream_t st);
 int launch_colsumsq(double *out, const double *M, int64_t ld, int64_t rows, int cols, cudaStream_t st);
 
+int launch_infer(const GLStatic &st, int C, int binary_layout, const int *cand, const double *logpj, int64_t ld, int64_t n,
+                 int topK, int logprob, int *idx_out, double *p_out, double *m_out, int sm_count, cudaStream_t stream);
+
 #include "statespace.cpp.inc"
 
 static bool is_device_ptr(const void *p) {
@@ -942,6 +945,20 @@ extern "C" int pet_e_step(pet_engine *e, const pet_anneal *a, const pet_params *
     PET_CHECK(sweep(e, a, p, GLF_WRITE_LOGPJ | GLF_LSE_ONLY, 0, logpj_out, ld_logpj, true, nullptr, nullptr, st));
     if (!is_device_ptr(logpj_out)) PET_CUDA(cudaStreamSynchronize(st));
     return PET_OK;
+}
+
+extern "C" int pet_posterior_topk(pet_engine *e, const double *logpj_dev, int64_t ld_logpj, int32_t topK, int32_t logprob,
+                                  int32_t *idx_out_dev, double *p_out_dev, double *m_out_dev, void *stream) {
+    if (!e || !logpj_dev || !idx_out_dev || !p_out_dev || ld_logpj < e->C) { set_error("pet_posterior_topk: bad arguments"); return PET_EINVAL; }
+    if (!is_device_ptr(logpj_dev)) { set_error("pet_posterior_topk: logpj must be a device pointer"); return PET_EINVAL; }
+    if (e->model == PET_MODEL_GSC) { set_error("pet_posterior_topk: GSC has no logpj matrix"); return PET_EINVAL; }
+    if (e->n <= 0 || e->cand_state == 0) { set_error("pet_posterior_topk: bind data and candidates first"); return PET_ESTATE; }
+    PET_CUDA(cudaSetDevice(e->device));
+    // marginals exist for the layouts [null | singleton blocks | states]: base class (BSC, MCA, MMCA) and DSC
+    const int binary_layout = (e->gls.has_null && e->C == 1 + (int64_t)e->gls.n_blocks * e->H + e->ss.S) ? 1 : 0;
+    if (m_out_dev && !binary_layout) { set_error("pet_posterior_topk: marginals need the [null | singletons | states] layout"); return PET_EINVAL; }
+    return launch_infer(e->gls, (int)e->C, binary_layout, e->cand, logpj_dev, ld_logpj, e->n, topK, logprob, idx_out_dev,
+                        p_out_dev, m_out_dev, e->sm_count, (cudaStream_t)stream);
 }
 
 extern "C" int pet_log_denominators(pet_engine *e, const pet_anneal *a, const pet_params *p, const double *logpj,

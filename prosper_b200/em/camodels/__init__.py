@@ -135,6 +135,22 @@ class Engine(object):
         _lib.check(self.lib.pet_e_step(self.h, C.byref(a), C.byref(p), _ptr(logpj), self.Cols, self.stream()))
         return logpj
 
+    def e_step_device(self, a, p):
+        """E_step whose logpj (n,C) stays in device memory (inference path)."""
+        logpj = torch.empty((max(self.n, 1), self.Cols), dtype=torch.float64, device=self.tdev)
+        _lib.check(self.lib.pet_e_step(self.h, C.byref(a), C.byref(p), _ptr(logpj), self.Cols, self.stream()))
+        return logpj[:self.n]
+
+    def posterior_topk(self, logpj, topK, logprob, marginals):
+        """(idx (n,topK) int32, p (n,topK), m (n,H) or None) of pet_posterior_topk; tensors on the device."""
+        n = self.n
+        idx = torch.empty((max(n, 1), topK), dtype=torch.int32, device=self.tdev)
+        pr = torch.empty((max(n, 1), topK), dtype=torch.float64, device=self.tdev)
+        m = torch.empty((max(n, 1), self.H), dtype=torch.float64, device=self.tdev) if marginals else None
+        _lib.check(self.lib.pet_posterior_topk(self.h, _ptr(logpj), logpj.stride(0), int(topK), 1 if logprob else 0,
+                                               _ptr(idx), _ptr(pr), _ptr(m), self.stream()))
+        return idx[:n], pr[:n], (m[:n] if marginals else None)
+
     def log_denominators(self, a, p, logpj=None, flags=0):
         _lib.check(self.lib.pet_log_denominators(self.h, C.byref(a), C.byref(p), _ptr(logpj),
                                                  0 if logpj is None else logpj.shape[1], flags,
@@ -305,6 +321,114 @@ class CAModel(Model):
         my_data = self.select_Hprimes(model_params, my_data)
         my_suff_stat = self.E_step(anneal, model_params, my_data)
         return my_suff_stat['logpj'], my_data['candidates']
+
+    # -- inference (camodels/__init__.py:255-375) ---------------------------------------------
+    _infer_block_rows = 32768        # datapoints per device block: logpj (rows x C) lives on the device only
+
+    def _regenerate_states(self):
+        self.state_list, self.no_states, self.state_matrix, self.state_abs = generate_state_matrix(self.Hprime, self.gamma)
+
+    def _infer_res(self, my_N, topK):
+        H = self.H
+        return {'s': np.zeros((my_N, topK, H), dtype=np.int8), 'm': np.zeros((my_N, H)), 'p': np.zeros((my_N, topK)),
+                'gamma': np.zeros((my_N,)), 'Hprime': np.zeros((my_N,))}
+
+    def _infer_fill(self, res, rows, idx, p, m, cand, logpj, topK, logprob):
+        """Write one block of results (rows = indices into res).  Base layout [null | h | states]:
+        camodels/__init__.py:317-342.  Like the reference, entries of res['s'] left by an earlier
+        adaptive round are overwritten, never cleared."""
+        H = self.H
+        res['p'][rows] = p.cpu().numpy()
+        res['m'][rows] = m.cpu().numpy()                     # log domain until the end (:371)
+        idx = idx.cpu().numpy().astype(np.int64)
+        s = res['s']
+        for k in range(topK):
+            col = idx[:, k]
+            single = (col >= 1) & (col < H + 1)
+            s[rows[single], k, col[single] - 1] = 1
+            multi = col >= H + 1
+            if multi.any():
+                sm = self.state_matrix[col[multi] - H - 1].astype(np.int8)          # (n_multi, Hprime)
+                s[rows[multi][:, None], k, cand[multi]] = sm
+
+    def _infer_marginals(self):
+        return True
+
+    def _infer_kernel_logprob(self, logprob):
+        return logprob
+
+    def _infer_finish(self, res, logprob):
+        if not logprob:
+            res['m'] = np.exp(res['m'])                      # :371
+
+    def _infer_map_activity(self, res):
+        return (res['s'][:, 0, :] != 0).sum(-1)              # :347
+
+    def inference(self, anneal, model_params, test_data, topK=10, logprob=False, adaptive=True,
+                  Hprime_max=None, gamma_max=None, **kwargs):
+        """Top-K posterior states, their probabilities and the marginals of every cause
+        (camodels/__init__.py:255-375; same arguments, same returned dict).  Candidate selection, the
+        E-step, the row normalisation, the top-K search and the marginals run on the device
+        (`pet_posterior_topk`); the adaptive H'/gamma growth loop stays on the host.  The engine's
+        limits (H' <= 16, gamma <= 8) act as implicit Hprime_max / gamma_max."""
+        assert 'y' in test_data, "Key 'y' in test_data dict not defined."
+        model_params = self.check_params(model_params)
+        comm = self.comm
+        my_y = test_data['y']
+        if isinstance(my_y, torch.Tensor):
+            my_y = my_y.cpu().numpy()
+        my_N, D = my_y.shape
+        Hprime_start, gamma_start = self.Hprime, self.gamma
+        hp_cap = min(self.H, _lib.MAX_HPRIME if Hprime_max is None else min(Hprime_max, _lib.MAX_HPRIME))
+        g_cap = min(self.H, _lib.MAX_GAMMA if gamma_max is None else min(gamma_max, _lib.MAX_GAMMA))
+        if topK == -1:
+            topK = self.state_matrix.shape[0]
+        res = self._infer_res(my_N, topK)
+        self._infer_kwargs = kwargs
+        which = np.ones(my_N, dtype=bool)
+        saved_engine, saved_bound = self._engine, self._bound
+        try:
+            while which.any():
+                ind_n = np.where(which)[0]
+                y_tmp = my_y[which]
+                a = self.engine.anneal(anneal)
+                for b0 in range(0, len(ind_n), self._infer_block_rows):
+                    rows = ind_n[b0:b0 + self._infer_block_rows]
+                    block = {'y': np.ascontiguousarray(y_tmp[b0:b0 + self._infer_block_rows])}
+                    block = self.select_Hprimes(model_params, block)
+                    cand = np.asarray(block['candidates']).astype(np.int64)
+                    p = self._pack_params(model_params)
+                    logpj = self.engine.e_step_device(a, p)
+                    idx, pr, m = self.engine.posterior_topk(logpj, topK, self._infer_kernel_logprob(logprob),
+                                                            self._infer_marginals())
+                    res['Hprime'][rows] = self.Hprime
+                    res['gamma'][rows] = self.gamma
+                    self._infer_fill(res, rows, idx, pr, m, cand, logpj, topK, logprob)
+                    del logpj
+                if not adaptive:
+                    break
+                which = self._infer_map_activity(res) == self.gamma
+                if not which.any():
+                    break
+                if self.Hprime >= hp_cap and self.gamma >= g_cap:
+                    break
+                print("Rank %i: For %i data points MAP state has activity equal to gamma." % (comm.rank, which.sum()))
+                if self.Hprime < hp_cap:
+                    self.Hprime += 1
+                if self.gamma >= g_cap:
+                    pass                                      # reference: `continue` without regenerating (:363-364)
+                else:
+                    self.gamma += 1
+                print("Rank %i: Updating state matrix and running again." % comm.rank)
+                self._regenerate_states()
+                self._engine, self._bound = None, None        # engine for the grown (H', gamma)
+        finally:
+            self.Hprime, self.gamma = Hprime_start, gamma_start
+            self._regenerate_states()
+            self._engine, self._bound = saved_engine, saved_bound
+        self._infer_finish(res, logprob)
+        comm.Barrier()
+        return res
 
     # -- shared M-step plumbing -----------------------------------------------------------
     def _global_cut(self, lse, N_use_target):

@@ -51,6 +51,31 @@ class DSC_ET(GaussianLinearET):
         from . import Engine
         return Engine(self.model_kind, self.D, self.H, self.Hprime, self.gamma, states=self.states)
 
+    # -- inference (dsc_et.py:927-1058) ---------------------------------------------------------
+    def _regenerate_states(self):
+        states, H = self.states, self.H
+        self.state_matrix = get_states(states, self.Hprime, self.gamma)
+        self.no_states = self.state_matrix.shape[0]
+        self.state_abs = np.stack([(self.state_matrix == states[i]).sum(axis=1) for i in range(self.K)]).astype(np.float64)
+        self.state_abs[self._K_0] = H - self.state_abs.sum(0) + self.state_abs[self._K_0]
+
+    def _infer_fill(self, res, rows, idx, p, m, cand, logpj, topK, logprob):
+        """dsc_et.py:996-1018: singleton columns carry their block's value; the marginal of a cause is the
+        log-sum of its FIRST-block singleton and the multi-states holding the value 1 at it (reference quirk)."""
+        H, nb = self.H, (self.K - 1) * self.H
+        res['p'][rows] = p.cpu().numpy()
+        res['m'][rows] = m.cpu().numpy()
+        idx = idx.cpu().numpy().astype(np.int64)
+        s = res['s']
+        for k in range(topK):
+            col = idx[:, k]
+            single = (col >= 1) & (col < nb + 1)
+            h = (col[single] - 1) % H
+            s[rows[single], k, h] = self.single_state_matrix[col[single] - 1, h].astype(np.int8)
+            multi = col >= nb + 1
+            if multi.any():
+                s[rows[multi][:, None], k, cand[multi]] = self.state_matrix[col[multi] - nb - 1].astype(np.int8)
+
     def check_params(self, model_params):
         """dsc_et.py:194-236."""
         assert np.isfinite(model_params['W']).all()

@@ -5,8 +5,10 @@ M_step :359-542.  The reference's constructor raises NameError upstream (`states
 :131); here the ternary values are fixed to [-1, 0, 1] as :125 intends.
 """
 import numpy as np
+import torch
 from scipy.special import comb
 
+from . import CAModel
 from ._gaussian_linear import GaussianLinearET
 from .. import Model
 from ... import _lib
@@ -48,6 +50,56 @@ class TSC_ET(GaussianLinearET):
         s = np.where(p < pi / 2, -1, np.where(p < pi, 1, 0)).astype(np.int8)
         y = s.astype(np.float64) @ W + np.random.normal(scale=sigma, size=(my_N, self.D))
         return {'y': y, 's': s}
+
+    # -- inference (tsc_et.py:546-680) ----------------------------------------------------------
+    def _regenerate_states(self):
+        self.single_state_matrix, self.state_matrix, self.no_states, self.state_abs = \
+            generate_state_matrix(self.Hprime, self.gamma, self.H, self.states)
+
+    def _infer_res(self, my_N, topK):
+        res = CAModel._infer_res(self, my_N, topK)
+        res['am'] = np.zeros((my_N, self.H))
+        return res
+
+    def _infer_marginals(self):
+        return False                 # TSC returns posterior means instead of per-cause log-marginals
+
+    def _infer_kernel_logprob(self, logprob):
+        return True                  # p is the NORMALISED probability here (tsc_et.py:632)
+
+    def _infer_fill(self, res, rows, idx, p, m, cand, logpj, topK, logprob):
+        import ctypes as C
+        eng = self.engine
+        n, S = logpj.shape
+        res['p'][rows] = p.cpu().numpy() if logprob else np.exp(p.cpu().numpy())
+        idx = idx.cpu().numpy().astype(np.int64)
+        for k in range(topK):                                                   # :633-634
+            res['s'][rows[:, None], k, cand] = self.state_matrix[idx[:, k]].astype(np.int8)
+        # posterior means over the candidates: (P . SM) and (P . |SM|), one DMMA GEMM (tsc_et.py:636-638)
+        ldp = (S + 1) // 2 * 2
+        P = torch.zeros((n, ldp), dtype=torch.float64, device=logpj.device)
+        P[:, :S] = torch.softmax(logpj, dim=1)
+        Hp = self.Hprime
+        B = torch.zeros((2 * Hp, ldp), dtype=torch.float64, device=logpj.device)
+        sm = torch.as_tensor(np.ascontiguousarray(self.state_matrix.T, dtype=np.float64)).to(logpj.device)
+        B[:Hp, :S] = sm
+        B[Hp:, :S] = sm.abs()
+        out = torch.empty((n, 2 * Hp), dtype=torch.float64, device=logpj.device)
+        _lib.check(eng.lib.pet_dgemm_kk(n, 2 * Hp, S, C.c_void_p(P.data_ptr()), ldp, C.c_void_p(B.data_ptr()), ldp,
+                                        C.c_void_p(out.data_ptr()), 2 * Hp, 1.0, 0.0, eng.stream()))
+        out = out.cpu().numpy()
+        res['m'][rows[:, None], cand] = out[:, :Hp]                            # duplicates: last write wins
+        if self._infer_kwargs.get('abs_marginal', True):
+            res['am'][rows[:, None], cand] = out[:, Hp:]
+
+    def _infer_finish(self, res, logprob):
+        if logprob:                                                             # :671-673
+            with np.errstate(divide='ignore', invalid='ignore'):
+                res['m'] = np.log(res['m'])
+                res['am'] = np.log(res['am'])
+
+    def _infer_map_activity(self, res):
+        return (res['s'][:, 0, :].astype(bool) != 0).sum(-1)                   # :643
 
     def _AB(self, pi):
         """Trinomial truncation sums (tsc_et.py:422-431)."""

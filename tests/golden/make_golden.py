@@ -117,9 +117,59 @@ def main_gsc():
     run_gsc('full_t1', 16, 8, 4, 2, 'full', 80, 3, 1.0)
 
 
+def run_inference(name, case, model, gt, N, seed, T, meta, **kw):
+    """CAModel.inference of the unmodified reference (camodels/__init__.py:255-375 and the TSC/DSC overrides)."""
+    np.random.seed(seed)
+    data = model.generate_data(gt, N)
+    an = LinearAnnealing(2)
+    an['T'] = T
+    an['anneal_prior'] = False
+    params = dict((k, np.copy(v)) for k, v in gt.items())
+    if name == 'bsc':
+        params['mu'] = np.zeros(meta[0])
+    res = model.inference(an, dict(params), {'y': data['y'].copy()}, **kw)
+    out = dict(model=name, meta=np.array(meta), T=T, y=data['y'], W=params['W'], pi=params['pi'], sigma=params['sigma'])
+    for k, v in kw.items():
+        out['kw_' + k] = -1 if v is None else v
+    for k, v in res.items():
+        out['res_' + k] = v
+    if name == 'dsc':
+        out['states'] = model.states
+    path = os.path.join(HERE, "infer_%s_%s.npz" % (name, case))
+    np.savez_compressed(path, **out)
+    print("wrote", path, "gamma used", np.unique(res['gamma']), "p[0]", res['p'][0][:3])
+
+
+def main_inference():
+    from prosper.em.camodels.bsc_et import BSC_ET
+    from prosper.em.camodels.tsc_et import TSC_ET
+    from prosper.em.camodels.dsc_et import DSC_ET
+    from prosper.em.camodels.mca_et import MCA_ET
+    from prosper.em.camodels.mmca_et import MMCA_ET
+    gt10 = {'W': 10 * generate_bars_dict(10), 'pi': 0.25, 'sigma': 2.0}
+    for name, cls in (('bsc', BSC_ET), ('mca', MCA_ET), ('mmca', MMCA_ET)):
+        run_inference(name, 'fixed', cls(25, 10, 6, 3), gt10, 60, 4, 1.0, (25, 10, 6, 3), topK=5, logprob=False, adaptive=False)
+        run_inference(name, 'logp', cls(25, 10, 6, 3), gt10, 60, 5, 1.0, (25, 10, 6, 3), topK=7, logprob=True, adaptive=False)
+    run_inference('bsc', 'adaptive', BSC_ET(25, 10, 5, 2), gt10, 80, 6, 1.0, (25, 10, 5, 2), topK=4, logprob=False,
+                  adaptive=True, Hprime_max=8, gamma_max=5)
+    gt12 = {'W': 10 * generate_bars_dict(12), 'pi': 0.2, 'sigma': 2.0}
+    run_inference('tsc', 'fixed', TSC_ET(36, 12, 6, 3), gt12, 50, 4, 1.0, (36, 12, 6, 3), topK=5, logprob=False, adaptive=False)
+    run_inference('tsc', 'logp', TSC_ET(36, 12, 6, 3), gt12, 50, 5, 1.0, (36, 12, 6, 3), topK=5, logprob=True, adaptive=False)
+    run_inference('tsc', 'adaptive', TSC_ET(36, 12, 5, 2), gt12, 60, 6, 1.0, (36, 12, 5, 2), topK=3, logprob=False,
+                  adaptive=True, Hprime_max=7, gamma_max=4)
+    gt12d = {'W': 10 * generate_bars_dict(12), 'pi': np.array([.08, .84, .08]), 'sigma': 2.0}
+    run_inference('dsc', 'fixed', DSC_ET(36, 12, 6, 3, np.array([-1., 0., 1.])), gt12d, 50, 4, 1.0, (36, 12, 6, 3),
+                  topK=5, logprob=False, adaptive=False)
+    run_inference('dsc', 'logp', DSC_ET(36, 12, 6, 3, np.array([-1., 0., 1.])), gt12d, 50, 5, 1.0, (36, 12, 6, 3),
+                  topK=5, logprob=True, adaptive=False)
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == 'gsc':
         main_gsc()
+    elif len(sys.argv) > 1 and sys.argv[1] == 'inference':
+        main_inference()
     else:
+        main_inference()
         main()
         main_gsc()

@@ -1,0 +1,88 @@
+"""GPU parity of CAModel.inference against outputs of the unmodified reference
+(tests/golden/infer_*.npz, minted by tests/golden/make_golden.py inference)."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+CASES = sorted(os.path.basename(p) for p in glob.glob(os.path.join(GOLD, "infer_*.npz")))
+
+
+class Anneal(dict):
+    crit_params = []
+
+    def __missing__(self, k):
+        return 0.0
+
+    def as_dict(self):
+        return dict(self)
+
+
+def make(name, meta, g):
+    assert torch.cuda.is_available(), "GPU tests need a B200"
+    D, H, Hp, gam = [int(x) for x in meta]
+    if name == 'bsc':
+        from prosper_b200.em.camodels.bsc_et import BSC_ET
+        return BSC_ET(D, H, Hp, gam)
+    if name == 'mca':
+        from prosper_b200.em.camodels.mca_et import MCA_ET
+        return MCA_ET(D, H, Hp, gam)
+    if name == 'mmca':
+        from prosper_b200.em.camodels.mmca_et import MMCA_ET
+        return MMCA_ET(D, H, Hp, gam)
+    if name == 'tsc':
+        from prosper_b200.em.camodels.tsc_et import TSC_ET
+        return TSC_ET(D, H, Hp, gam)
+    from prosper_b200.em.camodels.dsc_et import DSC_ET
+    return DSC_ET(D, H, Hp, gam, g['states'])
+
+
+def close(a, b, tol=1e-8):
+    """relative agreement that treats -inf / nan / tiny values consistently"""
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    same_nonfinite = (np.isnan(a) & np.isnan(b)) | (a == b)
+    with np.errstate(invalid='ignore'):
+        err = np.abs(a - b) <= tol * np.maximum(1.0, np.maximum(np.abs(a), np.abs(b)))
+    return bool((same_nonfinite | err).all())
+
+
+def test_golden_files_present():
+    assert len(CASES) >= 10
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_inference_matches_reference(case):
+    g = np.load(os.path.join(GOLD, case), allow_pickle=False)
+    name = str(g['model'])
+    m = make(name, g['meta'], g)
+    kw = {}
+    for k in g.files:
+        if k.startswith('kw_'):
+            v = g[k].item()
+            kw[k[3:]] = None if (k[3:] in ('Hprime_max', 'gamma_max') and v == -1) else (bool(v) if k[3:] in ('logprob', 'adaptive') else int(v))
+    an = Anneal(T=float(g['T']), anneal_prior=False)
+    pi = g['pi'] if g['pi'].ndim else float(g['pi'])
+    params = {'W': g['W'].copy(), 'pi': pi, 'sigma': float(g['sigma'])}
+    res = m.inference(an, params, {'y': g['y'].copy()}, **kw)
+    assert sorted(res.keys()) == sorted(k[4:] for k in g.files if k.startswith('res_'))
+    assert np.array_equal(res['gamma'], g['res_gamma']) and np.array_equal(res['Hprime'], g['res_Hprime'])
+    assert close(res['p'], g['res_p'])
+    assert close(res['m'], g['res_m'])
+    if 'am' in res:
+        assert close(res['am'], g['res_am'])
+    # states: identical wherever the probabilities of neighbouring ranks are distinct (ties may swap)
+    p = g['res_p']
+    gap_ok = np.ones(p.shape, dtype=bool)
+    d = np.abs(np.diff(p, axis=1)) > 1e-9 * np.maximum(np.abs(p[:, 1:]), 1e-300)
+    gap_ok[:, 1:] &= d
+    gap_ok[:, :-1] &= d
+    same = (res['s'] == g['res_s']).all(axis=2)
+    assert same[gap_ok].all()
+    assert same.mean() > 0.95
+    # the model is left as it was (H', gamma, state matrix restored)
+    assert (m.Hprime, m.gamma) == (int(g['meta'][2]), int(g['meta'][3]))

@@ -35,7 +35,7 @@ def _oracle_for(name, meta):
 
 
 def golden_files():
-    return sorted(p for p in glob.glob(os.path.join(GOLDEN, "*.npz")) if not os.path.basename(p).startswith("gsc_"))
+    return sorted(p for p in glob.glob(os.path.join(GOLDEN, "*.npz")) if not os.path.basename(p).startswith(("gsc_", "infer_")))
 
 
 @pytest.mark.parametrize("path", golden_files(), ids=[os.path.basename(p) for p in golden_files()])
@@ -184,3 +184,42 @@ def test_gsc_oracle_matches_reference_golden(path):
     new = o.m_step(an, params, suff, data)
     for k in ('W', 'pi', 'mu', 'psi_sq', 'sigma_sq'):
         assert rel_err(new[k], g[k + '_new']) < 1e-8, k
+
+
+# ---- inference: the oracle's restatement against outputs of the reference ------------------
+def _infer_close(a, b, tol=1e-9):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    with np.errstate(invalid='ignore'):
+        ok = (np.isnan(a) & np.isnan(b)) | (a == b) | (np.abs(a - b) <= tol * np.maximum(1.0, np.maximum(np.abs(a), np.abs(b))))
+    return bool(ok.all())
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "infer_*.npz"))), ids=lambda p: os.path.basename(p))
+def test_oracle_inference_matches_reference_golden(path):
+    from oracle import inference as oinf
+    from oracle.bsc import BSC
+    from oracle.tsc import TSC
+    from oracle.dsc import DSC
+    from oracle.mca import MCA, MMCA
+    from oracle.common import DictAnneal
+    g = np.load(path, allow_pickle=False)
+    name = str(g['model'])
+    D, H, Hp, gam = [int(x) for x in g['meta']]
+    cls = {'bsc': BSC, 'tsc': TSC, 'mca': MCA, 'mmca': MMCA}.get(name)
+    make = (lambda hp, ga: DSC(D, H, hp, ga, g['states'])) if name == 'dsc' else (lambda hp, ga: cls(D, H, hp, ga))
+    kw = {}
+    for k in g.files:
+        if k.startswith('kw_'):
+            v = g[k].item()
+            kw[k[3:]] = None if (k[3:] in ('Hprime_max', 'gamma_max') and v == -1) else (bool(v) if k[3:] in ('logprob', 'adaptive') else int(v))
+    an = DictAnneal(T=float(g['T']), anneal_prior=False)
+    params = {'W': g['W'].copy(), 'pi': g['pi'] if g['pi'].ndim else float(g['pi']), 'sigma': float(g['sigma'])}
+    if name == 'bsc':
+        params['mu'] = np.zeros(D)
+    res = oinf.inference(make, Hp, gam, an, params, g['y'].copy(), **kw)
+    assert np.array_equal(res['gamma'], g['res_gamma']) and np.array_equal(res['Hprime'], g['res_Hprime'])
+    assert _infer_close(res['p'], g['res_p'])
+    assert _infer_close(res['m'], g['res_m'])
+    if 'am' in res:
+        assert _infer_close(res['am'], g['res_am'])
+    assert (res['s'] == g['res_s']).all(axis=2).mean() > 0.97       # equal-probability ranks may swap
