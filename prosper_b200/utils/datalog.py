@@ -3,8 +3,8 @@
 Mirrors the interface of prosper/utils/datalog.py (`dlog.set_handler / append / append_all /
 progress / close`, datalog.py:179-254) so that the models log the same keys the reference
 does (`W, pi, sigma, mu, L, N, N_use, Q, prior_mass` and the annealing values,
-camodels/__init__.py:190-191).  Handlers here: TextPrinter, StoreToTxt, Keep (in-memory).
-The HDF5 writer (`result.h5`) is SURVEY section 8 row f1 and not built yet.
+camodels/__init__.py:190-191).  Handlers here: TextPrinter, StoreToTxt, StoreToH5 (`result.h5`
+through utils/autotable.py + utils/h5min.py), Keep (in-memory).
 """
 import sys
 
@@ -44,6 +44,39 @@ class StoreToTxt(DataHandler):
 
     def close(self):
         self.fd.close()
+
+
+class StoreToH5(DataHandler):
+    """Store every appended value as a new row of the table of that name in an HDF5 file
+    (datalog.py:53-93): `dlog.set_handler(('W', 'pi', 'sigma', 'L'), StoreToH5, 'output/result.h5')`.
+    `destination` is a file name, an AutoTable, or None (shared default table)."""
+    default_autotbl = None
+
+    def __init__(self, destination=None):
+        from .autotable import AutoTable
+        self.destination = destination
+        if isinstance(destination, AutoTable):
+            self.autotbl = destination
+        elif isinstance(destination, str):
+            self.autotbl = AutoTable(destination)
+        elif destination is None:
+            self.autotbl = AutoTable() if StoreToH5.default_autotbl is None else StoreToH5.default_autotbl
+        else:
+            raise TypeError("Expects an AutoTable instance or a string as argument")
+        if StoreToH5.default_autotbl is None:
+            StoreToH5.default_autotbl = self.autotbl
+
+    def __repr__(self):
+        return "StoreToH5 into file %s" % self.destination
+
+    def append(self, tblname, value):
+        self.autotbl.append(tblname, value)
+
+    def append_all(self, valdict):
+        self.autotbl.append_all(valdict)
+
+    def close(self):
+        self.autotbl.close()
 
 
 class Keep(DataHandler):

@@ -219,3 +219,34 @@ def test_edge_cases():
         model(25, 10, 11, 3)
     with pytest.raises(AssertionError):
         model(25, 10, 6, 7)
+
+
+def test_em_run_writes_result_h5(tmp_path):
+    """EM.run() with the StoreToH5 handler leaves a result.h5 whose tables have one row per
+    iteration (`/W (iters, D, H)`, `/pi`, `/sigma`, `/L`, `/N_use`, annealing keys), as bars-learning.py:61-69."""
+    from prosper_b200.em import EM
+    from prosper_b200.em.annealing import LinearAnnealing
+    from prosper_b200.utils.datalog import dlog, StoreToH5
+    from prosper_b200.utils import h5min
+    D, H, Hp, gam, N, iters = 25, 10, 6, 3, 400, 6
+    y, params, gt = bsc_problem(D, H, N, 3, bars=True, pi=0.2, sigma=2.0)
+    anneal = LinearAnnealing(iters)
+    anneal['T'] = [(0, 2.), (.7, 1.)]
+    anneal['Ncut_factor'] = [(0, 0.), (2. / 3, 1.)]
+    anneal['anneal_prior'] = False
+    path = str(tmp_path / "result.h5")
+    h = dlog.set_handler(('W', 'pi', 'sigma', 'mu', 'L', 'N_use', 'T', 'Ncut_factor'), StoreToH5, path)
+    try:
+        em = EM(model=model(D, H, Hp, gam), anneal=anneal, data={'y': y.copy()}, lparams=copy_params(params))
+        em.run()
+    finally:
+        h.close()
+        dlog.remove_handler(h)
+    r = h5min.read_h5(path)
+    assert r['W'].shape == (iters, D, H) and r['W'].dtype == np.float64
+    for k in ('pi', 'sigma', 'L', 'N_use', 'T', 'Ncut_factor'):
+        assert r[k].shape == (iters,), k
+    assert r['mu'].shape == (iters, D)
+    assert np.array_equal(r['W'][-1], em.lparams['W']) and r['sigma'][-1] == em.lparams['sigma']
+    assert r['T'][0] == 2.0 and r['T'][-1] == 1.0
+    assert np.isfinite(r['L']).all() and r['L'][-1] > r['L'][0]

@@ -1,0 +1,96 @@
+"""result.h5 writer: file structure, AutoTable row semantics, the dlog handler."""
+import os
+import struct
+
+import numpy as np
+import pytest
+
+from prosper_b200.utils import h5min
+from prosper_b200.utils.autotable import AutoTable
+from prosper_b200.utils.datalog import DataLog, StoreToH5, Keep
+
+
+def test_roundtrip_all_supported_types(tmp_path):
+    rng = np.random.RandomState(0)
+    d = {'W': rng.randn(3, 4, 5), 'pi': np.arange(3.0), 'N_use': np.array([5, 6, 7]), 'flag': np.array([True, False]),
+         'name': np.array([b'abc', b'de']), 'x32': np.arange(6, dtype=np.float32).reshape(2, 3), 'empty': np.zeros((0, 4)),
+         'i8': np.array([[-1, 0, 1]], dtype=np.int8), 'u16': np.array([1, 65535], dtype=np.uint16), 'scalar': np.array(3.5)}
+    path = str(tmp_path / "t.h5")
+    h5min.write_h5(path, d)
+    r = h5min.read_h5(path)
+    assert sorted(r) == sorted(d)
+    for k in d:
+        a = np.asarray(d[k])
+        assert r[k].shape == a.shape and (r[k] == a.astype(r[k].dtype)).all(), k
+    assert r['W'].dtype == np.float64 and r['N_use'].dtype == np.int64 and r['x32'].dtype == np.float32
+
+
+def test_file_structure_follows_the_hdf5_specification(tmp_path):
+    """Spot checks of the on-disk bytes against the HDF5 file format specification (v0 superblock, v1 objects)."""
+    path = str(tmp_path / "s.h5")
+    h5min.write_h5(path, {'b': np.arange(4.0), 'a': np.arange(6, dtype=np.int64).reshape(2, 3)})
+    raw = open(path, 'rb').read()
+    assert raw[:8] == b"\x89HDF\r\n\x1a\n"
+    assert raw[8:16] == bytes([0, 0, 0, 0, 0, 8, 8, 0])                 # versions, 8-byte offsets and lengths
+    base, free, eof, drv = struct.unpack_from("<QQQQ", raw, 24)
+    assert (base, free, eof, drv) == (0, h5min.UNDEF, len(raw), h5min.UNDEF)
+    root_hdr = struct.unpack_from("<Q", raw, 64)[0]
+    assert struct.unpack_from("<I", raw, 72)[0] == 1                    # cache type 1: scratch pad holds B-tree / heap
+    btree, heap = struct.unpack_from("<QQ", raw, 80)
+    assert raw[btree:btree + 4] == b"TREE" and raw[heap:heap + 4] == b"HEAP"
+    assert raw[root_hdr] == 1 and struct.unpack_from("<H", raw, root_hdr + 16)[0] == 0x0011   # symbol table message
+    assert struct.unpack_from("<Q", raw, heap + 16)[0] == 1             # libhdf5's "no free block" marker
+    snod = struct.unpack_from("<Q", raw, btree + 32)[0]
+    assert raw[snod:snod + 4] == b"SNOD" and struct.unpack_from("<H", raw, snod + 6)[0] == 2
+    # IEEE float64 little endian datatype message exactly as libhdf5 writes H5T_IEEE_F64LE
+    assert bytes.fromhex("11203f0008000000000040003 40b0034ff030000".replace(" ", "")) in raw
+    # signed 64-bit little endian integer (H5T_STD_I64LE)
+    assert bytes.fromhex("100800000800000000004000") in raw
+    r = h5min.read_h5(path)
+    assert list(r) == ['a', 'b']                                        # symbol table sorted by name
+
+
+def test_many_datasets_fit_one_symbol_table_node(tmp_path):
+    d = dict(('k%02d' % i, np.full((2, i + 1), float(i))) for i in range(40))
+    path = str(tmp_path / "m.h5")
+    h5min.write_h5(path, d)
+    r = h5min.read_h5(path)
+    assert sorted(r) == sorted(d) and all((r[k] == d[k]).all() for k in d)
+
+
+def test_autotable_appends_rows_like_the_reference(tmp_path):
+    """autotable.py:87-127: table shape = (number of appends,) + value.shape; scalars become 1-d tables."""
+    path = str(tmp_path / "result.h5")
+    with AutoTable(path) as tbl:
+        for it in range(5):
+            tbl.append('W', np.full((3, 2), float(it)))
+            tbl.append('pi', 0.1 * it)
+            tbl.append('N_use', 10 + it)
+        tbl.append_all({'L': -3.5, 'sigma': 1.0})
+        with pytest.raises(TypeError):
+            tbl.append('W', np.zeros((2, 2)))
+        with pytest.raises(TypeError):
+            tbl.append('W', object())
+    r = h5min.read_h5(path)
+    assert r['W'].shape == (5, 3, 2) and (r['W'][3] == 3.0).all()
+    assert r['pi'].shape == (5,) and np.allclose(r['pi'], 0.1 * np.arange(5))
+    assert r['N_use'].dtype.kind == 'i' and list(r['N_use']) == [10, 11, 12, 13, 14]
+    assert r['L'].shape == (1,) and r['sigma'][0] == 1.0
+
+
+def test_dlog_store_to_h5(tmp_path):
+    """datalog.py:53-93,179-254: the handler receives only the tables it was registered for."""
+    path = str(tmp_path / "out" / "result.h5")
+    os.makedirs(os.path.dirname(path))
+    log = DataLog()
+    log.set_handler(('W', 'pi', 'L'), StoreToH5, path)
+    keep = log.set_handler('*', Keep)
+    for it in range(3):
+        log.append_all({'W': np.eye(2) * it, 'pi': 0.2, 'sigma': 1.5})
+        log.append('L', -1.0 * it)
+    assert not log.ignored('W') and not log.ignored('sigma')
+    log.close()
+    r = h5min.read_h5(path)
+    assert sorted(r) == ['L', 'W', 'pi']
+    assert r['W'].shape == (3, 2, 2) and r['L'].tolist() == [0.0, -1.0, -2.0]
+    assert len(keep.values['sigma']) == 3
