@@ -222,6 +222,26 @@ int  pet_gsc_stats(pet_engine *e, const pet_anneal *a, const pet_gsc_params *p, 
 /* out[c] += sum_r M[r][c] (used by the compat GSC M-step on caller-supplied moment tensors) */
 int  pet_colsum(int64_t rows, int64_t cols, const double *M_dev, int64_t ld, double *out_dev, void *stream);
 
+/* ---- synthetic data and initialisation on the device (engine-independent) ------------ */
+/* model.generate_data (camodels/__init__.py:104-122, bsc_et.py:67-95, tsc_et.py:214-275,
+ * dsc_et.py, mca_et.py:65-91): every latent s[n,h] takes values_host[k] with probability
+ * probs_host[k] (K <= 16); y[n,:] = sum_h s_h W[:,h] (combine 0) or, per pixel, the entry
+ * s_h W[d,h] of largest magnitude (combine 1, MCA/MMCA), plus N(0, sigma^2).  Counter-based
+ * Philox RNG keyed by `seed` and the GLOBAL row index row0 + n, so shards generated by
+ * different ranks or in pieces are identical to one big call.  s_idx_dev (n,H) int8
+ * receives the index k of each latent's value, may be NULL.  W_dev is (D,H) row-major. */
+int  pet_generate_data(int32_t combine, int64_t n, int64_t row0, int32_t D, int32_t H,
+                       const double *W_dev, int64_t ldW, int32_t K, const double *values_host,
+                       const double *probs_host, double sigma, uint64_t seed,
+                       double *y_dev, int64_t ldy, int8_t *s_idx_dev, int64_t lds, void *stream);
+/* X[i][j] = (row_base[i] or 0) + scale * N(0,1): W_init of standard_init
+ * (camodels/__init__.py:224-226) and parameter noise (em/__init__.py:63-107) */
+int  pet_normal_fill(double *X_dev, int64_t ld, int64_t rows, int64_t cols,
+                     const double *row_base_dev, double scale, uint64_t seed, void *stream);
+/* out[c] += sum_r (M[r][c] - mean[c])^2: data variance of standard_init (:220) */
+int  pet_col_centered_sumsq(int64_t rows, int64_t cols, const double *M_dev, int64_t ld,
+                            const double *mean_dev, double *out_dev, void *stream);
+
 /* ---- building blocks exported for tests / benchmarks ------------------------------ */
 /* C(M,N) = A.B with both operands K-contiguous: A(M,K) lda, B(N,K) ldb (FP64 tensor-core
  * tiles).  Device pointers, 16-byte aligned, even lda/ldb. */

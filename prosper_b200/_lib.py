@@ -86,6 +86,11 @@ SIGNATURES = {
     "pet_gsc_e_step": (C.c_int, [C.c_void_p, C.POINTER(Anneal), C.POINTER(GSCParams), C.c_void_p, C.c_void_p,
                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "pet_gsc_stats": (C.c_int, [C.c_void_p, C.POINTER(Anneal), C.POINTER(GSCParams), C.c_int32, C.c_void_p, C.c_void_p]),
+    "pet_generate_data": (C.c_int, [C.c_int32, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_int32,
+                                    c_double_p, c_double_p, C.c_double, C.c_uint64, C.c_void_p, C.c_int64, C.c_void_p,
+                                    C.c_int64, C.c_void_p]),
+    "pet_normal_fill": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_double, C.c_uint64, C.c_void_p]),
+    "pet_col_centered_sumsq": (C.c_int, [C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "pet_colsum": (C.c_int, [C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "pet_dgemm_kk": (C.c_int, [C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
                                C.c_void_p, C.c_int64, C.c_double, C.c_double, C.c_void_p]),

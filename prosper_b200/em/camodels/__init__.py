@@ -304,6 +304,8 @@ class CAModel(Model):
         relies on identically seeded ranks)."""
         comm = self.comm
         my_y = data['y']
+        if isinstance(my_y, torch.Tensor) and my_y.is_cuda:
+            return self._standard_init_device(my_y)
         if isinstance(my_y, torch.Tensor):
             my_y = my_y.cpu().numpy()
         my_N, D = my_y.shape
@@ -314,6 +316,63 @@ class CAModel(Model):
         noise = np.random.normal(scale=sigma_init / 4., size=[D, self.H]) if comm.rank == 0 else None
         noise = comm.bcast(noise)
         return {'W': W_mean[:, None] + noise, 'pi': 1. / self.H, 'sigma': sigma_init}
+
+    def _standard_init_device(self, y):
+        """standard_init for a shard that lives on the device: column means and centred second
+        moments with the engine's reduction kernels (two passes, as the reference's formula :217-220), one
+        all-reduce each, W_init from the counter-based device RNG (same seed -> same W on every rank)."""
+        import ctypes as C
+        comm, D, H = self.comm, self.D, self.H
+        lib = _lib.load()
+        assert y.dim() == 2 and y.shape[1] == D and y.dtype == torch.float64 and y.stride(1) == 1
+        st = C.c_void_p(torch.cuda.current_stream(y.device).cuda_stream)
+        n, ld = y.shape[0], y.stride(0)
+        acc = torch.zeros(D + 1, dtype=torch.float64, device=y.device)
+        _lib.check(lib.pet_colsum(n, D, _ptr(y), ld, _ptr(acc), st))
+        acc[D] = float(n)
+        comm.allreduce_tensor_(acc)
+        N = float(acc[D].item())
+        W_mean = (acc[:D] / N).contiguous()
+        ssq = torch.zeros(D, dtype=torch.float64, device=y.device)
+        _lib.check(lib.pet_col_centered_sumsq(n, D, _ptr(y), ld, _ptr(W_mean), _ptr(ssq), st))
+        comm.allreduce_tensor_(ssq)
+        sigma_init = float(torch.sqrt(ssq / N).sum().item()) / D
+        seed = comm.bcast(int(np.random.randint(0, 2 ** 31 - 1)) if comm.rank == 0 else None)
+        W = torch.empty((D, H), dtype=torch.float64, device=y.device)
+        _lib.check(lib.pet_normal_fill(_ptr(W), H, D, H, _ptr(W_mean), sigma_init / 4., seed, st))
+        return {'W': W.cpu().numpy(), 'pi': 1. / H, 'sigma': sigma_init}
+
+    # -- data generation on the device (SURVEY 8 f3) -----------------------------------------
+    def _latent_law(self, model_params):
+        """(values, probabilities, combine) of one latent: Bernoulli(pi), linear superposition."""
+        pi = float(model_params['pi'])
+        return np.array([0., 1.]), np.array([1. - pi, pi]), 0
+
+    def generate_data_device(self, model_params, my_N, seed=0, row0=0, device=None, latents=True):
+        """`generate_data` (camodels/__init__.py:104-122) without the host: returns {'y': (my_N,D) float64 CUDA
+        tensor, 's': (my_N,H) latent values (int8 if they are integers, else float64)}.  `row0` is the global
+        index of the first datapoint: shards of one data set generated on different ranks (or in pieces) with
+        the same seed equal the corresponding rows of one big call."""
+        import ctypes as C
+        lib = _lib.load()
+        device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
+        values, probs, combine = self._latent_law(model_params)
+        values = np.ascontiguousarray(values, dtype=np.float64)
+        probs = np.ascontiguousarray(probs, dtype=np.float64)
+        W = torch.as_tensor(np.ascontiguousarray(model_params['W'], dtype=np.float64)).to(device)
+        assert W.shape == (self.D, self.H)
+        y = torch.empty((my_N, self.D), dtype=torch.float64, device=device)
+        sidx = torch.empty((my_N, self.H), dtype=torch.int8, device=device) if latents else None
+        st = C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+        _lib.check(lib.pet_generate_data(combine, my_N, row0, self.D, self.H, _ptr(W), self.H, len(values),
+                                         values.ctypes.data_as(_lib.c_double_p), probs.ctypes.data_as(_lib.c_double_p),
+                                         float(model_params['sigma']), int(seed), _ptr(y), self.D, _ptr(sidx), self.H, st))
+        out = {'y': y}
+        if latents:
+            vals = torch.as_tensor(values).to(device)
+            s = vals[sidx.long()]
+            out['s'] = s.to(torch.int8) if np.all(values == np.round(values)) else s
+        return out
 
     def compute_lpj(self, anneal, model_params, my_data):
         """camodels/__init__.py:238-253."""

@@ -20,6 +20,10 @@ class MaxCausesET(CAModel):
     def _pack_params(self, model_params):
         return self.engine.params(model_params['W'], model_params['pi'], model_params['sigma'])
 
+    def _latent_law(self, model_params):
+        pi = float(model_params['pi'])                       # magnitude-max combination (mca_et.py:83-85)
+        return np.array([0., 1.]), np.array([1. - pi, pi]), 1
+
     def _AB(self, pies):
         """mca_et.py:241-246 / mmca_et.py:269-274."""
         A = 0.

@@ -51,6 +51,9 @@ class DSC_ET(GaussianLinearET):
         from . import Engine
         return Engine(self.model_kind, self.D, self.H, self.Hprime, self.gamma, states=self.states)
 
+    def _latent_law(self, model_params):
+        return np.asarray(self.states, dtype=np.float64), np.asarray(model_params['pi'], dtype=np.float64), 0
+
     # -- inference (dsc_et.py:927-1058) ---------------------------------------------------------
     def _regenerate_states(self):
         states, H = self.states, self.H

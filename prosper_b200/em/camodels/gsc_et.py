@@ -85,6 +85,9 @@ class GSC(CAModel):
                 assert np.sum(np.asarray(model_params['sigma_sq']) <= 0) == 0
         return model_params
 
+    def generate_data_device(self, *args, **kwargs):
+        raise NotImplementedError("GSC draws continuous latents (gsc_et.py:150-200): use generate_data on the host")
+
     def generate_data(self, model_params, my_N):
         s = np.zeros((my_N, self.H), dtype=bool)
         for n in range(my_N):

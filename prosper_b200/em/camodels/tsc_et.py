@@ -51,6 +51,10 @@ class TSC_ET(GaussianLinearET):
         y = s.astype(np.float64) @ W + np.random.normal(scale=sigma, size=(my_N, self.D))
         return {'y': y, 's': s}
 
+    def _latent_law(self, model_params):
+        pi = float(model_params['pi'])                       # tsc_et.py:228-236
+        return np.array([-1., 0., 1.]), np.array([pi / 2, 1. - pi, pi / 2]), 0
+
     # -- inference (tsc_et.py:546-680) ----------------------------------------------------------
     def _regenerate_states(self):
         self.single_state_matrix, self.state_matrix, self.no_states, self.state_abs = \
