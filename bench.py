@@ -153,21 +153,15 @@ class ClockSampler(object):
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def synth_shard(n_local, seed, dev):
-    """This rank's shard, generated on the device (5.4 GB at 1M): SURVEY 8d config 5."""
-    import torch
+def synth_shard(model, n_local, first, dev):
+    """This rank's shard of SURVEY 8d config 5, generated ON the device by the product's own generator
+    (`pet_generate_data`, counter-based RNG keyed by the global row index: the N ranks' shards are the rows of one
+    data set): W_gt ~ N(0,1) with columns rescaled to norm 10, s ~ Bernoulli(2/H), y = W_gt s + N(0,1)."""
     rng = np.random.RandomState(5)
     Wgt = rng.standard_normal((D, H))
     Wgt *= 10.0 / np.linalg.norm(Wgt, axis=0, keepdims=True)
-    Wg = torch.as_tensor(Wgt).to(dev)
-    gen = torch.Generator(device=dev)
-    gen.manual_seed(1000 + seed)
-    y = torch.empty((n_local, D), dtype=torch.float64, device=dev)
-    for a in range(0, n_local, 65536):
-        b = min(n_local, a + 65536)
-        s = (torch.rand((b - a, H), device=dev, generator=gen) < 2.0 / H).to(torch.float64)
-        y[a:b] = s @ Wg.T + torch.randn((b - a, D), dtype=torch.float64, device=dev, generator=gen)
-    return y
+    gt = {'W': Wgt, 'pi': 2.0 / H, 'sigma': 1.0}
+    return model.generate_data_device(gt, n_local, seed=5, row0=first, device=dev, latents=False)['y']
 
 
 def measure_fp64_peak(dev):
@@ -207,16 +201,12 @@ def run_gpu(args):
 
     first, last = parallel.stride_data(N_TOTAL, comm=comm)
     n_local = last - first
-    y = synth_shard(n_local, rank, dev)
-    ymean = y.mean(0)
-    if world > 1:
-        dist.all_reduce(ymean); ymean /= world
-    rng = np.random.RandomState(7)
-    W0 = ymean.cpu().numpy()[:, None] + rng.normal(scale=0.3, size=(D, H))     # standard_init semantics
-    params0 = {'W': W0, 'pi': 1.0 / H, 'sigma': 1.2}
+    model = BSC_ET(D, H, HP, GAMMA, comm=comm)
+    y = synth_shard(model, n_local, first, dev)
+    np.random.seed(7)
+    params0 = model.standard_init({'y': y})        # on the device: column moments, one all-reduce, device RNG for W
     anneal = Anneal(T=1.0, Ncut_factor=0.0, anneal_prior=False)
 
-    model = BSC_ET(D, H, HP, GAMMA, comm=comm)
     data = {'y': y}
     eng = model.engine
 
