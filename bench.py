@@ -164,6 +164,16 @@ def synth_shard(model, n_local, first, dev):
     return model.generate_data_device(gt, n_local, seed=5, row0=first, device=dev, latents=False)['y']
 
 
+def ncu_traffic():
+    """DRAM bytes per launch of the sliced GEMM kernel from the committed ncu --set full capture (mean of the
+    score and the statistics shape, the two launches the roofline line averages over); None if not recorded."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")))
+        return 0.5 * (t["oz_gemm_score_bytes"] + t["oz_gemm_stats_bytes"])
+    except Exception:
+        return None
+
+
 def measure_fp64_peak(dev):
     """cuBLAS DGEMM 8192^3, best of 5 (same protocol as MEASURED_PEAKS.json, which has no FP64 entry)."""
     import torch
@@ -303,7 +313,7 @@ def run_gpu(args):
                         "pipe_achieved_tops": achieved * pairs, "pipe_peak_tops": int8_peak,
                         "peak_source": "2 x %s bf16_tflops_sustained (int8 dense rate), divided by the %d slice products; "
                                        "cuBLAS DGEMM measured in this run: %.1f TFLOP/s" % (peak_src, pairs, peak),
-                        "traffic": None}
+                        "traffic": ncu_traffic()}
             else:
                 roof = {"kernel": "dgemm_kernel (FP64 DMMA, score + statistics GEMM)", "bound": "tensor",
                         "pipe": "fp64 mma.sync m8n8k4", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
