@@ -219,6 +219,11 @@ int  pet_gsc_e_step(pet_engine *e, const pet_anneal *a, const pet_gsc_params *p,
  * materialised.  stats_dev: pet_gsc_layout.total doubles, overwritten. */
 int  pet_gsc_stats(pet_engine *e, const pet_anneal *a, const pet_gsc_params *p, int32_t flags,
                    double *stats_dev, void *stream);
+/* out_dev[d] += sum over the datapoints kept by the truncation rule (all if !use_cut) of the
+ * engine's copy of y[n,d] -- i.e. of y - mu for BSC, the shard is stored shifted by the mu in
+ * force: `data_sum` of the mu update, bsc_et.py:282,422-428.  Uses the log-denominators of
+ * the last pass. */
+int  pet_data_sum(pet_engine *e, int32_t use_cut, const double *cut_dev, double *out_dev, void *stream);
 /* out[c] += sum_r M[r][c] (used by the compat GSC M-step on caller-supplied moment tensors) */
 int  pet_colsum(int64_t rows, int64_t cols, const double *M_dev, int64_t ld, double *out_dev, void *stream);
 

@@ -45,12 +45,15 @@ int kth_largest(const double *vals, int64_t n, int64_t k, double *out, unsigned 
 int launch_transpose_w(double *Wt, int64_t ldk, const double *W, int64_t ldw, int D, int H, cudaStream_t st);
 int launch_gram_diag(const double *G, int64_t ldg, int H, double *wn2, double *invn, cudaStream_t st);
 int launch_subtract_mu(double *Y, int64_t ldy, int64_t n, int D, const double *mu, cudaStream_t st);
+int launch_wdotmu(const double *Wt, int64_t ldk, int H, int D, const double *mu, double *out, cudaStream_t st);
 int launch_rownorm_pad(const double *src, int64_t ld_src, double *Y, int64_t ldy, int64_t n, int D, double *yy, cudaStream_t st);
 int launch_cand_to_i64(int64_t *out, const int *in, int64_t count, cudaStream_t st);
 int launch_cand_from_i64(int *out, const int64_t *in, int64_t count, int H, cudaStream_t st);
 int launch_add_diag(double *Wq, int64_t ld, const double *colsum, int H, cudaStream_t st);
 int launch_colsum(double *out, const double *M, int64_t ld, int64_t rows, int cols, cudaStream_t st);
 int launch_colsumsq(double *out, const double *M, int64_t ld, int64_t rows, int cols, cudaStream_t st);
+int launch_colsum_kept(double *out, const double *M, int64_t ld, int64_t rows, int cols, const double *lse, const double *cut,
+                       int strict, cudaStream_t st);
 
 int launch_infer(const GLStatic &st, int C, int binary_layout, const int *cand, const double *logpj, int64_t ld, int64_t n,
                  int topK, int logprob, int *idx_out, double *p_out, double *m_out, int sm_count, cudaStream_t stream);
@@ -124,7 +127,7 @@ struct pet_engine {
     std::vector<double> mu_applied;
 
     // per-iteration
-    double *Wt = nullptr, *G = nullptr, *wn2 = nullptr, *invn = nullptr, *Wtmp = nullptr, *mu_dev = nullptr;
+    double *Wt = nullptr, *G = nullptr, *wn2 = nullptr, *invn = nullptr, *Wtmp = nullptr, *mu_dev = nullptr, *wmu = nullptr, *mu_full = nullptr;
     double *YW = nullptr; int64_t yw_rows = 0; bool yw_all = false;
     double *Sbuf = nullptr, *S2buf = nullptr;
     double *gemm_work = nullptr; int64_t gemm_work_doubles = 0;
@@ -181,7 +184,7 @@ extern "C" void pet_destroy(pet_engine *e) {
     cudaSetDevice(e->device);
     cudaDeviceSynchronize();
     free_dev(e->Y); free_dev(e->yy); free_dev(e->cand); free_dev(e->lse); free_dev(e->rs); free_dev(e->ywc); free_dev(e->scl);
-    free_dev(e->Wt); free_dev(e->G); free_dev(e->wn2); free_dev(e->invn); free_dev(e->Wtmp); free_dev(e->mu_dev);
+    free_dev(e->Wt); free_dev(e->G); free_dev(e->wn2); free_dev(e->invn); free_dev(e->Wtmp); free_dev(e->mu_dev); free_dev(e->wmu); free_dev(e->mu_full);
     free_dev(e->YW); free_dev(e->Sbuf); free_dev(e->S2buf); free_dev(e->gemm_work);
     free_dev(e->solveA); free_dev(e->solveB); free_dev(e->solve_work); free_dev(e->s2sum);
     free_dev(e->stage_logpj); free_dev(e->stage_i64); free_dev(e->ksel_state);
@@ -327,6 +330,8 @@ extern "C" int pet_create(const pet_config *cfg, pet_engine **out) {
     TRY(dev_alloc(&e->Wt, e->ldH * e->ldY));
     TRY(dev_alloc(&e->G, e->ldH * e->ldH));
     TRY(dev_alloc(&e->wn2, e->ldH)); TRY(dev_alloc(&e->invn, e->ldH));
+    TRY(dev_alloc(&e->wmu, e->ldH)); TRY(dev_alloc(&e->mu_full, e->ldY));
+    TRYC(cudaMemset(e->wmu, 0, e->ldH * 8));
     TRY(dev_alloc(&e->Wtmp, (int64_t)e->D * e->ldH));
     TRY(dev_alloc(&e->mu_dev, e->ldY));
     TRY(dev_alloc(&e->Sbuf, e->chunk_rows * e->ldH));
@@ -542,6 +547,17 @@ static int prepare(pet_engine *e, const pet_params *p, cudaStream_t st) {
     // G = W^T W  (H,H); its diagonal gives ||W_h||^2 (bsc_et.py:111 recomputes this per datapoint)
     PET_CHECK(dgemm_kk(e->H, e->H, e->D, e->Wt, e->ldY, e->Wt, e->ldY, e->G, e->ldH, 1.0, 0, st));
     PET_CHECK(launch_gram_diag(e->G, e->ldH, e->H, e->wn2, e->invn, st));
+    if (e->model == PET_MODEL_BSC) {          // W_h . mu for the selection scores of the un-shifted datapoints
+        bool nonzero = false;
+        for (double v : e->mu_applied) nonzero |= (v != 0.0);
+        if (nonzero) {
+            PET_CUDA(cudaMemcpyAsync(e->mu_full, e->mu_applied.data(), e->D * 8, cudaMemcpyHostToDevice, st));
+            PET_CUDA(cudaStreamSynchronize(st));      // mu_applied is host memory that may change before the copy runs
+            PET_CHECK(launch_wdotmu(e->Wt, e->ldY, e->H, e->D, e->mu_full, e->wmu, st));
+        } else {
+            PET_CUDA(cudaMemsetAsync(e->wmu, 0, e->ldH * 8, st));
+        }
+    }
     if (e->oz_on)
         PET_CHECK(ozaki_slice_rows(e->Wt, e->ldY, e->H, e->D, e->oz_ns, e->ozW, (int64_t)e->H * e->oz_kpd, e->ozWs, st));
     e->timer.end(st);
@@ -655,7 +671,7 @@ static int sweep_gl(pet_engine *e, const pet_anneal *a, const pet_params *p, int
     if (!reuse) PET_CHECK(prepare(e, p, st));
     ga.flags = kflags;
     if (e->model == PET_MODEL_DSC) ga.flags |= (kflags & GLF_USE_CUT) ? GLF_CUT_STRICT : 0;
-    ga.yy = e->yy; ga.wn2 = e->wn2; ga.invn = e->invn; ga.G = e->G;
+    ga.yy = e->yy; ga.wn2 = e->wn2; ga.invn = e->invn; ga.wmu = e->wmu; ga.G = e->G;
     ga.state_prior = e->d_state_prior;
     PET_CHECK(launch_state_prior(ga.st, ga.it, e->d_state_prior, st));
     ga.cand = e->cand; ga.lse = e->lse; ga.cut = cut_dev;
@@ -782,7 +798,7 @@ static int sweep_mca(pet_engine *e, const pet_anneal *a, const pet_params *p, in
     sel.st = e->gls;
     sel.it.beta = 1.0; sel.it.pre1 = -1.0;
     sel.flags = GLF_SELECT | GLF_SELECT_ONLY;
-    sel.yy = e->yy; sel.wn2 = e->wn2; sel.invn = e->invn; sel.G = e->G; sel.cand = e->cand; sel.lse = e->lse;
+    sel.yy = e->yy; sel.wn2 = e->wn2; sel.invn = e->invn; sel.wmu = e->wmu; sel.G = e->G; sel.cand = e->cand; sel.lse = e->lse;
     sel.state_prior = e->d_state_prior;
     sel.rs = e->rs; sel.ywc = e->ywc; sel.scl = e->scl;
 
@@ -1197,6 +1213,15 @@ extern "C" int pet_gsc_stats(pet_engine *e, const pet_anneal *a, const pet_gsc_p
     cudaStream_t st = (cudaStream_t)stream;
     PET_CUDA(cudaSetDevice(e->device));
     return sweep_gsc(e, a, p, GSCF_STATS | ((flags & PASS_SELECT) ? GSCF_SELECT : 0), nullptr, nullptr, nullptr, nullptr, nullptr, stats_dev, st);
+}
+
+extern "C" int pet_data_sum(pet_engine *e, int32_t use_cut, const double *cut_dev, double *out_dev, void *stream) {
+    if (!e || !out_dev || (use_cut && !cut_dev)) { set_error("pet_data_sum: bad arguments"); return PET_EINVAL; }
+    if (e->n <= 0) return PET_OK;
+    if (e->upload_pending) { set_error("pet_data_sum: run a pass over the shard first"); return PET_ESTATE; }
+    PET_CUDA(cudaSetDevice(e->device));
+    return launch_colsum_kept(out_dev, e->Y, e->ldY, e->n, e->D, e->lse, use_cut ? cut_dev : nullptr,
+                              e->model == PET_MODEL_DSC ? 1 : 0, (cudaStream_t)stream);
 }
 
 extern "C" int pet_colsum(int64_t rows, int64_t cols, const double *M_dev, int64_t ld, double *out_dev, void *stream) {

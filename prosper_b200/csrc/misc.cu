@@ -28,6 +28,17 @@ __global__ void gram_diag_kernel(const double *G, int64_t ldg, int H, double *wn
     invn[h] = 1.0 / sqrt(g);
 }
 
+// wmu[h] = W_h . mu (one warp per h): the BSC selection scores the RAW datapoint (bsc_et.py:110-112) while the shard
+// is stored shifted by mu, so (W_h . y) = (W_h . (y - mu)) + (W_h . mu)
+__global__ void wdotmu_kernel(const double *Wt, int64_t ldk, int H, int D, const double *mu, double *out) {
+    int h = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (h >= H) return;
+    double s = 0.0;
+    for (int d = lane; d < D; d += 32) s = fma(Wt[int64_t(h) * ldk + d], mu[d], s);
+    s = warp_sum(s);
+    if (lane == 0) out[h] = s;
+}
+
 // y <- y - mu (BSC offset, bsc_et.py:169); rare path, only when mu is non-zero
 __global__ void subtract_mu_kernel(double *Y, int64_t ldy, int64_t n, int D, const double *mu) {
     int64_t idx = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -81,6 +92,21 @@ __global__ void colsum_kernel(double *out, const double *M, int64_t ld, int64_t 
     int64_t r0 = int64_t(blockIdx.y) * 256, r1 = (rows < r0 + 256) ? rows : r0 + 256;
     double s = 0.0;
     for (int64_t r = r0; r < r1; ++r) s += M[r * ld + c];
+    atomicAdd(&out[c], s);
+}
+// out[c] += sum over the rows kept by the truncation rule lse >= cut (> cut if strict) of M[r][c]: data_sum of the BSC
+// mu update (bsc_et.py:282 after the cut of :250-257)
+__global__ void colsum_kept_kernel(double *out, const double *M, int64_t ld, int64_t rows, int cols, const double *lse,
+                                   const double *cut, int strict) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= cols) return;
+    int64_t r0 = int64_t(blockIdx.y) * 256, r1 = (rows < r0 + 256) ? rows : r0 + 256;
+    const double cv = cut ? *cut : 0.0;
+    double s = 0.0;
+    for (int64_t r = r0; r < r1; ++r) {
+        const bool keep = !cut || (strict ? lse[r] > cv : lse[r] >= cv);
+        if (keep) s += M[r * ld + c];
+    }
     atomicAdd(&out[c], s);
 }
 // out[c] += sum_r M[r][c]^2   (GSC sigma update: sum_n y_nd^2, gsc_et.py:696,710)
@@ -176,6 +202,11 @@ int launch_gram_diag(const double *G, int64_t ldg, int H, double *wn2, double *i
     PET_LAUNCH_CHECK();
     return PET_OK;
 }
+int launch_wdotmu(const double *Wt, int64_t ldk, int H, int D, const double *mu, double *out, cudaStream_t st) {
+    wdotmu_kernel<<<(unsigned)ceil_div(int64_t(H) * 32, 256), 256, 0, st>>>(Wt, ldk, H, D, mu, out);
+    PET_LAUNCH_CHECK();
+    return PET_OK;
+}
 int launch_subtract_mu(double *Y, int64_t ldy, int64_t n, int D, const double *mu, cudaStream_t st) {
     if (n <= 0) return PET_OK;
     subtract_mu_kernel<<<(unsigned)ceil_div(n * D, 256), 256, 0, st>>>(Y, ldy, n, D, mu);
@@ -216,6 +247,15 @@ int launch_colsum(double *out, const double *M, int64_t ld, int64_t rows, int co
     if (rows <= 0) return PET_OK;
     dim3 g((unsigned)ceil_div(cols, 128), (unsigned)ceil_div(rows, 256));
     colsum_kernel<<<g, 128, 0, st>>>(out, M, ld, rows, cols);
+    PET_LAUNCH_CHECK();
+    return PET_OK;
+}
+
+int launch_colsum_kept(double *out, const double *M, int64_t ld, int64_t rows, int cols, const double *lse, const double *cut,
+                       int strict, cudaStream_t st) {
+    if (rows <= 0) return PET_OK;
+    dim3 g((unsigned)ceil_div(cols, 128), (unsigned)ceil_div(rows, 256));
+    colsum_kept_kernel<<<g, 128, 0, st>>>(out, M, ld, rows, cols, lse, cut, strict);
     PET_LAUNCH_CHECK();
     return PET_OK;
 }

@@ -168,6 +168,13 @@ class Engine(object):
                                              _ptr(self.stats), self.stream()))
         return self.stats
 
+    def data_sum(self, use_cut):
+        """sum over the kept datapoints of the engine's (mu-shifted) copy of y; device tensor (D,)."""
+        out = torch.zeros(self.D, dtype=torch.float64, device=self.tdev)
+        _lib.check(self.lib.pet_data_sum(self.h, 1 if use_cut else 0, _ptr(self.cut) if use_cut else None, _ptr(out),
+                                         self.stream()))
+        return out
+
     def solve(self, p, stats):
         W_new = torch.empty((self.D, self.H), dtype=torch.float64, device=self.tdev)
         info = C.c_int32(0)

@@ -87,6 +87,7 @@ class GaussianLinearET(CAModel):
         pi_new = self._update_prior(model_params, sc[3:3 + n_cnt], N_use, A) if 'pi' in self.to_learn else model_params['pi']
         sigma_new = np.sqrt(sc[2] / self.D / N_use) if 'sigma' in self.to_learn else model_params['sigma']
         dlog.append('N_use', N_use)
+        self._mstep_ctx = (stats, N_use, anneal['Ncut_factor'] > 0.0)
         return self._result(model_params, W_new, pi_new, sigma_new)
 
     def _log_before_L(self, N_use, A):

@@ -62,7 +62,15 @@ class BSC_ET(GaussianLinearET):
         return E * counts[0] / self.H / N_use                            # bsc_et.py:387
 
     def _result(self, model_params, W_new, pi_new, sigma_new):
+        mu_new = model_params['mu']
         if 'mu' in self.to_learn:                                        # bsc_et.py:422-430
-            raise NotImplementedError("learning 'mu' (off by default upstream, and divided by the local "
-                                      "my_N there) is not built yet")
-        return {'W': W_new, 'pi': pi_new, 'sigma': sigma_new, 'mu': model_params['mu']}
+            # mu_new = sum_kept(y)/N - W_new . sum_kept(<s>)/N.  The reference divides by the LOCAL kept count
+            # (`my_N`, :428), which is only meaningful on one rank; here N = N_use over all ranks (identical on one).
+            stats, N_use, use_cut = self._mstep_ctx
+            eng, lay = self.engine, self.engine.layout
+            dsum = eng.data_sum(use_cut)                                 # of y - mu: the shard is stored shifted
+            self.comm.allreduce_tensor_(dsum)
+            mus = stats[lay.off_Wp + self.D * lay.ld_Wp:lay.off_Wp + self.D * lay.ld_Wp + self.H]   # sum_n <s> (ones row)
+            data_sum = dsum.cpu().numpy() + N_use * np.asarray(model_params['mu'], dtype=np.float64)
+            mu_new = data_sum / N_use - np.inner(W_new / N_use, mus.cpu().numpy())
+        return {'W': W_new, 'pi': pi_new, 'sigma': sigma_new, 'mu': mu_new}

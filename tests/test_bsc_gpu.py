@@ -250,3 +250,25 @@ def test_em_run_writes_result_h5(tmp_path):
     assert np.array_equal(r['W'][-1], em.lparams['W']) and r['sigma'][-1] == em.lparams['sigma']
     assert r['T'][0] == 2.0 and r['T'][-1] == 1.0
     assert np.isfinite(r['L']).all() and r['L'][-1] > r['L'][0]
+
+
+@pytest.mark.parametrize("ncut", [0.0, 0.6])
+def test_bsc_learns_mu_like_the_reference(ncut):
+    """bsc_et.py:422-430 with 'mu' in to_learn, from a non-zero mu, with and without truncation; two iterations so
+    that the second runs on the shard re-shifted by the learned mu."""
+    D, H, Hp, gam, N = 25, 10, 6, 3, 500
+    y, params, _ = bsc_problem(D, H, N, 9, bars=True, pi=0.2, sigma=2.0)
+    rng = np.random.RandomState(3)
+    y = y + 1.5                                              # a real offset to learn
+    params['mu'] = rng.randn(D) * 0.3
+    an = DictAnneal(T=1.3, Ncut_factor=ncut, anneal_prior=False)
+    learn = ['W', 'pi', 'sigma', 'mu']
+    o = BSC(D, H, Hp, gam, to_learn=learn)
+    m = model(D, H, Hp, gam, to_learn=learn)
+    po, pm = copy_params(params), copy_params(params)
+    for it in range(2):
+        po = o.step(an, po, {'y': y.copy()})
+        pm = m._fused_step(an, pm, {'y': y})
+        assert rel_err(pm['mu'], po['mu']) < TOL and rel_err(pm['W'], po['W']) < TOL
+        assert abs(pm['sigma'] - po['sigma']) < TOL * po['sigma'] and abs(pm['pi'] - po['pi']) < TOL * po['pi']
+    assert np.abs(pm['mu']).max() > 0.5                      # it moved towards the offset
