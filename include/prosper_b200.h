@@ -213,6 +213,12 @@ int  pet_gsc_select(pet_engine *e, const pet_gsc_params *p, int64_t *cand_out, v
 /* GSC.E_step (gsc_et.py:401-580): dense posterior moments, written at row dst_rows[n] (the
  * reference returns them grouped by candidate set; NULL = identity).  Device outputs:
  * xpt_s, xpt_sz (n,H); xpt_ss, xpt_szsz (n,H,H). */
+/* GSC.compute_lpj (gsc_et.py:811-944): preselection, then the log-joint of the null state, the H
+ * singletons and the S multi-cause states WITHOUT annealing or the `tiny` clamp of the
+ * E-step: logpj_dev (n, 1+H+S) device.  cand_out (n,Hprime) int64 host or device, may be NULL.
+ * Feeds pet_posterior_topk for GSC's inference. */
+int  pet_gsc_compute_lpj(pet_engine *e, const pet_gsc_params *p, double *logpj_dev, int64_t ld_logpj,
+                         int64_t *cand_out, void *stream);
 int  pet_gsc_e_step(pet_engine *e, const pet_anneal *a, const pet_gsc_params *p, const int64_t *dst_rows,
                     double *xpt_s_dev, double *xpt_ss_dev, double *xpt_sz_dev, double *xpt_szsz_dev, void *stream);
 /* Fused select (flags & PET_PASS_SELECT) + E-step + local statistics; nothing of size n*H*H is

@@ -87,6 +87,34 @@ class GSC(object):
         data['_sim'] = scores
         return data
 
+    # gsc_et.py:811-944 -----------------------------------------------------------------------
+    def compute_lpj(self, params, data):
+        """Un-annealed, un-clamped log-joints [null | H singletons | S multi-cause states] per datapoint, rows in
+        the order of data['y'] (the reference computes them cluster-major and sorts back, :941-944)."""
+        data = self.select_hprimes(params, data)
+        y, cand = data['y'], data['candidates']
+        B = self._B(params)
+        H, S = self.H, self.no_states
+        log_pi_pr = np.log(params['pi']) - np.log(1 - np.asarray(params['pi']))          # :846
+        out = np.zeros((y.shape[0], 1 + H + S))
+        out[:, 0] = -np.einsum('nd,de,ne->n', y, B, y)                                   # :864
+        for h in range(H):                                                               # :868-893
+            post, _, _ = self._log_weight(params, B, y, np.array([h]))
+            out[:, 1 + h] = post + log_pi_pr[h]
+        order = self.cluster_order(cand)
+        sc = cand[order]
+        starts = np.flatnonzero(np.r_[True, np.any(sc[1:] != sc[:-1], axis=1)])
+        ends = np.r_[starts[1:], len(order)]
+        for a, b in zip(starts, ends):                                                   # :897-926
+            rows = order[a:b]
+            comps_all = sc[a]
+            for s_i in range(S):
+                act = np.nonzero(self.state_matrix[s_i] > 0)[0]
+                comps = comps_all[act]
+                post, _, _ = self._log_weight(params, B, y[rows], comps)
+                out[rows, 1 + H + s_i] = post + log_pi_pr[comps].sum()
+        return out, cand
+
     @staticmethod
     def cluster_order(cand):
         """Row permutation that groups equal candidate sets, clusters in first-appearance order,

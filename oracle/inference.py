@@ -26,9 +26,12 @@ def inference(make, Hprime, gamma, anneal, params, y, topK=10, logprob=False, ad
     y_tmp = y
     while which.any():
         ind_n = np.where(which)[0]
-        data = model.select_hprimes(params, {'y': y_tmp})
-        logpj = model.e_step(anneal, params, data)['logpj']
-        cand = np.asarray(data['candidates']).astype(np.int64)
+        if kind == 'gsc':                                          # gsc_et.py:811-944 overrides compute_lpj only
+            logpj, cand = model.compute_lpj(params, {'y': y_tmp})
+        else:
+            data = model.select_hprimes(params, {'y': y_tmp})
+            logpj = model.e_step(anneal, params, data)['logpj']
+            cand = np.asarray(data['candidates']).astype(np.int64)
         corr = logpj.max(axis=1)                                   # :307
         logpjc = logpj - corr[:, None]
         pjc = np.exp(logpjc)                                       # :309 (before the normalisation below)

@@ -83,6 +83,7 @@ SIGNATURES = {
                                    C.POINTER(C.c_int32), C.c_void_p]),
     "pet_gsc_layout_get": (C.c_int, [C.c_void_p, C.POINTER(GSCLayout)]),
     "pet_gsc_select": (C.c_int, [C.c_void_p, C.POINTER(GSCParams), C.c_void_p, C.c_void_p]),
+    "pet_gsc_compute_lpj": (C.c_int, [C.c_void_p, C.POINTER(GSCParams), C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "pet_gsc_e_step": (C.c_int, [C.c_void_p, C.POINTER(Anneal), C.POINTER(GSCParams), C.c_void_p, C.c_void_p,
                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "pet_gsc_stats": (C.c_int, [C.c_void_p, C.POINTER(Anneal), C.POINTER(GSCParams), C.c_int32, C.c_void_p, C.c_void_p]),

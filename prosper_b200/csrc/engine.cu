@@ -967,7 +967,6 @@ extern "C" int pet_posterior_topk(pet_engine *e, const double *logpj_dev, int64_
                                   int32_t *idx_out_dev, double *p_out_dev, double *m_out_dev, void *stream) {
     if (!e || !logpj_dev || !idx_out_dev || !p_out_dev || ld_logpj < e->C) { set_error("pet_posterior_topk: bad arguments"); return PET_EINVAL; }
     if (!is_device_ptr(logpj_dev)) { set_error("pet_posterior_topk: logpj must be a device pointer"); return PET_EINVAL; }
-    if (e->model == PET_MODEL_GSC) { set_error("pet_posterior_topk: GSC has no logpj matrix"); return PET_EINVAL; }
     if (e->n <= 0 || e->cand_state == 0) { set_error("pet_posterior_topk: bind data and candidates first"); return PET_ESTATE; }
     PET_CUDA(cudaSetDevice(e->device));
     // marginals exist for the layouts [null | singleton blocks | states]: base class (BSC, MCA, MMCA) and DSC
@@ -1110,7 +1109,8 @@ static int prepare_gsc(pet_engine *e, const pet_gsc_params *p, cudaStream_t st) 
 
 // flags: GSCF_*.  Dense outputs are device pointers (n,H) / (n,H,H); dst maps datapoint -> output row.
 static int sweep_gsc(pet_engine *e, const pet_anneal *a, const pet_gsc_params *p, int flags, const int64_t *dst_dev,
-                     double *xs, double *xss, double *xsz, double *xszsz, double *stats_dev, cudaStream_t st) {
+                     double *xs, double *xss, double *xsz, double *xszsz, double *stats_dev, cudaStream_t st,
+                     double *logpj_dev = nullptr, int64_t ld_logpj = 0) {
     if (e->n <= 0) { set_error("no data bound (pet_set_data)"); return PET_ESTATE; }
     if (!(flags & GSCF_SELECT) && e->cand_state == 0) { set_error("no candidates: run select_Hprimes first"); return PET_ESTATE; }
     if (!a || !(a->T > 0.0)) { set_error("annealing temperature T must be > 0"); return PET_EINVAL; }
@@ -1124,6 +1124,7 @@ static int sweep_gsc(pet_engine *e, const pet_anneal *a, const pet_gsc_params *p
     g.beta = 1.0 / a->T;
     g.yyw = e->yyw; g.G = e->G; g.psi = e->psi_dev; g.cand = e->cand;
     g.dst = dst_dev; g.xpt_s = xs; g.xpt_ss = xss; g.xpt_sz = xsz; g.xpt_szsz = xszsz;
+    g.logpj = logpj_dev; g.ld_logpj = ld_logpj;
     pet_gsc_layout lay;
     pet_gsc_layout_get(e, &lay);
     if (flags & GSCF_STATS) {
@@ -1188,6 +1189,20 @@ extern "C" int pet_gsc_select(pet_engine *e, const pet_gsc_params *p, int64_t *c
     PET_CUDA(cudaSetDevice(e->device));
     pet_anneal a{1.0, 0.0, 0};
     PET_CHECK(sweep_gsc(e, &a, p, GSCF_SELECT | GSCF_SELECT_ONLY, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, st));
+    if (cand_out) PET_CHECK(copy_cand_out(e, cand_out, st));
+    return PET_OK;
+}
+
+extern "C" int pet_gsc_compute_lpj(pet_engine *e, const pet_gsc_params *p, double *logpj_dev, int64_t ld_logpj,
+                                   int64_t *cand_out, void *stream) {
+    if (!e || e->model != PET_MODEL_GSC || !logpj_dev || ld_logpj < e->C || !is_device_ptr(logpj_dev)) {
+        set_error("pet_gsc_compute_lpj: bad arguments (logpj must be a device array with ld >= 1 + H + S)");
+        return PET_EINVAL;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    PET_CUDA(cudaSetDevice(e->device));
+    pet_anneal a{1.0, 0.0, 0};
+    PET_CHECK(sweep_gsc(e, &a, p, GSCF_SELECT | GSCF_LOGPJ, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, st, logpj_dev, ld_logpj));
     if (cand_out) PET_CHECK(copy_cand_out(e, cand_out, st));
     return PET_OK;
 }

@@ -91,6 +91,7 @@ struct StateEval {          // everything phase 5 needs of one multi-cause state
     double kappa[KM];
     double lam_inv[KM * KM];
     double lw;              // beta * (post + prior), clamped
+    double raw;             // post + prior (compute_lpj, gsc_et.py:926)
 };
 
 __device__ __forceinline__ void eval_gsc_state(unsigned long long rec, int Hp, double beta, double yyw,
@@ -126,7 +127,8 @@ __device__ __forceinline__ void eval_gsc_state(unsigned long long rec, int Hp, d
         e.kappa[i] = v + muc[e.pos[i]];                      // gsc_et.py:329-331
         quad -= b[i] * v;
     }
-    double lw = beta * (-(logdetP + logdetL) - quad + prior);   // gsc_et.py:338-354
+    e.raw = -(logdetP + logdetL) - quad + prior;
+    double lw = beta * e.raw;                                // gsc_et.py:338-354
     if (!(lw >= LOG_TINY)) lw = LOG_TINY;                    // NaN or below tiny -> tiny (:355-357)
     e.lw = lw;
     if (need_moments)
@@ -210,6 +212,24 @@ __global__ void __launch_bounds__(GSC_WARPS * 32) gsc_kernel(const __grid_consta
         }
         __syncwarp();
 
+        if (a.flags & GSCF_LOGPJ) {                              // compute_lpj: gsc_et.py:864 (null), :893 (singletons), :926
+            double *out = a.logpj + n * a.ld_logpj;
+            if (lane == 0) out[0] = -yyw;
+            for (int h = lane; h < H; h += 32) {
+                const double v = row[h];
+                const double g = a.tb.g[h], mu = a.tb.mu[h];
+                const double b = v - g * mu;
+                const double quad = yyw + mu * (mu * g - 2.0 * v) - b * b * a.tb.ilam[h];
+                out[1 + h] = (-a.tb.lcdet[h] - quad) + a.tb.logit[h];
+            }
+            for (int s = lane; s < S; s += 32) {
+                StateEval e;
+                eval_gsc_state(states_s[s], Hp, 1.0, yyw, Gc, Pc, ywc, muc, lgc, e, false);
+                out[1 + H + s] = e.raw;
+            }
+            __syncwarp();
+            continue;
+        }
         // ---- 4: log-weights -----------------------------------------------------------------------
         const double lw0 = -a.beta * yyw;                    // null state, NOT clamped (gsc_et.py:459-463)
         double mx = lw0;

@@ -18,6 +18,7 @@ enum {
     GSCF_SELECT_ONLY = 1 << 1,
     GSCF_DENSE = 1 << 2,        // compat E_step: write dense xpt_* rows (at row dst[n])
     GSCF_STATS = 1 << 3,        // accumulate the M-step statistics
+    GSCF_LOGPJ = 1 << 4,        // compute_lpj (gsc_et.py:811-944): write the un-annealed, un-clamped log-joints and stop
 };
 
 struct GSCArgs {
@@ -38,6 +39,7 @@ struct GSCArgs {
     const int64_t *dst;
     double *xpt_s, *xpt_sz;      // (n, H)
     double *xpt_ss, *xpt_szsz;   // (n, H, H)
+    double *logpj; int64_t ld_logpj;   // GSCF_LOGPJ: (n, 1 + H + S), global row index
 };
 
 int launch_gsc_kernel(const GSCArgs &a, int gamma, int sm_count, cudaStream_t stream);

@@ -417,6 +417,12 @@ class CAModel(Model):
                 sm = self.state_matrix[col[multi] - H - 1].astype(np.int8)          # (n_multi, Hprime)
                 s[rows[multi][:, None], k, cand[multi]] = sm
 
+    def _infer_logpj_device(self, a, model_params, y_block):
+        """compute_lpj of one block with logpj left on the device -> (logpj (n,C) CUDA tensor, candidates (n,H') int64)."""
+        block = self.select_Hprimes(model_params, {'y': y_block})
+        cand = np.asarray(block['candidates']).astype(np.int64)
+        return self.engine.e_step_device(a, self._pack_params(model_params)), cand
+
     def _infer_marginals(self):
         return True
 
@@ -460,11 +466,7 @@ class CAModel(Model):
                 a = self.engine.anneal(anneal)
                 for b0 in range(0, len(ind_n), self._infer_block_rows):
                     rows = ind_n[b0:b0 + self._infer_block_rows]
-                    block = {'y': np.ascontiguousarray(y_tmp[b0:b0 + self._infer_block_rows])}
-                    block = self.select_Hprimes(model_params, block)
-                    cand = np.asarray(block['candidates']).astype(np.int64)
-                    p = self._pack_params(model_params)
-                    logpj = self.engine.e_step_device(a, p)
+                    logpj, cand = self._infer_logpj_device(a, model_params, np.ascontiguousarray(y_tmp[b0:b0 + self._infer_block_rows]))
                     idx, pr, m = self.engine.posterior_topk(logpj, topK, self._infer_kernel_logprob(logprob),
                                                             self._infer_marginals())
                     res['Hprime'][rows] = self.Hprime

@@ -146,6 +146,23 @@ class GSC(CAModel):
         rank_of_cluster = np.argsort(np.argsort(first))
         return np.argsort(rank_of_cluster[inv.ravel()], kind='stable')
 
+    # -- compute_lpj / inference (gsc_et.py:811-944; inference itself is inherited, camodels/__init__.py:255-375) ----
+    def _infer_logpj_device(self, a, model_params, y_block):
+        eng = self.engine
+        self._bind({'y': y_block})
+        logpj = torch.empty((max(eng.n, 1), eng.Cols), dtype=torch.float64, device=eng.tdev)
+        cand = np.empty((eng.n, self.Hprime), dtype=np.int64)
+        _lib.check(eng.lib.pet_gsc_compute_lpj(eng.h, C.byref(self._pack(model_params)), _ptr(logpj), eng.Cols, _ptr(cand),
+                                               eng.stream()))
+        return logpj[:eng.n], cand
+
+    def compute_lpj(self, anneal, model_params, my_data):
+        """gsc_et.py:811-944 -> (logpj (n, 1+H+S), candidates (n,H')), rows in the order of my_data['y']."""
+        assert 'y' in my_data, "Key 'y' in test_data dict not defined."
+        y = my_data['y']
+        logpj, cand = self._infer_logpj_device(None, model_params, y.cpu().numpy() if isinstance(y, torch.Tensor) else y)
+        return logpj.cpu().numpy(), cand
+
     # -- the three operators ----------------------------------------------------------------------
     def select_Hprimes(self, model_params, my_data):
         """gsc_et.py:721-749 -> my_data['data_clusters'] {key: {'hprimes','data','ind'}}."""

@@ -140,7 +140,32 @@ def run_inference(name, case, model, gt, N, seed, T, meta, **kw):
     print("wrote", path, "gamma used", np.unique(res['gamma']), "p[0]", res['p'][0][:3])
 
 
+def run_inference_gsc(case, D, H, Hp, gam, stype, N, seed, **kw):
+    from prosper.em.camodels.gsc_et import GSC
+    np.random.seed(seed)
+    model = GSC(D, H, Hp, gam, sigma_sq_type=stype)
+    sig = {'scalar': 1.5, 'diagonal': 1.0 + 0.5 * np.arange(D) / D}[stype]
+    gt = {'W': 10 * generate_bars_dict(H), 'pi': 0.2 * np.ones(H), 'mu': np.ones(H) + 0.1 * np.arange(H),
+          'psi_sq': np.eye(H) + 0.05, 'sigma_sq': sig}
+    data = model.generate_data(gt, N)
+    an = LinearAnnealing(2)
+    an['T'] = 1.0
+    params = dict((k, np.copy(v)) for k, v in gt.items())
+    res = model.inference(an, dict((k, np.copy(v)) for k, v in params.items()), {'y': data['y'].copy()}, **kw)
+    out = dict(model='gsc', meta=np.array((D, H, Hp, gam)), sigma_sq_type=stype, T=1.0, y=data['y'], W=params['W'],
+               pi=params['pi'], mu=params['mu'], psi_sq=params['psi_sq'], sigma_sq=params['sigma_sq'])
+    for k, v in kw.items():
+        out['kw_' + k] = -1 if v is None else v
+    for k, v in res.items():
+        out['res_' + k] = v
+    path = os.path.join(HERE, "infer_gsc_%s.npz" % case)
+    np.savez_compressed(path, **out)
+    print("wrote", path, "p[0]", res['p'][0][:3])
+
+
 def main_inference():
+    run_inference_gsc('scalar', 25, 10, 6, 3, 'scalar', 40, 4, topK=5, logprob=False, adaptive=False)
+    run_inference_gsc('diag_logp', 25, 10, 5, 2, 'diagonal', 40, 5, topK=6, logprob=True, adaptive=False)
     from prosper.em.camodels.bsc_et import BSC_ET
     from prosper.em.camodels.tsc_et import TSC_ET
     from prosper.em.camodels.dsc_et import DSC_ET

@@ -38,6 +38,9 @@ def make(name, meta, g):
     if name == 'tsc':
         from prosper_b200.em.camodels.tsc_et import TSC_ET
         return TSC_ET(D, H, Hp, gam)
+    if name == 'gsc':
+        from prosper_b200.em.camodels.gsc_et import GSC
+        return GSC(D, H, Hp, gam, sigma_sq_type=str(g['sigma_sq_type']))
     from prosper_b200.em.camodels.dsc_et import DSC_ET
     return DSC_ET(D, H, Hp, gam, g['states'])
 
@@ -66,8 +69,12 @@ def test_inference_matches_reference(case):
             v = g[k].item()
             kw[k[3:]] = None if (k[3:] in ('Hprime_max', 'gamma_max') and v == -1) else (bool(v) if k[3:] in ('logprob', 'adaptive') else int(v))
     an = Anneal(T=float(g['T']), anneal_prior=False)
-    pi = g['pi'] if g['pi'].ndim else float(g['pi'])
-    params = {'W': g['W'].copy(), 'pi': pi, 'sigma': float(g['sigma'])}
+    if name == 'gsc':
+        params = dict((k, g[k].copy()) for k in ('W', 'pi', 'mu', 'psi_sq', 'sigma_sq'))
+        if params['sigma_sq'].ndim == 0:
+            params['sigma_sq'] = float(params['sigma_sq'])
+    else:
+        params = {'W': g['W'].copy(), 'pi': g['pi'] if g['pi'].ndim else float(g['pi']), 'sigma': float(g['sigma'])}
     res = m.inference(an, params, {'y': g['y'].copy()}, **kw)
     assert sorted(res.keys()) == sorted(k[4:] for k in g.files if k.startswith('res_'))
     assert np.array_equal(res['gamma'], g['res_gamma']) and np.array_equal(res['Hprime'], g['res_Hprime'])

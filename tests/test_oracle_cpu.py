@@ -207,13 +207,21 @@ def test_oracle_inference_matches_reference_golden(path):
     D, H, Hp, gam = [int(x) for x in g['meta']]
     cls = {'bsc': BSC, 'tsc': TSC, 'mca': MCA, 'mmca': MMCA}.get(name)
     make = (lambda hp, ga: DSC(D, H, hp, ga, g['states'])) if name == 'dsc' else (lambda hp, ga: cls(D, H, hp, ga))
+    if name == 'gsc':
+        from oracle.gsc import GSC
+        make = lambda hp, ga: GSC(D, H, hp, ga, sigma_sq_type=str(g['sigma_sq_type']))
     kw = {}
     for k in g.files:
         if k.startswith('kw_'):
             v = g[k].item()
             kw[k[3:]] = None if (k[3:] in ('Hprime_max', 'gamma_max') and v == -1) else (bool(v) if k[3:] in ('logprob', 'adaptive') else int(v))
     an = DictAnneal(T=float(g['T']), anneal_prior=False)
-    params = {'W': g['W'].copy(), 'pi': g['pi'] if g['pi'].ndim else float(g['pi']), 'sigma': float(g['sigma'])}
+    if name == 'gsc':
+        params = dict((k, g[k].copy()) for k in ('W', 'pi', 'mu', 'psi_sq', 'sigma_sq'))
+        if params['sigma_sq'].ndim == 0:
+            params['sigma_sq'] = float(params['sigma_sq'])
+    else:
+        params = {'W': g['W'].copy(), 'pi': g['pi'] if g['pi'].ndim else float(g['pi']), 'sigma': float(g['sigma'])}
     if name == 'bsc':
         params['mu'] = np.zeros(D)
     res = oinf.inference(make, Hp, gam, an, params, g['y'].copy(), **kw)
