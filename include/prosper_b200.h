@@ -253,6 +253,21 @@ int  pet_normal_fill(double *X_dev, int64_t ld, int64_t rows, int64_t cols,
 int  pet_col_centered_sumsq(int64_t rows, int64_t cols, const double *M_dev, int64_t ld,
                             const double *mean_dev, double *out_dev, void *stream);
 
+/* ---- mixture models (prosper/em/mixturemodels; contractions are pet_dgemm_kk / pet_dgemm_mn) ---- */
+/* logpj[n][h] = beta (s1 T1[n][h] + s2 T2[n][h] + k[h]); post = exp(logpj) with the reference's clamps
+ * (NaN -> tiny, < tiny -> tiny, inf -> max/H), rows normalised: MoG.py:208-218, MoP.py:165-175.
+ * T2_dev may be NULL.  All device pointers. */
+int  pet_mix_posterior(int64_t n, int32_t H, const double *T1_dev, const double *T2_dev, int64_t ldt,
+                       double s1, double s2, const double *k_dev, double beta, double *logpj_dev,
+                       int64_t ld_logpj, double *post_dev, int64_t ld_post, void *stream);
+/* out[n * out_stride] = sum_d A[n][d] B[n][d] */
+int  pet_rowdot(int64_t n, int32_t D, const double *A_dev, int64_t lda, const double *B_dev, int64_t ldb,
+                double *out_dev, int64_t out_stride, void *stream);
+/* row-wise element operations into a zero-padded (n, ldo) array: op 0: X^2; 1: X * w[n * w_stride];
+ * 2: X - w[d]; 3: a / (sum_d X[n][d] + eps) * X + 1 (MoP.normalize, MoP.py:236-244) */
+int  pet_rowop(int32_t op, int64_t n, int32_t D, const double *X_dev, int64_t ldx, const double *w_dev,
+               int64_t w_stride, double a, double *out_dev, int64_t ldo, void *stream);
+
 /* ---- building blocks exported for tests / benchmarks ------------------------------ */
 /* C(M,N) = A.B with both operands K-contiguous: A(M,K) lda, B(N,K) ldb (FP64 tensor-core
  * tiles).  Device pointers, 16-byte aligned, even lda/ldb. */

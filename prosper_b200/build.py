@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIBPATH = os.path.join(LIBDIR, "libprosper_b200.so")
-SOURCES = ["engine.cu", "dgemm.cu", "gl_kernel.cu", "mca_kernel.cu", "gsc_kernel.cu", "solve.cu", "misc.cu", "ozaki.cu", "infer.cu", "synth.cu"]
+SOURCES = ["engine.cu", "dgemm.cu", "gl_kernel.cu", "mca_kernel.cu", "gsc_kernel.cu", "solve.cu", "misc.cu", "ozaki.cu", "infer.cu", "synth.cu", "mixture.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-shared"]
 

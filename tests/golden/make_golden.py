@@ -189,12 +189,58 @@ def main_inference():
                   topK=5, logprob=True, adaptive=False)
 
 
+def run_mixture(case, model, gt, N, seed, T):
+    """E_step + M_step of the unmodified mixture models (mixturemodels/MoG.py, MoP.py)."""
+    np.random.seed(seed)
+    data = model.generate_data(gt, N)
+    params = model.standard_init({'y': data['y']})
+    if 'pies' not in params:
+        params['pies'] = np.ones(model.H) / model.H
+    if 'sigmas_sq' in gt and 'sigmas_sq' not in params:
+        params['sigmas_sq'] = gt['sigmas_sq'].copy()
+    if case.startswith('mop'):
+        params['W'] = np.abs(params['W']) + 0.5                 # Poisson rates must be positive
+    an = LinearAnnealing(2)
+    an['T'] = T
+    p0 = dict((k, np.copy(v)) for k, v in params.items())
+    suff = model.E_step(an, params, {'y': data['y']})
+    new = model.M_step(an, dict((k, np.copy(v)) for k, v in params.items()), suff, {'y': data['y']})
+    out = dict(case=case, T=T, y=data['y'], post=suff['posteriors_h'], logpj=suff['logpj'])
+    for k, v in p0.items():
+        out['p0_' + k] = v
+    for k, v in new.items():
+        out['new_' + k] = v
+    path = os.path.join(HERE, "mix_%s.npz" % case)
+    np.savez_compressed(path, **out)
+    print("wrote", path, "pies_new", np.round(new['pies'], 4))
+
+
+def main_mixture():
+    from prosper.em.mixturemodels.MoG import MoG
+    from prosper.em.mixturemodels.MoP import MoP
+    rng = np.random.RandomState(0)
+    D, H = 6, 4
+    Wg = rng.randn(D, H) * 3
+    pies = np.array([.1, .2, .3, .4])
+    sd = 0.5 + rng.rand(H, D)
+    run_mixture('mog_diag', MoG(D, H, sigmas_sq_type='diagonal'), {'W': Wg, 'pies': pies, 'sigmas_sq': sd}, 300, 1, 1.0)
+    run_mixture('mog_diag_t2', MoG(D, H, sigmas_sq_type='diagonal'), {'W': Wg, 'pies': pies, 'sigmas_sq': sd}, 200, 2, 2.0)
+    sf = np.stack([np.diag(sd[h]) + 0.1 for h in range(H)])
+    run_mixture('mog_full', MoG(D, H, sigmas_sq_type='full'), {'W': Wg, 'pies': pies, 'sigmas_sq': sf}, 300, 3, 1.0)
+    Wp = np.abs(rng.randn(D, H)) * 10 + 1
+    run_mixture('mop', MoP(D, H), {'W': Wp, 'pies': pies}, 300, 4, 1.0)
+    run_mixture('mop_A', MoP(D, H, A=40.), {'W': Wp, 'pies': pies}, 300, 5, 1.3)
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == 'gsc':
         main_gsc()
     elif len(sys.argv) > 1 and sys.argv[1] == 'inference':
         main_inference()
+    elif len(sys.argv) > 1 and sys.argv[1] == 'mixture':
+        main_mixture()
     else:
+        main_mixture()
         main_inference()
         main()
         main_gsc()
