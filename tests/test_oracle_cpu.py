@@ -35,7 +35,7 @@ def _oracle_for(name, meta):
 
 
 def golden_files():
-    return sorted(p for p in glob.glob(os.path.join(GOLDEN, "*.npz")) if not os.path.basename(p).startswith(("gsc_", "infer_")))
+    return sorted(p for p in glob.glob(os.path.join(GOLDEN, "*.npz")) if not os.path.basename(p).startswith(("gsc_", "infer_", "mix_")))
 
 
 @pytest.mark.parametrize("path", golden_files(), ids=[os.path.basename(p) for p in golden_files()])
