@@ -698,6 +698,10 @@ static int sweep_gl(pet_engine *e, const pet_anneal *a, const pet_params *p, int
             e->stage_logpj_doubles = need;
         }
     }
+    // the int8 statistics path slices <s> anyway: the normalisation is folded into that load, no scale kernel
+    static const bool no_fold = getenv("PET_GL_NO_FOLD") != nullptr;
+    const bool fold_scale = do_stats && e->oz_on && !e->S2buf && !no_fold;
+    if (fold_scale) ga.flags |= GLF_FOLD_SCALE;
     const int64_t nchunks = ceil_div(e->n, e->chunk_rows);
     for (int64_t c = 0; c < nchunks; ++c) {
         const int64_t r0 = c * e->chunk_rows, rows = std::min(e->chunk_rows, e->n - r0);
@@ -731,9 +735,11 @@ static int sweep_gl(pet_engine *e, const pet_anneal *a, const pet_params *p, int
         e->timer.begin(ST_POST, st);
         PET_CHECK(launch_gl_state(ga, e->gamma, e->binary, e->sm_count, st));
         e->timer.end(st);
-        e->timer.begin(ST_SCALE, st);
-        PET_CHECK(launch_gl_scale(ga, st));
-        e->timer.end(st);
+        if (!fold_scale) {
+            e->timer.begin(ST_SCALE, st);
+            PET_CHECK(launch_gl_scale(ga, st));
+            e->timer.end(st);
+        }
         if (user_logpj && !logpj_on_dev && logpj_is_output)
             PET_CUDA(cudaMemcpy2DAsync(const_cast<double *>(logpj_user) + r0 * ld_logpj, ld_logpj * 8, e->stage_logpj,
                                        e->C * 8, size_t(e->C) * 8, rows, cudaMemcpyDeviceToHost, st));
@@ -745,7 +751,8 @@ static int sweep_gl(pet_engine *e, const pet_anneal *a, const pet_params *p, int
                 e->timer.end(st);
                 e->timer.begin(ST_SLICE, st);
                 PET_CHECK(ozaki_slice_cols(e->Sbuf, e->ldH, rows, e->H, e->oz_ns, e->oz_colmax, false, e->ozS,
-                                           e->chunk_rows, (int64_t)e->H * e->chunk_rows, e->ozSs, st));
+                                           e->chunk_rows, (int64_t)e->H * e->chunk_rows, e->ozSs, st,
+                                           fold_scale ? e->scl + r0 * (1 + PET_MAXHP) : nullptr, 1 + PET_MAXHP));
                 e->timer.end(st);
                 e->timer.begin(ST_STATS, st);
                 const OzOperand oy{e->ozYT + c * e->oz_ns * plane, e->chunk_rows, plane, e->ozYTs + c * e->ldY};

@@ -32,7 +32,8 @@ static __host__ __device__ inline int r2(int x) { return (x + 1) & ~1; }
 
 constexpr int GS = PET_MAXHP + 1;          // stride of the gathered Gram block; row/col Hp is all zero
 
-constexpr int GRP_LANES = 64;              // two warps work on one datapoint in the state kernel
+constexpr int GRP_LANES = PET_GRP_LANES;   // four warps work on one datapoint in the state kernel
+constexpr int GRP_WARPS = GRP_LANES / 32;
 constexpr int GL_CHUNK = 8;                // entries per gather chunk (fixed: the inner loop is fully unrolled)
 
 struct SmemLayout {
@@ -512,21 +513,27 @@ __global__ void __launch_bounds__(ROW_WARPS * 32, 3) gl_row_fast_kernel(const __
 // latency).  Combines with the row kernel's partial sums by log-sum-exp merging:
 //   m = max(m1, m2),  Z = Z1 e^(m1-m) + Z2,  lse = m + log Z.
 // =================================================================================================
-__device__ __forceinline__ void grp_sync(int gid) { asm volatile("bar.sync %0, 64;" ::"r"(gid + 1) : "memory"); }
+__device__ __forceinline__ void grp_sync(int gid) { asm volatile("bar.sync %0, %1;" ::"r"(gid + 1), "n"(GRP_LANES) : "memory"); }
 
 __device__ __forceinline__ double grp_max(double v, double *red, int gid, int wig) {
     v = warp_max(v);
     grp_sync(gid);
     if ((threadIdx.x & 31) == 0) red[wig] = v;
     grp_sync(gid);
-    return fmax(red[0], red[1]);
+    double m = red[0];
+#pragma unroll
+    for (int w = 1; w < GRP_WARPS; ++w) m = fmax(m, red[w]);
+    return m;
 }
 __device__ __forceinline__ double grp_sum(double v, double *red, int gid, int wig) {
     v = warp_sum(v);
     grp_sync(gid);
     if ((threadIdx.x & 31) == 0) red[wig] = v;
     grp_sync(gid);
-    return red[0] + red[1];
+    double t = red[0];
+#pragma unroll
+    for (int w = 1; w < GRP_WARPS; ++w) t += red[w];
+    return t;
 }
 
 template <int GMAX, bool BINARY>
@@ -742,7 +749,17 @@ __global__ void __launch_bounds__(GL_MAX_GROUPS * GRP_LANES) gl_state_kernel(con
         double cnt_states[PET_MAXV];
 #pragma unroll
         for (int v = 0; v < PET_MAXV; ++v) cnt_states[v] = 0.0;
-        if (l64 == 0) scl[0] = e1 * inv;
+        const bool fold = (a.flags & GLF_FOLD_SCALE) != 0;
+        double sce = e1 * inv;                                // <s>[n,:] = singles[n,:] * sce (+ candidate marginals)
+        double *Srow = a.S + r * st.ldH;
+        if (fold) {
+            if (sce == 0.0) {       // the singletons vanish next to the multi-cause states: zero row, unit scale
+                for (int h = l64; h < st.ldH; h += GRP_LANES) Srow[h] = 0.0;
+                sce = 1.0;
+            }
+            grp_sync(gid);
+        }
+        if (l64 == 0) scl[0] = sce;
         if (l64 < Hp) {
             double m1j = 0.0;
 #pragma unroll
@@ -752,7 +769,13 @@ __global__ void __launch_bounds__(GL_MAX_GROUPS * GRP_LANES) gl_state_kernel(con
                     m1j = fma(BINARY ? 1.0 : st.vals[v], P, m1j);
                     cnt_states[v] = P;
                 }
-            scl[1 + l64] = live_s[l64] ? m1j * inv : 0.0;
+            const double mj = live_s[l64] ? m1j * inv : 0.0;  // non-live duplicates carry 0 and do not write
+            if (fold) {
+                if (mj != 0.0) Srow[cand_s[l64]] += mj / sce;
+                scl[1 + l64] = 0.0;
+            } else {
+                scl[1 + l64] = mj;
+            }
         }
         // second moments scattered into Wq (numpy fancy-index semantics for duplicates)
         for (int idx = l64; idx < Hp * Hp; idx += GRP_LANES) {
@@ -854,7 +877,7 @@ static int launch_state(const GLArgs &a, int sm_count, cudaStream_t stream) {
         configured = smem;
     }
     int per_sm = int(std::max<size_t>(1, std::min<size_t>(4, (227 * 1024) / (smem + 1024))));
-    per_sm = std::min(per_sm, std::max(1, 32 / (2 * groups)));
+    per_sm = std::min(per_sm, std::max(1, 64 / (GRP_WARPS * groups)));
     int64_t want = ceil_div(a.n_rows, groups);
     int64_t grid = std::min<int64_t>(want, int64_t(sm_count) * per_sm);
     if (grid <= 0) return PET_OK;

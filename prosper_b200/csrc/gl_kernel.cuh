@@ -6,7 +6,8 @@ namespace pet {
 
 constexpr int PET_MAXV = 6;        // max number of non-zero latent values (K-1)
 constexpr int PET_MAXHP = 16;      // max H'
-constexpr int PET_MAXG = 8;        // max gamma (members per state record)
+constexpr int PET_MAXG = 8;
+constexpr int PET_GRP_LANES = 128;  // lanes of the state kernel that share one datapoint (also the owner count of the gather tables)        // max gamma (members per state record)
 
 // selection rules of the reference's select_Hprimes variants
 enum SelectMode {
@@ -26,6 +27,8 @@ enum {
     GLF_USE_CUT     = 1 << 4,   // skip datapoints below the truncation cut
     GLF_CUT_STRICT  = 1 << 5,   // '>' instead of '>=' (dsc_et.py:832)
     GLF_SELECT_ONLY = 1 << 6,   // stop after selection
+    GLF_FOLD_SCALE  = 1 << 7,   // no scale kernel: the state kernel folds the candidate marginals into the un-normalised
+                                // <s> row (divided by the row's scale); consumers multiply rows by scl[n][0] on load
 };
 
 struct GLStatic {                 // fixed per engine

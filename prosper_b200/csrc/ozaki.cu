@@ -334,14 +334,19 @@ static int make_map(CUtensorMap *map, const int8_t *slices, int64_t rows, int Kp
 
 // ---- column-wise slicing with a transposing store (operands whose reduction runs over ROWS) -------------------
 // max |X[r][c]| over r, as the bit pattern of a non-negative double (monotonic under integer max)
-__global__ void col_absmax_kernel(const double *X, int64_t ldx, int64_t rows, int cols, unsigned long long *out) {
+__global__ void col_absmax_kernel(const double *X, int64_t ldx, int64_t rows, int cols, const double *rowscale, int64_t rs_stride,
+                                  unsigned long long *out) {
     __shared__ double red[8][33];
     const int c = blockIdx.x * 32 + threadIdx.x;
     const int64_t r_per = (rows + gridDim.y - 1) / gridDim.y;
     const int64_t r0 = blockIdx.y * r_per, r1 = min(rows, r0 + r_per);
     double m = 0.0;
     if (c < cols)
-        for (int64_t r = r0 + threadIdx.y; r < r1; r += 8) m = fmax(m, fabs(X[r * ldx + c]));
+        for (int64_t r = r0 + threadIdx.y; r < r1; r += 8) {
+            double v = X[r * ldx + c];
+            if (rowscale) v *= rowscale[r * rs_stride];
+            m = fmax(m, fabs(v));
+        }
     red[threadIdx.y][threadIdx.x] = m;
     __syncthreads();
     if (threadIdx.y == 0 && c < cols) {
@@ -355,7 +360,8 @@ __global__ void col_absmax_kernel(const double *X, int64_t ldx, int64_t rows, in
 constexpr int SC_R = 128, SC_C = 32, SC_PITCH = SC_R + 4;
 __global__ void __launch_bounds__(256) slice_cols_kernel(const double *X, int64_t ldx, int64_t rows, int cols, int Kp,
                                                          const unsigned long long *colmax, int ns, int8_t *out,
-                                                         int64_t row_stride, int64_t slice_stride, double *scale) {
+                                                         int64_t row_stride, int64_t slice_stride, double *scale,
+                                                         const double *rowscale, int64_t rs_stride) {
     extern __shared__ int8_t tile[];                  // [ns][SC_C][SC_PITCH]
     int32_t *tile32 = reinterpret_cast<int32_t *>(tile);
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -374,7 +380,7 @@ __global__ void __launch_bounds__(256) slice_cols_kernel(const double *X, int64_
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
         const int64_t r = r0 + ty * 16 + i;
-        v[i] = (c < cols && r < rows) ? X[r * ldx + c] * s0 : 0.0;
+        v[i] = (c < cols && r < rows) ? X[r * ldx + c] * (rowscale ? rowscale[r * rs_stride] : 1.0) * s0 : 0.0;
     }
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
@@ -430,19 +436,22 @@ int ozaki_splits(int64_t M, int64_t N, int Kp, int sm_count) {
 
 // X (rows, cols) row-major -> transposed slices out[t][c][r] with per-column scales (colmax: cols scratch words)
 // have_colmax: colmax already holds (an upper bound of) the column maxima, e.g. from the scale kernel
+// rowscale (optional): every row r is multiplied by rowscale[r * rs_stride] on load (the posterior normalisation)
 int ozaki_slice_cols(const double *X, int64_t ldx, int64_t rows, int cols, int ns, unsigned long long *colmax, bool have_colmax,
-                     int8_t *out, int64_t row_stride, int64_t slice_stride, double *scale, cudaStream_t st) {
+                     int8_t *out, int64_t row_stride, int64_t slice_stride, double *scale, cudaStream_t st,
+                     const double *rowscale, int64_t rs_stride) {
     if (rows <= 0 || cols <= 0) return PET_OK;
     const int Kp = ozaki_kp(rows);
     if (!have_colmax) {
         PET_CUDA(cudaMemsetAsync(colmax, 0, size_t(cols) * 8, st));
         dim3 g1((unsigned)ceil_div(cols, 32), (unsigned)std::min<int64_t>(ceil_div(rows, 256), 64));
-        oz::col_absmax_kernel<<<g1, dim3(32, 8), 0, st>>>(X, ldx, rows, cols, colmax);
+        oz::col_absmax_kernel<<<g1, dim3(32, 8), 0, st>>>(X, ldx, rows, cols, rowscale, rs_stride, colmax);
         PET_LAUNCH_CHECK();
     }
     dim3 g2((unsigned)ceil_div(cols, oz::SC_C), (unsigned)ceil_div(Kp, oz::SC_R));
     const size_t smem = size_t(ns) * oz::SC_C * oz::SC_PITCH;
-    oz::slice_cols_kernel<<<g2, 256, smem, st>>>(X, ldx, rows, cols, Kp, colmax, ns, out, row_stride, slice_stride, scale);
+    oz::slice_cols_kernel<<<g2, 256, smem, st>>>(X, ldx, rows, cols, Kp, colmax, ns, out, row_stride, slice_stride, scale, rowscale,
+                                                 rs_stride);
     PET_LAUNCH_CHECK();
     return PET_OK;
 }

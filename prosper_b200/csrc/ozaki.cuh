@@ -16,7 +16,8 @@ int ozaki_splits(int64_t M, int64_t N, int Kp, int sm_count);
 int ozaki_slice_rows(const double *X, int64_t ldx, int64_t rows, int K, int ns, int8_t *out, int64_t slice_stride, double *scale,
                      cudaStream_t st);
 int ozaki_slice_cols(const double *X, int64_t ldx, int64_t rows, int cols, int ns, unsigned long long *colmax, bool have_colmax, int8_t *out,
-                     int64_t row_stride, int64_t slice_stride, double *scale, cudaStream_t st);
+                     int64_t row_stride, int64_t slice_stride, double *scale, cudaStream_t st,
+                     const double *rowscale = nullptr, int64_t rs_stride = 0);
 int ozaki_gemm(int64_t M, int64_t N, int Kp, int ns, const OzOperand &A, const OzOperand &B, double *C, int64_t ldc, int splits,
                int64_t split_stride, bool accumulate, int sm_count, cudaStream_t st);
 int ozaki_add_slabs(double *dst, const double *slabs, int64_t count, int n_slabs, cudaStream_t st);
