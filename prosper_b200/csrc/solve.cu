@@ -51,6 +51,11 @@ __global__ void __launch_bounds__(256) potrf_block_kernel(double *A, int64_t lda
         X[r][tx] = 0.0;
     }
     __syncthreads();
+    // X starts as the identity and receives the same row operations that reduce L to the identity (forward elimination
+    // of [L | I]), one column of L per step: row c is scaled by 1/L_cc, then rows r > c lose L[r][c] times row c.  The
+    // inverse is complete when the factorisation is; its updates ride on the trailing update's barriers.
+    if (threadIdx.x < NB) X[threadIdx.x][threadIdx.x] = 1.0;
+    __syncthreads();
     for (int c = 0; c < nb; ++c) {
         if (threadIdx.x == 0) {
             double d = T[c][c];
@@ -68,25 +73,31 @@ __global__ void __launch_bounds__(256) potrf_block_kernel(double *A, int64_t lda
         __syncthreads();
         const double inv = dinv[c];
         if (ty == 0 && tx > c && tx < nb) T[tx][c] *= inv;
+        if (ty == 1 && tx <= c) X[c][tx] *= inv;              // row c of the inverse is final
         __syncthreads();
         // trailing update of the lower triangle: T[r][cc] -= L[r][c] * L[cc][c], c < cc <= r
+        // (all loads first, then the stores: a load after a possibly aliasing shared store would serialise the loop)
         const int cc = c + 1 + tx;
-        if (cc < nb) {
-            const double lcc = T[cc][c];
-            for (int r = c + 1 + ty; r < nb; r += 4)
-                if (cc <= r) T[r][cc] -= T[r][c] * lcc;
+        const double lcc = (cc < nb) ? T[cc][c] : 0.0;
+        const double xck = (tx <= c) ? X[c][tx] : 0.0;         // inverse: X[r][k] -= L[r][c] * X[c][k] for r > c, k <= c
+        double lr[NB / 4], tv[NB / 4], xv[NB / 4];
+#pragma unroll
+        for (int i = 0; i < NB / 4; ++i) {
+            const int r = c + 1 + ty + 4 * i;
+            const bool in = r < nb;
+            lr[i] = in ? T[r][c] : 0.0;
+            tv[i] = (in && cc <= r) ? T[r][cc] : 0.0;
+            xv[i] = (in && tx <= c) ? X[r][tx] : 0.0;
+        }
+#pragma unroll
+        for (int i = 0; i < NB / 4; ++i) {
+            const int r = c + 1 + ty + 4 * i;
+            if (r < nb) {
+                if (cc <= r) T[r][cc] = tv[i] - lr[i] * lcc;
+                if (tx <= c) X[r][tx] = xv[i] - lr[i] * xck;
+            }
         }
         __syncthreads();
-    }
-    // inverse of the lower-triangular block, one column per thread (forward substitution on unit vectors)
-    if (threadIdx.x < nb) {
-        const int c = threadIdx.x;
-        X[c][c] = dinv[c];
-        for (int r = c + 1; r < nb; ++r) {
-            double sacc = 0.0;
-            for (int t = c; t < r; ++t) sacc = fma(T[r][t], X[t][c], sacc);
-            X[r][c] = -sacc * dinv[r];
-        }
     }
     __syncthreads();
     for (int r = ty; r < NB; r += 4) {
@@ -164,22 +175,24 @@ int spd_solve_right(int64_t n64, int64_t m, double *A, int64_t lda, double *B, i
         PET_LAUNCH_CHECK();
     }
     if (m <= 0) return PET_OK;
+    // Both sweeps are RIGHT-LOOKING: as soon as a block column of the solution is known, all the remaining columns are
+    // updated with it in ONE wide GEMM (K = 64, hundreds of tiles) -- the left-looking form has a growing K on a dozen tiles
+    // and is latency bound.
     // ---- Z . L^T = B, column blocks ascending ----
     for (int j0 = 0, jb = 0; j0 < n; j0 += NB, ++jb) {
         int nb = std::min(NB, n - j0);
-        if (j0 > 0)
-            PET_CHECK(dgemm_kk(m, nb, j0, B, ldb, A + int64_t(j0) * lda, lda, B + j0, ldb, -1.0, 1, st));
+        int j1 = j0 + nb;
         PET_CHECK(dgemm_kk(m, nb, nb, B + j0, ldb, Linv + int64_t(jb) * NB * NB, NB, B + j0, ldb, 1.0, 0, st));
+        if (j1 < n)      // B[:, j1:] -= Z_j . L[j1:, j0:j1]^T
+            PET_CHECK(dgemm_kk(m, n - j1, nb, B + j0, ldb, A + int64_t(j1) * lda + j0, lda, B + j1, ldb, -1.0, 1, st));
     }
     // ---- X . L = Z, column blocks descending ----
     for (int jb = nblk - 1; jb >= 0; --jb) {
         int j0 = jb * NB;
         int nb = std::min(NB, n - j0);
-        int j1 = j0 + nb;
-        if (j1 < n)
-            PET_CHECK(dgemm_kk(m, nb, n - j1, B + j1, ldb, Lt + int64_t(j0) * lda + j1, lda, B + j0, ldb, -1.0,
-                               1, st));
         PET_CHECK(dgemm_kk(m, nb, nb, B + j0, ldb, LinvT + int64_t(jb) * NB * NB, NB, B + j0, ldb, 1.0, 0, st));
+        if (j0 > 0)      // B[:, :j0] -= X_j . L[j0:j1, :j0]   (L^T rows are K-contiguous)
+            PET_CHECK(dgemm_kk(m, j0, nb, B + j0, ldb, Lt + j0, lda, B, ldb, -1.0, 1, st));
     }
     return PET_OK;
 }
