@@ -57,24 +57,20 @@ __global__ void __launch_bounds__(256) potrf_block_kernel(double *A, int64_t lda
     if (threadIdx.x < NB) X[threadIdx.x][threadIdx.x] = 1.0;
     __syncthreads();
     for (int c = 0; c < nb; ++c) {
+        // every thread derives 1/L_cc from the pivot itself (one barrier less than broadcasting it through shared memory);
+        // the diagonal entry is overwritten only after the barrier, nobody reads it in the second phase
+        const double d = T[c][c];
+        const bool keep = d > tol;
+        const double inv = keep ? rsqrt(d) : 0.0;
         if (threadIdx.x == 0) {
-            double d = T[c][c];
-            if (d > tol) {
-                double l = sqrt(d);
-                T[c][c] = l;
-                dinv[c] = 1.0 / l;
-            } else {
-                T[c][c] = 0.0;
-                dinv[c] = 0.0;
-                atomicAdd(&scal[1], 1.0);
-            }
-            invd[j0 + c] = dinv[c];
+            dinv[c] = inv;
+            invd[j0 + c] = inv;
+            if (!keep) atomicAdd(&scal[1], 1.0);
         }
-        __syncthreads();
-        const double inv = dinv[c];
         if (ty == 0 && tx > c && tx < nb) T[tx][c] *= inv;
         if (ty == 1 && tx <= c) X[c][tx] *= inv;              // row c of the inverse is final
         __syncthreads();
+        if (threadIdx.x == 0) T[c][c] = d * inv;
         // trailing update of the lower triangle: T[r][cc] -= L[r][c] * L[cc][c], c < cc <= r
         // (all loads first, then the stores: a load after a possibly aliasing shared store would serialise the loop)
         const int cc = c + 1 + tx;
