@@ -507,6 +507,120 @@ __global__ void __launch_bounds__(ROW_WARPS * 32, 3) gl_row_fast_kernel(const __
     }
 }
 
+// -------------------------------------------------------------------------------------------------
+// The fast path as TWO kernels (the default): the selection needs the 32 scores of a lane in registers and runs at
+// 24 warps/SM; the singleton posterior is a streaming pass that needs few registers and runs at full occupancy,
+// which is what hides the FP64 dependency chains of exp.  Results are those of gl_row_fast_kernel.
+// -------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(ROW_WARPS * 32, 3) gl_row_select_kernel(const __grid_constant__ GLArgs a) {
+    __shared__ int cand_all[ROW_WARPS][PET_MAXHP];
+    constexpr int HC = 32;
+    const GLStatic &st = a.st;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int H = st.H, Hp = st.Hp;
+    int *cand_s = cand_all[warp];
+    const int64_t wstride = int64_t(gridDim.x) * ROW_WARPS;
+    for (int64_t r = int64_t(blockIdx.x) * ROW_WARPS + warp; r < a.n_rows; r += wstride) {
+        const int64_t n = a.row0 + r;
+        const double *yw = a.YW + r * st.ldH;
+        if (a.flags & GLF_SELECT) {
+            double sc[HC];
+#pragma unroll
+            for (int k = 0; k < HC; ++k) {
+                const int h = k * 32 + lane;
+                if (h < H) {
+                    const double v = yw[h];
+                    double s = (st.select_mode == SEL_BSC) ? (v + a.wmu[h]) * a.invn[h]
+                             : (st.select_mode == SEL_NEGDIST) ? 2.0 * v - a.wn2[h] : -v;
+                    s += 0.0;                                  // -0.0 ties with +0.0, as in a floating-point compare
+                    sc[k] = (s != s) ? -INFINITY : s;          // NaN scores never win
+                } else {
+                    sc[k] = -INFINITY;
+                }
+            }
+            unsigned taken = 0;
+            double v1, v2;
+            int k1, k2, left = 2;
+            top2_of<HC>(sc, taken, v1, k1, v2, k2);
+            for (int rnd = 0; rnd < Hp; ++rnd) {
+                const unsigned long long key = order_key(v1);
+                const unsigned hi = unsigned(key >> 32), lo = unsigned(key);
+                const unsigned mhi = __reduce_max_sync(0xffffffffu, hi);
+                const unsigned mlo = __reduce_max_sync(0xffffffffu, hi == mhi ? lo : 0u);
+                const unsigned mine = (hi == mhi && lo == mlo) ? unsigned(k1 * 32 + lane) + 1u : 0u;
+                int bi = int(__reduce_max_sync(0xffffffffu, mine)) - 1;
+                if (bi < 0 || bi >= H) bi = 0;
+                if (lane == 0) store_cand(st, cand_s, rnd, bi);
+                if ((bi & 31) == lane && (bi >> 5) == k1 && mine != 0u) {
+                    taken |= 1u << k1;
+                    v1 = v2; k1 = k2; v2 = -INFINITY;
+                    --left;
+                }
+                if (__any_sync(0xffffffffu, left == 0)) {                 // rare: a lane ran out of prepared entries
+                    if (left == 0) { top2_of<HC>(sc, taken, v1, k1, v2, k2); left = 2; }
+                }
+            }
+            __syncwarp();
+            if (lane < Hp) a.cand[n * Hp + lane] = cand_s[lane];
+        } else {
+            if (lane < Hp) cand_s[lane] = a.cand[n * Hp + lane];
+            __syncwarp();
+        }
+        if (!(a.flags & GLF_SELECT_ONLY) && lane < Hp) a.ywc[n * Hp + lane] = yw[cand_s[lane]];
+        __syncwarp();
+    }
+}
+
+// null state + all-H singletons of one datapoint per warp: max, partition sum, sigma / prior partial sums and the
+// un-normalised posterior row.  F_h decreases with q_h = yy + wn2_h - 2 yw_h (beta pre1 < 0), so the maximum is the
+// log-joint of the smallest q_h.
+__global__ void __launch_bounds__(256, 4) gl_row_post_kernel(const __grid_constant__ GLArgs a) {
+    const GLStatic &st = a.st;
+    const GLIter &it = a.it;
+    const int lane = threadIdx.x & 31;
+    const int H = st.H;
+    const bool do_stats = !(a.flags & GLF_LSE_ONLY);
+    const double pb = it.prior_block[0];
+    const int64_t r = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    if (r >= a.n_rows) return;
+    const int64_t n = a.row0 + r;
+    const double *yw = a.YW + r * st.ldH;
+    const double yy = a.yy[n];
+    double tmin = INFINITY;
+    for (int h = lane; h < H; h += 32) tmin = fmin(tmin, a.wn2[h] - 2.0 * yw[h]);
+    tmin = -warp_max(-tmin);
+    const double F0 = combine(it, it.prior_null, yy);
+    const double m1 = fmax(F0, combine(it, pb, yy + tmin));
+    double Z1 = 0.0, sig1 = 0.0, cnt = 0.0;
+    if (lane == 0) {
+        const double x = F0 - m1;
+        const double p = (x > GL_EXP_CUTOFF) ? exp_nonpos(x) : 0.0;
+        Z1 += p;
+        sig1 += p * yy;
+    }
+    double *Srow = a.S + r * st.ldH;
+#pragma unroll 2
+    for (int h = lane; h < st.ldH; h += 32) {
+        double p = 0.0;
+        if (h < H) {
+            const double q = yy + (a.wn2[h] - 2.0 * yw[h]);
+            const double x = combine(it, pb, q) - m1;
+            p = (x > GL_EXP_CUTOFF) ? exp_nonpos(x) : 0.0;
+            Z1 += p;
+            sig1 = fma(p, q, sig1);
+            cnt += p;
+        }
+        if (do_stats) Srow[h] = p;                           // scaled by exp(m1 - m)/Z downstream
+    }
+    Z1 = warp_sum(Z1);
+    sig1 = warp_sum(sig1);
+    cnt = warp_sum(cnt);
+    if (lane == 0) {
+        double *rs = a.rs + n * RS;
+        rs[0] = m1; rs[1] = Z1; rs[2] = sig1; rs[4] = cnt;
+    }
+}
+
 // =================================================================================================
 // Kernel B -- state kernel: the truncated multi-cause state space of one datapoint, TWO warps per
 // datapoint (the shared-memory footprint is per datapoint, so more lanes per datapoint is what hides
@@ -913,8 +1027,19 @@ int launch_gl_row(const GLArgs &a, int sm_count, cudaStream_t stream) {
             PET_CUDA(cudaFuncSetAttribute(gl_row_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
             configured_fast = smem;
         }
-        gl_row_fast_kernel<<<(unsigned)grid, ROW_WARPS * 32, smem, stream>>>(a);
+        static const bool one_kernel = getenv("PET_GL_ROW_FUSED") != nullptr;
+        if (one_kernel) {
+            gl_row_fast_kernel<<<(unsigned)grid, ROW_WARPS * 32, smem, stream>>>(a);
+            PET_LAUNCH_CHECK();
+            return PET_OK;
+        }
+        grid = std::min<int64_t>(ceil_div(a.n_rows, ROW_WARPS), int64_t(sm_count) * 3);
+        gl_row_select_kernel<<<(unsigned)grid, ROW_WARPS * 32, 0, stream>>>(a);
         PET_LAUNCH_CHECK();
+        if (!(a.flags & GLF_SELECT_ONLY)) {
+            gl_row_post_kernel<<<(unsigned)ceil_div(a.n_rows * 32, 256), 256, 0, stream>>>(a);
+            PET_LAUNCH_CHECK();
+        }
         return PET_OK;
     }
     gl_row_kernel<<<(unsigned)grid, ROW_WARPS * 32, smem, stream>>>(a);
