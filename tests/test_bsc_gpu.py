@@ -272,3 +272,24 @@ def test_bsc_learns_mu_like_the_reference(ncut):
         assert rel_err(pm['mu'], po['mu']) < TOL and rel_err(pm['W'], po['W']) < TOL
         assert abs(pm['sigma'] - po['sigma']) < TOL * po['sigma'] and abs(pm['pi'] - po['pi']) < TOL * po['pi']
     assert np.abs(pm['mu']).max() > 0.5                      # it moved towards the offset
+
+
+@pytest.mark.parametrize("slices", ["0", "6"])
+def test_gemm_fallback_paths_agree_with_oracle(monkeypatch, slices):
+    """The FP64 DMMA kernels (PET_OZAKI=0: what runs when the int8 slices do not fit in memory) and the 6-slice int8
+    variant go through the same pipeline; both must reproduce the oracle (6 slices: ~1e-12 per product)."""
+    if slices == "0":
+        monkeypatch.setenv("PET_OZAKI", "0")
+    else:
+        monkeypatch.setenv("PET_OZAKI_SLICES", slices)
+    D, H, Hp, gam, N = 40, 24, 8, 4, 3000
+    y, params, _ = bsc_problem(D, H, N, 11)
+    an = DictAnneal(T=1.2, Ncut_factor=0.4, anneal_prior=False)
+    o = BSC(D, H, Hp, gam)
+    onew = o.step(an, copy_params(params), {'y': y.copy()})
+    m = model(D, H, Hp, gam)
+    got = m._fused_step(an, copy_params(params), {'y': y.copy()})
+    assert m.engine.gemm_path() == (0 if slices == "0" else 6)      # known once a shard is bound
+    tol = TOL if slices == "0" else 1e-7
+    assert rel_err(got['W'], onew['W']) < tol
+    assert abs(got['pi'] - onew['pi']) < tol * onew['pi'] and abs(got['sigma'] - onew['sigma']) < tol * onew['sigma']
