@@ -204,6 +204,8 @@ typedef struct pet_gsc_layout {
     int64_t off_sum_sz2;  /* (H,): singleton part of the diagonal of sum_n <sz sz^T>       */
     int64_t off_ysq;      /* (D,): sum_n y_nd^2                                            */
     int64_t off_scalars;  /* [0] = datapoints of this rank                                 */
+    int64_t off_yyT;      /* (D, ldY): sum_n y_n y_n^T, filled for sigma_sq_type 'full' only; ldY = ld_yyT */
+    int64_t ld_yyT;
 } pet_gsc_layout;
 int  pet_gsc_layout_get(const pet_engine *e, pet_gsc_layout *out);
 

@@ -53,7 +53,7 @@ class GSCParams(C.Structure):
 
 class GSCLayout(C.Structure):
     _fields_ = [(n, C.c_int64) for n in ("total", "ld", "off_A", "off_Mssz", "off_Mout", "off_ss", "off_szsz",
-                                        "off_sum_s", "off_sum_sz2", "off_ysq", "off_scalars")]
+                                        "off_sum_s", "off_sum_sz2", "off_ysq", "off_scalars", "off_yyT", "ld_yyT")]
 
 
 # every symbol the header declares: name -> (restype, argtypes)

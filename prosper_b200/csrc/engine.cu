@@ -135,7 +135,7 @@ struct pet_engine {
     double *solveA = nullptr, *solveB = nullptr, *solve_work = nullptr;
     double *s2sum = nullptr;
     double *Wl = nullptr, *Wr = nullptr, *simbuf = nullptr; int64_t ldD = 0;   // MCA/MMCA tables
-    double *Wt2 = nullptr, *gsc_tab = nullptr, *psi_dev = nullptr, *bdiag = nullptr, *XSZ = nullptr, *SZ2 = nullptr, *yyw = nullptr;   // GSC
+    double *Wt2 = nullptr, *gsc_tab = nullptr, *psi_dev = nullptr, *bdiag = nullptr, *Bfull = nullptr, *gsc_T = nullptr, *XSZ = nullptr, *SZ2 = nullptr, *yyw = nullptr;   // GSC
     int64_t *dst_dev = nullptr; int64_t dst_cap = 0;
     const double *Wsrc = nullptr; int64_t Wsrc_ld = 0;                          // W (D,H) on the device for this call
     double *stage_logpj = nullptr; int64_t stage_logpj_doubles = 0;
@@ -190,7 +190,7 @@ extern "C" void pet_destroy(pet_engine *e) {
     free_dev(e->solveA); free_dev(e->solveB); free_dev(e->solve_work); free_dev(e->s2sum);
     free_dev(e->stage_logpj); free_dev(e->stage_i64); free_dev(e->ksel_state);
     free_dev(e->Wl); free_dev(e->Wr); free_dev(e->simbuf);
-    free_dev(e->Wt2); free_dev(e->gsc_tab); free_dev(e->psi_dev); free_dev(e->bdiag); free_dev(e->XSZ); free_dev(e->SZ2); free_dev(e->yyw); free_dev(e->dst_dev);
+    free_dev(e->Bfull); free_dev(e->gsc_T); free_dev(e->Wt2); free_dev(e->gsc_tab); free_dev(e->psi_dev); free_dev(e->bdiag); free_dev(e->XSZ); free_dev(e->SZ2); free_dev(e->yyw); free_dev(e->dst_dev);
     free_dev(e->ozY); free_dev(e->ozYT); free_dev(e->ozW); free_dev(e->ozS); free_dev(e->ozYs); free_dev(e->ozYTs);
     free_dev(e->ozWs); free_dev(e->ozSs); free_dev(e->oz_slabs); free_dev(e->oz_colmax);
     free_dev(e->d_inc); free_dev(e->d_states); free_dev(e->d_entries); free_dev(e->d_chunk); free_dev(e->d_direct); free_dev(e->d_single); free_dev(e->d_state_prior);
@@ -1058,6 +1058,32 @@ extern "C" int pet_m_step_solve(pet_engine *e, const pet_params *p, const double
 
 
 // ---- GSC (spike-and-slab) ----------------------------------------------------------------------
+extern "C" int pet_rowdot(int64_t n, int32_t D, const double *A_dev, int64_t lda, const double *B_dev, int64_t ldb, double *out_dev,
+                          int64_t out_stride, void *stream);
+
+// inverse of a (D,D) row-major matrix on the host, Gauss-Jordan with partial pivoting (np.linalg.inv of gsc_et.py:416)
+static bool host_inverse(std::vector<double> &a, int D) {
+    std::vector<double> inv((size_t)D * D, 0.0);
+    for (int i = 0; i < D; ++i) inv[(size_t)i * D + i] = 1.0;
+    for (int c = 0; c < D; ++c) {
+        int piv = c;
+        for (int r = c + 1; r < D; ++r) if (fabs(a[(size_t)r * D + c]) > fabs(a[(size_t)piv * D + c])) piv = r;
+        if (a[(size_t)piv * D + c] == 0.0) return false;
+        if (piv != c)
+            for (int k = 0; k < D; ++k) { std::swap(a[(size_t)piv * D + k], a[(size_t)c * D + k]); std::swap(inv[(size_t)piv * D + k], inv[(size_t)c * D + k]); }
+        const double d = 1.0 / a[(size_t)c * D + c];
+        for (int k = 0; k < D; ++k) { a[(size_t)c * D + k] *= d; inv[(size_t)c * D + k] *= d; }
+        for (int r = 0; r < D; ++r) {
+            if (r == c) continue;
+            const double f = a[(size_t)r * D + c];
+            if (f == 0.0) continue;
+            for (int k = 0; k < D; ++k) { a[(size_t)r * D + k] -= f * a[(size_t)c * D + k]; inv[(size_t)r * D + k] -= f * inv[(size_t)c * D + k]; }
+        }
+    }
+    a.swap(inv);
+    return true;
+}
+
 extern "C" int pet_gsc_layout_get(const pet_engine *e, pet_gsc_layout *out) {
     if (!e || !out) { set_error("pet_gsc_layout_get: null argument"); return PET_EINVAL; }
     const int64_t H = e->H, ld = e->ldH;
@@ -1071,13 +1097,15 @@ extern "C" int pet_gsc_layout_get(const pet_engine *e, pet_gsc_layout *out) {
     out->off_sum_sz2 = out->off_sum_s + ld;           // (H,)   singleton part of diag sum <sz sz^T>
     out->off_ysq = out->off_sum_sz2 + ld;             // (D,)   sum_n y_nd^2
     out->off_scalars = out->off_ysq + e->ldY;         // [0] = datapoints
-    out->total = out->off_scalars + 8;
+    out->off_yyT = out->off_scalars + 8;              // (D, ldY) sum_n y y^T ('full' noise covariance only)
+    out->ld_yyT = e->ldY;
+    out->total = out->off_yyT + (int64_t)e->D * e->ldY;
     return PET_OK;
 }
 
 static int prepare_gsc(pet_engine *e, const pet_gsc_params *p, cudaStream_t st) {
     if (!p || !p->W || !p->pi_host || !p->mu_host || !p->psi_sq_host || !p->sigma_sq_host) { set_error("bad GSC parameters"); return PET_EINVAL; }
-    if (p->sigma_sq_type == 2) { set_error("sigma_sq_type 'full' is not built on the device yet (use 'scalar' or 'diagonal')"); return PET_EINVAL; }
+    const bool full = (p->sigma_sq_type == 2);
     e->timer.begin(ST_PREPARE, st);
     pet_params pw;
     memset(&pw, 0, sizeof(pw));
@@ -1093,7 +1121,21 @@ static int prepare_gsc(pet_engine *e, const pet_gsc_params *p, cudaStream_t st) 
         PET_CUDA(cudaStreamSynchronize(st));
         bdiag = e->bdiag;
     } else bscalar = 1.0 / p->sigma_sq_host[0];
-    PET_CHECK(launch_scale_rows(e->Wt2, e->Wt, e->ldY, e->H, e->D, bdiag, bscalar, st));
+    if (full) {
+        // B = Sigma^-1 dense (symmetric Sigma assumed): Wt2 = (B W)^T by one GEMM
+        std::vector<double> Bh(p->sigma_sq_host, p->sigma_sq_host + (size_t)e->D * e->D);
+        if (!host_inverse(Bh, e->D)) { set_error("GSC: sigma_sq is singular"); return PET_EINVAL; }
+        if (!e->Bfull) {
+            PET_CHECK(dev_alloc(&e->Bfull, (int64_t)e->D * e->ldY));
+            PET_CHECK(dev_alloc(&e->gsc_T, e->chunk_rows * e->ldY));
+            PET_CUDA(cudaMemset(e->Bfull, 0, (int64_t)e->D * e->ldY * 8));
+        }
+        PET_CUDA(cudaMemcpy2DAsync(e->Bfull, e->ldY * 8, Bh.data(), size_t(e->D) * 8, size_t(e->D) * 8, e->D, cudaMemcpyHostToDevice, st));
+        PET_CUDA(cudaStreamSynchronize(st));
+        PET_CHECK(dgemm_kk(e->H, e->D, e->D, e->Wt, e->ldY, e->Bfull, e->ldY, e->Wt2, e->ldY, 1.0, 0, st));
+    } else {
+        PET_CHECK(launch_scale_rows(e->Wt2, e->Wt, e->ldY, e->H, e->D, bdiag, bscalar, st));
+    }
     PET_CHECK(dgemm_kk(e->H, e->H, e->D, e->Wt, e->ldY, e->Wt2, e->ldY, e->G, e->ldH, 1.0, 0, st));   // W^T Sigma^-1 W
     // psi_sq (H,H), pi, mu to the device
     PET_CUDA(cudaMemcpy2DAsync(e->psi_dev, e->ldH * 8, p->psi_sq_host, size_t(e->H) * 8, size_t(e->H) * 8, e->H, cudaMemcpyHostToDevice, st));
@@ -1109,7 +1151,12 @@ static int prepare_gsc(pet_engine *e, const pet_gsc_params *p, cudaStream_t st) 
     for (int64_t c = 0; c < nchunks; ++c) {
         const int64_t r0 = c * e->chunk_rows, rows = std::min(e->chunk_rows, e->n - r0);
         PET_CHECK(ensure_chunk_inputs(e, c, r0, rows, st));
-        PET_CHECK(launch_weighted_rownorm(e->Y + r0 * e->ldY, e->ldY, rows, e->D, bdiag, bscalar, e->yyw + r0, st));
+        if (full) {      // y^T B y = rowdot(Y B, Y)
+            PET_CHECK(dgemm_kk(rows, e->D, e->D, e->Y + r0 * e->ldY, e->ldY, e->Bfull, e->ldY, e->gsc_T, e->ldY, 1.0, 0, st));
+            PET_CHECK(pet_rowdot(rows, e->D, e->gsc_T, e->ldY, e->Y + r0 * e->ldY, e->ldY, e->yyw + r0, 1, st));
+        } else {
+            PET_CHECK(launch_weighted_rownorm(e->Y + r0 * e->ldY, e->ldY, rows, e->D, bdiag, bscalar, e->yyw + r0, st));
+        }
     }
     e->yy_valid = true;
     return PET_OK;
@@ -1163,6 +1210,18 @@ static int sweep_gsc(pet_engine *e, const pet_anneal *a, const pet_gsc_params *p
             PET_CHECK(launch_colsum(stats_dev + lay.off_sum_s, e->Sbuf, e->ldH, rows, e->H, st));
             PET_CHECK(launch_colsum(stats_dev + lay.off_sum_sz2, e->SZ2, e->ldH, rows, e->H, st));
             PET_CHECK(launch_colsumsq(stats_dev + lay.off_ysq, Yc, e->ldY, rows, e->D, st));
+            if (p->sigma_sq_type == 2) {           // sum_n y y^T for the full covariance update (gsc_et.py:679-682)
+                const int sp = dgemm_mn_splits(e->D, e->D, rows, e->sm_count);
+                const int64_t need = int64_t(sp) * e->D * e->ldY;
+                if (need > e->gemm_work_doubles) {
+                    cudaStreamSynchronize(st);
+                    free_dev(e->gemm_work); e->gemm_work = nullptr; e->gemm_work_doubles = 0;
+                    PET_CHECK(dev_alloc(&e->gemm_work, need));
+                    e->gemm_work_doubles = need;
+                }
+                PET_CHECK(dgemm_mn(e->D, e->D, rows, Yc, e->ldY, Yc, e->ldY, stats_dev + lay.off_yyT, e->ldY, 1,
+                                   e->gemm_work, e->gemm_work_doubles, e->sm_count, st));
+            }
             e->timer.end(st);
         }
     }

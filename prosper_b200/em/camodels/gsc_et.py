@@ -7,7 +7,8 @@ E_step :401-580 (+ compute_posterior_hprime :260-398), M_step :584-718.
 Device pipeline: Sigma^-1-weighted score GEMM and Gram matrix -> posterior kernel with k x k algebra per
 state (`csrc/gsc_kernel.cu`) -> three statistics GEMMs + block scatter -> ONE all-reduce -> parameter
 update (two H x H solves through the engine's Cholesky; the remaining O(H^2 D) arithmetic is
-data-independent torch float64 on the device).  `sigma_sq_type='full'` is not built on the device.
+data-independent torch float64 on the device).  `sigma_sq_type='full'`: Sigma^-1 is formed on the host (D x D) and applied by
+GEMMs (W^T Sigma^-1, y^T Sigma^-1 y); a symmetric Sigma is assumed.
 """
 import ctypes as C
 
@@ -252,6 +253,11 @@ class GSC(CAModel):
                 M.fill_diagonal_(0.0)
             st[off:off + H * ld].reshape(H, ld)[:, :H] = M
         _lib.check(lib.pet_colsum(n, D, _ptr(torch.square(ya[:, :D]).contiguous()), D, C.c_void_p(st.data_ptr() + 8 * lay.off_ysq), s0))
+        if self.sigma_sq_type == 'full':        # sum_n y y^T (gsc_et.py:679-682)
+            splits = lib.pet_dgemm_mn(D, D, n, None, ldy, None, ldy, None, lay.ld_yyT, 0, None, 0, s0)
+            work = torch.empty(max(1, splits * D * lay.ld_yyT), dtype=torch.float64, device=dev)
+            _lib.check(lib.pet_dgemm_mn(D, D, n, _ptr(ya), ldy, _ptr(ya), ldy, C.c_void_p(st.data_ptr() + 8 * lay.off_yyT), lay.ld_yyT, 0,
+                                        _ptr(work), work.numel(), s0))
         st[lay.off_scalars] = float(n)
         return self._update(model_params, st)
 
@@ -308,6 +314,8 @@ class GSC(CAModel):
                 model_params['sigma_sq'] = ((ysq - torch.einsum('dh,hk,dk->d', W_n, M_out, W_n)) / N + eps).cpu().numpy()
             elif self.sigma_sq_type == 'scalar':
                 model_params['sigma_sq'] = float((ysq.sum() - torch.sum(M_out * (W_n.T @ W_n))) / N / D + eps)
-            else:
-                raise NotImplementedError("sigma_sq_type 'full' is not built on the device")
+            else:                                                               # :677-691
+                yyT = stats[lay.off_yyT:lay.off_yyT + D * lay.ld_yyT].reshape(D, lay.ld_yyT)[:, :D]
+                model_params['sigma_sq'] = ((yyT - W_n @ M_out @ W_n.T) / N
+                                            + eps * torch.eye(D, dtype=torch.float64, device=stats.device)).cpu().numpy()
         return model_params

@@ -50,7 +50,7 @@ def check(D, H, Hp, gam, stype, params, y, T, golden=None):
         assert np.abs(suff['xpt_szsz'] - golden['xpt_szsz']).max() < 1e-9 * np.abs(golden['xpt_szsz']).max()
 
 
-@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "gsc_scalar*.npz")) + glob.glob(os.path.join(GOLDEN, "gsc_diag*.npz"))),
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "gsc_*.npz"))),
                          ids=lambda p: os.path.basename(p))
 def test_against_reference_golden(path):
     g = np.load(path)
@@ -88,11 +88,22 @@ def test_against_oracle(D, H, Hp, gam, stype, N, seed, T):
     check(D, H, Hp, gam, stype, params, y, T)
 
 
-def test_full_covariance_is_rejected_loudly():
+def test_full_covariance_against_oracle():
+    """sigma_sq_type='full' with a symmetric positive-definite Sigma (what the M-step produces, gsc_et.py:677-691)."""
+    D, H, Hp, gam, N = 20, 9, 5, 3, 150
+    y, params = synth(D, H, N, 8, 'scalar')
+    rng = np.random.RandomState(2)
+    u = rng.standard_normal((D, 3)) * 0.4
+    params['sigma_sq'] = np.diag(0.8 + rng.random_sample(D)) + u @ u.T
+    check(D, H, Hp, gam, 'full', params, y, 1.0)
+    check(D, H, Hp, gam, 'full', params, y, 1.6)
+
+
+def test_singular_full_covariance_is_rejected_loudly():
     from prosper_b200._lib import PetError
     from prosper_b200.em.camodels.gsc_et import GSC
     y, params = synth(16, 8, 30, 1, 'scalar')
-    params['sigma_sq'] = np.eye(16)
+    params['sigma_sq'] = np.zeros((16, 16))
     m = GSC(16, 8, 4, 2, sigma_sq_type='full')
-    with pytest.raises(PetError):
-        m.select_Hprimes(params, {'y': y})
+    with pytest.raises((PetError, AssertionError)):
+        m.select_Hprimes(m.check_params(params) if False else params, {'y': y})
