@@ -327,6 +327,19 @@ extern "C" int pet_create(const pet_config *cfg, pet_engine **out) {
     if (const char *env = getenv("PET_CHUNK_ROWS")) { if (atoll(env) > 0) cr = atoll(env); }
     cr = std::max<int64_t>(128, std::min<int64_t>(cr, 1 << 20));
     e->chunk_rows = round_up(cr, 128);
+    if (cfg->chunk_rows <= 0 && !getenv("PET_CHUNK_ROWS") && cr >= 2048) {
+        // the score GEMM works in 128 x 64 tiles on sm_count persistent CTAs: among the multiples of 128 within +-25 % pick
+        // the chunk whose tile count fills whole waves best (16 768 rows at H = 1000 would leave the last wave 16 % full)
+        const int64_t ntile = ceil_div(e->H, 64);
+        double best_eff = 0.0;
+        int64_t best = e->chunk_rows;
+        for (int64_t c = round_up(cr * 3 / 4, 128); c <= cr * 5 / 4; c += 128) {
+            const int64_t tiles = (c / 128) * ntile, waves = ceil_div(tiles, e->sm_count);
+            const double eff = double(tiles) / double(waves * e->sm_count);
+            if (eff > best_eff + 1e-9 || (eff > best_eff - 1e-9 && llabs(c - cr) < llabs(best - cr))) { best_eff = eff; best = c; }
+        }
+        e->chunk_rows = best;
+    }
 
     TRY(dev_alloc(&e->Wt, e->ldH * e->ldY));
     TRY(dev_alloc(&e->G, e->ldH * e->ldH));
