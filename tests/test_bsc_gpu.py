@@ -77,6 +77,9 @@ CASES = [
     (64, 16, 16, 2, 100, 7, 1.0, 0.0, False),         # H' == H
     (676, 1000, 12, 5, 192, 5, 1.0, 0.0, False),      # north-star shape, small N
     (676, 1000, 12, 5, 192, 5, 1.2, 1.0, False),
+    (30, 1100, 6, 3, 96, 8, 1.0, 0.5, False),         # H > 1024: generic row kernel (no register-resident scores)
+    (24, 18, 8, 6, 150, 9, 1.1, 0.0, False),          # gamma = 6: 8-member state records, direct state evaluation
+    (24, 18, 8, 8, 120, 10, 1.0, 0.7, True),          # gamma = H' = 8: all 247 states
 ]
 
 
