@@ -230,8 +230,9 @@ def run_gpu(args):
         new = model._fused_step(anneal, params, d)
         return {'W': new['W'], 'pi': new['pi'], 'sigma': new['sigma']}
 
-    # ---- device-resident measurement ("value") -------------------------------------------------
+    # ---- device-resident measurement ("value"): shard AND parameters stay in HBM ------------------
     params = dict(params0)
+    params['W'] = torch.as_tensor(params0['W']).to(dev)     # W comes back as a CUDA tensor; pi / sigma are host scalars
     for _ in range(args.warmup):
         params = one_step(params, data)
     barrier()

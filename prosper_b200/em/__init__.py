@@ -36,6 +36,10 @@ class Model(object):
         for param, policy in self.noise_policy.items():
             pvalue = model_params[param]
             scale = anneal[param + "_noise"]
+            on_device = None
+            if scale != 0.0 and hasattr(pvalue, 'detach') and hasattr(pvalue, 'cpu'):   # device-resident parameter
+                on_device = pvalue.device
+                pvalue = pvalue.detach().cpu().numpy()
             if scale != 0.0:
                 if np.isscalar(pvalue):
                     new_pvalue = 0
@@ -53,6 +57,9 @@ class Model(object):
                         if absify:
                             new_pvalue = np.abs(new_pvalue)
                     pvalue = comm.bcast(new_pvalue)
+            if on_device is not None:
+                import torch
+                pvalue = torch.as_tensor(pvalue).to(on_device)
             model_params[param] = pvalue
         return model_params
 

@@ -7,6 +7,7 @@ constant and the prior update.  Subclasses provide `_truncation_mass`, `_likelih
 `_update_prior` and `_pack_params`.
 """
 import numpy as np
+import torch
 
 from . import CAModel
 from ... import _lib
@@ -80,7 +81,9 @@ class GaussianLinearET(CAModel):
             W_dev, self.last_dropped_pivots = eng.solve(p, stats)
             if self.last_dropped_pivots > 0:      # singular Wq: reproduce lstsq/pinv's minimum-norm answer
                 W_dev = eng.solve_rank_deficient(stats, self._solve_rcond, self.model_kind == _lib.MODEL_BSC)
-            W_new = W_dev.cpu().numpy()
+            # device-resident EM loop: parameters given as CUDA tensors come back as CUDA tensors; dlog
+            # copies them to the host only if a handler subscribed to 'W' (datalog.py:215-232 `ignored()` pattern)
+            W_new = W_dev if isinstance(model_params['W'], torch.Tensor) else W_dev.cpu().numpy()
         else:
             W_new = model_params['W']
         n_cnt = max(1, len(getattr(self, 'states', [0, 1])) - 1)

@@ -72,5 +72,6 @@ class BSC_ET(GaussianLinearET):
             self.comm.allreduce_tensor_(dsum)
             mus = stats[lay.off_Wp + self.D * lay.ld_Wp:lay.off_Wp + self.D * lay.ld_Wp + self.H]   # sum_n <s> (ones row)
             data_sum = dsum.cpu().numpy() + N_use * np.asarray(model_params['mu'], dtype=np.float64)
-            mu_new = data_sum / N_use - np.inner(W_new / N_use, mus.cpu().numpy())
+            Wn = W_new.cpu().numpy() if hasattr(W_new, 'cpu') else W_new
+            mu_new = data_sum / N_use - np.inner(Wn / N_use, mus.cpu().numpy())
         return {'W': W_new, 'pi': pi_new, 'sigma': sigma_new, 'mu': mu_new}

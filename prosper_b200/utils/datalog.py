@@ -128,7 +128,12 @@ class DataLog(object):
     def append(self, tblname, value):
         if self._rank() != 0:
             return
-        for h in self._lookup(tblname):
+        handlers = self._lookup(tblname)
+        if not handlers:
+            return                       # nobody listens: a device-resident value is never copied to the host
+        if hasattr(value, 'detach') and hasattr(value, 'cpu'):
+            value = value.detach().cpu().numpy()
+        for h in handlers:
             h.append(tblname, value)
 
     def append_all(self, valdict):

@@ -296,3 +296,35 @@ def test_gemm_fallback_paths_agree_with_oracle(monkeypatch, slices):
     tol = TOL if slices == "0" else 1e-7
     assert rel_err(got['W'], onew['W']) < tol
     assert abs(got['pi'] - onew['pi']) < tol * onew['pi'] and abs(got['sigma'] - onew['sigma']) < tol * onew['sigma']
+
+
+def test_device_resident_parameters_through_em_run(tmp_path):
+    """SURVEY 8 f1: with W given as a CUDA tensor the EM loop never copies it to the host unless a dlog handler asks;
+    the trajectory equals the host-parameter one."""
+    from prosper_b200.em import EM
+    from prosper_b200.em.annealing import LinearAnnealing
+    from prosper_b200.utils.datalog import dlog, Keep
+    D, H, Hp, gam, N, iters = 25, 10, 6, 3, 600, 5
+    y, params, _ = bsc_problem(D, H, N, 5, bars=True, pi=0.2, sigma=2.0)
+
+    def run(p0, listen):
+        anneal = LinearAnnealing(iters)
+        anneal['T'] = [(0, 2.), (.7, 1.)]
+        anneal['Ncut_factor'] = [(0, 0.), (2. / 3, 1.)]
+        anneal['anneal_prior'] = False
+        keep = dlog.set_handler(listen, Keep) if listen else None
+        try:
+            em = EM(model=model(D, H, Hp, gam), anneal=anneal, data={'y': y.copy()}, lparams=p0)
+            em.run()
+        finally:
+            if keep is not None:
+                dlog.remove_handler(keep)
+        return em.lparams, keep
+
+    host, _ = run(copy_params(params), None)
+    pd = copy_params(params)
+    pd['W'] = torch.as_tensor(pd['W']).cuda()
+    devp, keep = run(pd, ('W', 'sigma'))
+    assert isinstance(devp['W'], torch.Tensor) and devp['W'].is_cuda
+    assert rel_err(devp['W'].cpu().numpy(), host['W']) < 1e-12 and abs(devp['sigma'] - host['sigma']) < 1e-12 * host['sigma']
+    assert len(keep.values['W']) == iters and isinstance(keep.values['W'][-1], np.ndarray)      # the listener got host arrays
