@@ -118,7 +118,7 @@ struct pet_engine {
     StateSpace ss;
     int64_t C = 0;
     GLStatic gls{};
-    int64_t ldY = 0, ldH = 0, chunk_rows = 0;
+    int64_t ldY = 0, ldH = 0, chunk_rows = 0, chunk_cfg = 0;
 
     // device-resident shard
     double *Y = nullptr; int64_t n = 0, n_cap = 0;
@@ -322,24 +322,10 @@ extern "C" int pet_create(const pet_config *cfg, pet_engine **out) {
     }
     g.states = e->d_states; g.entries = e->d_entries; g.chunk_tab = e->d_chunk; g.direct = e->d_direct; g.single_idx = e->d_single;
 
-    // chunking: posterior / score buffers of ~128 MB each
-    int64_t cr = cfg->chunk_rows > 0 ? cfg->chunk_rows : (int64_t(128) << 20) / (e->ldH * 8);
-    if (const char *env = getenv("PET_CHUNK_ROWS")) { if (atoll(env) > 0) cr = atoll(env); }
-    cr = std::max<int64_t>(128, std::min<int64_t>(cr, 1 << 20));
-    e->chunk_rows = round_up(cr, 128);
-    if (cfg->chunk_rows <= 0 && !getenv("PET_CHUNK_ROWS") && cr >= 2048) {
-        // the score GEMM works in 128 x 64 tiles on sm_count persistent CTAs: among the multiples of 128 within +-25 % pick
-        // the chunk whose tile count fills whole waves best (16 768 rows at H = 1000 would leave the last wave 16 % full)
-        const int64_t ntile = ceil_div(e->H, 64);
-        double best_eff = 0.0;
-        int64_t best = e->chunk_rows;
-        for (int64_t c = round_up(cr * 3 / 4, 128); c <= cr * 5 / 4; c += 128) {
-            const int64_t tiles = (c / 128) * ntile, waves = ceil_div(tiles, e->sm_count);
-            const double eff = double(tiles) / double(waves * e->sm_count);
-            if (eff > best_eff + 1e-9 || (eff > best_eff - 1e-9 && llabs(c - cr) < llabs(best - cr))) { best_eff = eff; best = c; }
-        }
-        e->chunk_rows = best;
-    }
+    // chunk-sized buffers are allocated when the shard is bound (size_chunks): the chunk length depends on its size
+    e->chunk_cfg = cfg->chunk_rows;
+    if (const char *env = getenv("PET_CHUNK_ROWS")) { if (atoll(env) > 0) e->chunk_cfg = atoll(env); }
+    e->chunk_rows = 0;
 
     TRY(dev_alloc(&e->Wt, e->ldH * e->ldY));
     TRY(dev_alloc(&e->G, e->ldH * e->ldH));
@@ -348,32 +334,18 @@ extern "C" int pet_create(const pet_config *cfg, pet_engine **out) {
     TRYC(cudaMemset(e->wmu, 0, e->ldH * 8));
     TRY(dev_alloc(&e->Wtmp, (int64_t)e->D * e->ldH));
     TRY(dev_alloc(&e->mu_dev, e->ldY));
-    TRY(dev_alloc(&e->Sbuf, e->chunk_rows * e->ldH));
-    if (e->model == PET_MODEL_DSC) { TRY(dev_alloc(&e->S2buf, e->chunk_rows * e->ldH)); TRY(dev_alloc(&e->s2sum, e->ldH)); }
+    if (e->model == PET_MODEL_DSC) TRY(dev_alloc(&e->s2sum, e->ldH));
     if (e->model == PET_MODEL_GSC) {
         TRY(dev_alloc(&e->Wt2, e->ldH * e->ldY));
         TRY(dev_alloc(&e->gsc_tab, 8 * e->ldH));          // g, ilam, lcdet, logit, mu, pi, (spare)
         TRY(dev_alloc(&e->psi_dev, e->ldH * e->ldH));
         TRY(dev_alloc(&e->bdiag, e->ldY));
-        TRY(dev_alloc(&e->XSZ, e->chunk_rows * e->ldH));
-        TRY(dev_alloc(&e->SZ2, e->chunk_rows * e->ldH));
         TRYC(cudaMemset(e->Wt2, 0, e->ldH * e->ldY * 8));
         TRYC(cudaMemset(e->psi_dev, 0, e->ldH * e->ldH * 8));
     }
     if (maxmodel) {
         e->ldD = round_up(e->D, 2);
         TRY(dev_alloc(&e->Wl, (int64_t)e->H * e->ldD)); TRY(dev_alloc(&e->Wr, (int64_t)e->H * e->ldD));
-        if (e->model == PET_MODEL_MCA) TRY(dev_alloc(&e->simbuf, e->chunk_rows * e->ldH));
-    }
-    {
-        int splits = dgemm_mn_splits(e->D + 1, e->H, e->chunk_rows, e->sm_count);
-        e->gemm_work_doubles = int64_t(splits) * (e->D + 1) * e->ldH;
-        TRY(dev_alloc(&e->gemm_work, e->gemm_work_doubles));
-    }
-    if (e->model == PET_MODEL_GSC) {
-        int sp = dgemm_mn_splits(e->H, e->H, e->chunk_rows, e->sm_count);
-        int64_t need = int64_t(sp) * e->H * e->ldH;
-        if (need > e->gemm_work_doubles) { free_dev(e->gemm_work); e->gemm_work = nullptr; TRY(dev_alloc(&e->gemm_work, need)); e->gemm_work_doubles = need; }
     }
     if (e->model == PET_MODEL_BSC || e->model == PET_MODEL_TSC || e->model == PET_MODEL_DSC) {
         // score and statistics GEMMs on the int8 tensor cores (PET_OZAKI=0 keeps the FP64 DMMA kernels)
@@ -382,13 +354,10 @@ extern "C" int pet_create(const pet_config *cfg, pet_engine **out) {
         e->oz_ns = (envs && atoi(envs) == 6) ? 6 : 7;
         if (e->oz_want) {
             e->oz_kpd = ozaki_kp(e->D);
-            e->oz_splits = ozaki_splits(e->D + 1, e->H, ozaki_kp(e->chunk_rows), e->sm_count);
             TRY(dev_alloc(&e->ozW, (int64_t)e->oz_ns * e->H * e->oz_kpd));
             TRY(dev_alloc(&e->ozWs, e->ldH));
-            TRY(dev_alloc(&e->ozS, (int64_t)e->oz_ns * e->H * e->chunk_rows));
             TRY(dev_alloc(&e->ozSs, e->ldH));
             TRY(dev_alloc(&e->oz_colmax, std::max<int64_t>(e->ldH, e->ldY)));
-            TRY(dev_alloc(&e->oz_slabs, (int64_t)e->oz_splits * (e->D + 1) * e->ldH));
         }
     }
     TRY(dev_alloc(&e->solveA, (int64_t)e->H * e->ldH));
@@ -429,6 +398,58 @@ extern "C" int pet_stage_times_ms(pet_engine *e, double *out) {
 }
 
 // ---- data ------------------------------------------------------------------------------
+// Chunk length for a shard of n datapoints and the buffers that scale with it.  Long chunks amortise the wave tails of
+// every kernel of the pipeline (measured at the north-star shape: 83 ms per iteration with 128 MB chunks of <S>, 73 ms
+// with 600 MB), so the default aims at ~600 MB of <S> per chunk, bounded by the shard itself; the length is then tuned
+// so that the 128 x 64 tiles of the score GEMM fill whole waves of sm_count persistent CTAs.
+static int size_chunks(pet_engine *e, int64_t n) {
+    int64_t cr;
+    if (e->chunk_cfg > 0) cr = round_up(std::max<int64_t>(128, std::min<int64_t>(e->chunk_cfg, 1 << 20)), 128);
+    else {
+        const int64_t target = std::max<int64_t>(2048, (int64_t(600) << 20) / (e->ldH * 8));
+        if (n <= target * 5 / 4) cr = round_up(std::max<int64_t>(n, 128), 128);          // one chunk
+        else {
+            cr = round_up(target, 128);
+            const int64_t ntile = ceil_div(e->H, 64);
+            double best_eff = 0.0;
+            int64_t best = cr;
+            for (int64_t c = round_up(target * 3 / 4, 128); c <= target * 5 / 4; c += 128) {
+                const int64_t tiles = (c / 128) * ntile, waves = ceil_div(tiles, e->sm_count);
+                const double eff = double(tiles) / double(waves * e->sm_count);
+                if (eff > best_eff + 1e-9 || (eff > best_eff - 1e-9 && llabs(c - target) < llabs(best - target))) { best_eff = eff; best = c; }
+            }
+            cr = best;
+        }
+    }
+    if (cr == e->chunk_rows && e->Sbuf) return PET_OK;
+    cudaDeviceSynchronize();
+    free_dev(e->Sbuf); free_dev(e->S2buf); free_dev(e->XSZ); free_dev(e->SZ2); free_dev(e->simbuf); free_dev(e->gemm_work);
+    free_dev(e->ozS); free_dev(e->oz_slabs); free_dev(e->gsc_T); free_dev(e->stage_logpj);
+    e->Sbuf = e->S2buf = e->XSZ = e->SZ2 = e->simbuf = e->gemm_work = e->oz_slabs = e->gsc_T = e->stage_logpj = nullptr;
+    e->ozS = nullptr;
+    e->stage_logpj_doubles = 0;
+    for (int i = 0; i < 3; ++i) { free_dev(e->up_slot[i]); e->up_slot[i] = nullptr; }
+    e->chunk_rows = cr;
+    e->n_cap = 0;                                     // per-shard buffers are laid out by chunk: reallocate them too
+    PET_CHECK(dev_alloc(&e->Sbuf, cr * e->ldH));
+    if (e->model == PET_MODEL_DSC) PET_CHECK(dev_alloc(&e->S2buf, cr * e->ldH));
+    if (e->model == PET_MODEL_GSC) { PET_CHECK(dev_alloc(&e->XSZ, cr * e->ldH)); PET_CHECK(dev_alloc(&e->SZ2, cr * e->ldH)); }
+    if (e->model == PET_MODEL_MCA) PET_CHECK(dev_alloc(&e->simbuf, cr * e->ldH));
+    {
+        int splits = dgemm_mn_splits(e->D + 1, e->H, cr, e->sm_count);
+        e->gemm_work_doubles = int64_t(splits) * (e->D + 1) * e->ldH;
+        if (e->model == PET_MODEL_GSC)
+            e->gemm_work_doubles = std::max<int64_t>(e->gemm_work_doubles, int64_t(dgemm_mn_splits(e->H, e->H, cr, e->sm_count)) * e->H * e->ldH);
+        PET_CHECK(dev_alloc(&e->gemm_work, e->gemm_work_doubles));
+    }
+    if (e->oz_want) {
+        e->oz_splits = ozaki_splits(e->D + 1, e->H, ozaki_kp(cr), e->sm_count);
+        PET_CHECK(dev_alloc(&e->ozS, (int64_t)e->oz_ns * e->H * cr));
+        PET_CHECK(dev_alloc(&e->oz_slabs, (int64_t)e->oz_splits * (e->D + 1) * e->ldH));
+    }
+    return PET_OK;
+}
+
 static int ensure_rows(pet_engine *e, int64_t n) {
     if (n <= e->n_cap) return PET_OK;
     cudaDeviceSynchronize();
@@ -480,6 +501,7 @@ extern "C" int pet_set_data(pet_engine *e, const double *y, int64_t n, int64_t l
     if (!e || !y || n < 0 || ld < e->D) { set_error("pet_set_data: bad arguments"); return PET_EINVAL; }
     cudaStream_t st = (cudaStream_t)stream;
     PET_CUDA(cudaSetDevice(e->device));
+    PET_CHECK(size_chunks(e, n));
     PET_CHECK(ensure_rows(e, n));
     e->n = n;
     e->yy_valid = false;
@@ -503,7 +525,7 @@ extern "C" int pet_set_data(pet_engine *e, const double *y, int64_t n, int64_t l
         if (e->up_staged && !e->up_slot[0]) {
             for (int i = 0; i < 3 && e->up_staged; ++i) {
                 if (dev_alloc(&e->up_slot[i], e->chunk_rows * e->D) != PET_OK ||
-                    cudaEventCreateWithFlags(&e->up_free[i], cudaEventDisableTiming) != cudaSuccess) {
+                    (!e->up_free[i] && cudaEventCreateWithFlags(&e->up_free[i], cudaEventDisableTiming) != cudaSuccess)) {
                     cudaGetLastError();
                     e->up_staged = false;          // no room for staging: direct pitched copies
                 }
@@ -1140,9 +1162,9 @@ static int prepare_gsc(pet_engine *e, const pet_gsc_params *p, cudaStream_t st) 
         if (!host_inverse(Bh, e->D)) { set_error("GSC: sigma_sq is singular"); return PET_EINVAL; }
         if (!e->Bfull) {
             PET_CHECK(dev_alloc(&e->Bfull, (int64_t)e->D * e->ldY));
-            PET_CHECK(dev_alloc(&e->gsc_T, e->chunk_rows * e->ldY));
             PET_CUDA(cudaMemset(e->Bfull, 0, (int64_t)e->D * e->ldY * 8));
         }
+        if (!e->gsc_T) PET_CHECK(dev_alloc(&e->gsc_T, e->chunk_rows * e->ldY));
         PET_CUDA(cudaMemcpy2DAsync(e->Bfull, e->ldY * 8, Bh.data(), size_t(e->D) * 8, size_t(e->D) * 8, e->D, cudaMemcpyHostToDevice, st));
         PET_CUDA(cudaStreamSynchronize(st));
         PET_CHECK(dgemm_kk(e->H, e->D, e->D, e->Wt, e->ldY, e->Bfull, e->ldY, e->Wt2, e->ldY, 1.0, 0, st));

@@ -422,11 +422,12 @@ int ozaki_kp(int64_t K) { return int(round_up(K, oz::KB)); }
 int ozaki_splits(int64_t M, int64_t N, int Kp, int sm_count) {
     const int64_t tiles = ceil_div(M, oz::BM) * ceil_div(N, oz::BN);
     const int kblocks = Kp / oz::KB;
-    int best = 1;
+    int best = std::max(1, int(ceil_div(kblocks, 1024)));
     double best_cost = 1e300;
-    for (int s = 1; s <= 16 && s <= kblocks; ++s) {
+    const int s_min = int(ceil_div(kblocks, 1024));        // int32 accumulators: at most 1170 K blocks per split
+    for (int s = s_min; s <= std::max(16, 4 * s_min) && s <= kblocks; ++s) {
         const int kbs = int(ceil_div(kblocks, s));
-        if (kbs < 16 && s > 1) break;
+        if (kbs < 16 && s > s_min) break;
         const double waves = double(ceil_div(tiles * ceil_div(kblocks, kbs), sm_count));
         const double cost = waves * (kbs + 3.0);
         if (cost < best_cost * 0.999) { best_cost = cost; best = s; }
