@@ -155,8 +155,8 @@ struct pet_engine {
     // host shards are uploaded lazily, a few chunks ahead of the sweep that consumes them (so that the small
     // per-iteration uploads are not queued behind the whole shard on the copy engine); contiguous sources go
     // through 1-D copies into staging slots (pitched 2-D DMA is ~35% slower) and are expanded on the device
-    const double *up_src = nullptr; int64_t up_ld = 0, up_copied = 0, up_expanded = 0; bool up_staged = false;
-    double *up_slot[3] = {nullptr, nullptr, nullptr}; cudaEvent_t up_free[3] = {nullptr, nullptr, nullptr};
+    const double *up_src = nullptr; int64_t up_ld = 0, up_copied = 0, up_expanded = 0, up_gran = 16384; bool up_staged = false;
+    std::vector<double *> up_slots; std::vector<cudaEvent_t> up_frees;     // ring of staging slots, one event per slot
     cudaEvent_t compute_done = nullptr; bool compute_done_valid = false;
     StageTimer timer;
     int64_t launches0 = 0;
@@ -195,7 +195,8 @@ extern "C" void pet_destroy(pet_engine *e) {
     free_dev(e->ozWs); free_dev(e->ozSs); free_dev(e->oz_slabs); free_dev(e->oz_colmax);
     free_dev(e->d_inc); free_dev(e->d_states); free_dev(e->d_entries); free_dev(e->d_chunk); free_dev(e->d_direct); free_dev(e->d_single); free_dev(e->d_state_prior);
     for (auto ev : e->chunk_ready) cudaEventDestroy(ev);
-    for (int i = 0; i < 3; ++i) { free_dev(e->up_slot[i]); if (e->up_free[i]) cudaEventDestroy(e->up_free[i]); }
+    for (auto p : e->up_slots) free_dev(p);
+    for (auto ev : e->up_frees) cudaEventDestroy(ev);
     for (auto ev : e->timer.pool) cudaEventDestroy(ev);
     if (e->compute_done) cudaEventDestroy(e->compute_done);
     if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
@@ -428,7 +429,8 @@ static int size_chunks(pet_engine *e, int64_t n) {
     e->Sbuf = e->S2buf = e->XSZ = e->SZ2 = e->simbuf = e->gemm_work = e->oz_slabs = e->gsc_T = e->stage_logpj = nullptr;
     e->ozS = nullptr;
     e->stage_logpj_doubles = 0;
-    for (int i = 0; i < 3; ++i) { free_dev(e->up_slot[i]); e->up_slot[i] = nullptr; }
+    for (auto p : e->up_slots) free_dev(p);
+    e->up_slots.clear();
     e->chunk_rows = cr;
     e->n_cap = 0;                                     // per-shard buffers are laid out by chunk: reallocate them too
     PET_CHECK(dev_alloc(&e->Sbuf, cr * e->ldH));
@@ -515,23 +517,32 @@ extern "C" int pet_set_data(pet_engine *e, const double *y, int64_t n, int64_t l
     } else {
         // the copy stream must not overwrite Y / the staging slots while earlier kernels still read them
         if (e->compute_done_valid) PET_CUDA(cudaStreamWaitEvent(e->copy_stream, e->compute_done, 0));
-        while ((int64_t)e->chunk_ready.size() < nchunks) {
+        e->up_gran = std::min<int64_t>(e->chunk_rows, 16384);
+        const int64_t ngran = ceil_div(n, e->up_gran);
+        while ((int64_t)e->chunk_ready.size() < ngran) {
             cudaEvent_t ev;
             PET_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
             e->chunk_ready.push_back(ev);
         }
         e->up_src = y; e->up_ld = ld; e->up_copied = 0; e->up_expanded = 0;
-        e->up_staged = (ld == e->D) && nchunks > 1;
-        if (e->up_staged && !e->up_slot[0]) {
-            for (int i = 0; i < 3 && e->up_staged; ++i) {
-                if (dev_alloc(&e->up_slot[i], e->chunk_rows * e->D) != PET_OK ||
-                    (!e->up_free[i] && cudaEventCreateWithFlags(&e->up_free[i], cudaEventDisableTiming) != cudaSuccess)) {
-                    cudaGetLastError();
-                    e->up_staged = false;          // no room for staging: direct pitched copies
-                }
+        e->up_staged = (ld == e->D) && ngran > 1;
+        if (e->up_staged && e->up_slots.empty()) {
+            const int want = int(std::min<int64_t>(ngran, 2 * ceil_div(e->chunk_rows, e->up_gran) + 2));
+            for (int i = 0; i < want; ++i) {
+                double *p = nullptr;
+                if (dev_alloc(&p, e->up_gran * e->D) != PET_OK) { cudaGetLastError(); break; }
+                e->up_slots.push_back(p);
             }
-            if (!e->up_staged)
-                for (int i = 0; i < 3; ++i) { free_dev(e->up_slot[i]); e->up_slot[i] = nullptr; }
+            while (e->up_frees.size() < e->up_slots.size()) {
+                cudaEvent_t ev;
+                PET_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+                e->up_frees.push_back(ev);
+            }
+            if (e->up_slots.size() < 3) {          // no room for staging: direct pitched copies
+                for (auto p : e->up_slots) free_dev(p);
+                e->up_slots.clear();
+                e->up_staged = false;
+            }
         }
         e->upload_pending = true;
     }
@@ -633,16 +644,20 @@ static int fill_iter(const pet_engine *e, const pet_anneal *a, const pet_params 
     return PET_OK;
 }
 
-// make chunk k of a pending host upload resident (stream-ordered on st); chunks are taken in order
-static int upload_chunk(pet_engine *e, int64_t k, cudaStream_t st, bool *fresh) {
-    const int64_t nchunks = ceil_div(e->n, e->chunk_rows);
-    const int LOOKAHEAD = 2;
-    while (e->up_copied < std::min<int64_t>(nchunks, k + 1 + LOOKAHEAD)) {
-        const int64_t j = e->up_copied, r0 = j * e->chunk_rows, rows = std::min(e->chunk_rows, e->n - r0);
+// The upload moves in GRANULES of up_gran rows (independent of the compute chunks, which are several times longer):
+// 1-D copies into a ring of staging slots on the copy stream, expansion (padding, ones column, ||y||^2) on the CONSUMER's
+// stream just before the chunk that needs the rows -- a kernel on the copy stream would queue behind the persistent compute
+// kernels for SMs and stall the copy engine.  The ring holds two chunks' worth of granules, so the copies of chunk c + 1
+// run while chunk c computes.  Granules are enqueued lazily, one compute chunk ahead of the consumer.
+static int upload_enqueue_upto(pet_engine *e, int64_t row_end) {
+    const int64_t ngran = ceil_div(e->n, e->up_gran);
+    const int64_t g_end = std::min<int64_t>(ngran, ceil_div(row_end, e->up_gran));
+    const int ns = (int)e->up_slots.size();
+    while (e->up_copied < g_end) {
+        const int64_t j = e->up_copied, r0 = j * e->up_gran, rows = std::min(e->up_gran, e->n - r0);
         if (e->up_staged) {
-            const int slot = int(j % 3);
-            if (j >= 3) PET_CUDA(cudaStreamWaitEvent(e->copy_stream, e->up_free[slot], 0));
-            PET_CUDA(cudaMemcpyAsync(e->up_slot[slot], e->up_src + r0 * e->up_ld, size_t(rows) * e->D * 8, cudaMemcpyHostToDevice,
+            if (j >= ns) PET_CUDA(cudaStreamWaitEvent(e->copy_stream, e->up_frees[j % ns], 0));
+            PET_CUDA(cudaMemcpyAsync(e->up_slots[j % ns], e->up_src + r0 * e->up_ld, size_t(rows) * e->D * 8, cudaMemcpyHostToDevice,
                                      e->copy_stream));
         } else {
             PET_CUDA(cudaMemcpy2DAsync(e->Y + r0 * e->ldY, e->ldY * 8, e->up_src + r0 * e->up_ld, e->up_ld * 8, size_t(e->D) * 8,
@@ -651,28 +666,39 @@ static int upload_chunk(pet_engine *e, int64_t k, cudaStream_t st, bool *fresh) 
         PET_CUDA(cudaEventRecord(e->chunk_ready[j], e->copy_stream));
         e->up_copied++;
     }
-    PET_CUDA(cudaStreamWaitEvent(st, e->chunk_ready[k], 0));
-    if (e->up_staged) {
-        const int64_t r0 = k * e->chunk_rows, rows = std::min(e->chunk_rows, e->n - r0);
-        const int slot = int(k % 3);
-        PET_CHECK(launch_rownorm_pad(e->up_slot[slot], e->D, e->Y + r0 * e->ldY, e->ldY, rows, e->D, e->yy + r0, st));
-        PET_CUDA(cudaEventRecord(e->up_free[slot], st));
-        if (fresh) *fresh = true;
+    return PET_OK;
+}
+
+// wait for and expand the granules covering rows < row_end on stream st
+static int upload_consume_upto(pet_engine *e, int64_t row_end, cudaStream_t st) {
+    const int64_t g_end = std::min<int64_t>(ceil_div(e->n, e->up_gran), ceil_div(row_end, e->up_gran));
+    const int ns = (int)e->up_slots.size();
+    while (e->up_expanded < g_end) {
+        const int64_t k = e->up_expanded, r0 = k * e->up_gran, rows = std::min(e->up_gran, e->n - r0);
+        PET_CHECK(upload_enqueue_upto(e, (k + 1) * e->up_gran));
+        PET_CUDA(cudaStreamWaitEvent(st, e->chunk_ready[k], 0));
+        if (e->up_staged) {
+            PET_CHECK(launch_rownorm_pad(e->up_slots[k % ns], e->D, e->Y + r0 * e->ldY, e->ldY, rows, e->D, e->yy + r0, st));
+            PET_CUDA(cudaEventRecord(e->up_frees[k % ns], st));
+        }
+        e->up_expanded++;
     }
-    e->up_expanded = k + 1;
-    if (e->up_expanded >= nchunks) e->upload_pending = false;
+    if (e->up_expanded * e->up_gran >= e->n) e->upload_pending = false;
     return PET_OK;
 }
 
 static int flush_upload(pet_engine *e, cudaStream_t st) {
-    const int64_t nchunks = ceil_div(e->n, e->chunk_rows);
-    while (e->upload_pending && e->up_expanded < nchunks) PET_CHECK(upload_chunk(e, e->up_expanded, st, nullptr));
-    return PET_OK;
+    if (!e->upload_pending) return PET_OK;
+    return upload_consume_upto(e, e->n, st);
 }
 
 static int ensure_chunk_inputs(pet_engine *e, int64_t c, int64_t r0, int64_t rows, cudaStream_t st) {
-    bool fresh = false;          // yy and the padding columns were just written by the staged expansion
-    while (e->upload_pending && e->up_expanded <= c) PET_CHECK(upload_chunk(e, e->up_expanded, st, &fresh));
+    bool fresh = false;      // yy and the padding columns of rows that arrive through the staged expansion are already written
+    if (e->upload_pending) {
+        fresh = e->up_staged && e->up_expanded * e->up_gran <= r0;
+        PET_CHECK(upload_consume_upto(e, r0 + rows, st));
+        if (e->upload_pending) PET_CHECK(upload_enqueue_upto(e, std::min<int64_t>(e->n, r0 + rows + e->chunk_rows)));
+    }
     if (!e->yy_valid) {
         if (!fresh) PET_CHECK(launch_rownorm_pad(e->Y + r0 * e->ldY, e->ldY, e->Y + r0 * e->ldY, e->ldY, rows, e->D, e->yy + r0, st));
         if (e->oz_on) {
