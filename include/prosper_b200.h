@@ -114,6 +114,12 @@ int  pet_state_matrix(const pet_engine *e, double *out_host);
  * operator call after pet_set_data has completed.  Contiguous sources (ld == D) travel as
  * 1-D copies through staging slots and are padded on the device. */
 int  pet_set_data(pet_engine *e, const double *y, int64_t n, int64_t ld, void *stream);
+/* Chunk length policy of the NEXT pet_set_data (when pet_config.chunk_rows is 0): bytes of the
+ * posterior matrix <S> per chunk.  Default 600 MB: long chunks amortise the wave tails of every
+ * kernel and suit a shard that stays resident; a caller that re-uploads the shard for every
+ * pass is bound by the upload and wants short chunks (128 MB) for a fine-grained overlap.
+ * 0 restores the default. */
+int  pet_set_chunk_target(pet_engine *e, int64_t bytes_of_posterior_per_chunk);
 int64_t pet_num_data(const pet_engine *e);
 
 /* ---- the three operators --------------------------------------------------------- */

@@ -66,6 +66,7 @@ SIGNATURES = {
     "pet_num_columns": (C.c_int64, [C.c_void_p]),
     "pet_state_matrix": (C.c_int, [C.c_void_p, c_double_p]),
     "pet_set_data": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]),
+    "pet_set_chunk_target": (C.c_int, [C.c_void_p, C.c_int64]),
     "pet_num_data": (C.c_int64, [C.c_void_p]),
     "pet_select_hprimes": (C.c_int, [C.c_void_p, C.POINTER(Params), C.c_void_p, C.c_void_p]),
     "pet_set_candidates": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),

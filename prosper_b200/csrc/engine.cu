@@ -118,7 +118,8 @@ struct pet_engine {
     StateSpace ss;
     int64_t C = 0;
     GLStatic gls{};
-    int64_t ldY = 0, ldH = 0, chunk_rows = 0, chunk_cfg = 0;
+    int64_t ldY = 0, ldH = 0, chunk_rows = 0, chunk_cfg = 0, chunk_target_bytes = int64_t(600) << 20;
+    std::vector<int64_t> chunk_start;        // rows [chunk_start[c], chunk_start[c+1]) form chunk c (each at most chunk_rows long)
 
     // device-resident shard
     double *Y = nullptr; int64_t n = 0, n_cap = 0;
@@ -407,7 +408,7 @@ static int size_chunks(pet_engine *e, int64_t n) {
     int64_t cr;
     if (e->chunk_cfg > 0) cr = round_up(std::max<int64_t>(128, std::min<int64_t>(e->chunk_cfg, 1 << 20)), 128);
     else {
-        const int64_t target = std::max<int64_t>(2048, (int64_t(600) << 20) / (e->ldH * 8));
+        const int64_t target = std::max<int64_t>(2048, e->chunk_target_bytes / (e->ldH * 8));
         if (n <= target * 5 / 4) cr = round_up(std::max<int64_t>(n, 128), 128);          // one chunk
         else {
             cr = round_up(target, 128);
@@ -483,7 +484,7 @@ static int ensure_rows(pet_engine *e, int64_t n) {
     if (e->oz_want) {
         // row slices (score GEMM) and per-chunk transposed column slices (statistics GEMM) of the shard;
         // without room for them the FP64 kernels take over
-        const int64_t nchunks = ceil_div(n, e->chunk_rows);
+        const int64_t nchunks = ceil_div(n, e->chunk_rows) + 4;      // + the short chunks of a ramped chunk table
         const int64_t b1 = (int64_t)e->oz_ns * n * e->oz_kpd, b2 = (int64_t)e->oz_ns * nchunks * (e->D + 1) * e->chunk_rows;
         cudaMemGetInfo(&free_b, &total_b);
         if (b1 + b2 + (int64_t(1) << 30) < (int64_t)free_b &&
@@ -499,6 +500,33 @@ static int ensure_rows(pet_engine *e, int64_t n) {
     return PET_OK;
 }
 
+// Uniform chunks for a resident shard.  A shard that is being uploaded is consumed at PCIe speed, so what counts is when
+// the first chunk can start and how much work is left after the last byte arrived: short chunks at both ends, long ones
+// in between.
+static void build_chunk_table(pet_engine *e, int64_t n, bool ramp) {
+    std::vector<int64_t> &t = e->chunk_start;
+    t.assign(1, 0);
+    const int64_t cr = e->chunk_rows;
+    const int64_t s1 = round_up(std::max<int64_t>(cr / 4, 128), 128), s2 = std::min(cr, 2 * s1);
+    if (ramp && e->chunk_cfg <= 0 && n >= 3 * cr && 2 * (s1 + s2) < n) {
+        t.push_back(s1);
+        t.push_back(s1 + s2);
+        const int64_t mid = n - 2 * (s1 + s2), k = ceil_div(mid, cr), len = round_up(ceil_div(mid, k), 128);
+        for (int64_t i = 0; i < k; ++i) t.push_back(std::min(t.back() + len, s1 + s2 + mid));
+        t.push_back(n - s1);
+        t.push_back(n);
+    } else {
+        for (int64_t r = cr; r < n; r += cr) t.push_back(r);
+        t.push_back(n);
+    }
+}
+
+extern "C" int pet_set_chunk_target(pet_engine *e, int64_t bytes_of_posterior_per_chunk) {
+    if (!e) { set_error("pet_set_chunk_target: null engine"); return PET_EINVAL; }
+    e->chunk_target_bytes = bytes_of_posterior_per_chunk > 0 ? bytes_of_posterior_per_chunk : (int64_t(600) << 20);
+    return PET_OK;
+}
+
 extern "C" int pet_set_data(pet_engine *e, const double *y, int64_t n, int64_t ld, void *stream) {
     if (!e || !y || n < 0 || ld < e->D) { set_error("pet_set_data: bad arguments"); return PET_EINVAL; }
     cudaStream_t st = (cudaStream_t)stream;
@@ -509,9 +537,11 @@ extern "C" int pet_set_data(pet_engine *e, const double *y, int64_t n, int64_t l
     e->yy_valid = false;
     e->cand_state = 0;
     e->mu_applied.assign(e->D, 0.0);
+    e->chunk_start.assign(1, 0);
     if (n == 0) return PET_OK;
-    const int64_t nchunks = ceil_div(n, e->chunk_rows);
-    if (is_device_ptr(y)) {
+    const bool on_device = is_device_ptr(y);
+    build_chunk_table(e, n, !on_device);
+    if (on_device) {
         PET_CUDA(cudaMemcpy2DAsync(e->Y, e->ldY * 8, y, ld * 8, size_t(e->D) * 8, n, cudaMemcpyDeviceToDevice, st));
         e->upload_pending = false;
     } else {
@@ -764,9 +794,9 @@ static int sweep_gl(pet_engine *e, const pet_anneal *a, const pet_params *p, int
     static const bool no_fold = getenv("PET_GL_NO_FOLD") != nullptr;
     const bool fold_scale = do_stats && e->oz_on && !e->S2buf && !no_fold;
     if (fold_scale) ga.flags |= GLF_FOLD_SCALE;
-    const int64_t nchunks = ceil_div(e->n, e->chunk_rows);
+    const int64_t nchunks = (int64_t)e->chunk_start.size() - 1;
     for (int64_t c = 0; c < nchunks; ++c) {
-        const int64_t r0 = c * e->chunk_rows, rows = std::min(e->chunk_rows, e->n - r0);
+        const int64_t r0 = e->chunk_start[c], rows = e->chunk_start[c + 1] - r0;
         PET_CHECK(ensure_chunk_inputs(e, c, r0, rows, st));
         double *yw = e->yw_all ? e->YW + r0 * e->ldH : e->YW;
         if (!reuse) {
@@ -902,9 +932,9 @@ static int sweep_mca(pet_engine *e, const pet_anneal *a, const pet_params *p, in
             e->stage_logpj_doubles = need;
         }
     }
-    const int64_t nchunks = ceil_div(e->n, e->chunk_rows);
+    const int64_t nchunks = (int64_t)e->chunk_start.size() - 1;
     for (int64_t c = 0; c < nchunks; ++c) {
-        const int64_t r0 = c * e->chunk_rows, rows = std::min(e->chunk_rows, e->n - r0);
+        const int64_t r0 = e->chunk_start[c], rows = e->chunk_start[c + 1] - r0;
         PET_CHECK(ensure_chunk_inputs(e, c, r0, rows, st));
         double *yw = e->yw_all ? e->YW + r0 * e->ldH : e->YW;
         if (!reuse) {
@@ -1208,9 +1238,9 @@ static int prepare_gsc(pet_engine *e, const pet_gsc_params *p, cudaStream_t st) 
                                 tab + 2 * e->ldH, tab + 3 * e->ldH, st));
     e->timer.end(st);
     // y^T Sigma^-1 y for every datapoint (sigma changes every iteration)
-    const int64_t nchunks = ceil_div(e->n, e->chunk_rows);
+    const int64_t nchunks = (int64_t)e->chunk_start.size() - 1;
     for (int64_t c = 0; c < nchunks; ++c) {
-        const int64_t r0 = c * e->chunk_rows, rows = std::min(e->chunk_rows, e->n - r0);
+        const int64_t r0 = e->chunk_start[c], rows = e->chunk_start[c + 1] - r0;
         PET_CHECK(ensure_chunk_inputs(e, c, r0, rows, st));
         if (full) {      // y^T B y = rowdot(Y B, Y)
             PET_CHECK(dgemm_kk(rows, e->D, e->D, e->Y + r0 * e->ldY, e->ldY, e->Bfull, e->ldY, e->gsc_T, e->ldY, 1.0, 0, st));
@@ -1248,9 +1278,9 @@ static int sweep_gsc(pet_engine *e, const pet_anneal *a, const pet_gsc_params *p
         PET_CUDA(cudaMemsetAsync(stats_dev, 0, lay.total * 8, st));
         g.sum_ss = stats_dev + lay.off_ss; g.sum_szsz = stats_dev + lay.off_szsz;
     }
-    const int64_t nchunks = ceil_div(e->n, e->chunk_rows);
+    const int64_t nchunks = (int64_t)e->chunk_start.size() - 1;
     for (int64_t c = 0; c < nchunks; ++c) {
-        const int64_t r0 = c * e->chunk_rows, rows = std::min(e->chunk_rows, e->n - r0);
+        const int64_t r0 = e->chunk_start[c], rows = e->chunk_start[c + 1] - r0;
         double *yw = e->yw_all ? e->YW + r0 * e->ldH : e->YW;
         e->timer.begin(ST_SCORE, st);
         PET_CHECK(dgemm_kk(rows, e->H, e->D, e->Y + r0 * e->ldY, e->ldY, e->Wt2, e->ldY, yw, e->ldH, 1.0, 0, st));

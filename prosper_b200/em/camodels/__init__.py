@@ -83,8 +83,10 @@ class Engine(object):
         return out
 
     # -- data ---------------------------------------------------------------------------
-    def set_data(self, y):
-        """y: (n,D) float64 NumPy array (host; pinned if it came from torch) or CUDA tensor."""
+    def set_data(self, y, transient=False):
+        """y: (n,D) float64 NumPy array (host; pinned if it came from torch) or CUDA tensor.
+        transient: the shard will be re-uploaded for every pass (upload bound): short chunks, fine-grained overlap."""
+        _lib.check(self.lib.pet_set_chunk_target(self.h, (128 << 20) if (transient and not isinstance(y, torch.Tensor)) else 0))
         if isinstance(y, torch.Tensor):
             if y.dtype != torch.float64 or y.dim() != 2 or y.stride(1) != 1:
                 y = y.to(torch.float64).contiguous()
@@ -264,7 +266,7 @@ class CAModel(Model):
             key = ('n', y.ctypes.data, y.shape, y.strides)
         if self.cache_data and self._bound == key and self.engine.n == y.shape[0]:
             return False
-        self.engine.set_data(y)
+        self.engine.set_data(y, transient=not self.cache_data)
         self._bound = key
         return True
 

@@ -32,3 +32,9 @@ for rep in range(2):
     sync(); t0 = time.perf_counter()
     new = m.step(an, dict(params), data); sync(); t1 = time.perf_counter()
     print("full step (cached shard) %.1f ms" % ((t1 - t0) * 1e3))
+# upload-bound reference: select only (little compute) on freshly bound host data
+m.cache_data = False
+for rep in range(3):
+    sync(); t0 = time.perf_counter()
+    m.select_Hprimes(dict(params, mu=np.zeros(D)), {'y': data['y']}); sync(); t1 = time.perf_counter()
+    print("select only (host y) %.1f ms" % ((t1 - t0) * 1e3))
