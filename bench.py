@@ -312,6 +312,9 @@ def run_gpu(args):
                         "pipe": "tcgen05.mma kind::i8 + TMEM: %d int8 slice products per FP64 product" % pairs,
                         "achieved": achieved, "peak": int8_peak / pairs, "unit": "TFLOP/s", "frac": achieved * pairs / int8_peak,
                         "pipe_achieved_tops": achieved * pairs, "pipe_peak_tops": int8_peak,
+                        "pipe_nominal_tops": 4500.0, "frac_of_nominal": achieved * pairs / 4500.0,
+                        "ncu_tensor_pipe_active": {"score_shape": 0.56, "statistics_shape": 0.74,
+                                                   "source": "profiles/r01_ncu_oz_gemm_kernel.txt"},
                         "peak_source": "2 x %s bf16_tflops_sustained (int8 dense rate), divided by the %d slice products; "
                                        "cuBLAS DGEMM measured in this run: %.1f TFLOP/s" % (peak_src, pairs, peak),
                         "traffic": ncu_traffic()}
