@@ -114,6 +114,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_kernel(const __grid_constant_
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + STAGES * STAGE_BYTES);
     uint64_t *full = bars, *empty = bars + STAGES, *tmem_full = bars + 2 * STAGES, *tmem_empty = bars + 2 * STAGES + 1;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * STAGES + 2);
+    double *sB_s = reinterpret_cast<double *>(bars + 2 * STAGES + 4);      // [2][BN] column scales of the current tile
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
@@ -207,6 +208,14 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_kernel(const __grid_constant_
             const int64_t tile = u % tiles;
             const int split = int(u / tiles);
             const int64_t m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
+            // column scales of this tile through shared memory (one global load per column and tile instead of one per
+            // element); double buffered by tile parity, one barrier of the 128 epilogue threads per tile
+            double *sBt = sB_s + (tphase ? BN : 0);
+            {
+                const int et = threadIdx.x - 128;
+                if (et < BN) sBt[et] = (n0 + et < a.N) ? a.sB[n0 + et] : 0.0;
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+            }
             mbar_wait(tmem_full, tphase);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const int64_t row = m0 + q * 32 + lane;
@@ -251,12 +260,12 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_kernel(const __grid_constant_
                         double o0 = fma(double(lo[c]), w_lo, double(hi[c])) * sa;
                         double o1 = fma(double(lo[c + 1]), w_lo, double(hi[c + 1])) * sa;
                         if (nb + c + 1 < a.N) {
-                            o0 *= a.sB[nb + c]; o1 *= a.sB[nb + c + 1];
+                            o0 *= sBt[half * 32 + c]; o1 *= sBt[half * 32 + c + 1];
                             double2 *dst = reinterpret_cast<double2 *>(cp + c);
                             if (a.accumulate) { double2 old = *dst; o0 += old.x; o1 += old.y; }
                             *dst = make_double2(o0, o1);
                         } else if (nb + c < a.N) {
-                            o0 *= a.sB[nb + c];
+                            o0 *= sBt[half * 32 + c];
                             if (a.accumulate) o0 += cp[c];
                             cp[c] = o0;
                         }
@@ -500,13 +509,13 @@ int ozaki_gemm(int64_t M, int64_t N, int Kp, int ns, const OzOperand &A, const O
     const unsigned grid = (unsigned)std::min<int64_t>(units, sm_count);
     if (ns == 7) {
         constexpr int ST = 2;
-        const size_t smem = size_t(ST) * 7 * (oz::BM + oz::BN) * oz::KB + 1024 + 256;
+        const size_t smem = size_t(ST) * 7 * (oz::BM + oz::BN) * oz::KB + 1024 + 256 + 2 * oz::BN * 8;
         static bool cfg = false;
         if (!cfg) { PET_CUDA(cudaFuncSetAttribute(oz::gemm_kernel<7, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem))); cfg = true; }
         oz::gemm_kernel<7, ST><<<grid, oz::THREADS, smem, st>>>(mapA, mapB, a);
     } else if (ns == 6) {
         constexpr int ST = 3;
-        const size_t smem = size_t(ST) * 6 * (oz::BM + oz::BN) * oz::KB + 1024 + 256;
+        const size_t smem = size_t(ST) * 6 * (oz::BM + oz::BN) * oz::KB + 1024 + 256 + 2 * oz::BN * 8;
         static bool cfg = false;
         if (!cfg) { PET_CUDA(cudaFuncSetAttribute(oz::gemm_kernel<6, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem))); cfg = true; }
         oz::gemm_kernel<6, ST><<<grid, oz::THREADS, smem, st>>>(mapA, mapB, a);
