@@ -51,6 +51,22 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         "r"(parity)
         : "memory");
 }
+// same, for waits that are off the critical path (the producer runs stages ahead): back off between polls so that the
+// spinning lane does not take issue slots from the epilogue warp that shares its scheduler
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAITR_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONER_%=;\n\t"
+        "nanosleep.u32 64;\n\t"
+        "bra WAITR_%=;\n\t"
+        "DONER_%=:\n\t"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
 __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2) {
     asm volatile(
         "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
@@ -146,7 +162,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_kernel(const __grid_constant_
                 const int m0 = int(tile / tiles_n) * BM, n0 = int(tile % tiles_n) * BN;
                 const int kb0 = split * a.kb_per_split, kb1 = min(kb0 + a.kb_per_split, a.kblocks);
                 for (int kb = kb0; kb < kb1; ++kb) {
-                    mbar_wait(&empty[stage], phase ^ 1);
+                    mbar_wait_relaxed(&empty[stage], phase ^ 1);
                     mbar_expect_tx(&full[stage], STAGE_BYTES);
                     uint8_t *sa = smem + stage * STAGE_BYTES, *sb = sa + NS * A_SLICE;
 #pragma unroll
@@ -168,7 +184,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_kernel(const __grid_constant_
             for (int64_t u = blockIdx.x; u < units; u += gridDim.x) {
                 const int split = int(u / tiles);
                 const int kb0 = split * a.kb_per_split, kb1 = min(kb0 + a.kb_per_split, a.kblocks);
-                mbar_wait(tmem_empty, tphase ^ 1);           // epilogue has drained the accumulators
+                mbar_wait_relaxed(tmem_empty, tphase ^ 1);   // epilogue has drained the accumulators
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(&full[stage], phase);
@@ -216,7 +232,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_kernel(const __grid_constant_
                 if (et < BN) sBt[et] = (n0 + et < a.N) ? a.sB[n0 + et] : 0.0;
                 asm volatile("bar.sync 1, 128;" ::: "memory");
             }
-            mbar_wait(tmem_full, tphase);
+            mbar_wait_relaxed(tmem_full, tphase);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const int64_t row = m0 + q * 32 + lane;
             const double sa = (row < a.M) ? a.sA[row] * w_hi : 0.0;
