@@ -125,7 +125,7 @@ struct pet_engine {
     double *Y = nullptr; int64_t n = 0, n_cap = 0;
     double *yy = nullptr; int *cand = nullptr; double *lse = nullptr;
     double *rs = nullptr, *ywc = nullptr, *scl = nullptr;      // per-datapoint records exchanged by the posterior kernels
-    bool yy_valid = false; int cand_state = 0;
+    bool yy_valid = false, wmu_nonzero = false; int cand_state = 0;
     std::vector<double> mu_applied;
 
     // per-iteration
@@ -627,6 +627,7 @@ static int prepare(pet_engine *e, const pet_params *p, cudaStream_t st) {
     if (e->model == PET_MODEL_BSC) {          // W_h . mu for the selection scores of the un-shifted datapoints
         bool nonzero = false;
         for (double v : e->mu_applied) nonzero |= (v != 0.0);
+        e->wmu_nonzero = nonzero;
         if (nonzero) {
             PET_CUDA(cudaMemcpyAsync(e->mu_full, e->mu_applied.data(), e->D * 8, cudaMemcpyHostToDevice, st));
             PET_CUDA(cudaStreamSynchronize(st));      // mu_applied is host memory that may change before the copy runs
@@ -763,7 +764,7 @@ static int sweep_gl(pet_engine *e, const pet_anneal *a, const pet_params *p, int
     if (!reuse) PET_CHECK(prepare(e, p, st));
     ga.flags = kflags;
     if (e->model == PET_MODEL_DSC) ga.flags |= (kflags & GLF_USE_CUT) ? GLF_CUT_STRICT : 0;
-    ga.yy = e->yy; ga.wn2 = e->wn2; ga.invn = e->invn; ga.wmu = e->wmu; ga.G = e->G;
+    ga.yy = e->yy; ga.wn2 = e->wn2; ga.invn = e->invn; ga.wmu = e->wmu_nonzero ? e->wmu : nullptr; ga.G = e->G;
     ga.state_prior = e->d_state_prior;
     PET_CHECK(launch_state_prior(ga.st, ga.it, e->d_state_prior, st));
     ga.cand = e->cand; ga.lse = e->lse; ga.cut = cut_dev;
@@ -897,7 +898,7 @@ static int sweep_mca(pet_engine *e, const pet_anneal *a, const pet_params *p, in
     sel.st = e->gls;
     sel.it.beta = 1.0; sel.it.pre1 = -1.0;
     sel.flags = GLF_SELECT | GLF_SELECT_ONLY;
-    sel.yy = e->yy; sel.wn2 = e->wn2; sel.invn = e->invn; sel.wmu = e->wmu; sel.G = e->G; sel.cand = e->cand; sel.lse = e->lse;
+    sel.yy = e->yy; sel.wn2 = e->wn2; sel.invn = e->invn; sel.wmu = e->wmu_nonzero ? e->wmu : nullptr; sel.G = e->G; sel.cand = e->cand; sel.lse = e->lse;
     sel.state_prior = e->d_state_prior;
     sel.rs = e->rs; sel.ywc = e->ywc; sel.scl = e->scl;
 

@@ -167,7 +167,7 @@ __device__ __forceinline__ double sel_score(const GLArgs &a, const double *row, 
     const GLStatic &st = a.st;
     switch (st.select_mode) {
         case SEL_BSC:
-            return (row[i] + a.wmu[i]) * a.invn[i];
+            return (a.wmu ? row[i] + a.wmu[i] : row[i]) * a.invn[i];
         case SEL_NEGDIST:
             return 2.0 * row[i] - a.wn2[i];
         case SEL_GIVEN:
@@ -431,7 +431,7 @@ __global__ void __launch_bounds__(ROW_WARPS * 32, 3) gl_row_fast_kernel(const __
             if (h < H) {
                 const double v = yw[h];
                 row[h] = v;
-                double s = (st.select_mode == SEL_BSC) ? (v + a.wmu[h]) * a.invn[h]
+                double s = (st.select_mode == SEL_BSC) ? (a.wmu ? v + a.wmu[h] : v) * a.invn[h]
                          : (st.select_mode == SEL_NEGDIST) ? 2.0 * v - a.wn2[h] : -v;
                 s += 0.0;                                  // -0.0 ties with +0.0, as in a floating-point compare
                 sc[k] = (s != s) ? -INFINITY : s;          // NaN scores never win
@@ -530,7 +530,7 @@ __global__ void __launch_bounds__(ROW_WARPS * 32, 3) gl_row_select_kernel(const 
                 const int h = k * 32 + lane;
                 if (h < H) {
                     const double v = yw[h];
-                    double s = (st.select_mode == SEL_BSC) ? (v + a.wmu[h]) * a.invn[h]
+                    double s = (st.select_mode == SEL_BSC) ? (a.wmu ? v + a.wmu[h] : v) * a.invn[h]
                              : (st.select_mode == SEL_NEGDIST) ? 2.0 * v - a.wn2[h] : -v;
                     s += 0.0;                                  // -0.0 ties with +0.0, as in a floating-point compare
                     sc[k] = (s != s) ? -INFINITY : s;          // NaN scores never win

@@ -77,7 +77,7 @@ struct GLArgs {
     const double *yy;             // (n,) squared norms (global index)
     const double *wn2;            // (H,)  ||W_h||^2
     const double *invn;           // (H,)  1/||W_h||
-    const double *wmu;            // (H,)  W_h . mu (BSC selection scores the un-shifted datapoint), zeros without mu
+    const double *wmu;            // (H,)  W_h . mu (BSC selection scores the un-shifted datapoint); NULL when mu = 0
     const double *G;              // (H, ldH) Gram matrix
     const double *state_prior;    // (S,) log-prior of every multi-state for this iteration
     int *cand;                    // (n, Hp) global index
