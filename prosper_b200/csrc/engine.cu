@@ -188,7 +188,7 @@ extern "C" void pet_destroy(pet_engine *e) {
     free_dev(e->Y); free_dev(e->yy); free_dev(e->cand); free_dev(e->lse); free_dev(e->rs); free_dev(e->ywc); free_dev(e->scl);
     free_dev(e->Wt); free_dev(e->G); free_dev(e->wn2); free_dev(e->invn); free_dev(e->Wtmp); free_dev(e->mu_dev); free_dev(e->wmu); free_dev(e->mu_full);
     free_dev(e->YW); free_dev(e->Sbuf); free_dev(e->S2buf); free_dev(e->gemm_work);
-    free_dev(e->solveA); free_dev(e->solveB); free_dev(e->solve_work); free_dev(e->s2sum);
+    free_dev(e->solveA); free_dev(e->solve_work); free_dev(e->s2sum);
     free_dev(e->stage_logpj); free_dev(e->stage_i64); free_dev(e->ksel_state);
     free_dev(e->Wl); free_dev(e->Wr); free_dev(e->simbuf);
     free_dev(e->Bfull); free_dev(e->gsc_T); free_dev(e->Wt2); free_dev(e->gsc_tab); free_dev(e->psi_dev); free_dev(e->bdiag); free_dev(e->XSZ); free_dev(e->SZ2); free_dev(e->yyw); free_dev(e->dst_dev);
@@ -362,8 +362,8 @@ extern "C" int pet_create(const pet_config *cfg, pet_engine **out) {
             TRY(dev_alloc(&e->oz_colmax, std::max<int64_t>(e->ldH, e->ldY)));
         }
     }
-    TRY(dev_alloc(&e->solveA, (int64_t)e->H * e->ldH));
-    TRY(dev_alloc(&e->solveB, (int64_t)e->D * e->ldH));
+    TRY(dev_alloc(&e->solveA, (int64_t)(e->H + e->D) * e->ldH));     // B stacked under A: the solve fuses its forward sweep
+    e->solveB = e->solveA + (int64_t)e->H * e->ldH;
     TRY(dev_alloc(&e->solve_work, spd_solve_work_doubles(e->H, e->ldH)));
     TRY(dev_alloc(&e->ksel_state, 2 + 256));
     TRYC(cudaMemset(e->Wt, 0, e->ldH * e->ldY * 8));

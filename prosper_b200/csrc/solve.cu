@@ -34,73 +34,164 @@ __global__ void maxdiag_kernel(const double *A, int64_t lda, int n, double *scal
     }
 }
 
-// Unblocked Cholesky of the nb x nb diagonal block at (j0,j0); writes L (lower, zero upper) back, and the
-// inverse of the triangular block both plain and transposed (NB x NB, ld NB) so that every triangular solve of
-// the blocked algorithm becomes a DMMA GEMM:   x . L_jj^T = r  <=>  x = r . inv(L_jj)^T .
+// Cholesky of the nb x nb diagonal block at (j0,j0); writes L (lower, zero upper) back, and the inverse of the
+// triangular block both plain and transposed (NB x NB, ld NB) so that every triangular solve of the blocked algorithm
+// becomes a DMMA GEMM:   x . L_jj^T = r  <=>  x = r . inv(L_jj)^T .
 // A pivot below tol is dropped: its row/column of L and of inv(L) are zero (minimum-norm behaviour for dead units).
+//
+// The block T and its inverse X live in REGISTERS: 256 threads, thread (pi, pj) owns the 4 x 4 patch at rows 4pi..,
+// columns 4pj.. of both.  The kernel is a chain of dependent instructions (two warps per scheduler), so it is written for
+// few instructions and few barriers: FOUR columns per step and two barriers per step --
+//   1. the owner of the diagonal patch factors it and inverts the 4 x 4 factor (M) in registers;
+//   2. the patches below it become L_p = T_p . M^T, the patches of X's row block become M . X_C; both are published;
+//   3. every remaining patch takes its rank-4 update  T -= L_p(rows) . L_p(cols)^T ,  X -= L_p(rows) . X_C .
+// X starts as the identity and receives the row operations that reduce L to the identity (forward elimination of [L | I]).
 __global__ void __launch_bounds__(256) potrf_block_kernel(double *A, int64_t lda, int j0, int nb, int n,
                                                           double *invd, double *scal, double *Linv, double *LinvT) {
-    extern __shared__ __align__(16) double potrf_smem[];
-    double (*T)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(potrf_smem);
-    double (*X)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(potrf_smem + NB * (NB + 1));
-    double *dinv = potrf_smem + 2 * NB * (NB + 1);
-    const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;      // 64 x 4
+    __shared__ __align__(16) double dinv_s[2][16];          // M = inverse of the 4 x 4 diagonal factor, row-major
+    __shared__ __align__(16) double lp_s[2][4][NB];          // L_p: the four new columns of L (column-major: conflict-free rows)
+    __shared__ __align__(16) double xc_s[2][4][NB];          // X_C: the four finished rows of the inverse
+    const int pi = threadIdx.x & 15, pj = threadIdx.x >> 4;  // a warp holds two patch columns: conditions on pj are warp-uniform
+    const int r0 = 4 * pi, c0 = 4 * pj;
     const double tol = scal[0] * scal[2];
-    for (int r = ty; r < NB; r += 4) {
-        T[r][tx] = (r < nb && tx < nb && tx <= r) ? A[int64_t(j0 + r) * lda + j0 + tx] : 0.0;
-        X[r][tx] = 0.0;
-    }
-    __syncthreads();
-    // X starts as the identity and receives the same row operations that reduce L to the identity (forward elimination
-    // of [L | I]), one column of L per step: row c is scaled by 1/L_cc, then rows r > c lose L[r][c] times row c.  The
-    // inverse is complete when the factorisation is; its updates ride on the trailing update's barriers.
-    if (threadIdx.x < NB) X[threadIdx.x][threadIdx.x] = 1.0;
-    __syncthreads();
-    for (int c = 0; c < nb; ++c) {
-        // every thread derives 1/L_cc from the pivot itself (one barrier less than broadcasting it through shared memory);
-        // the diagonal entry is overwritten only after the barrier, nobody reads it in the second phase
-        const double d = T[c][c];
-        const bool keep = d > tol;
-        const double inv = keep ? rsqrt(d) : 0.0;
-        if (threadIdx.x == 0) {
-            dinv[c] = inv;
-            invd[j0 + c] = inv;
-            if (!keep) atomicAdd(&scal[1], 1.0);
+    double t[4][4], x[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int r = r0 + i, cc = c0 + j;
+            t[i][j] = (r < nb && cc <= r) ? A[int64_t(j0 + r) * lda + j0 + cc] : 0.0;
+            x[i][j] = (r == cc) ? 1.0 : 0.0;
         }
-        if (ty == 0 && tx > c && tx < nb) T[tx][c] *= inv;
-        if (ty == 1 && tx <= c) X[c][tx] *= inv;              // row c of the inverse is final
+    const int nsteps = (nb + 3) >> 2;
+    for (int C = 0; C < nsteps; ++C) {
+        const int b = C & 1;
+        // ---- 1. diagonal patch: 4 x 4 Cholesky and the inverse of its factor ----
+        if (pi == C && pj == C) {
+            double iv[4];
+            int ndrop = 0;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const double d = t[c][c];
+                const bool valid = 4 * C + c < nb;
+                const bool keep = valid && d > tol;
+                const double inv = keep ? rsqrt(d) : 0.0;
+                iv[c] = inv;
+                if (valid) {
+                    invd[j0 + 4 * C + c] = inv;
+                    ndrop += keep ? 0 : 1;
+                }
+                t[c][c] = d * inv;
+#pragma unroll
+                for (int r = c + 1; r < 4; ++r) t[r][c] *= inv;
+#pragma unroll
+                for (int cc = c + 1; cc < 4; ++cc)
+#pragma unroll
+                    for (int r = cc; r < 4; ++r) t[r][cc] -= t[r][c] * t[cc][c];
+            }
+            if (ndrop) atomicAdd(&scal[1], double(ndrop));
+            double M[4][4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+#pragma unroll
+                for (int r = 0; r < 4; ++r) M[r][c] = 0.0;
+                M[c][c] = iv[c];
+#pragma unroll
+                for (int r = c + 1; r < 4; ++r) {
+                    double sum = 0.0;
+#pragma unroll
+                    for (int k = c; k < r; ++k) sum += t[r][k] * M[k][c];
+                    M[r][c] = -iv[r] * sum;
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) dinv_s[b][4 * r + c] = M[r][c];
+        }
         __syncthreads();
-        if (threadIdx.x == 0) T[c][c] = d * inv;
-        // trailing update of the lower triangle: T[r][cc] -= L[r][c] * L[cc][c], c < cc <= r
-        // (all loads first, then the stores: a load after a possibly aliasing shared store would serialise the loop)
-        const int cc = c + 1 + tx;
-        const double lcc = (cc < nb) ? T[cc][c] : 0.0;
-        const double xck = (tx <= c) ? X[c][tx] : 0.0;         // inverse: X[r][k] -= L[r][c] * X[c][k] for r > c, k <= c
-        double lr[NB / 4], tv[NB / 4], xv[NB / 4];
+        // ---- 2. the new columns of L below the diagonal patch, the finished rows of the inverse ----
+        if ((pj == C && pi > C) || (pi == C && pj <= C)) {
+            double M[4][4];
 #pragma unroll
-        for (int i = 0; i < NB / 4; ++i) {
-            const int r = c + 1 + ty + 4 * i;
-            const bool in = r < nb;
-            lr[i] = in ? T[r][c] : 0.0;
-            tv[i] = (in && cc <= r) ? T[r][cc] : 0.0;
-            xv[i] = (in && tx <= c) ? X[r][tx] : 0.0;
-        }
+            for (int r = 0; r < 4; ++r)
 #pragma unroll
-        for (int i = 0; i < NB / 4; ++i) {
-            const int r = c + 1 + ty + 4 * i;
-            if (r < nb) {
-                if (cc <= r) T[r][cc] = tv[i] - lr[i] * lcc;
-                if (tx <= c) X[r][tx] = xv[i] - lr[i] * xck;
+                for (int c = 0; c < 4; ++c) M[r][c] = dinv_s[b][4 * r + c];
+            if (pi > C) {                                    // L_p = T_p . M^T
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    double l[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        double sum = t[i][0] * M[k][0];
+#pragma unroll
+                        for (int q = 1; q <= k; ++q) sum += t[i][q] * M[k][q];
+                        l[k] = sum;
+                    }
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) { t[i][k] = l[k]; lp_s[b][k][r0 + i] = l[k]; }
+                }
+            } else {                                         // X_C = M . X_C
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    double xn[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        double sum = M[i][0] * x[0][j];
+#pragma unroll
+                        for (int q = 1; q <= i; ++q) sum += M[i][q] * x[q][j];
+                        xn[i] = sum;
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) { x[i][j] = xn[i]; xc_s[b][i][c0 + j] = xn[i]; }
+                }
             }
         }
         __syncthreads();
+        // ---- 3. rank-4 updates of everything below ----
+        if (pi > C && pj <= pi) {
+            double lr[4][4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) lr[i][k] = lp_s[b][k][r0 + i];
+            if (pj > C) {                                    // T[r][cc] -= sum_k L[r][k] L[cc][k]
+                double lc[4][4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) lc[j][k] = lp_s[b][k][c0 + j];
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) t[i][j] -= lr[i][k] * lc[j][k];
+            } else {                                         // X[r][q] -= sum_k L[r][k] X_C[k][q]
+                double xr[4][4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) xr[k][j] = xc_s[b][k][c0 + j];
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) x[i][j] -= lr[i][k] * xr[k][j];
+            }
+        }
     }
-    __syncthreads();
-    for (int r = ty; r < NB; r += 4) {
-        if (r < nb && tx < nb) A[int64_t(j0 + r) * lda + j0 + tx] = T[r][tx];
-        Linv[r * NB + tx] = X[r][tx];
-        LinvT[r * NB + tx] = X[tx][r];
-    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int r = r0 + i, cc = c0 + j;
+            if (r < nb && cc < nb) A[int64_t(j0 + r) * lda + j0 + cc] = (cc <= r) ? t[i][j] : 0.0;
+            const double xv = (cc <= r) ? x[i][j] : 0.0;
+            Linv[r * NB + cc] = xv;
+            LinvT[cc * NB + r] = xv;
+        }
 }
 
 // out(n,n) = in^T (lower factor -> its transpose), tiled through shared memory
@@ -138,29 +229,27 @@ int spd_solve_right(int64_t n64, int64_t m, double *A, int64_t lda, double *B, i
     double *scal = invd + round_up(n64, 2);
     double *Linv = scal + 4;
     double *LinvT = Linv + int64_t(nblk) * NB * NB;
-    constexpr size_t POTRF_SMEM = (2 * NB * (NB + 1) + NB) * sizeof(double);
-    static bool configured = false;
-    if (!configured) {
-        PET_CUDA(cudaFuncSetAttribute(potrf_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(POTRF_SMEM)));
-        configured = true;
-    }
     maxdiag_kernel<<<1, 256, 0, st>>>(A, lda, n, scal, tol_scale);
     PET_LAUNCH_CHECK();
+    // B stacked under A with the same leading dimension: the rows of B ride along as extra rows of every panel, which IS
+    // the forward sweep Z . L^T = B (the panel product gives Z_j, the trailing update removes Z_j . L[j1:, j0:j1]^T from the
+    // remaining columns) -- 32 launches of the dependent chain less than a separate sweep.
+    const bool stacked = m > 0 && B == A + n64 * lda && ldb == lda;
+    const int64_t extra = stacked ? m : 0;
     // ---- factor ----
     for (int j0 = 0, jb = 0; j0 < n; j0 += NB, ++jb) {
         int nb = std::min(NB, n - j0);
         double *Li = Linv + int64_t(jb) * NB * NB;
-        potrf_block_kernel<<<1, 256, POTRF_SMEM, st>>>(A, lda, j0, nb, n, invd, scal, Li, LinvT + int64_t(jb) * NB * NB);
+        potrf_block_kernel<<<1, 256, 0, st>>>(A, lda, j0, nb, n, invd, scal, Li, LinvT + int64_t(jb) * NB * NB);
         PET_LAUNCH_CHECK();
         int j1 = j0 + nb;
-        if (j1 < n) {
-            int64_t rows = n - j1;
-            double *panel = A + int64_t(j1) * lda + j0;
-            // panel: L[j1:, j0:j1] = A[j1:, j0:j1] . inv(L_jj)^T   (in place: one column tile, rows are CTA-private)
-            PET_CHECK(dgemm_kk(rows, nb, nb, panel, lda, Li, NB, panel, lda, 1.0, 0, st));
-            // trailing: A[j1:, j1:] -= L[j1:, j0:j1] . L[j1:, j0:j1]^T
-            PET_CHECK(dgemm_kk(rows, rows, nb, panel, lda, panel, lda, A + int64_t(j1) * lda + j1, lda, -1.0, 1, st));
-        }
+        int64_t rows = n - j1;
+        double *panel = A + int64_t(j1) * lda + j0;
+        // panel: L[j1:, j0:j1] = A[j1:, j0:j1] . inv(L_jj)^T   (in place: one column tile, rows are CTA-private)
+        if (rows + extra > 0) PET_CHECK(dgemm_kk(rows + extra, nb, nb, panel, lda, Li, NB, panel, lda, 1.0, 0, st));
+        // trailing: A[j1:, j1:] -= L[j1:, j0:j1] . L[j1:, j0:j1]^T
+        if (rows > 0)
+            PET_CHECK(dgemm_kk(rows + extra, rows, nb, panel, lda, panel, lda, A + int64_t(j1) * lda + j1, lda, -1.0, 1, st));
     }
     {
         int64_t tot = n64 * n64;
@@ -175,7 +264,7 @@ int spd_solve_right(int64_t n64, int64_t m, double *A, int64_t lda, double *B, i
     // updated with it in ONE wide GEMM (K = 64, hundreds of tiles) -- the left-looking form has a growing K on a dozen tiles
     // and is latency bound.
     // ---- Z . L^T = B, column blocks ascending ----
-    for (int j0 = 0, jb = 0; j0 < n; j0 += NB, ++jb) {
+    for (int j0 = 0, jb = 0; j0 < n && !stacked; j0 += NB, ++jb) {
         int nb = std::min(NB, n - j0);
         int j1 = j0 + nb;
         PET_CHECK(dgemm_kk(m, nb, nb, B + j0, ldb, Linv + int64_t(jb) * NB * NB, NB, B + j0, ldb, 1.0, 0, st));

@@ -58,15 +58,22 @@ def test_dgemm_mn_matches_fp64_matmul(lib, dev, M, N, K):
     assert bool((Cm[:, N:] == 0).all())
 
 
+@pytest.mark.parametrize("stacked", [False, True])
 @pytest.mark.parametrize("n,m", [(1, 1), (10, 25), (64, 30), (100, 77), (129, 65), (1000, 676)])
-def test_spd_solve_right(lib, dev, n, m):
+def test_spd_solve_right(lib, dev, n, m, stacked):
+    """stacked: B directly under A in one buffer (what the engine does) -- the forward sweep is fused into the factorisation."""
     rng = np.random.RandomState(n)
     lda = (n + 7) // 8 * 8
     X = rng.standard_normal((n + 20, n))
     A = X.T @ X + 0.1 * np.eye(n)
     Bm = rng.standard_normal((m, n))
-    Ad = torch.zeros(n, lda, dtype=torch.float64, device=dev); Ad[:, :n] = torch.as_tensor(A)
-    Bd = torch.zeros(m, lda, dtype=torch.float64, device=dev); Bd[:, :n] = torch.as_tensor(Bm)
+    if stacked:
+        AB = torch.zeros(n + m, lda, dtype=torch.float64, device=dev)
+        Ad, Bd = AB[:n], AB[n:]
+    else:
+        Ad = torch.zeros(n, lda, dtype=torch.float64, device=dev)
+        Bd = torch.zeros(m, lda, dtype=torch.float64, device=dev)
+    Ad[:, :n] = torch.as_tensor(A); Bd[:, :n] = torch.as_tensor(Bm)
     work = torch.empty(lib.pet_spd_solve_work_doubles(n, lda), dtype=torch.float64, device=dev)
     info = C.c_int32(-1)
     assert lib.pet_spd_solve_right(n, m, P(Ad), lda, P(Bd), lda, P(work), C.byref(info), stream()) == 0
@@ -75,7 +82,8 @@ def test_spd_solve_right(lib, dev, n, m):
     assert rel_err(Bd[:, :n].cpu().numpy(), ref) < 1e-9
 
 
-def test_spd_solve_dead_unit_gives_lstsq_answer(lib, dev):
+@pytest.mark.parametrize("stacked", [False, True])
+def test_spd_solve_dead_unit_gives_lstsq_answer(lib, dev, stacked):
     """A unit that never fires leaves a zero row/column in Wq; np.linalg.lstsq returns the
     minimum-norm solution (zero column) and so must the device solve (bsc_et.py:380)."""
     rng = np.random.RandomState(0)
@@ -83,7 +91,11 @@ def test_spd_solve_dead_unit_gives_lstsq_answer(lib, dev):
     X = rng.standard_normal((60, n)); X[:, 7] = 0
     A = X.T @ X
     Bm = rng.standard_normal((m, n)); Bm[:, 7] = 0
-    Ad = torch.as_tensor(A).to(dev).contiguous(); Bd = torch.as_tensor(Bm).to(dev).contiguous()
+    if stacked:
+        AB = torch.as_tensor(np.concatenate([A, Bm])).to(dev).contiguous()
+        Ad, Bd = AB[:n], AB[n:]
+    else:
+        Ad = torch.as_tensor(A).to(dev).contiguous(); Bd = torch.as_tensor(Bm).to(dev).contiguous()
     work = torch.empty(lib.pet_spd_solve_work_doubles(n, n), dtype=torch.float64, device=dev)
     info = C.c_int32(-1)
     assert lib.pet_spd_solve_right(n, m, P(Ad), n, P(Bd), n, P(work), C.byref(info), stream()) == 0
