@@ -60,11 +60,11 @@ class GaussianLinearET(CAModel):
         comm, eng = self.comm, self.engine
         p = self._pack_params(model_params)
         a = eng.anneal(anneal)
-        N = comm.allreduce(eng.n)
         A = self._truncation_mass(model_params)
         sel = _lib.PASS_SELECT if fused else 0
         if anneal['Ncut_factor'] > 0.0:
             # N_use = int(N * (1 - (1 - A) * Ncut)); cut = allsort(denoms)[-N_use]   (bsc_et.py:250-252)
+            N = comm.allreduce(eng.n)            # without a cut N = N_use comes back with the packed statistics
             N_use_target = int(N * (1 - (1 - A) * anneal['Ncut_factor']))
             lse = eng.log_denominators(a, p, logpj, sel)
             self._global_cut(lse, N_use_target)
@@ -72,13 +72,16 @@ class GaussianLinearET(CAModel):
         else:
             stats = eng.m_step_stats(a, p, logpj, sel)
         comm.allreduce_tensor_(stats)     # ONE collective replaces bsc_et.py:258,266,373-374,387,417
+        # the solve only needs the reduced statistics: enqueue it before the host waits for the scalars
+        W_dev = None
+        if 'W' in self.to_learn:
+            W_dev, self.last_dropped_pivots = eng.solve(p, stats)
         sc = eng.scalars(stats)
         N_use = int(round(sc[0]))
         self._log_before_L(N_use, A)
         L = self._likelihood_const(model_params, A) + sc[1] / N_use
         dlog.append('L', L)
-        if 'W' in self.to_learn:
-            W_dev, self.last_dropped_pivots = eng.solve(p, stats)
+        if W_dev is not None:
             if self.last_dropped_pivots > 0:      # singular Wq: reproduce lstsq/pinv's minimum-norm answer
                 W_dev = eng.solve_rank_deficient(stats, self._solve_rcond, self.model_kind == _lib.MODEL_BSC)
             # device-resident EM loop: parameters given as CUDA tensors come back as CUDA tensors; dlog
