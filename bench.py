@@ -365,10 +365,13 @@ def run_gpu(args):
         roof["avg_launch_ms"] = avg_launch_ms
         roof["stage_ms_per_step"] = per_step
         roof["whole_step_fp64_frac"] = (flops_per_dp() * N_TOTAL / world / (ms_max / args.steps / 1e3) / 1e12) / peak
-        n_cpu = int(os.environ.get("PET_CPU_SAMPLE", 256))
-        cpu_vals, cores = cpu_port_throughput(n_cpu, 2)
-        cpu = {"value": float(cpu_vals[-1]), "unit": "datapoints/s", "cores": cores, "kind": "port",
-               "sample": "%d datapoints per core x %d cores, 1 iteration after 1 warm-up" % (n_cpu, cores)}
+        if world == 1:
+            n_cpu = int(os.environ.get("PET_CPU_SAMPLE", 256))
+            cpu_vals, cores = cpu_port_throughput(n_cpu, 2)
+            cpu = {"value": float(cpu_vals[-1]), "unit": "datapoints/s", "cores": cores, "kind": "port",
+                   "sample": "%d datapoints per core x %d cores, 1 iteration after 1 warm-up" % (n_cpu, cores)}
+        else:       # the CPU arm is timed at N=1 only (the other ranks would idle behind it); `--impl reference` times it at any N
+            cpu = {"value": None, "unit": "datapoints/s", "cores": 0, "kind": "port", "sample": "not timed at n_gpus > 1"}
         out = {
             "metric": METRIC, "value": value, "unit": "datapoints/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "strong",
