@@ -344,8 +344,8 @@ def run_gpu(args):
                         "achieved": achieved, "peak": int8_peak / pairs, "unit": "TFLOP/s", "frac": achieved * pairs / int8_peak,
                         "pipe_achieved_tops": achieved * pairs, "pipe_peak_tops": int8_peak,
                         "pipe_nominal_tops": 4500.0, "frac_of_nominal": achieved * pairs / 4500.0,
-                        "ncu_tensor_pipe_active": {"score_shape": 0.56, "statistics_shape": 0.74,
-                                                   "source": "profiles/r01_ncu_oz_gemm_kernel.txt"},
+                        "ncu_tensor_pipe_active": {"score_shape": 0.66, "statistics_shape": 0.73,
+                                                   "source": "profiles/r01i_ncu_oz_gemm_kernel.txt"},
                         "peak_source": "2 x %s bf16_tflops_sustained (int8 dense rate), divided by the %d slice products; "
                                        "cuBLAS DGEMM measured in this run: %.1f TFLOP/s" % (peak_src, pairs, peak),
                         "traffic": ncu_traffic()}
