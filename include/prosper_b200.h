@@ -305,7 +305,9 @@ int  pet_ozaki_gemm_mn(int64_t M, int64_t N, int64_t K, const double *A_dev, int
 double pet_ozaki_last_ms(void);
 /* Solve X.A = B for X with A (n,n) symmetric positive semi-definite (pivots below
  * tol are dropped, giving the minimum-norm behaviour of lstsq for dead units).
- * A is overwritten by its Cholesky factor; B (m,n) overwritten by X. Synchronises. */
+ * A is overwritten by its Cholesky factor; B (m,n) overwritten by X. Synchronises.
+ * When B lies directly under A in one buffer (B_dev == A_dev + n*lda, ldb == lda) the
+ * forward sweep is fused into the factorisation (32 launches less at n = 1000). */
 int  pet_spd_solve_right(int64_t n, int64_t m, double *A_dev, int64_t lda,
                          double *B_dev, int64_t ldb, double *work_dev,
                          int32_t *info_host, void *stream);
