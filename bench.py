@@ -204,7 +204,10 @@ def run_gpu(args):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa_cpus = None
     if world > 1:
+        # one process per GPU, bound to the GPU's NUMA node before any pinned buffer is allocated
+        numa_cpus = parallel.bind_to_gpu_numa_node(local_rank)
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         # NCCL prints its version banner on stdout when the communicator is created: stdout carries ONE JSON line, so the
         # file descriptor points at stderr while the communicator comes up
@@ -377,7 +380,8 @@ def run_gpu(args):
             "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "parallelism": "dp%d" % world, "l2": "inputs (%.1f GB per rank) larger than L2" % (n_local * D * 8 / 1e9),
-                       "parity": "tests/test_bsc_gpu.py (float64, <=1e-8 vs oracle)"},
+                       "parity": "tests/test_bsc_gpu.py (float64, <=1e-8 vs oracle)",
+                       "cpu_affinity": ("GPU-local NUMA node, %d CPUs" % len(numa_cpus)) if numa_cpus else "unchanged"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "datapoints/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "note": "model.step() with pinned host y re-uploaded every step, W/pi/sigma returned to host"},

@@ -141,3 +141,39 @@ def allmean(my_a, axis=None, comm=None):
 def allsum(my_a, axis=None, comm=None):
     comm = comm or default_comm()
     return comm.allreduce(np.sum(my_a, axis))
+
+
+def bind_to_gpu_numa_node(device_index):
+    """Restrict the calling thread to the CPUs NVML reports as local to GPU `device_index`.
+
+    One process per GPU: pinned host buffers are first-touched by this thread, so they land on the NUMA node the GPU's
+    PCIe link hangs off and host->device copies of several ranks do not cross the socket interconnect (the reference's
+    counterpart is `mpirun --bind-to ...`; prosper itself leaves placement to MPI).  Returns the CPU list, or None when
+    nothing was changed (no NVML, a single node, a cpuset that excludes the local CPUs)."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        props = torch.cuda.get_device_properties(device_index)
+        handle = None
+        uuid = getattr(props, 'uuid', None)
+        if uuid is not None:
+            try:
+                handle = pynvml.nvmlDeviceGetHandleByUUID(("GPU-%s" % uuid).encode())
+            except Exception:
+                handle = None
+        if handle is None:
+            if os.environ.get("CUDA_VISIBLE_DEVICES"):
+                return None                              # indices are remapped and the UUID lookup failed: leave it
+            handle = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        ncpu = os.cpu_count() or 1
+        mask = pynvml.nvmlDeviceGetCpuAffinity(handle, (ncpu + 63) // 64)
+        local = set(64 * w + b for w, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1)
+        allowed = os.sched_getaffinity(0)
+        target = local & allowed
+        if len(target) < 2 or target == allowed:
+            return None
+        os.sched_setaffinity(0, target)
+        return sorted(target)
+    except Exception:
+        return None

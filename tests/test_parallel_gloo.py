@@ -104,3 +104,12 @@ def test_world_size_2_gloo(tmp_path):
         assert rel_err(r[i]['W'], want['W']) < 1e-10
         assert abs(r[i]['pi'] - want['pi']) < 1e-12 and abs(r[i]['sigma'] - want['sigma']) < 1e-12
         assert abs(r[i]['L'] - m.log['L']) < 1e-10 and r[i]['N_use'] == m.log['N_use']
+
+
+def test_numa_binding_is_a_no_op_without_a_gpu():
+    """bind_to_gpu_numa_node must never raise or change the affinity when NVML / the GPU is absent."""
+    import os
+    from prosper_b200.utils import parallel
+    before = os.sched_getaffinity(0)
+    assert parallel.bind_to_gpu_numa_node(0) is None
+    assert os.sched_getaffinity(0) == before
