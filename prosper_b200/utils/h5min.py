@@ -168,34 +168,52 @@ def _read_datatype(buf):
 
 
 def read_h5(path):
-    """{name: ndarray} of the root group of a file written by write_h5 (or any HDF5 file with the same
-    old-style objects: v0 superblock, symbol-table root group, contiguous datasets)."""
+    """{name: ndarray} of the root group of a file written by write_h5 -- or by libhdf5 itself, as long as it uses the
+    same old-style objects (v0 superblock, symbol-table root group, v1 object headers, contiguous datasets; a user block
+    in front of the superblock and the v1/v2 layout message of libhdf5 1.6 are understood).  tests/test_h5_cpu.py reads a
+    file written by libhdf5 (MATLAB 7.4) with it, which pins this reader -- and through it the writer -- to the real format."""
     with open(path, "rb") as f:
         raw = f.read()
-    assert raw[:8] == SIGNATURE, "not an HDF5 file"
-    sb_ver, _, _, _, _, so, sl, _ = struct.unpack_from("<BBBBBBBB", raw, 8)
+    sb = 0
+    while raw[sb:sb + 8] != SIGNATURE:                       # the superblock may sit behind a user block of 512 * 2^k bytes
+        sb = 512 if sb == 0 else 2 * sb
+        assert sb < len(raw), "not an HDF5 file"
+    sb_ver, _, _, _, _, so, sl, _ = struct.unpack_from("<BBBBBBBB", raw, sb + 8)
     assert sb_ver == 0 and so == 8 and sl == 8
-    leaf_k, internal_k, _ = struct.unpack_from("<HHI", raw, 16)
-    base, _, eof, _ = struct.unpack_from("<QQQQ", raw, 24)
-    assert base == 0 and eof == len(raw)
-    _, root_hdr, cache_type, _ = struct.unpack_from("<QQII", raw, 56)
-    btree_addr, heap_addr = struct.unpack_from("<QQ", raw, 80)
+    leaf_k, internal_k, _ = struct.unpack_from("<HHI", raw, sb + 16)
+    base, _, eof, _ = struct.unpack_from("<QQQQ", raw, sb + 24)
+    assert base == sb and eof in (len(raw), len(raw) - base)
+    _, root_hdr, cache_type, _ = struct.unpack_from("<QQII", raw, sb + 56)
+    btree_addr, heap_addr = struct.unpack_from("<QQ", raw, sb + 80)
+    root_hdr += base
+    btree_addr += base
+    heap_addr += base
 
     def messages(addr):
         ver, _, nmsg, _, size = struct.unpack_from("<BBHII", raw, addr)
         assert ver == 1
-        p, out = addr + 16, []
-        for _ in range(nmsg):
-            mtype, msize, _flags = struct.unpack_from("<HHB", raw, p)
-            out.append((mtype, raw[p + 8:p + 8 + msize]))
-            p += 8 + msize
-        assert p - (addr + 16) == size
+        blocks, out, total = [(addr + 16, size)], [], 0
+        while blocks:
+            p, left = blocks.pop(0)
+            while left > 0 and total < nmsg:
+                mtype, msize, _flags = struct.unpack_from("<HHB", raw, p)
+                body = raw[p + 8:p + 8 + msize]
+                out.append((mtype, body))
+                total += 1
+                if mtype == 0x0010:                          # continuation block
+                    caddr, clen = struct.unpack_from("<QQ", body, 0)
+                    blocks.append((caddr + base, clen))
+                p += 8 + msize
+                left -= 8 + msize
+            assert left >= 0
+        assert total == nmsg
         return out
 
     sym = dict(messages(root_hdr))[0x0011]
-    assert struct.unpack("<QQ", sym[:16]) == (btree_addr, heap_addr)
+    assert struct.unpack("<QQ", sym[:16]) == (btree_addr - base, heap_addr - base)
     assert raw[heap_addr:heap_addr + 4] == b"HEAP"
     heap_size, free_head, heap_data = struct.unpack_from("<QQQ", raw, heap_addr + 8)
+    heap_data += base
     assert free_head == HEAP_FREE_NULL or free_head < heap_size
 
     def name_at(off):
@@ -210,7 +228,7 @@ def read_h5(path):
         assert ntype == 0
         p = addr + 24
         for i in range(used):
-            child = struct.unpack_from("<Q", raw, p + 8)[0]
+            child = struct.unpack_from("<Q", raw, p + 8)[0] + base
             if level > 0:
                 walk(child)
             else:
@@ -222,22 +240,30 @@ def read_h5(path):
                     nm = name_at(noff)
                     assert prev is None or prev.encode() < nm.encode(), "symbol table entries must be sorted"
                     prev = nm
-                    out[nm] = dataset(ohdr)
+                    out[nm] = dataset(ohdr + base)
             p += 16
 
     def dataset(addr):
         msgs = dict(messages(addr))
         sp = msgs[0x0001]
         ver, rank, flags = struct.unpack_from("<BBB", sp, 0)
-        assert ver == 1 and flags == 0
+        assert ver == 1 and (flags & ~1) == 0                # bit 0: maximum dimensions follow the current ones
         dims = struct.unpack_from("<%dQ" % rank, sp, 8)
         dt = _read_datatype(msgs[0x0003])
-        lv, lclass, daddr, dsize = struct.unpack_from("<BBQQ", msgs[0x0008], 0)
-        assert lv == 3 and lclass == 1
+        lay = msgs[0x0008]
         count = int(np.prod(dims)) if rank else 1
+        if lay[0] == 3:
+            lv, lclass, daddr, dsize = struct.unpack_from("<BBQQ", lay, 0)
+        else:                                                # libhdf5 1.6: version, dimensionality, class, 5 reserved, address, 32-bit sizes
+            assert lay[0] in (1, 2)
+            ndim, lclass = lay[1], lay[2]
+            daddr = struct.unpack_from("<Q", lay, 8)[0]
+            dsize = int(np.prod(struct.unpack_from("<%dI" % ndim, lay, 16)))
+        assert lclass == 1
         assert dsize == count * dt.itemsize
         if dsize == 0:
             return np.zeros(dims, dtype=dt)
+        daddr += base
         assert daddr % 8 == 0
         return np.frombuffer(raw, dtype=dt, count=count, offset=daddr).reshape(dims).copy()
 

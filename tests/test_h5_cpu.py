@@ -94,3 +94,53 @@ def test_dlog_store_to_h5(tmp_path):
     assert sorted(r) == ['L', 'W', 'pi']
     assert r['W'].shape == (3, 2, 2) and r['L'].tolist() == [0.0, -1.0, -2.0]
     assert len(keep.values['sigma']) == 3
+
+
+LIBHDF5_FILE = os.path.join(os.path.dirname(np.__file__), "..", "scipy", "io", "matlab", "tests", "data",
+                            "testhdf5_7.4_GLNX86.mat")
+
+
+def _object_messages(raw, addr):
+    """(type, body) of the v1 object header at absolute address addr (first block only)."""
+    ver, _, nmsg, _, size = struct.unpack_from("<BBHII", raw, addr)
+    assert ver == 1
+    p, out = addr + 16, []
+    while p < addr + 16 + size and len(out) < nmsg:
+        mtype, msize, _flags = struct.unpack_from("<HHB", raw, p)
+        out.append((mtype, raw[p + 8:p + 8 + msize]))
+        p += 8 + msize
+    return out
+
+
+@pytest.mark.skipif(not os.path.exists(LIBHDF5_FILE), reason="SciPy's test data (a file written by libhdf5) is not installed")
+def test_reader_and_writer_against_a_file_written_by_libhdf5(tmp_path):
+    """Neither libhdf5 nor PyTables is in the image, but SciPy ships a MATLAB 7.4 v7.3 file, i.e. genuine libhdf5 1.6
+    output (512-byte user block, v0 superblock, symbol-table root group, one contiguous float64 dataset 0:pi/4:2pi).
+    (a) the reader that checks our writer parses it, (b) the messages our writer emits for the same array are byte-identical
+    to libhdf5's where the format leaves no choice (superblock versions and sizes, datatype, dataspace)."""
+    want = np.linspace(0.0, 2 * np.pi, 9).reshape(9, 1)
+    got = h5min.read_h5(LIBHDF5_FILE)
+    assert list(got) == ['testdouble'] and got['testdouble'].dtype == np.float64
+    assert np.allclose(got['testdouble'], want, rtol=0, atol=1e-15)
+
+    ours_path = str(tmp_path / "ours.h5")
+    h5min.write_h5(ours_path, {'testdouble': got['testdouble']})
+    ours, ref = open(ours_path, 'rb').read(), open(LIBHDF5_FILE, 'rb').read()
+    assert ours[:16] == ref[512:528]                           # signature, all version bytes, offset / length sizes
+    # libhdf5 stores the same symbol-table leaf K (4) and B-tree internal K (16) that this writer declares
+    assert struct.unpack_from("<HH", ours, 16) == struct.unpack_from("<HH", ref, 512 + 16)
+
+    def dataset_messages(raw, base):
+        root_hdr = struct.unpack_from("<Q", raw, base + 64)[0] + base
+        btree = struct.unpack_from("<Q", raw, base + 80)[0] + base
+        assert dict(_object_messages(raw, root_hdr))[0x0011][:8] == struct.pack("<Q", btree - base)
+        snod = struct.unpack_from("<Q", raw, btree + 32)[0] + base
+        assert raw[btree:btree + 4] == b"TREE" and raw[snod:snod + 4] == b"SNOD"
+        ohdr = struct.unpack_from("<Q", raw, snod + 8 + 8)[0] + base
+        return dict(_object_messages(raw, ohdr))
+
+    mo, mr = dataset_messages(ours, 0), dataset_messages(ref, 512)
+    assert mo[0x0003] == mr[0x0003]                            # H5T_IEEE_F64LE, byte for byte
+    assert mo[0x0001] == mr[0x0001]                            # dataspace: version 1, rank 2, dims (9, 1)
+    assert mo[0x0008][0] == 3 and mr[0x0008][0] == 2           # layout: we write version 3 (libhdf5 >= 1.6.3), MATLAB's 1.6 wrote 2
+    assert (h5min.read_h5(ours_path)['testdouble'] == got['testdouble']).all()
