@@ -435,6 +435,13 @@ class CAModel(Model):
         if not logprob:
             res['m'] = np.exp(res['m'])                      # :371
 
+    def _responsibilities(self, anneal, model_params, data):
+        """mca_et.py:380-387 / dsc_et.py:776-784: row-normalised exp(logpj) of the compat E-step; the candidates are put
+        back into ascending order first, as the reference does (in place)."""
+        data['candidates'].sort(axis=1)
+        F = torch.as_tensor(self.E_step(anneal, model_params, data)['logpj'])
+        return torch.softmax(F, dim=1).cpu().numpy()
+
     def _infer_map_activity(self, res):
         return (res['s'][:, 0, :] != 0).sum(-1)              # :347
 

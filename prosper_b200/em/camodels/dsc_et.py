@@ -87,12 +87,60 @@ class DSC_ET(GaussianLinearET):
         assert model_params['sigma'] >= 0.
         return model_params
 
-    def generate_data(self, model_params, my_N):
-        """dsc_et.py:238-345 (default path): s_h ~ Categorical(pi) over `states`."""
+    def generate_data(self, model_params, my_N, noise_on=True, gs=None, gp=None):
+        """dsc_et.py:238-299: s_h ~ Categorical(pi) over `states` unless the latents are given (`gs`, optionally weighted
+        by a posterior `gp` and summed over its first axis); `s` is stored as int8 like the reference's (a non-integer
+        state value is truncated there too) and y is generated from that stored s; noise only if `noise_on`."""
         pi, W, sigma = model_params['pi'], model_params['W'].T, model_params['sigma']
-        s = np.random.choice(self.states, size=(my_N, self.H), p=pi)
-        y = s @ W + np.random.normal(scale=sigma, size=(my_N, self.D))
+        if gs is None:
+            # one draw of my_N x H values consumes np.random exactly like the reference's my_N draws of H
+            s = np.random.choice(self.states, size=(my_N, self.H), replace=True, p=pi).astype(np.int8)
+        else:
+            gs = np.asarray(gs)
+            assert gs.shape[0] == my_N
+            if gp is None:
+                assert gs.ndim == 2
+                s = gs.astype(np.int8)
+            else:
+                gp = np.asarray(gp)
+                assert gp.shape[0] == my_N
+                assert gp.shape[1] == gs.shape[1]
+                s = (gs * gp).sum(1).astype(np.int8)
+        y = np.dot(s, W).astype(np.float64)
+        if noise_on:
+            y += np.random.normal(scale=sigma, size=(my_N, self.D))
         return {'y': y, 's': s}
+
+    def calculate_respons(self, anneal, model_params, data):
+        """dsc_et.py:776-784."""
+        return self._responsibilities(anneal, model_params, data)
+
+    def free_energy(self, model_params, my_data):
+        """dsc_et.py:786-790 (deprecated upstream)."""
+        return 0.0
+
+    def gain(self, old_parameters, new_parameters):
+        """dsc_et.py:792-796 (deprecated upstream)."""
+        return 0.0
+
+    def _get_sorted_data(self, N, anneal, A_pi_gamma, all_denoms, candidates, logpj_all, my_y):
+        """dsc_et.py:825-843: datapoint truncation of the compat path, strict `>` against the N_use-th largest
+        denominator (the fused path does the same on the device: `pet_kth_largest` + the GLF_CUT_STRICT flag)."""
+        if anneal['Ncut_factor'] > 0.0:
+            N_use = int(N * (1 - (1 - A_pi_gamma) * anneal['Ncut_factor']))
+            cut_denom = parallel.allsort(all_denoms, comm=self.comm)[-N_use]
+            which = np.array(all_denoms > cut_denom)
+            candidates, logpj_all, my_y = candidates[which], logpj_all[which], my_y[which]
+            N_use = self.comm.allreduce(my_y.shape[0])
+        else:
+            N_use = N
+        return N_use, my_y, candidates, logpj_all
+
+    def get_likelihood(self, D, sigma, logpj_all, N):
+        """dsc_et.py:845-870: -D/2 log(2 pi sigma^2) + sum_n logsumexp_c logpj[n, c] / N over all ranks."""
+        import torch
+        Fs = float(torch.logsumexp(torch.as_tensor(np.asarray(logpj_all, dtype=np.float64)), dim=1).sum())
+        return -0.5 * D * np.log(2 * np.pi * sigma ** 2) + self.comm.allreduce(Fs) / N
 
     def noisify_params(self, model_params, anneal):
         """dsc_et.py:412-490: as the base class, except pi gets uniform noise and is renormalised."""

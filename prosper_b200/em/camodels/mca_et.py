@@ -41,3 +41,7 @@ class MCA_ET(MaxCausesET):
                 y[n] = np.maximum(0., W[s[n]].max(axis=0))
         y += np.random.normal(scale=sigma, size=(my_N, self.D))
         return {'y': y, 's': s}
+
+    def calculate_respons(self, anneal, model_params, data):
+        """mca_et.py:380-387."""
+        return self._responsibilities(anneal, model_params, data)

@@ -60,6 +60,12 @@ class TSC_ET(GaussianLinearET):
         self.single_state_matrix, self.state_matrix, self.no_states, self.state_abs = \
             generate_state_matrix(self.Hprime, self.gamma, self.H, self.states)
 
+    def inference(self, anneal, model_params, test_data, topK=10, logprob=False, abs_marginal=True,
+                  adaptive=True, Hprime_max=None, gamma_max=None):
+        """tsc_et.py:546-547: the reference's positional order (`abs_marginal` sits before `adaptive`); adds res['am']."""
+        return CAModel.inference(self, anneal, model_params, test_data, topK=topK, logprob=logprob, adaptive=adaptive,
+                                 Hprime_max=Hprime_max, gamma_max=gamma_max, abs_marginal=abs_marginal)
+
     def _infer_res(self, my_N, topK):
         res = CAModel._infer_res(self, my_N, topK)
         res['am'] = np.zeros((my_N, self.H))

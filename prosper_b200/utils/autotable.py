@@ -56,6 +56,19 @@ class AutoTable(object):
             raise TypeError('Wrong datatype "%s" for "%s" field' % (value.dtype, name))
         self.tables[name].append(np.array(value, copy=True))
 
+    def appendList(self, name, value):
+        """autotable.py:190-223: like `append`, but `value` holds SEVERAL rows (its first axis, or a list of strings)."""
+        if type(value) == list and len(value) > 0 and type(value[0]) == str:
+            for v in value:
+                self.append(name, v)
+            return
+        if np.isscalar(value):
+            value = np.asarray(value)
+        if not isinstance(value, np.ndarray):
+            raise TypeError("Don't know how to handle values of type '%s'", type(value))
+        for row in (value if value.ndim > 0 else value.reshape(1)):
+            self.append(name, row)
+
     def append_all(self, valdict):
         """autotable.py:156-166."""
         for name, value in valdict.items():

@@ -106,14 +106,19 @@ class DataLog(object):
     def _lookup(self, tblname):
         return [h for (name, h) in self.policy if name == tblname or name == '*']
 
-    def set_handler(self, tblnames, handler_class, *args, **kargs):
+    def set_handler(self, tblname, handler_class, *args, **kargs):
+        """datalog.py:234-254: one handler instance for the table name (or every name of an iterable)."""
         if self._rank() != 0:
             return None
         if not issubclass(handler_class, DataHandler):
             raise TypeError("handler_class must be a subclass of DataHandler")
         handler = handler_class(*args, **kargs)
-        if isinstance(tblnames, str):
-            tblnames = (tblnames,)
+        if isinstance(tblname, str):
+            tblnames = (tblname,)
+        elif hasattr(tblname, '__iter__'):
+            tblnames = tuple(tblname)
+        else:
+            raise TypeError('Table-name must be a string (or a list of strings)')
         for t in tblnames:
             self.policy.append((t, handler))
             handler.register(t)

@@ -144,3 +144,30 @@ def test_reader_and_writer_against_a_file_written_by_libhdf5(tmp_path):
     assert mo[0x0001] == mr[0x0001]                            # dataspace: version 1, rank 2, dims (9, 1)
     assert mo[0x0008][0] == 3 and mr[0x0008][0] == 2           # layout: we write version 3 (libhdf5 >= 1.6.3), MATLAB's 1.6 wrote 2
     assert (h5min.read_h5(ours_path)['testdouble'] == got['testdouble']).all()
+
+
+def test_appendlist_adds_one_row_per_entry(tmp_path):
+    """autotable.py:190-223: appendList(name, array) appends array.shape[0] rows; a list of strings one row each."""
+    path = str(tmp_path / "l.h5")
+    with AutoTable(path) as tbl:
+        tbl.append('x', np.zeros(3))
+        tbl.appendList('x', np.arange(6.0).reshape(2, 3))
+        tbl.appendList('names', ['ab', 'c'])
+        tbl.appendList('t', np.arange(4.0))
+        with pytest.raises(TypeError):
+            tbl.appendList('x', [1, 2, 3])
+    r = h5min.read_h5(path)
+    assert r['x'].shape == (3, 3) and (r['x'][1:] == np.arange(6.0).reshape(2, 3)).all()
+    assert list(r['names']) == [b'ab', b'c'] and (r['t'] == np.arange(4.0)).all()
+
+
+def test_set_handler_accepts_a_name_or_an_iterable_of_names():
+    """datalog.py:234-254."""
+    log = DataLog()
+    h = log.set_handler(('a', 'b'), Keep)
+    log.append('a', 1.0); log.append('b', 2.0); log.append('c', 3.0)
+    assert h.values['a'] == [1.0] and h.values['b'] == [2.0] and 'c' not in h.values
+    with pytest.raises(TypeError):
+        log.set_handler(5, Keep)
+    with pytest.raises(TypeError):
+        log.set_handler('a', dict)
