@@ -92,6 +92,22 @@ def default_comm():
     return TorchComm() if dist.is_available() and dist.is_initialized() else SerialComm()
 
 
+def init_from_env():
+    """Under torchrun (RANK / WORLD_SIZE / MASTER_* in the environment) bring up the process group this package's
+    communicator wraps: NCCL with one GPU per rank (cuda:LOCAL_RANK), gloo on a host without GPUs.  The counterpart of
+    `mpirun` creating MPI.COMM_WORLD for the reference.  Returns the communicator."""
+    import os
+    if dist.is_available() and not dist.is_initialized() and int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if torch.cuda.is_available():
+            local = int(os.environ.get("LOCAL_RANK", "0"))
+            torch.cuda.set_device(local)
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        else:
+            dist.init_process_group("gloo")
+    return default_comm()
+
+
 def pprint(obj="", comm=None, end='\n'):
     comm = comm or default_comm()
     if comm.rank != 0:

@@ -171,3 +171,46 @@ def test_set_handler_accepts_a_name_or_an_iterable_of_names():
         log.set_handler(5, Keep)
     with pytest.raises(TypeError):
         log.set_handler('a', dict)
+
+
+def test_reference_example_flow_with_wildcard_handlers(tmp_path, capsys):
+    """The logging flow of the reference's examples/barstests/bars-learning.py (TextPrinter + StoreToTxt on a print list,
+    StoreToH5 on '*', EM.run over a LinearAnnealing schedule, dlog.close) with a model whose step() logs what
+    CAModel.step logs (camodels/__init__.py:190-191) -- everything but the CUDA step, so it runs without a GPU."""
+    from prosper_b200.em import EM, Model
+    from prosper_b200.em.annealing import LinearAnnealing
+    from prosper_b200.utils.datalog import dlog, TextPrinter, StoreToTxt
+
+    class Stub(Model):
+        def step(self, anneal, model_params, my_data):
+            new = {'W': model_params['W'] + 1.0, 'pi': float(model_params['pi']) * 0.5, 'sigma': 1.0,
+                   'mu': np.zeros(4), 'Q': 0.}
+            dlog.append('L', -1.5)
+            dlog.append('N', 10)
+            dlog.append_all(new)
+            dlog.append_all(anneal.as_dict())
+            return new
+
+    anneal = LinearAnnealing(5)
+    anneal['T'] = [(0, 2.), (.7, 1.)]
+    anneal['Ncut_factor'] = [(0, 0.), (2. / 3, 1.)]
+    anneal['anneal_prior'] = False
+    print_list = ('T', 'Q', 'pi', 'sigma', 'N', 'MAE')
+    handlers = [dlog.set_handler(print_list, TextPrinter),
+                dlog.set_handler(print_list, StoreToTxt, str(tmp_path / "terminal.txt")),
+                dlog.set_handler(('*'), StoreToH5, str(tmp_path / "result.h5"))]
+    try:
+        em = EM(model=Stub(), anneal=anneal)
+        em.data = {'y': np.zeros((10, 4))}
+        em.lparams = {'W': np.zeros((4, 3)), 'pi': 0.5, 'sigma': 1.0}
+        em.run()
+        dlog.close()
+    finally:
+        for h in handlers:
+            dlog.remove_handler(h)
+    r = h5min.read_h5(str(tmp_path / "result.h5"))
+    assert r['W'].shape == (5, 4, 3) and (r['W'][:, 0, 0] == np.arange(1.0, 6.0)).all()
+    assert r['pi'].shape == (5,) and r['T'][0] == 2.0 and r['T'][-1] == 1.0 and r['N'].tolist() == [10] * 5
+    assert r['Ncut_factor'][0] == 0.0 and r['Ncut_factor'][-1] == 1.0 and 'anneal_prior' in r and 'L' in r
+    assert (em.lparams['W'] == 5.0).all()
+    assert "sigma" in open(str(tmp_path / "terminal.txt")).read() and "pi" in capsys.readouterr().out

@@ -315,3 +315,87 @@ def test_dsc_generate_data_without_the_reference():
     from scipy.special import logsumexp
     lp = rng.randn(9, 5)
     assert abs(m.get_likelihood(6, 0.3, lp, 9) - (-3 * np.log(2 * np.pi * 0.09) + logsumexp(lp, 1).sum() / 9)) < 1e-12
+
+
+def test_bars_helpers(tmp_path, monkeypatch):
+    """utils/barstest.py (barstest.py:8-98) and utils.create_output_path (utils/__init__.py:17-62), self-contained."""
+    from prosper_b200.utils import barstest, create_output_path
+    W = barstest.generate_bars_dict(10)
+    assert W.shape == (25, 10) and (W.sum(0) == 5).all() and (W.reshape(5, 5, 10)[2, :, 2] == 1).all()
+    assert (W.reshape(5, 5, 10)[:, 3, 8] == 1).all()
+    np.random.seed(0)
+    y = barstest.generate_bars_data(200, 5, 0.2).reshape(200, 5, 5)
+    rows, cols = y.min(2) == 1, y.min(1) == 1
+    assert ((y == 1) == (rows[:, :, None] | cols[:, None, :])).all() and 0.1 < rows.mean() < 0.3
+    rng = np.random.RandomState(1)
+    perm = rng.permutation(10)
+    Wl = 10 * W[:, perm] + 0.5 * rng.randn(25, 10)
+    found = barstest.find_permutation(Wl, 10 * W)
+    assert (perm[found] == np.arange(10)).all() and (barstest.find_permutation2(Wl, 10 * W) == found).all()
+    monkeypatch.chdir(tmp_path)
+    monkeypatch.setenv("SLURM_JOBID", "77")
+    monkeypatch.delenv("PBS_JOBID", raising=False)
+    assert create_output_path("run") == "output/run.d77/" and create_output_path("run") == "output/run.d77+1/"
+    assert os.path.isdir(str(tmp_path / "output" / "run.d77+1"))
+
+
+@pytest.mark.skipif(not ref_harness.available(), reason="reference tree not present (GPU box)")
+def test_bars_helpers_match_the_live_reference():
+    ref_harness.load()
+    from prosper.utils import barstest as R
+    from prosper_b200.utils import barstest as O
+    for H in (4, 10, 16):
+        for neg in (False, True):
+            np.random.seed(1)
+            a = R.generate_bars_dict(H, neg)
+            np.random.seed(1)
+            assert np.array_equal(a, O.generate_bars_dict(H, neg))
+    np.random.seed(2)
+    a = R.generate_bars_data(50, 5, 0.3)
+    np.random.seed(2)
+    assert np.array_equal(a, O.generate_bars_data(50, 5, 0.3))
+    rng = np.random.RandomState(0)
+    for _ in range(12):
+        H = int(rng.choice([4, 6, 8, 10]))
+        Wgt = 10 * O.generate_bars_dict(H)
+        W = Wgt[:, rng.permutation(H)] + rng.randn(Wgt.shape[0], H) * rng.choice([0.1, 2.0, 6.0])
+        assert np.array_equal(R.find_permutation(W, Wgt), O.find_permutation(W, Wgt))
+        assert np.array_equal(R.find_permutation2(W, Wgt), O.find_permutation2(W, Wgt))
+    Wgt = 10 * O.generate_bars_dict(6)
+    W = np.concatenate([Wgt[:, ::-1] + rng.randn(9, 6), rng.randn(9, 3)], 1)
+    assert np.array_equal(R.find_permutation(W, Wgt), O.find_permutation(W, Wgt))
+
+
+def test_install_as_prosper_serves_every_import_of_the_reference_examples():
+    """`prosper_b200.install_as_prosper()`: the import lines of the reference's examples/ resolve to this package."""
+    import subprocess
+    import sys
+    code = r'''
+import sys
+sys.path.insert(0, %r)
+import prosper_b200
+prosper_b200.install_as_prosper()
+from prosper.utils.barstest import generate_bars_dict
+from prosper.em.annealing import LinearAnnealing
+from prosper.utils.parallel import pprint, stride_data
+from prosper.utils.datalog import dlog, StoreToH5, TextPrinter, StoreToTxt
+from prosper.utils import create_output_path
+from prosper.em import EM
+from prosper.em.camodels.bsc_et import BSC_ET
+from prosper.em.camodels.mca_et import MCA_ET
+from prosper.em.camodels.mmca_et import MMCA_ET
+from prosper.em.camodels.tsc_et import TSC_ET
+from prosper.em.camodels.dsc_et import DSC_ET
+from prosper.em.camodels.gsc_et import GSC
+from prosper.em.mixturemodels.MoG import MoG
+from prosper.em.mixturemodels.MoP import MoP
+import prosper.em.camodels.bsc_et as m
+assert m.__name__ == "prosper_b200.em.camodels.bsc_et" and BSC_ET.__module__ == m.__name__
+model = BSC_ET(25, 10, 6, 3)                       # the parameter files of the examples build the model at import time
+anneal = LinearAnnealing(50)
+anneal['T'] = [(0, 2.), (.7, 1.)]
+assert model.state_matrix.shape == (35, 6) and generate_bars_dict(10).shape == (25, 10)
+print("ALIAS_OK")
+''' % os.path.join(os.path.dirname(GOLDEN), "..")
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "ALIAS_OK" in out.stdout, out.stderr[-2000:]
