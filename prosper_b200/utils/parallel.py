@@ -133,9 +133,34 @@ def stride_data(N, balanced=False, comm=None):
     return first, first + base
 
 
-def allsort(my_array, comm=None):
-    """All ranks get the globally sorted 1-D array (parallel.py:87-110)."""
+def _allgather_flat(my_array, axis, comm):
+    """Rank-ordered concatenation of equally shaped local arrays as ONE flat buffer, viewed with the length of `axis`
+    multiplied by the number of ranks -- what MPI's Allgather into an array of that shape does (parallel.py:104-107)."""
+    all_shape = list(my_array.shape)
+    all_shape[axis] = int(comm.allreduce(my_array.shape[axis]))
+    if comm.size == 1:
+        return my_array.reshape(all_shape)
+    t = torch.as_tensor(np.ascontiguousarray(my_array)).to(comm._host_device())
+    flat = np.concatenate([p.cpu().numpy().ravel() for p in comm.allgather_tensor(t)])
+    return flat.reshape(all_shape)
+
+
+def _check_sortable(my_array):
+    if my_array.dtype.kind not in 'fiub':
+        raise TypeError("Dont know how to handle arrays of type %s" % my_array.dtype)
+
+
+def allsort(my_array, axis=-1, kind='quicksort', order=None, comm=None):
+    """All ranks get the globally sorted array (parallel.py:87-110): local sort, all-gather, merge sort.
+
+    1-D arrays (the truncation cut of the M-step, bsc_et.py:252) may have a different length on every rank -- the
+    reference's Allgather needs equal lengths, `stride_data` shards differ by one.  N-D arrays follow the reference
+    exactly: equal shapes on all ranks, the gathered buffer viewed with `axis` lengthened, sorted along `axis`."""
     comm = comm or default_comm()
+    my_array = np.asarray(my_array)
+    _check_sortable(my_array)
+    if my_array.ndim != 1:
+        return np.sort(_allgather_flat(np.sort(my_array, axis, kind, order), axis, comm), axis, 'mergesort', order)
     if comm.size == 1:
         return np.sort(my_array)
     n = int(comm.allreduce(len(my_array)))
@@ -145,18 +170,29 @@ def allsort(my_array, comm=None):
     t = torch.as_tensor(pad).to(comm._host_device())
     parts = comm.allgather_tensor(t)
     allv = np.sort(np.concatenate([p.cpu().numpy() for p in parts]))
-    return allv[:n]
+    return allv[:n].astype(my_array.dtype, copy=False)
 
 
-def allmean(my_a, axis=None, comm=None):
+def allargsort(my_array, axis=-1, kind='quicksort', order=None, comm=None):
+    """parallel.py:113-135, as upstream: the argsort of the gathered LOCAL argsort indices (not a global argsort of the
+    values -- the reference gathers `np.argsort(my_array)` and argsorts that)."""
+    comm = comm or default_comm()
+    my_array = np.asarray(my_array)
+    _check_sortable(my_array)
+    return np.argsort(_allgather_flat(np.argsort(my_array, axis, kind, order), axis, comm), axis, kind, order)
+
+
+def allmean(my_a, axis=None, dtype=None, out=None, comm=None):
+    """parallel.py:138-156."""
     comm = comm or default_comm()
     N = comm.allreduce(my_a.size if axis is None else my_a.shape[axis])
-    return comm.allreduce(np.sum(my_a, axis)) / N
+    return comm.allreduce(np.sum(my_a, axis, dtype)) / N
 
 
-def allsum(my_a, axis=None, comm=None):
+def allsum(my_a, axis=None, dtype=None, out=None, comm=None):
+    """parallel.py:159-170."""
     comm = comm or default_comm()
-    return comm.allreduce(np.sum(my_a, axis))
+    return comm.allreduce(np.sum(my_a, axis, dtype))
 
 
 def bind_to_gpu_numa_node(device_index):

@@ -65,6 +65,12 @@ def _worker(rank, world, port, out_dir):
     allv = np.random.RandomState(0).standard_normal(N)
     res['allsort'] = parallel.allsort(allv[first:last], comm=comm)
     res['allmean'] = parallel.allmean(allv[first:last, None] * np.ones((1, 3)), axis=0, comm=comm)
+    # N-D arrays, equal shapes on all ranks (the reference's own tests/utils/test_parallel.py cases)
+    a2 = np.random.RandomState(10 + rank).uniform(size=(10, 2))
+    res['allsort_ax0'] = parallel.allsort(a2, axis=0, kind='quicksort', comm=comm)
+    res['allsort_last'] = parallel.allsort(a2, comm=comm)
+    res['allargsort_ax0'] = parallel.allargsort(a2, axis=0, kind='quicksort', comm=comm)
+    res['allsum'] = parallel.allsum(np.ones(10), comm=comm)
     # a sharded EM step equals the single-rank step on the concatenated data
     y, params, _ = bsc_problem(25, 10, 301, 1, bars=True, pi=0.2, sigma=2.0)
     f, l = parallel.stride_data(y.shape[0], comm=comm)
@@ -95,6 +101,16 @@ def test_world_size_2_gloo(tmp_path):
     for i in range(2):
         assert np.array_equal(r[i]['allsort'], np.sort(allv))
         assert np.allclose(r[i]['allmean'], allv.mean())
+    # N-D: local sort, rank-ordered flat gather viewed with the axis lengthened (MPI Allgather), sort again
+    loc = [np.random.RandomState(10 + i).uniform(size=(10, 2)) for i in range(2)]
+    flat0 = np.concatenate([np.sort(x, 0).ravel() for x in loc])
+    flat1 = np.concatenate([np.sort(x, -1).ravel() for x in loc])
+    flata = np.concatenate([np.argsort(x, 0).ravel() for x in loc])
+    for i in range(2):
+        assert np.array_equal(r[i]['allsort_ax0'], np.sort(flat0.reshape(20, 2), 0))
+        assert r[i]['allsort_last'].shape == (10, 4) and np.array_equal(r[i]['allsort_last'], np.sort(flat1.reshape(10, 4), -1))
+        assert np.array_equal(r[i]['allargsort_ax0'], np.argsort(flata.reshape(20, 2), 0))
+        assert r[i]['allsum'] == 20.0
     # 2-rank EM step == 1-rank EM step
     y, params, _ = bsc_problem(25, 10, 301, 1, bars=True, pi=0.2, sigma=2.0)
     an = DictAnneal(T=1.5, Ncut_factor=0.6, anneal_prior=False)
@@ -113,3 +129,23 @@ def test_numa_binding_is_a_no_op_without_a_gpu():
     before = os.sched_getaffinity(0)
     assert parallel.bind_to_gpu_numa_node(0) is None
     assert os.sched_getaffinity(0) == before
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/prosper/tests/utils"), reason="reference tree not present (GPU box)")
+def test_the_references_own_unit_tests_pass_on_this_package(tmp_path):
+    """prosper/tests/utils/test_{parallel,barstest,autotable}.py -- the only tests the reference has -- run
+    UNMODIFIED against `prosper_b200.install_as_prosper()` (test_tracing.py is out of scope: tracing is CUDA events here)."""
+    import subprocess
+    code = (
+        "import sys, unittest, importlib.util\n"
+        "sys.path.insert(0, %r)\n"
+        "import prosper_b200; prosper_b200.install_as_prosper()\n"
+        "bad = 0; ran = 0\n"
+        "for name in ('test_parallel', 'test_barstest', 'test_autotable'):\n"
+        "    spec = importlib.util.spec_from_file_location('ref_' + name, '/root/reference/prosper/tests/utils/%%s.py' %% name)\n"
+        "    mod = importlib.util.module_from_spec(spec); spec.loader.exec_module(mod)\n"
+        "    r = unittest.TextTestRunner(verbosity=0).run(unittest.defaultTestLoader.loadTestsFromModule(mod))\n"
+        "    ran += r.testsRun; bad += len(r.failures) + len(r.errors)\n"
+        "print('REFTESTS', ran, bad)\n" % ROOT)
+    out = subprocess.run([sys.executable, "-c", code], cwd=str(tmp_path), capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "REFTESTS 12 0" in out.stdout, out.stdout[-500:] + out.stderr[-3000:]
