@@ -12,7 +12,7 @@ __version__ = "0.1.0"
 _PROSPER_MODULES = ("em", "em.annealing", "em.camodels", "em.camodels.bsc_et", "em.camodels.mca_et", "em.camodels.mmca_et",
                     "em.camodels.tsc_et", "em.camodels.dsc_et", "em.camodels.gsc_et", "em.mixturemodels",
                     "em.mixturemodels.MoG", "em.mixturemodels.MoP", "utils", "utils.parallel", "utils.datalog",
-                    "utils.autotable", "utils.barstest")
+                    "utils.autotable", "utils.barstest", "utils.tracing")
 
 
 def install_as_prosper(mpi_shim=True):

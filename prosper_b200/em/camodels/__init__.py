@@ -13,7 +13,7 @@ import torch
 
 from .. import Model
 from ... import _lib
-from ...utils import parallel
+from ...utils import parallel, tracing
 from ...utils.datalog import dlog
 
 
@@ -292,6 +292,7 @@ class CAModel(Model):
     def check_params(self, model_params):
         return model_params
 
+    @tracing.traced
     def step(self, anneal, model_params, my_data):
         """One EM step in the order of camodels/__init__.py:163-193; the three starred calls
         of the reference are fused into `_fused_step` (logpj is never materialised)."""

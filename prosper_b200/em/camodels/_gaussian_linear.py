@@ -12,6 +12,7 @@ import torch
 from . import CAModel
 from ... import _lib
 from ...utils.datalog import dlog
+from ...utils import tracing
 
 
 class GaussianLinearET(CAModel):
@@ -33,17 +34,20 @@ class GaussianLinearET(CAModel):
         raise NotImplementedError
 
     # -- the three operators ----------------------------------------------------------------------
+    @tracing.traced
     def select_Hprimes(self, model_params, data):
         self._bind(data)
         data['candidates'] = self.engine.select(self._pack_params(model_params))
         return data
 
+    @tracing.traced
     def E_step(self, anneal, model_params, my_data):
         eng = self.engine
         self._bind(my_data)
         eng.set_candidates(my_data['candidates'])
         return {'logpj': eng.e_step(eng.anneal(anneal), self._pack_params(model_params))}
 
+    @tracing.traced
     def M_step(self, anneal, model_params, my_suff_stat, my_data):
         eng = self.engine
         self._bind(my_data)

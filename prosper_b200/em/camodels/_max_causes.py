@@ -13,6 +13,7 @@ from scipy.special import comb
 from . import CAModel
 from ... import _lib
 from ...utils.datalog import dlog
+from ...utils import tracing
 
 
 class MaxCausesET(CAModel):
@@ -34,11 +35,13 @@ class MaxCausesET(CAModel):
             B += gp * a
         return A, B
 
+    @tracing.traced
     def select_Hprimes(self, model_params, data):
         self._bind(data)
         data['candidates'] = self.engine.select(self._pack_params(model_params))
         return data
 
+    @tracing.traced
     def E_step(self, anneal, model_params, my_data):
         """-> {'logpj'}: NOT annealed (beta is applied in the M-step, mca_et.py:237-238)."""
         eng = self.engine
@@ -48,6 +51,7 @@ class MaxCausesET(CAModel):
         assert np.isfinite(logpj).all()                                   # mca_et.py:177
         return {'logpj': logpj}
 
+    @tracing.traced
     def M_step(self, anneal, model_params, my_suff_stat, my_data):
         eng = self.engine
         self._bind(my_data)

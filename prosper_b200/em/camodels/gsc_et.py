@@ -18,6 +18,7 @@ import torch
 from . import CAModel, Engine, _ptr
 from ... import _lib
 from ...utils import parallel
+from ...utils import tracing
 
 _SIGMA_TYPES = {'scalar': 0, 'diagonal': 1, 'full': 2}
 
@@ -165,6 +166,7 @@ class GSC(CAModel):
         return logpj.cpu().numpy(), cand
 
     # -- the three operators ----------------------------------------------------------------------
+    @tracing.traced
     def select_Hprimes(self, model_params, my_data):
         """gsc_et.py:721-749 -> my_data['data_clusters'] {key: {'hprimes','data','ind'}}."""
         eng = self.engine
@@ -187,6 +189,7 @@ class GSC(CAModel):
         self._cand_key = self._bound
         return my_data
 
+    @tracing.traced
     def E_step(self, anneal, model_params, my_data):
         """gsc_et.py:401-580 -> {'xpt_s','xpt_ss','xpt_sz','xpt_szsz'}; reorders my_data['y'] cluster-major and
         overwrites my_data['candidates'] (float), as the reference does (:572-573)."""
@@ -212,6 +215,7 @@ class GSC(CAModel):
         self._cand = None
         return {'xpt_s': xs.cpu().numpy(), 'xpt_ss': xss.cpu().numpy(), 'xpt_sz': xsz.cpu().numpy(), 'xpt_szsz': xszsz.cpu().numpy()}
 
+    @tracing.traced
     def M_step(self, anneal, model_params, suff_stats, my_data):
         """gsc_et.py:584-718 on caller-supplied moment tensors (compat path): the reductions over
         datapoints run through the engine's statistics GEMM / column-sum kernels."""

@@ -15,6 +15,7 @@ from .. import Model
 from ... import _lib
 from ...utils import parallel
 from ...utils.datalog import dlog
+from ...utils import tracing
 
 
 def _p(t):
@@ -142,6 +143,7 @@ class MixtureModel(Model):
         sel = np.random.permutation(my_N)[:my_pN]
         return data[sel]
 
+    @tracing.traced
     def step(self, anneal, model_params, data):
         """:115-138; E and M back to back on the device (the posterior never visits the host)."""
         model_params = self.noisify_params(model_params, anneal)
@@ -153,11 +155,13 @@ class MixtureModel(Model):
         dlog.append_all(anneal.as_dict())
         return new_model_params
 
+    @tracing.traced
     def E_step(self, anneal, model_params, my_data):
         lp, post = self._e_step_device(anneal, model_params, my_data)
         n = my_data['y'].shape[0]
         return {'posteriors_h': post[:n, :self.H].cpu().numpy(), 'logpj': lp[:n, :self.H].cpu().numpy()}
 
+    @tracing.traced
     def M_step(self, anneal, model_params, suff_stats, my_data):
         post = self.ops.padded(suff_stats['posteriors_h'])
         return self._m_step_device(anneal, model_params, post, my_data)

@@ -214,3 +214,26 @@ def test_reference_example_flow_with_wildcard_handlers(tmp_path, capsys):
     assert r['Ncut_factor'][0] == 0.0 and r['Ncut_factor'][-1] == 1.0 and 'anneal_prior' in r and 'L' in r
     assert (em.lparams['W'] == 5.0).all()
     assert "sigma" in open(str(tmp_path / "terminal.txt")).read() and "pi" in capsys.readouterr().out
+
+
+def test_tracepoints_of_the_stage_methods(tmp_path):
+    """utils/tracing.py (tracing.py:38-141): set_tracefile / traced / close, one file per rank packed into traces.tgz."""
+    import tarfile
+    from prosper_b200.utils import tracing
+    from prosper_b200.em.camodels.bsc_et import BSC_ET
+    assert BSC_ET.E_step.__name__ == 'E_step' and BSC_ET.step.__wrapped__ is not None
+
+    @tracing.traced
+    def work(x):
+        """doc"""
+        return x + 1
+
+    assert work(1) == 2                                   # inactive: plain call
+    tracing.set_tracefile(str(tmp_path / "trace-%04d.txt"))
+    assert work(2) == 3
+    tracing.tracepoint("custom")
+    tracing.close()
+    assert tracing.trace_file is None and not (tmp_path / "trace-0000.txt").exists()
+    with tarfile.open(str(tmp_path / "traces.tgz")) as tar:
+        text = tar.extractfile("trace-0000.txt").read().decode()
+    assert "[work:begin]" in text and "[work:end]" in text and "[custom]" in text and text.startswith("# Start time")

@@ -133,19 +133,19 @@ def test_numa_binding_is_a_no_op_without_a_gpu():
 
 @pytest.mark.skipif(not os.path.isdir("/root/reference/prosper/tests/utils"), reason="reference tree not present (GPU box)")
 def test_the_references_own_unit_tests_pass_on_this_package(tmp_path):
-    """prosper/tests/utils/test_{parallel,barstest,autotable}.py -- the only tests the reference has -- run
-    UNMODIFIED against `prosper_b200.install_as_prosper()` (test_tracing.py is out of scope: tracing is CUDA events here)."""
+    """prosper/tests/utils/test_{parallel,barstest,autotable,tracing}.py -- the only tests the reference has --
+    run UNMODIFIED against `prosper_b200.install_as_prosper()`."""
     import subprocess
     code = (
         "import sys, unittest, importlib.util\n"
         "sys.path.insert(0, %r)\n"
         "import prosper_b200; prosper_b200.install_as_prosper()\n"
         "bad = 0; ran = 0\n"
-        "for name in ('test_parallel', 'test_barstest', 'test_autotable'):\n"
+        "for name in ('test_parallel', 'test_barstest', 'test_autotable', 'test_tracing'):\n"
         "    spec = importlib.util.spec_from_file_location('ref_' + name, '/root/reference/prosper/tests/utils/%%s.py' %% name)\n"
         "    mod = importlib.util.module_from_spec(spec); spec.loader.exec_module(mod)\n"
         "    r = unittest.TextTestRunner(verbosity=0).run(unittest.defaultTestLoader.loadTestsFromModule(mod))\n"
         "    ran += r.testsRun; bad += len(r.failures) + len(r.errors)\n"
         "print('REFTESTS', ran, bad)\n" % ROOT)
     out = subprocess.run([sys.executable, "-c", code], cwd=str(tmp_path), capture_output=True, text=True, timeout=600)
-    assert out.returncode == 0 and "REFTESTS 12 0" in out.stdout, out.stdout[-500:] + out.stderr[-3000:]
+    assert out.returncode == 0 and "REFTESTS 14 0" in out.stdout, out.stdout[-500:] + out.stderr[-3000:]
