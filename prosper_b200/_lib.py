@@ -113,6 +113,8 @@ SIGNATURES = {
                                       C.c_void_p, C.POINTER(C.c_int32), C.c_void_p]),
     "pet_spd_solve_work_doubles": (C.c_int64, [C.c_int64, C.c_int64]),
     "pet_gemm_path": (C.c_int32, [C.c_void_p]),
+    "pet_set_state_kernel": (C.c_int, [C.c_void_p, C.c_int32]),
+    "pet_state_kernel_path": (C.c_int32, [C.c_void_p]),
     "pet_stage_times_ms": (C.c_int, [C.c_void_p, c_double_p]),
     "pet_enable_timing": (C.c_int, [C.c_void_p, C.c_int32]),
     "pet_launch_count": (C.c_int64, [C.c_void_p]),

@@ -13,6 +13,7 @@
 
 #include "common.cuh"
 #include "gl_kernel.cuh"
+#include "gl_state_tc.cuh"
 #include "mca_kernel.cuh"
 #include "gsc_kernel.cuh"
 #include "ozaki.cuh"
@@ -144,6 +145,9 @@ struct pet_engine {
     unsigned long long *ksel_state = nullptr;
     unsigned long long *d_states = nullptr, *d_inc = nullptr; unsigned short *d_entries = nullptr, *d_chunk = nullptr; unsigned int *d_direct = nullptr;
     int *d_single = nullptr; double *d_state_prior = nullptr;
+    // multi-cause states on the tensor cores (gl_state_tc.cu): constant membership tables; tc_mode 0 = automatic
+    // (large state spaces), 1 = never, 2 = whenever the state space is supported
+    GLTcHost tc_host; uint8_t *d_tc_fwd = nullptr, *d_tc_rev = nullptr; bool tc_ok = false; int tc_mode = 0;
 
     // int8-sliced operands of the two large GEMMs (ozaki.cu); oz_on = buffers present and the path selected
     bool oz_want = false, oz_on = false; int oz_ns = 7, oz_kpd = 0, oz_splits = 1; int64_t oz_rows = 0;
@@ -194,6 +198,7 @@ extern "C" void pet_destroy(pet_engine *e) {
     free_dev(e->Bfull); free_dev(e->gsc_T); free_dev(e->Wt2); free_dev(e->gsc_tab); free_dev(e->psi_dev); free_dev(e->bdiag); free_dev(e->XSZ); free_dev(e->SZ2); free_dev(e->yyw); free_dev(e->dst_dev);
     free_dev(e->ozY); free_dev(e->ozYT); free_dev(e->ozW); free_dev(e->ozS); free_dev(e->ozYs); free_dev(e->ozYTs);
     free_dev(e->ozWs); free_dev(e->ozSs); free_dev(e->oz_slabs); free_dev(e->oz_colmax);
+    free_dev(e->d_tc_fwd); free_dev(e->d_tc_rev);
     free_dev(e->d_inc); free_dev(e->d_states); free_dev(e->d_entries); free_dev(e->d_chunk); free_dev(e->d_direct); free_dev(e->d_single); free_dev(e->d_state_prior);
     for (auto ev : e->chunk_ready) cudaEventDestroy(ev);
     for (auto p : e->up_slots) free_dev(p);
@@ -322,6 +327,16 @@ extern "C" int pet_create(const pet_config *cfg, pet_engine **out) {
         TRYC(cudaMemcpy(e->d_inc, e->ss.inc_records.data(), e->ss.S * 8, cudaMemcpyHostToDevice));
         g.inc_states = e->d_inc;
     }
+    if (e->model == PET_MODEL_BSC && gl_tc_supported(g, e->gamma, e->binary)) {
+        TRY(gl_tc_build_tables(g, e->gamma, e->ss.matrix, e->tc_host));
+        TRY(dev_alloc(&e->d_tc_fwd, (int64_t)e->tc_host.bfwd.size()));
+        TRY(dev_alloc(&e->d_tc_rev, (int64_t)e->tc_host.brev.size()));
+        TRYC(cudaMemcpy(e->d_tc_fwd, e->tc_host.bfwd.data(), e->tc_host.bfwd.size(), cudaMemcpyHostToDevice));
+        TRYC(cudaMemcpy(e->d_tc_rev, e->tc_host.brev.data(), e->tc_host.brev.size(), cudaMemcpyHostToDevice));
+        e->tc_host.dev.bfwd = e->d_tc_fwd; e->tc_host.dev.brev = e->d_tc_rev;
+        e->tc_ok = true;
+        if (const char *env = getenv("PET_GL_TC")) e->tc_mode = atoi(env) == 0 ? 1 : 2;
+    }
     g.states = e->d_states; g.entries = e->d_entries; g.chunk_tab = e->d_chunk; g.direct = e->d_direct; g.single_idx = e->d_single;
 
     // chunk-sized buffers are allocated when the shard is bound (size_chunks): the chunk length depends on its size
@@ -386,6 +401,18 @@ extern "C" int pet_state_matrix(const pet_engine *e, double *out_host) {
     return PET_OK;
 }
 extern "C" int32_t pet_gemm_path(const pet_engine *e) { return (e && e->oz_on) ? e->oz_ns : 0; }
+// the tensor-core state kernel pays off once the state space fills a few 64-state chunks
+static bool use_state_tc(const pet_engine *e, int kflags) {
+    if (!e->tc_ok || e->tc_mode == 1 || (kflags & (GLF_READ_LOGPJ | GLF_WRITE_LOGPJ))) return false;
+    return e->tc_mode == 2 || e->ss.S >= 256;
+}
+extern "C" int pet_set_state_kernel(pet_engine *e, int32_t mode) {
+    if (!e || mode < 0 || mode > 2) { set_error("pet_set_state_kernel: mode must be 0 (auto), 1 (scalar) or 2 (tensor cores)"); return PET_EINVAL; }
+    if (mode == 2 && !e->tc_ok) { set_error("pet_set_state_kernel: this model / state space has no tensor-core state kernel"); return PET_EINVAL; }
+    e->tc_mode = mode;
+    return PET_OK;
+}
+extern "C" int32_t pet_state_kernel_path(const pet_engine *e) { return (e && use_state_tc(e, 0)) ? 2 : 1; }
 extern "C" int pet_enable_timing(pet_engine *e, int32_t on) {
     if (!e) return PET_EINVAL;
     e->timer.reset();
@@ -826,7 +853,8 @@ static int sweep_gl(pet_engine *e, const pet_anneal *a, const pet_params *p, int
         PET_CHECK(launch_gl_row(ga, e->sm_count, st));
         e->timer.end(st);
         e->timer.begin(ST_POST, st);
-        PET_CHECK(launch_gl_state(ga, e->gamma, e->binary, e->sm_count, st));
+        if (use_state_tc(e, kflags)) PET_CHECK(launch_gl_state_tc(ga, e->tc_host.dev, e->sm_count, st));
+        else PET_CHECK(launch_gl_state(ga, e->gamma, e->binary, e->sm_count, st));
         e->timer.end(st);
         if (!fold_scale) {
             e->timer.begin(ST_SCALE, st);

@@ -218,6 +218,13 @@ class Engine(object):
         """0 = FP64 DMMA kernels, n > 0 = int8 tcgen05 kernels with n slices per operand."""
         return int(self.lib.pet_gemm_path(self.h))
 
+    def set_state_kernel(self, mode):
+        """0 = automatic, 1 = scalar FP64 state kernel, 2 = int8 tensor-core state kernel (fused BSC path)."""
+        _lib.check(self.lib.pet_set_state_kernel(self.h, int(mode)))
+
+    def state_kernel_path(self):
+        return int(self.lib.pet_state_kernel_path(self.h))
+
     def launch_count(self):
         return int(self.lib.pet_launch_count(self.h))
 
@@ -257,17 +264,37 @@ class CAModel(Model):
     def invalidate_data(self):
         """Forget the device copy of the data (call after mutating my_data['y'] in place)."""
         self._bound = None
+        self._bound_ref = None
+
+    @staticmethod
+    def _data_key(y):
+        """Identity of a data array for the device-copy cache.  The bound array itself is kept alive next to the
+        key (`_bound_ref`), so its address cannot be handed to another array while the cache entry lives; a
+        NumPy buffer refilled in place is caught by a small content fingerprint (<= 4096 strided samples: the
+        first and last rows and a diagonal walk), a torch tensor by its version counter."""
+        if isinstance(y, torch.Tensor):
+            return ('t', y.data_ptr(), tuple(y.shape), tuple(y.stride()), y.dtype, y._version)
+        n = y.shape[0]
+        if y.size:
+            flat = y.reshape(-1) if y.flags.c_contiguous else None
+            if flat is not None:
+                step = max(1, flat.size // 4096)
+                fp = (float(flat[::step].sum()), float(y[0].sum()), float(y[n - 1].sum()))
+            else:
+                fp = (float(y[::max(1, n // 64)].sum()), float(y[0].sum()), float(y[n - 1].sum()))
+        else:
+            fp = (0.0, 0.0, 0.0)
+        return ('n', y.ctypes.data, y.shape, y.strides, y.dtype.str, fp)
 
     def _bind(self, my_data):
         y = my_data['y']
-        if isinstance(y, torch.Tensor):
-            key = ('t', y.data_ptr(), tuple(y.shape), y._version)
-        else:
-            key = ('n', y.ctypes.data, y.shape, y.strides)
-        if self.cache_data and self._bound == key and self.engine.n == y.shape[0]:
+        key = self._data_key(y)
+        if (self.cache_data and self._bound == key and getattr(self, '_bound_ref', None) is y
+                and self.engine.n == y.shape[0]):
             return False
         self.engine.set_data(y, transient=not self.cache_data)
         self._bound = key
+        self._bound_ref = y                # keeps the host array (and hence its address) alive while it is cached
         return True
 
     # -- reference interface --------------------------------------------------------------
@@ -468,7 +495,7 @@ class CAModel(Model):
         res = self._infer_res(my_N, topK)
         self._infer_kwargs = kwargs
         which = np.ones(my_N, dtype=bool)
-        saved_engine, saved_bound = self._engine, self._bound
+        saved_engine = self._engine
         try:
             while which.any():
                 ind_n = np.where(which)[0]
@@ -503,7 +530,10 @@ class CAModel(Model):
         finally:
             self.Hprime, self.gamma = Hprime_start, gamma_start
             self._regenerate_states()
-            self._engine, self._bound = saved_engine, saved_bound
+            # the training engine (if it was used at all) now holds the last inference block: forget the binding so
+            # that the next step()/compute_lpj re-uploads its shard instead of silently running on the test data
+            self._engine = saved_engine
+            self.invalidate_data()
         self._infer_finish(res, logprob)
         comm.Barrier()
         return res

@@ -66,10 +66,13 @@ class GaussianLinearET(CAModel):
         a = eng.anneal(anneal)
         A = self._truncation_mass(model_params)
         sel = _lib.PASS_SELECT if fused else 0
+        self._check_data_noise(anneal)
+        N_use_target = 0
         if anneal['Ncut_factor'] > 0.0:
             # N_use = int(N * (1 - (1 - A) * Ncut)); cut = allsort(denoms)[-N_use]   (bsc_et.py:250-252)
             N = comm.allreduce(eng.n)            # without a cut N = N_use comes back with the packed statistics
             N_use_target = int(N * (1 - (1 - A) * anneal['Ncut_factor']))
+        if N_use_target > 0:                     # allsort(...)[-0] is the smallest denominator: N_use <= 0 keeps every point
             lse = eng.log_denominators(a, p, logpj, sel)
             self._global_cut(lse, N_use_target)
             stats = eng.m_step_stats(a, p, logpj, _lib.PASS_REUSE_SCORES if fused else 0, use_cut=True)
@@ -102,6 +105,17 @@ class GaussianLinearET(CAModel):
 
     def _log_before_L(self, N_use, A):
         pass
+
+    @staticmethod
+    def _check_data_noise(anneal):
+        """bsc_et.py:228-230 adds my_data['data_noise'] to the M-step's copy of y when anneal['data_noise'] > 0.  The
+        engine's shard is shared by the E- and the M-step, so that option is refused instead of silently ignored."""
+        try:
+            dn = anneal['data_noise']
+        except (KeyError, IndexError):
+            return
+        if dn is not None and dn > 0:
+            raise NotImplementedError("anneal['data_noise'] > 0 (bsc_et.py:228-230) is not supported on the device path")
 
     def _result(self, model_params, W_new, pi_new, sigma_new):
         return {'W': W_new, 'pi': pi_new, 'sigma': sigma_new, 'Q': 0.}

@@ -73,8 +73,8 @@ class MaxCausesET(CAModel):
         N = comm.allreduce(eng.n)
         A, B = self._AB(pies)
         sel = _lib.PASS_SELECT if fused else 0
-        if anneal['Ncut_factor'] > 0.0:                                   # mca_et.py:249-262 (annealed log-denominators)
-            N_use_target = int(N * (1 - (1 - A) * anneal['Ncut_factor']))
+        N_use_target = int(N * (1 - (1 - A) * anneal['Ncut_factor'])) if anneal['Ncut_factor'] > 0.0 else 0
+        if N_use_target > 0:            # mca_et.py:249-262 (annealed log-denominators); [-0] keeps every point
             lse = eng.log_denominators(a, p, logpj, sel)
             self._global_cut(lse, N_use_target)
             stats = eng.m_step_stats(a, p, logpj, _lib.PASS_REUSE_SCORES if fused else 0, use_cut=True)

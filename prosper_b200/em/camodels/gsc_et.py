@@ -41,6 +41,12 @@ class GSC(CAModel):
         elif Hprime < gamma:
             self.gamma = self.Hprime
         self._Hp_states, self._gamma_states = Hprime, gamma
+        if Hprime <= 0 or gamma <= 0:
+            # the reference's default Hprime=0 / gamma=0 means "no truncation": all 2^H states.  Only the truncated
+            # posterior is built on the device (H' <= 16, gamma <= 8); say so here rather than on the first step.
+            raise NotImplementedError("GSC(Hprime=%r, gamma=%r): the untruncated model (Hprime<=0 or gamma<=0, i.e. all "
+                                      "2^H states) is not built on the device; pass 1 <= gamma <= Hprime <= %d"
+                                      % (Hprime, gamma, _lib.MAX_HPRIME))
         self.sigma_sq_type = sigma_sq_type
         self.dtype_precision = np.float64
 
@@ -284,7 +290,31 @@ class GSC(CAModel):
         work = torch.empty(eng.lib.pet_spd_solve_work_doubles(H, ld), dtype=torch.float64, device=M.device)
         info = C.c_int32(0)
         _lib.check(eng.lib.pet_spd_solve_right(H, H, _ptr(A), ld, _ptr(B), ld, _ptr(work), C.byref(info), eng.stream()))
+        self._inv_dropped = int(info.value)      # pivots the truncated Cholesky dropped (0: M was positive definite)
         return B[:, :H].clone()
+
+    def _inv_szsz(self, sum_szsz, Wp, model_params, eps):
+        """W_n = Wp . inv(sum <sz sz^T>) with the reference's fallbacks for a singular matrix (gsc_et.py:623-637):
+        np.linalg.inv raises on an exactly singular matrix (a dead unit: zero row and column) -> pinv of the matrix
+        plus an eps-sized rank-one perturbation -> if that fails too, the old W plus eps noise.  Here "singular" is
+        the Cholesky dropping a pivot; pinv is a symmetric eigendecomposition with NumPy's cutoff (1e-15 sigma_max)."""
+        inv = self._inv(sum_szsz)
+        if self._inv_dropped == 0:
+            return Wp @ inv
+        dev, H = sum_szsz.device, self.H
+        noise = self.comm.bcast(np.random.normal(0, eps, H) if self.comm.rank == 0 else None)
+        noise = torch.as_tensor(np.outer(noise, noise), dtype=torch.float64, device=dev)
+        try:
+            M = sum_szsz + noise
+            lam, V = torch.linalg.eigh(0.5 * (M + M.T))
+            keep = lam.abs() > 1e-15 * lam.abs().max()
+            if not bool(torch.isfinite(lam).all()) or not bool(keep.any()):
+                raise RuntimeError("eigendecomposition of sum_szsz failed")
+            return ((Wp @ V[:, keep]) / lam[keep]) @ V[:, keep].T
+        except RuntimeError:
+            W_old = torch.as_tensor(np.asarray(model_params['W'], dtype=np.float64), device=dev)
+            jitter = self.comm.bcast(np.random.normal(0, 1, [self.D, H]) if self.comm.rank == 0 else None)
+            return W_old + eps * torch.as_tensor(jitter, dtype=torch.float64, device=dev)
 
     def _update(self, model_params, stats):
         comm = self.comm
@@ -301,7 +331,7 @@ class GSC(CAModel):
         sum_szsz = blk(lay.off_szsz, H) + torch.diag(stats[lay.off_sum_sz2:lay.off_sum_sz2 + H])
         M_ssz, M_out = blk(lay.off_Mssz, H), blk(lay.off_Mout, H)
         ysq = stats[lay.off_ysq:lay.off_ysq + D]
-        W_n = Wp @ self._inv(sum_szsz)                                        # :624-626
+        W_n = self._inv_szsz(sum_szsz, Wp, model_params, eps)                 # :623-637
         if 'pi' in self.to_learn:                                             # :640-645
             model_params['pi'] = torch.clamp(sum_s / N, 5e-5, 1 - 5e-5).cpu().numpy()
         if 'W' in self.to_learn:

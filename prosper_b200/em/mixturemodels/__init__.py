@@ -95,15 +95,20 @@ class MixtureModel(Model):
             self._ops = DeviceOps()
         return self._ops
 
+    def invalidate_data(self):
+        """Forget the device copy of the data (call after refilling a data buffer in place)."""
+        self._bound = None
+
     def _bind(self, my_y):
-        """Device copy of the data (n, even(D)), cached on the identity of the host array."""
-        if isinstance(my_y, torch.Tensor):
-            key = ('t', my_y.data_ptr(), tuple(my_y.shape), my_y._version)
-        else:
-            key = ('n', my_y.ctypes.data, my_y.shape, my_y.strides)
-        if self._bound is None or self._bound[0] != key:
+        """Device copy of the data (n, even(D)), cached on the IDENTITY of the host array: the cache entry keeps a
+        reference to the array it was made from, so another batch that happens to land at the same address with
+        the same shape (e.g. successive `data[idx]` temporaries) is a different object and is uploaded again; a
+        buffer refilled in place is caught by the content fingerprint of CAModel._data_key."""
+        from ..camodels import CAModel
+        key = CAModel._data_key(my_y)
+        if self._bound is None or self._bound[0] != key or self._bound[3] is not my_y:
             host = my_y.cpu().numpy() if isinstance(my_y, torch.Tensor) else my_y
-            self._bound = (key, self.ops.padded(host), {})
+            self._bound = (key, self.ops.padded(host), {}, my_y)
         return self._bound[1], self._bound[2]
 
     def standard_init(self, data):
