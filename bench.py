@@ -28,6 +28,135 @@ N_TOTAL = int(os.environ.get("PET_BENCH_N", 1000000))
 WORKLOAD = "BSC-ET D=676 H=1000 Hprime=12 gamma=5 N=%d synthetic patches, T=1, Ncut_factor=0" % N_TOTAL
 METRIC = "datapoints/sec per EM iteration (select_Hprimes+E_step+M_step)"
 
+# BASELINE.json configs[0..3] with the inputs of SURVEY 8(d); `--config 5` (the default) is configs[4] above.
+# cpu_n: datapoints per host core of the CPU arm (cfgs 1-2 full N, cfg 3 N = 2000 P / 8, cfg 4 N = 64 P).
+SMALL = {
+    "1": dict(model="bsc", D=25, H=10, Hp=6, g=3, N=1000, cpu_n=1000,
+              T=[(0, 2.), (.7, 1.)], Ncut=[(0, 0.), (2. / 3, 1.)],
+              workload="BSC-ET bars 5x5 D=25 H=10 Hprime=6 gamma=3 N=1000, LinearAnnealing(50) T 2->1, Ncut_factor 0->1"),
+    "2": dict(model="mca", D=25, H=10, Hp=6, g=3, N=2000, cpu_n=2000,
+              T=[(0, 4.), (.8, 1.)], Ncut=[(0, 0.), (2. / 3, 1.)],
+              workload="MCA-ET bars 5x5 D=25 H=10 Hprime=6 gamma=3 N=2000, LinearAnnealing(50) T 4->1, Ncut_factor 0->1"),
+    "3": dict(model="tsc", D=64, H=16, Hp=8, g=4, N=50000, cpu_n=250,
+              T=[(0, 2.), (.7, 1.)], Ncut=[(0, 0.), (2. / 3, 1.)],
+              workload="TSC-ET bars 8x8 D=64 H=16 Hprime=8 gamma=4 N=50000, LinearAnnealing(50) T 2->1, Ncut_factor 0->1"),
+    "3dsc": dict(model="dsc", D=64, H=16, Hp=8, g=4, N=50000, cpu_n=250,
+                 T=[(0, 2.), (.7, 1.)], Ncut=[(0, 0.), (2. / 3, 1.)],
+                 workload="DSC-ET (states -1,0,1) bars 8x8 D=64 H=16 Hprime=8 gamma=4 N=50000, LinearAnnealing(50) T 2->1, Ncut_factor 0->1"),
+    "4": dict(model="gsc", D=144, H=64, Hp=8, g=3, N=200000, cpu_n=64,
+              T=[(0, 1.)], Ncut=[(0, 0.)],
+              workload="GSC-ET (spike-and-slab, scalar noise) D=144 H=64 Hprime=8 gamma=3 N=200000 synthetic patches, T=1"),
+}
+
+
+def bars_dict(Hb):
+    R = Hb // 2
+    W = np.zeros((R, R, Hb))
+    for i in range(R):
+        W[i, :, i] = 1.
+        W[:, i, R + i] = 1.
+    return W.reshape(R * R, Hb)
+
+
+def small_problem(cfg_id, n, seed):
+    """Synthetic inputs of SURVEY 8(d) for configs 1-4, plain NumPy so that both arms generate the same law: returns
+    (y (n,D) float64, initial parameters with standard_init semantics)."""
+    c = SMALL[cfg_id]
+    Dm, Hm = c["D"], c["H"]
+    rng = np.random.RandomState(seed)
+    kind = c["model"]
+    if kind in ("bsc", "mca"):
+        W = 10.0 * bars_dict(Hm)
+        s = rng.random_sample((n, Hm)) < 0.2
+        if kind == "bsc":
+            y = s.astype(np.float64) @ W.T
+        else:                                              # max-rule superposition (mca_et.py:58-86)
+            y = np.where(s[:, None, :], W[None, :, :], 0.0).max(axis=2)
+        y += 2.0 * rng.standard_normal((n, Dm))
+    elif kind in ("tsc", "dsc"):
+        W = 10.0 * bars_dict(Hm)
+        if kind == "tsc":
+            u = rng.random_sample((n, Hm))
+            s = np.where(u < 0.0625, -1.0, np.where(u < 0.125, 1.0, 0.0))
+        else:
+            s = rng.choice(np.array([-1., 0., 1.]), size=(n, Hm), p=[.06, .88, .06])
+        y = s @ W.T + 2.0 * rng.standard_normal((n, Dm))
+    else:                                                  # gsc: RandomState(3) law of SURVEY 8d
+        W = rng.standard_normal((Dm, Hm))
+        s = rng.random_sample((n, Hm)) < 2.0 / Hm
+        z = s * (1.0 + rng.standard_normal((n, Hm)))
+        y = z @ W.T + rng.standard_normal((n, Dm))
+    mean = y.mean(axis=0)
+    var = ((y - mean) ** 2).mean(axis=0)
+    sig0 = np.sqrt(var).sum() / Dm
+    W0 = mean[:, None] + rng.normal(scale=sig0 / 4., size=(Dm, Hm))
+    if kind == "gsc":                                      # gsc_et.py:59-110
+        pi = np.maximum(rng.rand(Hm) * 0.95, 0.05)
+        params = {'W': W0, 'pi': pi, 'sigma_sq': float(np.mean(var) + 0.001), 'mu': rng.normal(0, 1, Hm),
+                  'psi_sq': np.diag(np.maximum(rng.rand(Hm) * 2, 0.05))}
+    elif kind == "dsc":                                    # dsc_et.py:872-925
+        r = rng.rand(2)
+        r = (1.0 / Hm) * r / r.sum()
+        params = {'W': W0, 'pi': np.array([r[0], 1.0 - 1.0 / Hm, r[1]]), 'sigma': sig0}
+    else:
+        params = {'W': W0, 'pi': 1. / Hm, 'sigma': sig0}
+    return y, params
+
+
+def small_oracle(cfg_id):
+    c = SMALL[cfg_id]
+    a = (c["D"], c["H"], c["Hp"], c["g"])
+    if c["model"] == "bsc":
+        from oracle.bsc import BSC
+        return BSC(*a)
+    if c["model"] == "mca":
+        from oracle.mca import MCA
+        return MCA(*a)
+    if c["model"] == "tsc":
+        from oracle.tsc import TSC
+        return TSC(*a)
+    if c["model"] == "dsc":
+        from oracle.dsc import DSC
+        return DSC(*a, np.array([-1., 0., 1.]))
+    from oracle.gsc import GSC
+    return GSC(*a, sigma_sq_type='scalar')
+
+
+def small_model(cfg_id, comm=None):
+    c = SMALL[cfg_id]
+    a = (c["D"], c["H"], c["Hp"], c["g"])
+    from prosper_b200.em import camodels
+    if c["model"] == "bsc":
+        from prosper_b200.em.camodels.bsc_et import BSC_ET
+        return BSC_ET(*a, comm=comm)
+    if c["model"] == "mca":
+        from prosper_b200.em.camodels.mca_et import MCA_ET
+        return MCA_ET(*a, comm=comm)
+    if c["model"] == "tsc":
+        from prosper_b200.em.camodels.tsc_et import TSC_ET
+        return TSC_ET(*a, comm=comm)
+    if c["model"] == "dsc":
+        from prosper_b200.em.camodels.dsc_et import DSC_ET
+        return DSC_ET(*a, np.array([-1., 0., 1.]), comm=comm)
+    from prosper_b200.em.camodels.gsc_et import GSC
+    return GSC(*a, sigma_sq_type='scalar', comm=comm)
+
+
+def small_schedule(cfg_id, steps=50):
+    """The annealing values of iteration i (cyclic over the 50-iteration schedule of the bars examples,
+    bars-learning.py:77-80 / param-bars-mca.py:34-37) as a list of Anneal dicts."""
+    from prosper_b200.em.annealing import LinearAnnealing
+    c = SMALL[cfg_id]
+    la = LinearAnnealing(steps)
+    la['T'] = c["T"]
+    la['Ncut_factor'] = c["Ncut"]
+    la['anneal_prior'] = False
+    out = []
+    for i in range(steps):
+        la.cur_pos = i
+        out.append(Anneal(T=float(la['T']), Ncut_factor=float(la['Ncut_factor']), anneal_prior=False))
+    return out
+
 
 class Anneal(dict):
     """anneal['key'] with prosper's missing-key-is-0.0 rule (annealing.py:93-94)."""
@@ -48,7 +177,7 @@ def flops_per_dp():
 # CPU arm: the oracle (NumPy port of the reference) on all host cores, bounded sample
 # ----------------------------------------------------------------------------------------------
 def _cpu_worker(args):
-    seed, n, reps = args
+    seed, n, reps, cfg_id = args
     os.environ["OMP_NUM_THREADS"] = "1"
     try:
         import threadpoolctl
@@ -56,27 +185,35 @@ def _cpu_worker(args):
     except Exception:
         pass
     sys.path.insert(0, os.path.join(ROOT, "tests"))
-    from helpers import bsc_problem
-    from oracle.bsc import BSC
-    y, params, _ = bsc_problem(D, H, n, seed)
-    model = BSC(D, H, HP, GAMMA)
-    an = Anneal(T=1.0, Ncut_factor=0.0, anneal_prior=False)
+    if cfg_id == "5":
+        from helpers import bsc_problem
+        from oracle.bsc import BSC
+        y, params, _ = bsc_problem(D, H, n, seed)
+        model = BSC(D, H, HP, GAMMA)
+        sched = [Anneal(T=1.0, Ncut_factor=0.0, anneal_prior=False)]
+    else:
+        y, params = small_problem(cfg_id, n, seed)
+        model = small_oracle(cfg_id)
+        sched = small_schedule(cfg_id)
     times = []
-    for _ in range(reps):
+    for i in range(reps):
+        p = dict((k, (np.copy(v) if isinstance(v, np.ndarray) else v)) for k, v in params.items())
+        if hasattr(model, 'check_params'):
+            p = model.check_params(p)
         t0 = time.perf_counter()
-        model.step(an, dict(params), {'y': y})
+        model.step(sched[i % len(sched)], p, {'y': y.copy()})
         times.append(time.perf_counter() - t0)
     return times
 
 
-def cpu_port_throughput(n_per_core, reps, cores=None):
+def cpu_port_throughput(n_per_core, reps, cores=None, cfg_id="5"):
     """dp/s of the oracle with one single-threaded worker per host core (the stand-in for
     `mpirun -np <cores>`; collectives are <0.1% of the reference's CPU time)."""
     import multiprocessing as mp
     cores = cores or os.cpu_count() or 1
     ctx = mp.get_context("spawn")   # never fork a process that holds a CUDA context
     with ctx.Pool(cores) as pool:
-        res = pool.map(_cpu_worker, [(100 + i, n_per_core, reps) for i in range(cores)])
+        res = pool.map(_cpu_worker, [(100 + i, n_per_core, reps, cfg_id) for i in range(cores)])
     per_rep = [max(r[i] for r in res) for i in range(reps)]      # slowest rank per iteration
     return [cores * n_per_core / t for t in per_rep], cores
 
@@ -85,9 +222,10 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n_per_core = int(os.environ.get("PET_CPU_SAMPLE", 256))
+    small = args.config != "5"
+    n_per_core = int(os.environ.get("PET_CPU_SAMPLE", SMALL[args.config]["cpu_n"] if small else 256))
     reps = args.warmup + args.steps
-    vals, cores = cpu_port_throughput(n_per_core, reps)
+    vals, cores = cpu_port_throughput(n_per_core, reps, cfg_id=args.config)
     vals = vals[args.warmup:]
     v = float(np.mean(vals))
     sample = "%d datapoints per core x %d cores per step (cost is linear in N)" % (n_per_core, cores)
@@ -95,7 +233,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": v, "unit": "datapoints/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * cores * n_per_core / v,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample": sample},
+        "config": {"workload": SMALL[args.config]["workload"] if small else WORKLOAD, "sample": sample},
         "cpu_baseline": {"value": v, "unit": "datapoints/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "datapoints/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -400,16 +538,186 @@ def run_gpu(args):
         dist.destroy_process_group()
 
 
+def run_gpu_small(args):
+    """`--config 1..4`: the same JSON line for the small configurations of BASELINE.json (bars tests, discrete states,
+    spike-and-slab).  A step is one fused EM iteration at the annealing values of iteration i of the 50-iteration
+    schedule (cyclic); these shapes are bound by launch latency and per-state FP64 ALU / SFU work, not by HBM or the
+    tensor pipe, so the roofline object reports the dominant kernel's algorithmic bytes against HBM and the
+    launch count per step next to it."""
+    import torch
+    import torch.distributed as dist
+    from prosper_b200.utils import parallel
+
+    cfg_id = args.config
+    c = SMALL[cfg_id]
+    Dm, Hm, N = c["D"], c["H"], int(os.environ.get("PET_BENCH_N_SMALL", c["N"]))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
+    comm = parallel.default_comm()
+    y_all, params0 = small_problem(cfg_id, N, {"1": 1, "2": 1, "3": 2, "3dsc": 2, "4": 3}[cfg_id])
+    first, last = parallel.stride_data(N, comm=comm)
+    n_local = last - first
+    y_host = torch.empty((n_local, Dm), dtype=torch.float64, pin_memory=True)
+    y_host.copy_(torch.as_tensor(y_all[first:last]))
+    del y_all
+    model = small_model(cfg_id, comm=comm)
+    sched = small_schedule(cfg_id)
+    data = {'y': y_host.to(dev)}
+    eng = model.engine
+    keys = list(params0.keys())
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def copy_params(p):
+        return dict((k, (np.copy(v) if isinstance(v, np.ndarray) else v)) for k, v in p.items())
+
+    def one_step(i, params, d):
+        new = model._fused_step(sched[i % len(sched)], model.check_params(params), d)
+        return dict((k, new[k]) for k in keys)
+
+    params = copy_params(params0)
+    for i in range(args.warmup):
+        params = one_step(i, params, data)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    eng.enable_timing(True)
+    launches0 = eng.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        params = one_step(args.warmup + i, params, data)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = eng.launch_count() - launches0
+    stages = eng.stage_times()
+    eng.enable_timing(False)
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = N * args.steps / (ms_max / 1e3)
+
+    # ---- end to end: host buffers through model.step(), shard re-uploaded every step ----
+    del data
+    model.invalidate_data()
+    model.cache_data = False
+    host_data = {'y': y_host.numpy()}
+    e2e_steps = max(1, min(args.steps, 10))
+    p_e2e = copy_params(params0)
+    p_e2e = model.step(sched[0], p_e2e, host_data)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        p_e2e = model.step(sched[(1 + i) % len(sched)], p_e2e, host_data)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = N * e2e_steps / float(t.item())
+    par_bytes = sum(int(np.asarray(v).size) * 8 for v in params0.values())
+
+    if rank == 0:
+        hbm, peak_src = 6527.5, "fallback (B200_PROFILING.md)"
+        try:
+            hbm = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+            peak_src = "MEASURED_PEAKS.json hbm_gbs"
+        except Exception:
+            pass
+        per_step = dict((k, v['ms'] / args.steps) for k, v in stages.items())
+        names = {'state_kernel': {'bsc': 'gl_row_* + gl_state_kernel', 'tsc': 'gl_row_kernel + gl_state_kernel<4,0>',
+                                  'dsc': 'gl_row_kernel + gl_state_kernel<4,0>', 'mca': 'mca_kernel',
+                                  'gsc': 'gsc_kernel'}[c["model"]],
+                 'score_gemm': 'dgemm_kernel (score GEMM, FP64 DMMA)', 'stats_gemm': 'dgemm_kernel (statistics GEMMs, FP64 DMMA)',
+                 'row_kernel': 'gl_row_kernel', 'solve': 'spd_solve', 'prepare': 'prepare', 'kth': 'kth_largest',
+                 'scale_kernel': 'gl_scale_kernel', 'slice_kernels': 'ozaki slicing'}
+        dom = max(per_step, key=lambda k: per_step[k])
+        spans = max(1, stages[dom]['spans'])
+        avg_launch_ms = stages[dom]['ms'] / spans
+        rows_per_launch = n_local * args.steps / spans
+        # algorithmic bytes of the posterior kernels per datapoint: the datapoint (8 D), its score row in (8 H) and
+        # its <s> row out (8 H); of a GEMM stage: y in (8 D) and the H-long row in / out (8 H)
+        kb = 8.0 * (Dm + 2 * Hm) if dom in ('state_kernel', 'row_kernel') else 8.0 * (Dm + Hm)
+        achieved = kb * rows_per_launch / (avg_launch_ms / 1e3) / 1e9
+        step_ms = ms_max / args.steps
+        roof = {"kernel": names.get(dom, dom), "bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s",
+                "frac": achieved / hbm, "peak_source": peak_src, "traffic": None, "avg_launch_ms": avg_launch_ms,
+                "stage_ms_per_step": per_step, "algorithmic_bytes_per_datapoint": kb,
+                "whole_step_hbm_frac": (2.0 * 8 * Dm * n_local / (step_ms / 1e3) / 1e9) / hbm,
+                "launches_per_step": launches / float(args.steps),
+                "us_per_launch": 1e3 * step_ms / max(1.0, launches / float(args.steps)),
+                "note": "small configuration: bound by launch latency (%d launches in a %.2f ms step) and per-state FP64 "
+                        "ALU / SFU work, far below the HBM roof by construction (SURVEY 8d)"
+                        % (round(launches / float(args.steps)), step_ms)}
+        if world == 1:
+            n_cpu = int(os.environ.get("PET_CPU_SAMPLE", c["cpu_n"]))
+            cpu_vals, cores = cpu_port_throughput(n_cpu, 2, cfg_id=cfg_id)
+            cpu = {"value": float(cpu_vals[-1]), "unit": "datapoints/s", "cores": cores, "kind": "port",
+                   "sample": "%d datapoints per core x %d cores, 1 iteration after 1 warm-up" % (n_cpu, cores)}
+        else:
+            cpu = {"value": None, "unit": "datapoints/s", "cores": 0, "kind": "port", "sample": "not timed at n_gpus > 1"}
+        check = dict((k, float(np.mean(np.asarray(params[k].cpu() if hasattr(params[k], 'cpu') else params[k]))))
+                     for k in keys if k != 'W')
+        out = {
+            "metric": METRIC, "value": value, "unit": "datapoints/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": c["workload"], "baseline_config": cfg_id, "parallelism": "dp%d" % world,
+                       "l2": "inputs (%.1f MB per rank) FIT in L2; the step is launch-bound, no flush between steps" % (n_local * Dm * 8 / 1e6),
+                       "parity": "tests/test_trajectories_gpu.py, tests/test_%s_gpu.py" % {'bsc': 'bsc', 'mca': 'mca', 'tsc': 'tsc_dsc', 'dsc': 'tsc_dsc', 'gsc': 'gsc'}[c["model"]]},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "datapoints/s", "h2d_bytes_per_step": n_local * Dm * 8 + par_bytes,
+                    "d2h_bytes_per_step": par_bytes + 16 * 8, "steps": e2e_steps,
+                    "note": "model.step() with pinned host y re-uploaded every step, parameters returned to host"},
+            "gpu_launches": int(launches),
+            "roofline": roof,
+            "cpu_baseline": cpu,
+            "result_check": check,
+        }
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="5", choices=["1", "2", "3", "3dsc", "4", "5"],
+                    help="BASELINE.json configs[k-1]; 5 (default) is the configuration the metric is quoted on")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         run_reference(args)
+    elif args.config != "5":
+        run_gpu_small(args)
     else:
         run_gpu(args)
 

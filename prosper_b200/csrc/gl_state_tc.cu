@@ -70,11 +70,23 @@ __device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+// Every wait has a watchdog: a protocol error surfaces as a trapped kernel with a message, never as a hung GPU.
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
     asm volatile(
-        "{\n\t.reg .pred p;\n\tWAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __noinline__ void mbar_timeout(int which, uint32_t parity) {
+    printf("gl_state_tc_kernel: wait on barrier %d (parity %u) timed out in block %d thread %d\n", which, parity, blockIdx.x, threadIdx.x);
+    __trap();
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity, int which) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity))
+        if (++spins > (1u << 22)) mbar_timeout(which, parity);
 }
 __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -295,12 +307,12 @@ __global__ void __launch_bounds__(THREADS, 1) gl_state_tc_kernel(const __grid_co
         for (int c = 0; c < t.n_chunks; ++c) {
             if (tid == 0) {
                 const int b = item & 1;
-                mbar_wait(&bar_tab[b], (item >> 1) & 1);
+                mbar_wait(&bar_tab[b], (item >> 1) & 1, b);
                 tc_fence_after();
                 issue_fwd(sm, tmem, b, 2);
                 mma_commit(bar_mma);
             }
-            mbar_wait(bar_mma, mma_phase & 1);
+            mbar_wait(bar_mma, mma_phase & 1, 2);
             ++mma_phase;
             tc_fence_after();
             if (tid == 0) {                                   // next item: chunk c + 1 of pass 1, or chunk 0 of pass 2
@@ -312,6 +324,7 @@ __global__ void __launch_bounds__(THREADS, 1) gl_state_tc_kernel(const __grid_co
                 if (rev_too) bulk_g2s(sm.b_rev(b), t.brev + size_t(cn) * B_REV_BYTES, B_REV_BYTES, &bar_tab[b]);
             }
             ++item;
+            __syncwarp();                                     // the TMEM loads below are warp-collective
             const int off = int(t.chunk_nfeat[c]) << 20;      // the digits carry v 2^(48-e) + 2^48 per feature
 #pragma unroll
             for (int bt = 0; bt < 2; ++bt) {
@@ -344,13 +357,13 @@ __global__ void __launch_bounds__(THREADS, 1) gl_state_tc_kernel(const __grid_co
         for (int c = 0; c < t.n_chunks; ++c) {
             if (tid == 0) {
                 const int b = item & 1;
-                mbar_wait(&bar_tab[b], (item >> 1) & 1);
+                mbar_wait(&bar_tab[b], (item >> 1) & 1, b);
                 tc_fence_after();
                 if (STATS && c > 0) issue_rev(sm, tmem, b ^ 1, c == 1);
                 issue_fwd(sm, tmem, b, 0);
                 mma_commit(bar_mma);
             }
-            mbar_wait(bar_mma, mma_phase & 1);
+            mbar_wait(bar_mma, mma_phase & 1, 2);
             ++mma_phase;
             tc_fence_after();
             if (tid == 0 && c + 1 < t.n_chunks) {
@@ -360,6 +373,7 @@ __global__ void __launch_bounds__(THREADS, 1) gl_state_tc_kernel(const __grid_co
                 if (STATS) bulk_g2s(sm.b_rev(b), t.brev + size_t(c + 1) * B_REV_BYTES, B_REV_BYTES, &bar_tab[b]);
             }
             ++item;
+            __syncwarp();
             const int off = int(t.chunk_nfeat[c]) << 20;
             const int cnt = t.chunk_cnt[c];
 #pragma unroll
@@ -409,7 +423,7 @@ __global__ void __launch_bounds__(THREADS, 1) gl_state_tc_kernel(const __grid_co
                 issue_rev(sm, tmem, (item & 1) ^ 1, t.n_chunks == 1);
                 mma_commit(bar_mma);
             }
-            mbar_wait(bar_mma, mma_phase & 1);
+            mbar_wait(bar_mma, mma_phase & 1, 2);
             ++mma_phase;
             tc_fence_after();
         }
@@ -417,45 +431,51 @@ __global__ void __launch_bounds__(THREADS, 1) gl_state_tc_kernel(const __grid_co
         part_s[(1 * 2 + hf) * TM + r] = SF;
         __syncthreads();
 
-        // ---- per-datapoint results (one thread per datapoint) ----
-        if (hf == 0 && valid) {
-            bool keep = true;
-            if (use_cut) {
+        // ---- per-datapoint results (one thread per datapoint; the TMEM loads are warp-collective, so every lane of
+        // warps 0..3 walks the accumulators and only the side effects are predicated) ----
+        if (hf == 0) {
+            bool keep = valid;
+            if (valid && use_cut) {
                 const double l = a.lse[n];
                 keep = (a.flags & GLF_CUT_STRICT) ? (l > cut) : (l >= cut);
             }
             double *scl = a.scl + n * (1 + PET_MAXHP);
-            if (!keep) {                                      // truncated away: contributes nothing (bsc_et.py:254-257)
+            if (valid && !keep)                               // truncated away: contributes nothing (bsc_et.py:254-257)
                 for (int j = 0; j <= Hp; ++j) scl[j] = 0.0;
-            } else {
+            double m1 = 0.0, Z1 = 0.0, sig1 = 0.0, cnt1 = 0.0, mx = 0.0, e1 = 0.0, inv = 0.0, sce = 1.0, lse = 0.0;
+            double *Srow = a.S + rr * st.ldH;
+            if (keep) {
                 const double *rs = a.rs + n * (4 + PET_MAXV);
-                const double m1 = rs[0];
-                const double mx = cq * a.yy[n] - bias;
+                m1 = rs[0]; Z1 = rs[1]; sig1 = rs[2]; cnt1 = rs[4];
+                mx = cq * a.yy[n] - bias;
                 Z2 = part_s[r] + part_s[TM + r];
                 SF = part_s[2 * TM + r] + part_s[3 * TM + r];
-                const double e1 = (m1 == -INFINITY) ? 0.0 : exp(m1 - mx);
-                const double Z = fma(rs[1], e1, Z2);
-                const double lse = mx + log(Z);
+                e1 = (m1 == -INFINITY) ? 0.0 : exp(m1 - mx);
+                const double Z = fma(Z1, e1, Z2);
+                lse = mx + log(Z);
                 a.lse[n] = lse;
                 if (STATS) {
-                    const double inv = 1.0 / Z;
-                    double sce = e1 * inv;
-                    double *Srow = a.S + rr * st.ldH;
+                    inv = 1.0 / Z;
+                    sce = e1 * inv;
                     if (fold && sce == 0.0) {      // the singletons vanish next to the multi-cause states: zero row, unit scale
                         for (int h = 0; h < st.ldH; ++h) Srow[h] = 0.0;
                         sce = 1.0;
                     }
                     scl[0] = sce;
-                    // reverse accumulators: value = (a2 2^28 + a1 2^14 + a0) 2^-42, columns = features
-                    double sum_marg = 0.0;
-                    int pj = 0, pk = 1;                       // pair of the current pair feature
+                }
+            }
+            if (STATS) {
+                // reverse accumulators: value = (a2 2^28 + a1 2^14 + a0) 2^-42, columns = features
+                double sum_marg = 0.0;
+                int pj = 0, pk = 1;                           // pair of the current pair feature
 #pragma unroll 1
-                    for (int c0 = 0; c0 < NOUT; c0 += 16) {
-                        uint32_t r0[16], r1[16], r2[16];
-                        tmem_ld16(tlane + 4 * NC + 0 * NOUT + c0, r0);
-                        tmem_ld16(tlane + 4 * NC + 1 * NOUT + c0, r1);
-                        tmem_ld16(tlane + 4 * NC + 2 * NOUT + c0, r2);
-                        tmem_wait_ld();
+                for (int c0 = 0; c0 < NOUT; c0 += 16) {
+                    uint32_t r0[16], r1[16], r2[16];
+                    tmem_ld16(tlane + 4 * NC + 0 * NOUT + c0, r0);
+                    tmem_ld16(tlane + 4 * NC + 1 * NOUT + c0, r1);
+                    tmem_ld16(tlane + 4 * NC + 2 * NOUT + c0, r2);
+                    tmem_wait_ld();
+                    if (keep) {
 #pragma unroll
                         for (int i = 0; i < 16; ++i) {
                             const int f = c0 + i;
@@ -482,12 +502,14 @@ __global__ void __launch_bounds__(THREADS, 1) gl_state_tc_kernel(const __grid_co
                             }
                         }
                     }
+                }
+                if (keep) {
                     // sum_s p_s q_s from sum_s p_s (F_s - mx):  F_s = c q_s + lpm |s|,  sum_s p_s |s| = sum_j marginal_j
                     const double sig2 = (fma(mx, Z2, SF) - lpm * sum_marg) / cq;
                     acc_n += 1.0;
                     acc_lse += lse;
-                    acc_sig += fma(rs[2], e1, sig2) * inv;
-                    acc_cnt += fma(rs[4], e1, sum_marg) * inv;
+                    acc_sig += fma(sig1, e1, sig2) * inv;
+                    acc_cnt += fma(cnt1, e1, sum_marg) * inv;
                 }
             }
         }

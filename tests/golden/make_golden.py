@@ -232,8 +232,42 @@ def main_mixture():
     run_mixture('mop_A', MoP(D, H, A=40.), {'W': Wp, 'pies': pies}, 300, 5, 1.3)
 
 
+def main_northstar():
+    """The unmodified reference at the north-star shape (bsc_et.py:98-438, D=676 H=1000 H'=12 gamma=5) on 48 seeded
+    datapoints (59 ms per datapoint and step here).  Inputs come from tests/helpers.northstar_inputs and are
+    regenerated by the tests; stored: y (as a cross-check of the regeneration), candidates, logpj and the results
+    (every fourth row of W_new, which keeps the file at 4 MB) of one step at T=1 without truncation and one at T=1.3 with Ncut_factor=1."""
+    sys.path.insert(0, os.path.join(HERE, ".."))
+    from helpers import northstar_inputs
+    from prosper.em.camodels.bsc_et import BSC_ET
+    y, p0 = northstar_inputs()
+    out = dict(meta=np.array((676, 1000, 12, 5)), N=y.shape[0], seed=5, y=y, W0_checksum=np.array([p0['W'].sum(), np.abs(p0['W']).sum()]),
+               pi0=p0['pi'], sigma0=p0['sigma'])
+    model = BSC_ET(676, 1000, 12, 5)
+    for tag, T, ncut in (('a', 1.0, 0.0), ('b', 1.3, 1.0)):
+        an = LinearAnnealing(2)
+        an['T'] = T
+        an['Ncut_factor'] = ncut
+        an['anneal_prior'] = False
+        params = {'W': p0['W'].copy(), 'pi': p0['pi'], 'sigma': p0['sigma']}
+        data = model.select_Hprimes(params, {'y': y.copy()})
+        suff = model.E_step(an, params, data)
+        new = model.M_step(an, params, suff, data)
+        out.update({'T_' + tag: T, 'Ncut_' + tag: ncut, 'W_new_rows4_' + tag: new['W'][::4].copy(), 'pi_new_' + tag: new['pi'],
+                    'sigma_new_' + tag: new['sigma'], 'L_' + tag: log.values['L'][-1], 'N_use_' + tag: log.last('N_use')})
+        if tag == 'a':
+            out['candidates'] = np.asarray(data['candidates'], dtype=np.int64)
+            out['logpj'] = suff['logpj']
+        print("northstar", tag, "pi_new", new['pi'], "sigma_new", new['sigma'], "L", out['L_' + tag], "N_use", out['N_use_' + tag])
+    path = os.path.join(HERE, "northstar_bsc.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path))
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == 'gsc':
+    if len(sys.argv) > 1 and sys.argv[1] == 'northstar':
+        main_northstar()
+    elif len(sys.argv) > 1 and sys.argv[1] == 'gsc':
         main_gsc()
     elif len(sys.argv) > 1 and sys.argv[1] == 'inference':
         main_inference()
@@ -244,3 +278,4 @@ if __name__ == "__main__":
         main_inference()
         main()
         main_gsc()
+        main_northstar()

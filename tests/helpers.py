@@ -50,3 +50,20 @@ def cand_mismatch_gap(sim, cand_a, cand_b):
             v = sim[n, diff]
             worst = max(worst, float(v.max() - v.min()))
     return bad, worst
+
+
+def northstar_inputs(N=48, seed=5):
+    """Inputs of the north-star shape (BASELINE configs[4]: D=676, H=1000, H'=12, gamma=5) regenerated from a seed with
+    the law of SURVEY 8(d): W_gt ~ N(0,1) with columns of norm 10, s ~ Bernoulli(2/H), y = W_gt s + N(0,1), initial
+    parameters with standard_init semantics.  tests/golden/northstar_bsc.npz holds what the UNMODIFIED reference
+    returns for exactly these arrays (minted by tests/golden/make_golden.py northstar), so W0 is not stored twice."""
+    D, H = 676, 1000
+    rng = np.random.RandomState(seed)
+    Wgt = rng.standard_normal((D, H))
+    Wgt *= 10.0 / np.linalg.norm(Wgt, axis=0, keepdims=True)
+    s = rng.random_sample((N, H)) < 2.0 / H
+    y = s.astype(np.float64) @ Wgt.T + rng.standard_normal((N, D))
+    W_mean = y.mean(axis=0)
+    sig0 = np.sqrt(((y - W_mean) ** 2).mean(axis=0)).sum() / D
+    W0 = W_mean[:, None] + rng.normal(scale=sig0 / 4., size=(D, H))
+    return y, {'W': W0, 'pi': 1. / H, 'sigma': sig0}

@@ -115,6 +115,60 @@ def test_bsc_against_oracle(D, H, Hp, gam, N, seed, T, ncut, ap):
         dlog.remove_handler(keep)
 
 
+@pytest.mark.parametrize("state_kernel", [1, 2], ids=["scalar-state-kernel", "tensor-state-kernel"])
+def test_bsc_against_reference_golden_at_north_star_shape(state_kernel):
+    """BASELINE configs[4] shape: the CUDA path against what the UNMODIFIED reference returned (bsc_et.py:98-438) for
+    the 48 seeded datapoints of helpers.northstar_inputs; compat calls and the fused step, both state kernels."""
+    from helpers import northstar_inputs
+    g = np.load(os.path.join(GOLDEN, "northstar_bsc.npz"))
+    y, p0 = northstar_inputs(int(g['N']), int(g['seed']))
+    assert np.array_equal(y, g['y'])
+    m = model(676, 1000, 12, 5)
+    m.engine.set_state_kernel(state_kernel)
+    dlog, keep = keep_log()
+    try:
+        for tag in ('a', 'b'):
+            an = DictAnneal(T=float(g['T_' + tag]), Ncut_factor=float(g['Ncut_' + tag]), anneal_prior=False)
+            params = {'W': p0['W'].copy(), 'pi': p0['pi'], 'sigma': p0['sigma']}
+            outs = []
+            if state_kernel == 1:
+                data = m.select_Hprimes(params, {'y': y.copy()})
+                suff = m.E_step(an, params, data)
+                if tag == 'a':
+                    assert np.array_equal(data['candidates'], g['candidates'])
+                    assert np.abs(suff['logpj'] - g['logpj']).max() < 1e-10 * np.abs(g['logpj']).max()
+                outs.append(m.M_step(an, params, suff, data))
+            outs.append(m._fused_step(an, {'W': p0['W'].copy(), 'pi': p0['pi'], 'sigma': p0['sigma']}, {'y': y.copy()}))
+            for new in outs:
+                # N = 48 < H: Wq is rank deficient, the update is the minimum-norm solution (lstsq, bsc_et.py:377-380)
+                assert rel_err(new['W'][::4], g['W_new_rows4_' + tag]) < 1e-7
+                assert abs(new['pi'] - float(g['pi_new_' + tag])) < TOL * float(g['pi_new_' + tag])
+                assert abs(new['sigma'] - float(g['sigma_new_' + tag])) < TOL * float(g['sigma_new_' + tag])
+                assert abs(keep.last('L') - float(g['L_' + tag])) < TOL * abs(float(g['L_' + tag]))
+                assert keep.last('N_use') == int(g['N_use_' + tag])
+    finally:
+        dlog.remove_handler(keep)
+
+
+@pytest.mark.parametrize("ncut", [0.0, 1.0])
+def test_bsc_north_star_shape_many_chunks_against_oracle(ncut, monkeypatch):
+    """North-star shape with N = 4000 and 1536-row chunks: three chunks, the last one ending in a partial 128-row tile
+    (score GEMM tiles, state-kernel tiles, split-K statistics GEMM all cross chunk borders).  The oracle takes about a
+    minute on the host."""
+    monkeypatch.setenv("PET_CHUNK_ROWS", "1536")
+    D, H, Hp, gam, N = 676, 1000, 12, 5, 4000
+    y, params, _ = bsc_problem(D, H, N, 9)
+    an = DictAnneal(T=1.1, Ncut_factor=ncut, anneal_prior=False)
+    want = BSC(D, H, Hp, gam).step(an, copy_params(params), {'y': y.copy()})
+    for kern in (2, 1):
+        m = model(D, H, Hp, gam)
+        m.engine.set_state_kernel(kern)
+        got = m._fused_step(an, copy_params(params), {'y': y.copy()})
+        assert rel_err(got['W'], want['W']) < TOL, kern
+        assert abs(got['pi'] - want['pi']) < TOL * want['pi'], kern
+        assert abs(got['sigma'] - want['sigma']) < TOL * want['sigma'], kern
+
+
 def test_bsc_trajectory_50_iterations_tracks_oracle():
     """BASELINE configs[0]: bars test 5x5, H=10, H'=6, gamma=3, N=1000, 50 annealed EM iterations."""
     from prosper_b200.em import EM

@@ -5,7 +5,7 @@ import os
 import numpy as np
 import pytest
 
-from helpers import bars_dict, rel_err
+from helpers import bars_dict, rel_err, cand_mismatch_gap
 from oracle.common import DictAnneal
 from oracle.mca import MCA, MMCA
 
@@ -41,6 +41,9 @@ def check_all(m, o, an, params, y, golden=None):
     assert np.array_equal(p1['W'], po['W'])
     d = m.select_Hprimes(p1, {'y': y.copy()})
     same_rows = (d['candidates'] == od['candidates']).all(axis=1)
+    # north_star rule: candidate SETS are identical wherever the score gap exceeds the tolerance; order only among ties
+    bad, gap = cand_mismatch_gap(od['_sim'], od['candidates'], d['candidates'])
+    assert bad == 0 or gap < 1e-9 * max(1.0, np.abs(od['_sim']).max()), (bad, gap)
     assert same_rows.mean() > 0.99, same_rows.mean()
     d['candidates'] = od['candidates'].copy()
     ss = m.E_step(an, p1, d)

@@ -35,7 +35,7 @@ def _oracle_for(name, meta):
 
 
 def golden_files():
-    return sorted(p for p in glob.glob(os.path.join(GOLDEN, "*.npz")) if not os.path.basename(p).startswith(("gsc_", "infer_", "mix_")))
+    return sorted(p for p in glob.glob(os.path.join(GOLDEN, "*.npz")) if not os.path.basename(p).startswith(("gsc_", "infer_", "mix_", "northstar_")))
 
 
 @pytest.mark.parametrize("path", golden_files(), ids=[os.path.basename(p) for p in golden_files()])
@@ -60,6 +60,33 @@ def test_oracle_matches_reference_golden(path):
     else:
         assert abs(o.log['L'] - float(g['L'])) < 1e-9 * abs(float(g['L']))
     assert o.log['N_use'] == int(g['N_use'])
+
+
+def test_oracle_matches_the_reference_at_the_north_star_shape():
+    """BASELINE configs[4] shape (D=676, H=1000, H'=12, gamma=5): the oracle against what the unmodified reference
+    returned for the 48 seeded datapoints of helpers.northstar_inputs (bsc_et.py:98-438), with and without truncation.
+    N < H makes Wq rank deficient: the update is lstsq's minimum-norm solution, compared row by row."""
+    from helpers import northstar_inputs
+    from oracle.bsc import BSC
+    g = np.load(os.path.join(GOLDEN, "northstar_bsc.npz"))
+    y, p0 = northstar_inputs(int(g['N']), int(g['seed']))
+    assert np.array_equal(y, g['y'])
+    assert np.allclose([p0['W'].sum(), np.abs(p0['W']).sum()], g['W0_checksum'], rtol=1e-14)
+    o = BSC(676, 1000, 12, 5)
+    for tag in ('a', 'b'):
+        an = DictAnneal(T=float(g['T_' + tag]), Ncut_factor=float(g['Ncut_' + tag]), anneal_prior=False)
+        params = {'W': p0['W'].copy(), 'pi': p0['pi'], 'sigma': p0['sigma']}
+        data = o.select_hprimes(params, {'y': y.copy()})
+        suff = o.e_step(an, params, data)
+        if tag == 'a':
+            assert np.array_equal(data['candidates'], g['candidates'])
+            assert np.abs(suff['logpj'] - g['logpj']).max() < 1e-10 * np.abs(g['logpj']).max()
+        new = o.m_step(an, params, suff, data)
+        assert rel_err(new['W'][::4], g['W_new_rows4_' + tag]) < 1e-8
+        assert abs(new['pi'] - float(g['pi_new_' + tag])) < 1e-10 * float(g['pi_new_' + tag])
+        assert abs(new['sigma'] - float(g['sigma_new_' + tag])) < 1e-10 * float(g['sigma_new_' + tag])
+        assert abs(o.log['L'] - float(g['L_' + tag])) < 1e-10 * abs(float(g['L_' + tag]))
+        assert o.log['N_use'] == int(g['N_use_' + tag])
 
 
 def test_state_spaces_match_reference_orders():
