@@ -324,9 +324,10 @@ int64_t pet_spd_solve_work_doubles(int64_t n, int64_t lda);   /* size of work_de
  * (dgemm.cu), n > 0 = int8 tcgen05 with n slices per operand (ozaki.cu) */
 int32_t pet_gemm_path(const pet_engine *e);
 /* Which kernel evaluates the multi-cause states of the fused BSC path (bsc_et.py:180-185, 349-366): mode 0 = automatic
- * (tensor cores once the state space has >= 256 states), 1 = the scalar FP64 kernel, 2 = the int8 tensor-core kernel
- * (binary states, H' <= 12, gamma <= 5; PET_EINVAL otherwise).  pet_state_kernel_path reports the choice in force
- * (1 or 2).  The compat E_step / M_step that materialise logpj always use the scalar kernel. */
+ * (tensor cores once the state space has >= 256 states and a chunk of the shard fills half a wave of 128-datapoint
+ * tiles), 1 = the scalar FP64 kernel, 2 = the int8 tensor-core kernel (binary states, H' <= 12, gamma <= 5; PET_EINVAL
+ * otherwise).  pet_state_kernel_path reports the choice for the first chunk of the bound shard (1 or 2; before data
+ * is bound: for a large shard).  The compat E_step / M_step that materialise logpj always use the scalar kernel. */
 int  pet_set_state_kernel(pet_engine *e, int32_t mode);
 int32_t pet_state_kernel_path(const pet_engine *e);
 int  pet_stage_times_ms(pet_engine *e, double *out_host);

@@ -402,9 +402,11 @@ extern "C" int pet_state_matrix(const pet_engine *e, double *out_host) {
 }
 extern "C" int32_t pet_gemm_path(const pet_engine *e) { return (e && e->oz_on) ? e->oz_ns : 0; }
 // the tensor-core state kernel pays off once the state space fills a few 64-state chunks
-static bool use_state_tc(const pet_engine *e, int kflags) {
+// (a 128-datapoint tile is one CTA's sequential work: ~250 us at 1573 states) and the chunk fills at least half a wave of
+// tiles; below that the scalar kernel (8 datapoints per CTA pass) finishes sooner
+static bool use_state_tc(const pet_engine *e, int kflags, int64_t rows) {
     if (!e->tc_ok || e->tc_mode == 1 || (kflags & (GLF_READ_LOGPJ | GLF_WRITE_LOGPJ))) return false;
-    return e->tc_mode == 2 || e->ss.S >= 256;
+    return e->tc_mode == 2 || (e->ss.S >= 256 && rows >= int64_t(64) * e->sm_count);
 }
 extern "C" int pet_set_state_kernel(pet_engine *e, int32_t mode) {
     if (!e || mode < 0 || mode > 2) { set_error("pet_set_state_kernel: mode must be 0 (auto), 1 (scalar) or 2 (tensor cores)"); return PET_EINVAL; }
@@ -412,7 +414,9 @@ extern "C" int pet_set_state_kernel(pet_engine *e, int32_t mode) {
     e->tc_mode = mode;
     return PET_OK;
 }
-extern "C" int32_t pet_state_kernel_path(const pet_engine *e) { return (e && use_state_tc(e, 0)) ? 2 : 1; }
+extern "C" int32_t pet_state_kernel_path(const pet_engine *e) {
+    return (e && use_state_tc(e, 0, e->chunk_start.size() > 1 ? e->chunk_start[1] : (e->n > 0 ? e->n : (int64_t(1) << 40)))) ? 2 : 1;
+}
 extern "C" int pet_enable_timing(pet_engine *e, int32_t on) {
     if (!e) return PET_EINVAL;
     e->timer.reset();
@@ -776,6 +780,7 @@ static void mark_compute_done(pet_engine *e, cudaStream_t st) {
 }
 
 enum { PASS_SELECT = 1, PASS_REUSE_SCORES = 2 };
+static inline bool user_logpj_flags(int kflags) { return (kflags & (GLF_READ_LOGPJ | GLF_WRITE_LOGPJ)) != 0; }
 
 // One sweep over the shard.  kflags: GLF_* for the posterior kernel.
 static int sweep_gl(pet_engine *e, const pet_anneal *a, const pet_params *p, int kflags, int pass_flags,
@@ -820,7 +825,12 @@ static int sweep_gl(pet_engine *e, const pet_anneal *a, const pet_params *p, int
     }
     // the int8 statistics path slices <s> anyway: the normalisation is folded into that load, no scale kernel
     static const bool no_fold = getenv("PET_GL_NO_FOLD") != nullptr;
-    const bool fold_scale = do_stats && e->oz_on && !e->S2buf && !no_fold;
+    bool fold_scale = do_stats && e->oz_on && !e->S2buf && !no_fold;
+    // BSC with the register-resident row kernels: the <s> chunk is never written -- the slicer recomputes the singleton
+    // posteriors from the score rows (one exp per entry) and adds the candidate marginals the state kernel left in scl
+    static const bool no_defer = getenv("PET_GL_NO_DEFER") != nullptr || getenv("PET_GL_NO_FAST_ROW") != nullptr;
+    const bool defer_s = fold_scale && !no_defer && !user_logpj_flags(kflags) && e->model == PET_MODEL_BSC && e->H <= 1024;
+    if (defer_s) { ga.flags |= GLF_NO_SROW; fold_scale = false; }
     if (fold_scale) ga.flags |= GLF_FOLD_SCALE;
     const int64_t nchunks = (int64_t)e->chunk_start.size() - 1;
     for (int64_t c = 0; c < nchunks; ++c) {
@@ -853,10 +863,10 @@ static int sweep_gl(pet_engine *e, const pet_anneal *a, const pet_params *p, int
         PET_CHECK(launch_gl_row(ga, e->sm_count, st));
         e->timer.end(st);
         e->timer.begin(ST_POST, st);
-        if (use_state_tc(e, kflags)) PET_CHECK(launch_gl_state_tc(ga, e->tc_host.dev, e->sm_count, st));
+        if (use_state_tc(e, kflags, rows)) PET_CHECK(launch_gl_state_tc(ga, e->tc_host.dev, e->sm_count, st));
         else PET_CHECK(launch_gl_state(ga, e->gamma, e->binary, e->sm_count, st));
         e->timer.end(st);
-        if (!fold_scale) {
+        if (!fold_scale && !defer_s) {
             e->timer.begin(ST_SCALE, st);
             PET_CHECK(launch_gl_scale(ga, st));
             e->timer.end(st);
@@ -871,9 +881,13 @@ static int sweep_gl(pet_engine *e, const pet_anneal *a, const pet_params *p, int
                 const int64_t plane = (int64_t)(e->D + 1) * e->chunk_rows, wp = (int64_t)(e->D + 1) * e->ldH;
                 e->timer.end(st);
                 e->timer.begin(ST_SLICE, st);
-                PET_CHECK(ozaki_slice_cols(e->Sbuf, e->ldH, rows, e->H, e->oz_ns, e->oz_colmax, false, e->ozS,
-                                           e->chunk_rows, (int64_t)e->H * e->chunk_rows, e->ozSs, st,
-                                           fold_scale ? e->scl + r0 * (1 + PET_MAXHP) : nullptr, 1 + PET_MAXHP));
+                if (defer_s)
+                    PET_CHECK(launch_gl_post_slice(ga, e->oz_ns, ozaki_kp(rows), e->ozS, e->chunk_rows, (int64_t)e->H * e->chunk_rows,
+                                                   e->ozSs, st));
+                else
+                    PET_CHECK(ozaki_slice_cols(e->Sbuf, e->ldH, rows, e->H, e->oz_ns, e->oz_colmax, false, e->ozS,
+                                               e->chunk_rows, (int64_t)e->H * e->chunk_rows, e->ozSs, st,
+                                               fold_scale ? e->scl + r0 * (1 + PET_MAXHP) : nullptr, 1 + PET_MAXHP));
                 e->timer.end(st);
                 e->timer.begin(ST_STATS, st);
                 const OzOperand oy{e->ozYT + c * e->oz_ns * plane, e->chunk_rows, plane, e->ozYTs + c * e->ldY};

@@ -414,7 +414,7 @@ __global__ void __launch_bounds__(ROW_WARPS * 32, 3) gl_row_fast_kernel(const __
     const int H = st.H, Hp = st.Hp;
     double *row = smem + size_t(r2(H) + PET_MAXHP) * warp;
     int *cand_s = reinterpret_cast<int *>(row + r2(H));
-    const bool do_stats = !(a.flags & (GLF_LSE_ONLY | GLF_SELECT_ONLY));
+    const bool do_stats = !(a.flags & (GLF_LSE_ONLY | GLF_SELECT_ONLY | GLF_NO_SROW));
     const double pb = it.prior_block[0];
 
     const int64_t wstride = int64_t(gridDim.x) * ROW_WARPS;
@@ -579,7 +579,7 @@ __global__ void __launch_bounds__(256, 4) gl_row_post_kernel(const __grid_consta
     const GLIter &it = a.it;
     const int lane = threadIdx.x & 31;
     const int H = st.H;
-    const bool do_stats = !(a.flags & GLF_LSE_ONLY);
+    const bool do_stats = !(a.flags & (GLF_LSE_ONLY | GLF_NO_SROW));
     const double pb = it.prior_block[0];
     const int64_t r = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     if (r >= a.n_rows) return;
@@ -965,6 +965,107 @@ __global__ void __launch_bounds__(256) gl_scale_kernel(const __grid_constant__ G
         double mj = scl[1 + lane];
         if (mj != 0.0) Srow[a.cand[n * st.Hp + lane]] += mj;      // non-live duplicates carry 0 and do not write
     }
+}
+
+
+// =================================================================================================
+// Kernel D -- posterior rows straight into the int8 slices of the statistics GEMM (binary single-block layout).
+// Replaces, for the fused int8 path: the <s> write of the singleton kernel, the read-modify-write of the candidate
+// marginals, the column-maximum pass and the slicing pass (bsc_et.py:349,355,362-366).  CTA tile: 128 datapoints x 32
+// causes; thread (tx, ty) owns cause c0 + tx and the 16 consecutive datapoints r0 + 16 ty ..; the candidate marginals of
+// the tile are scattered into a shared-memory tile first, the digits are staged in shared memory so that both the
+// loads (score rows) and the stores (slice rows, datapoints contiguous) are coalesced.
+// =================================================================================================
+constexpr int PS_R = 128, PS_C = 32, PS_PITCH = PS_R + 4;
+__global__ void __launch_bounds__(256) gl_post_slice_kernel(const __grid_constant__ GLArgs a, int ns, int Kp, int8_t *out,
+                                                            int64_t row_stride, int64_t slice_stride, double *scale_out) {
+    extern __shared__ __align__(16) int8_t ps_smem[];
+    double *add = reinterpret_cast<double *>(ps_smem);                     // [PS_R][PS_C + 1] candidate marginals
+    double *rowc = add + PS_R * (PS_C + 1);                                // [PS_R][3]  m1, scale, yy
+    int32_t *tile32 = reinterpret_cast<int32_t *>(rowc + PS_R * 3);        // [ns][PS_C][PS_PITCH] bytes
+    const GLStatic &st = a.st;
+    const GLIter &it = a.it;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int c0 = blockIdx.x * PS_C, c = c0 + tx;
+    const int64_t r0 = int64_t(blockIdx.y) * PS_R;
+    const int Hp = st.Hp;
+    for (int i = threadIdx.x; i < PS_R * (PS_C + 1); i += 256) add[i] = 0.0;
+    if (threadIdx.x < PS_R) {
+        const int64_t rr = r0 + threadIdx.x;
+        double m1 = 0.0, sc = 0.0, yy = 0.0;
+        if (rr < a.n_rows) {
+            const int64_t n = a.row0 + rr;
+            m1 = a.rs[n * RS];
+            sc = a.scl[n * (1 + PET_MAXHP)];
+            yy = a.yy[n];
+        }
+        rowc[threadIdx.x * 3 + 0] = m1; rowc[threadIdx.x * 3 + 1] = sc; rowc[threadIdx.x * 3 + 2] = yy;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < PS_R * Hp; i += 256) {                   // candidates are distinct: plain stores
+        const int rl = i / Hp, j = i % Hp;
+        const int64_t rr = r0 + rl;
+        if (rr < a.n_rows) {
+            const int64_t n = a.row0 + rr;
+            const int h = a.cand[n * Hp + j] - c0;
+            if (h >= 0 && h < PS_C) add[rl * (PS_C + 1) + h] = a.scl[n * (1 + PET_MAXHP) + 1 + j];
+        }
+    }
+    __syncthreads();
+    const double pb = it.prior_block[0];
+    const double wn2 = (c < st.H) ? a.wn2[c] : 0.0;
+    double v[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const int rl = ty * 16 + i;
+        const int64_t rr = r0 + rl;
+        double val = 0.0;
+        if (c < st.H && rr < a.n_rows) {
+            const double q = rowc[rl * 3 + 2] + (wn2 - 2.0 * a.YW[rr * st.ldH + c]);
+            const double x = combine(it, pb, q) - rowc[rl * 3 + 0];
+            const double p = (x > GL_EXP_CUTOFF) ? exp_nonpos(x) : 0.0;
+            val = fma(p, rowc[rl * 3 + 1], add[rl * (PS_C + 1) + tx]);
+        }
+        v[i] = val * 32.0;                                                 // 64 / 2^e with 2^e = 2 > max <s>
+    }
+    if (blockIdx.y == 0 && ty == 0 && c < st.H) scale_out[c] = 2.0;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        for (int t = 0; t < ns; ++t) {
+            uint32_t w = 0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const double qd = rint(v[4 * g + i]);
+                w |= (uint32_t(int(qd)) & 0xFFu) << (8 * i);
+                v[4 * g + i] = (v[4 * g + i] - qd) * 128.0;
+            }
+            tile32[((t * PS_C + tx) * PS_PITCH) / 4 + ty * 4 + g] = int32_t(w);
+        }
+    }
+    __syncthreads();
+    const int n_rows_out = ns * PS_C;
+    for (int ro = ty; ro < n_rows_out; ro += 8) {                          // one warp stores one (slice, cause) row of 128 bytes
+        const int t = ro / PS_C, cc = ro % PS_C;
+        const int col = c0 + cc;
+        const int64_t r = r0 + tx * 4;
+        if (col < st.H && r < Kp)
+            *reinterpret_cast<int32_t *>(out + t * slice_stride + col * row_stride + r) = tile32[((t * PS_C + cc) * PS_PITCH) / 4 + tx];
+    }
+}
+
+int launch_gl_post_slice(const GLArgs &a, int ns, int Kp, int8_t *out, int64_t row_stride, int64_t slice_stride, double *scale_out,
+                         cudaStream_t st) {
+    if (a.n_rows <= 0) return PET_OK;
+    const size_t smem = size_t(PS_R) * (PS_C + 1) * 8 + size_t(PS_R) * 3 * 8 + size_t(ns) * PS_C * PS_PITCH;
+    static size_t configured = 0;
+    if (smem > configured) {
+        PET_CUDA(cudaFuncSetAttribute(gl_post_slice_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        configured = smem;
+    }
+    dim3 grid((unsigned)ceil_div(a.st.H, PS_C), (unsigned)ceil_div(Kp, PS_R));
+    gl_post_slice_kernel<<<grid, 256, smem, st>>>(a, ns, Kp, out, row_stride, slice_stride, scale_out);
+    PET_LAUNCH_CHECK();
+    return PET_OK;
 }
 
 // datapoint groups per CTA of the state kernel whose shared memory fits one SM (0 = does not fit at all)

@@ -27,6 +27,9 @@ enum {
     GLF_USE_CUT     = 1 << 4,   // skip datapoints below the truncation cut
     GLF_CUT_STRICT  = 1 << 5,   // '>' instead of '>=' (dsc_et.py:832)
     GLF_SELECT_ONLY = 1 << 6,   // stop after selection
+    GLF_NO_SROW     = 1 << 8,   // the <s> chunk is never materialised: the singleton kernel only reduces, the state kernel
+                                // leaves scl[n] = {e^(m1-m)/Z, candidate marginals} and gl_post_slice recomputes the
+                                // singleton posteriors from the score row while it cuts them into int8 slices
     GLF_FOLD_SCALE  = 1 << 7,   // no scale kernel: the state kernel folds the candidate marginals into the un-normalised
                                 // <s> row (divided by the row's scale); consumers multiply rows by scl[n][0] on load
 };
@@ -97,6 +100,11 @@ int launch_gl_kernel(const GLArgs &a, int gamma, bool binary, int sm_count, cuda
 int launch_gl_row(const GLArgs &a, int sm_count, cudaStream_t st);
 int launch_gl_state(const GLArgs &a, int gamma, bool binary, int sm_count, cudaStream_t st);
 int launch_gl_scale(const GLArgs &a, cudaStream_t st);
+// <s>[n,h] = exp(F_h - m1[n]) scl[n][0] (+ scl[n][1+j] if h = cand[n][j]) cut into ns signed 7-bit slices relative to the
+// fixed scale 2 (a posterior mean lies in [0, 1]) and stored transposed, out[t][h][r] (r < Kp, zero beyond n_rows):
+// the B operand of the statistics GEMM straight from the score rows.  scale_out[h] = 2.
+int launch_gl_post_slice(const GLArgs &a, int ns, int Kp, int8_t *out, int64_t row_stride, int64_t slice_stride, double *scale_out,
+                         cudaStream_t st);
 size_t gl_smem_bytes(const GLStatic &s, int warps);
 int gl_pick_warps(const GLStatic &s);
 int launch_state_prior(const GLStatic &st, const GLIter &it, double *out, cudaStream_t stream);

@@ -40,12 +40,14 @@ constexpr int TM = 128;                 // datapoints per tile (TMEM lanes)
 constexpr int NC = TC_NC;               // states per chunk (MMA N of the forward product)
 constexpr int KF = 96;                  // features, padded (K of one digit plane)
 constexpr int KFC = KF / 16;            // 16-byte K chunks per digit plane
-constexpr int NDF = 7;                  // digits of the features (49 bits)
+constexpr int NDF = 8;                  // digits of the features (56 bits)
 constexpr int NDP = 6;                  // digits of the posterior (42 bits)
 constexpr int NOUT = TC_NOUT;           // outputs of the reverse product, padded (MMA N)
 constexpr int THREADS = 256;
 constexpr int CSTR = 13;                // stride of the candidate rows in shared memory (conflict-free)
 constexpr double EXP_CUTOFF = -100.0;   // as gl_kernel.cu
+constexpr int XB = 7 * NDF - 1;         // the features are scaled to integers below 2^XB and offset by 2^XB
+constexpr int OFFB = XB - 28;           // ... which is 2^OFFB in units of the upper half (accumulators 2, 3: weight 2^28)
 
 constexpr int A_FWD_BYTES = NDF * KFC * TM * 16;            // 86016
 constexpr int B_FWD_BYTES = TC_BFWD_BYTES;                  // 2 * KF * NC = 12288 per chunk
@@ -273,17 +275,17 @@ __global__ void __launch_bounds__(THREADS, 1) gl_state_tc_kernel(const __grid_co
             const double m = fmax(rowmax_s[r], rowmax_s[TM + r]);
             int e = 0;
             if (m > 0.0 && m < INFINITY) frexp(m, &e);                   // m = f 2^e, f in [0.5, 1): |v| 2^-e < 1
-            const double up = ldexp(1.0, 48 - e);                        // x = rint(v 2^(48-e)) in (-2^48, 2^48)
-            if (hf == 0) scale_s[r] = ldexp(1.0, e - 48);
+            const double up = ldexp(1.0, XB - e);                        // x = rint(v 2^(XB-e)) in (-2^XB, 2^XB)
+            if (hf == 0) scale_s[r] = ldexp(1.0, e - XB);
 #pragma unroll
             for (int kc = 0; kc < 3; ++kc) {
                 uint32_t lo[16], hi[16];
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
                     const int f = hf * 48 + kc * 16 + i;
-                    long long xi = (f < nf) ? __double2ll_rn(v[kc * 16 + i] * up) + (1ll << 48) : 0ll;   // padding features: digit 0
+                    long long xi = (f < nf) ? __double2ll_rn(v[kc * 16 + i] * up) + (1ll << XB) : 0ll;   // padding features: digit 0
                     if (xi < 0) xi = 0;                                   // (NaN / inf inputs: keep the digits in range)
-                    if (xi >= (1ll << 49)) xi = (1ll << 49) - 1;
+                    if (xi >= (2ll << XB)) xi = (2ll << XB) - 1;
                     lo[i] = uint32_t(xi);
                     hi[i] = uint32_t(xi >> 32);
                 }
@@ -295,6 +297,7 @@ __global__ void __launch_bounds__(THREADS, 1) gl_state_tc_kernel(const __grid_co
                 *reinterpret_cast<uint4 *>(dst + 4 * KFC * TM * 16) = pack_digit16<4, false>(lo, hi);
                 *reinterpret_cast<uint4 *>(dst + 5 * KFC * TM * 16) = pack_digit16<5, false>(lo, hi);
                 *reinterpret_cast<uint4 *>(dst + 6 * KFC * TM * 16) = pack_digit16<6, false>(lo, hi);
+                if (NDF == 8) *reinterpret_cast<uint4 *>(dst + 7 * KFC * TM * 16) = pack_digit16<7, false>(lo, hi);
             }
         }
         fence_async_smem();
@@ -325,7 +328,7 @@ __global__ void __launch_bounds__(THREADS, 1) gl_state_tc_kernel(const __grid_co
             }
             ++item;
             __syncwarp();                                     // the TMEM loads below are warp-collective
-            const int off = int(t.chunk_nfeat[c]) << 20;      // the digits carry v 2^(48-e) + 2^48 per feature
+            const uint32_t off = uint32_t(t.chunk_nfeat[c]) << OFFB;    // the digits carry v 2^(XB-e) + 2^XB per feature
 #pragma unroll
             for (int bt = 0; bt < 2; ++bt) {
                 uint32_t a2[16], a3[16];
@@ -333,7 +336,7 @@ __global__ void __launch_bounds__(THREADS, 1) gl_state_tc_kernel(const __grid_co
                 tmem_ld16(tlane + 3 * NC + hf * 32 + bt * 16, a3);
                 tmem_wait_ld();
 #pragma unroll
-                for (int i = 0; i < 16; ++i) imax = max(imax, int(a3[i] * 16384u + a2[i]) - off);
+                for (int i = 0; i < 16; ++i) imax = max(imax, int(a3[i] * 16384u + a2[i] - off));
             }
             tc_fence_before();
             __syncthreads();
@@ -374,7 +377,7 @@ __global__ void __launch_bounds__(THREADS, 1) gl_state_tc_kernel(const __grid_co
             }
             ++item;
             __syncwarp();
-            const int off = int(t.chunk_nfeat[c]) << 20;
+            const uint32_t off = uint32_t(t.chunk_nfeat[c]) << OFFB;
             const int cnt = t.chunk_cnt[c];
 #pragma unroll
             for (int bt = 0; bt < 2; ++bt) {
@@ -388,7 +391,7 @@ __global__ void __launch_bounds__(THREADS, 1) gl_state_tc_kernel(const __grid_co
                 uint32_t ylo[16], yhi[16];
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
-                    const int hi = int(a3[i] * 16384u + a2[i]) - off;
+                    const int hi = int(a3[i] * 16384u + a2[i] - off);
                     const uint32_t lo = a1[i] * 16384u + a0[i];
                     const double f = fma(double(hi), 268435456.0, double(lo));
                     const double x = fma(f, scale, bias);

