@@ -95,6 +95,31 @@ __device__ __forceinline__ double exp_nonpos(double x) {
     return __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));
 }
 
+// exp(x) for -700 < x <= 0 with a 32-entry table: x = (32 k + j) ln2/32 + r, |r| <= ln2/64, exp = 2^k T[j] e^r with a
+// degree-6 Taylor polynomial (truncation 3.5e-18): 11 FP64 instructions instead of the 17 of exp_nonpos, ~1.5 ulp.
+static __constant__ double c_exp32[12] = {
+    6755399441055744.0,               // 2^52 + 2^51
+    46.166241308446828384,            // 32 / ln2
+    -0.021660849393811077,            // -ln2/32, high part (33 significant bits: n * hi is exact)
+    1.312785960212839e-12,            // -ln2/32, low part
+    1.0 / 720, 1.0 / 120, 1.0 / 24, 1.0 / 6, 0.5, 1.0, 1.0, 0.0};
+__device__ __forceinline__ double exp_tab32(double x, const double *tab) {
+    const double t = fma(x, c_exp32[1], c_exp32[0]);
+    const int n = __double2loint(t);
+    const double fn = t - c_exp32[0];
+    double r = fma(fn, c_exp32[2], x);
+    r = fma(fn, c_exp32[3], r);
+    double p = c_exp32[4];
+#pragma unroll
+    for (int i = 5; i < 11; ++i) p = fma(p, r, c_exp32[i]);
+    p *= tab[n & 31];
+    return __hiloint2double(__double2hiint(p) + ((n >> 5) << 20), __double2loint(p));
+}
+// fills the 32-entry table 2^(j/32) (shared memory; the callers synchronise before the first use)
+__device__ __forceinline__ void exp_tab32_init(double *tab) {
+    if (threadIdx.x < 32) tab[threadIdx.x] = exp2(double(threadIdx.x) * 0.03125);
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

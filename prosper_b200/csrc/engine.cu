@@ -477,7 +477,7 @@ static int size_chunks(pet_engine *e, int64_t n) {
         PET_CHECK(dev_alloc(&e->gemm_work, e->gemm_work_doubles));
     }
     if (e->oz_want) {
-        e->oz_splits = ozaki_splits(e->D + 1, e->H, ozaki_kp(cr), e->sm_count);
+        e->oz_splits = ozaki_splits(e->D + 1, e->H, ozaki_kp(cr), e->sm_count, 512);      // <s> may arrive as unsigned digits
         PET_CHECK(dev_alloc(&e->ozS, (int64_t)e->oz_ns * e->H * cr));
         PET_CHECK(dev_alloc(&e->oz_slabs, (int64_t)e->oz_splits * (e->D + 1) * e->ldH));
     }
@@ -893,7 +893,7 @@ static int sweep_gl(pet_engine *e, const pet_anneal *a, const pet_params *p, int
                 const OzOperand oy{e->ozYT + c * e->oz_ns * plane, e->chunk_rows, plane, e->ozYTs + c * e->ldY};
                 const OzOperand os{e->ozS, e->chunk_rows, (int64_t)e->H * e->chunk_rows, e->ozSs};
                 PET_CHECK(ozaki_gemm(e->D + 1, e->H, ozaki_kp(rows), e->oz_ns, oy, os, e->oz_slabs, e->ldH, e->oz_splits, wp,
-                                     true, e->sm_count, st));
+                                     true, e->sm_count, st, defer_s ? 64 * 127 : 4096));
             } else {
                 PET_CHECK(dgemm_mn(e->D + 1, e->H, rows, e->Y + r0 * e->ldY, e->ldY, e->Sbuf, e->ldH,
                                    stats_dev + lay.off_Wp, e->ldH, 1, e->gemm_work, e->gemm_work_doubles, e->sm_count, st));

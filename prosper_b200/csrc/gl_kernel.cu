@@ -575,6 +575,9 @@ __global__ void __launch_bounds__(ROW_WARPS * 32, 3) gl_row_select_kernel(const 
 // un-normalised posterior row.  F_h decreases with q_h = yy + wn2_h - 2 yw_h (beta pre1 < 0), so the maximum is the
 // log-joint of the smallest q_h.
 __global__ void __launch_bounds__(256, 4) gl_row_post_kernel(const __grid_constant__ GLArgs a) {
+    __shared__ double exptab[32];
+    exp_tab32_init(exptab);
+    __syncthreads();
     const GLStatic &st = a.st;
     const GLIter &it = a.it;
     const int lane = threadIdx.x & 31;
@@ -594,7 +597,7 @@ __global__ void __launch_bounds__(256, 4) gl_row_post_kernel(const __grid_consta
     double Z1 = 0.0, sig1 = 0.0, cnt = 0.0;
     if (lane == 0) {
         const double x = F0 - m1;
-        const double p = (x > GL_EXP_CUTOFF) ? exp_nonpos(x) : 0.0;
+        const double p = (x > GL_EXP_CUTOFF) ? exp_tab32(x, exptab) : 0.0;
         Z1 += p;
         sig1 += p * yy;
     }
@@ -605,7 +608,7 @@ __global__ void __launch_bounds__(256, 4) gl_row_post_kernel(const __grid_consta
         if (h < H) {
             const double q = yy + (a.wn2[h] - 2.0 * yw[h]);
             const double x = combine(it, pb, q) - m1;
-            p = (x > GL_EXP_CUTOFF) ? exp_nonpos(x) : 0.0;
+            p = (x > GL_EXP_CUTOFF) ? exp_tab32(x, exptab) : 0.0;
             Z1 += p;
             sig1 = fma(p, q, sig1);
             cnt += p;
@@ -982,7 +985,9 @@ __global__ void __launch_bounds__(256) gl_post_slice_kernel(const __grid_constan
     extern __shared__ __align__(16) int8_t ps_smem[];
     double *add = reinterpret_cast<double *>(ps_smem);                     // [PS_R][PS_C + 1] candidate marginals
     double *rowc = add + PS_R * (PS_C + 1);                                // [PS_R][3]  m1, scale, yy
-    int32_t *tile32 = reinterpret_cast<int32_t *>(rowc + PS_R * 3);        // [ns][PS_C][PS_PITCH] bytes
+    double *exptab = rowc + PS_R * 3;                                      // [32]
+    int32_t *tile32 = reinterpret_cast<int32_t *>(exptab + 32);            // [ns][PS_C][PS_PITCH] bytes
+    exp_tab32_init(exptab);
     const GLStatic &st = a.st;
     const GLIter &it = a.it;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -1014,7 +1019,9 @@ __global__ void __launch_bounds__(256) gl_post_slice_kernel(const __grid_constan
     __syncthreads();
     const double pb = it.prior_block[0];
     const double wn2 = (c < st.H) ? a.wn2[c] : 0.0;
-    double v[16];
+    // <s> in [0, 1] as the integer rint(<s> 2^48): slice 0 = bits 42.. (<= 64), slice t = the 7 bits below (0..127, valid
+    // as signed bytes); value = sum_t slice_t 2^-(6+7t), i.e. the slicing convention of ozaki.cu with column scale 1
+    uint32_t lo[16], hi[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
         const int rl = ty * 16 + i;
@@ -1023,23 +1030,33 @@ __global__ void __launch_bounds__(256) gl_post_slice_kernel(const __grid_constan
         if (c < st.H && rr < a.n_rows) {
             const double q = rowc[rl * 3 + 2] + (wn2 - 2.0 * a.YW[rr * st.ldH + c]);
             const double x = combine(it, pb, q) - rowc[rl * 3 + 0];
-            const double p = (x > GL_EXP_CUTOFF) ? exp_nonpos(x) : 0.0;
+            const double p = (x > GL_EXP_CUTOFF) ? exp_tab32(x, exptab) : 0.0;
             val = fma(p, rowc[rl * 3 + 1], add[rl * (PS_C + 1) + tx]);
         }
-        v[i] = val * 32.0;                                                 // 64 / 2^e with 2^e = 2 > max <s>
+        long long xi = __double2ll_rn(val * 281474976710656.0);            // 2^48
+        xi = xi < 0 ? 0 : (xi > (1ll << 48) ? (1ll << 48) : xi);           // (rounding noise around 0 and 1)
+        lo[i] = uint32_t(xi);
+        hi[i] = uint32_t(xi >> 32);
     }
-    if (blockIdx.y == 0 && ty == 0 && c < st.H) scale_out[c] = 2.0;
+    if (blockIdx.y == 0 && ty == 0 && c < st.H) scale_out[c] = 1.0;
 #pragma unroll
-    for (int g = 0; g < 4; ++g) {
-        for (int t = 0; t < ns; ++t) {
-            uint32_t w = 0;
+    for (int t = 0; t < 7; ++t) {
+        if (t < ns) {
+            const int sh = 42 - 7 * t;                                      // slice t = bits [sh, sh + 7)
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const double qd = rint(v[4 * g + i]);
-                w |= (uint32_t(int(qd)) & 0xFFu) << (8 * i);
-                v[4 * g + i] = (v[4 * g + i] - qd) * 128.0;
+            for (int g = 0; g < 4; ++g) {
+                uint32_t w = 0;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int e = 4 * g + i;
+                    uint32_t d;
+                    if (sh >= 32) d = hi[e] >> (sh - 32);
+                    else if (sh + 7 <= 32) d = lo[e] >> sh;
+                    else d = __funnelshift_r(lo[e], hi[e], sh);
+                    w |= (d & 0x7Fu) << (8 * i);
+                }
+                tile32[((t * PS_C + tx) * PS_PITCH) / 4 + ty * 4 + g] = int32_t(w);
             }
-            tile32[((t * PS_C + tx) * PS_PITCH) / 4 + ty * 4 + g] = int32_t(w);
         }
     }
     __syncthreads();
@@ -1056,7 +1073,7 @@ __global__ void __launch_bounds__(256) gl_post_slice_kernel(const __grid_constan
 int launch_gl_post_slice(const GLArgs &a, int ns, int Kp, int8_t *out, int64_t row_stride, int64_t slice_stride, double *scale_out,
                          cudaStream_t st) {
     if (a.n_rows <= 0) return PET_OK;
-    const size_t smem = size_t(PS_R) * (PS_C + 1) * 8 + size_t(PS_R) * 3 * 8 + size_t(ns) * PS_C * PS_PITCH;
+    const size_t smem = size_t(PS_R) * (PS_C + 1) * 8 + size_t(PS_R) * 3 * 8 + 32 * 8 + size_t(ns) * PS_C * PS_PITCH;
     static size_t configured = 0;
     if (smem > configured) {
         PET_CUDA(cudaFuncSetAttribute(gl_post_slice_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));

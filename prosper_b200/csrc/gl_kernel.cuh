@@ -101,8 +101,9 @@ int launch_gl_row(const GLArgs &a, int sm_count, cudaStream_t st);
 int launch_gl_state(const GLArgs &a, int gamma, bool binary, int sm_count, cudaStream_t st);
 int launch_gl_scale(const GLArgs &a, cudaStream_t st);
 // <s>[n,h] = exp(F_h - m1[n]) scl[n][0] (+ scl[n][1+j] if h = cand[n][j]) cut into ns signed 7-bit slices relative to the
-// fixed scale 2 (a posterior mean lies in [0, 1]) and stored transposed, out[t][h][r] (r < Kp, zero beyond n_rows):
-// the B operand of the statistics GEMM straight from the score rows.  scale_out[h] = 2.
+// fixed scale 1 (a posterior mean lies in [0, 1]: slice 0 <= 64, the others are UNSIGNED 7-bit digits 0..127, so the
+// int32 accumulators of ozaki_gemm hold K <= 37 000 terms per split) and stored transposed, out[t][h][r] (r < Kp, zero
+// beyond n_rows): the B operand of the statistics GEMM straight from the score rows.  scale_out[h] = 1.
 int launch_gl_post_slice(const GLArgs &a, int ns, int Kp, int8_t *out, int64_t row_stride, int64_t slice_stride, double *scale_out,
                          cudaStream_t st);
 size_t gl_smem_bytes(const GLStatic &s, int warps);

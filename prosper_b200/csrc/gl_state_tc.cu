@@ -10,8 +10,9 @@
 //   * v is scaled per datapoint by a power of two, offset to be non-negative and cut into 7 digits of 7 bits; digits
 //     2u and 2u+1 share accumulator u because the membership operand is stored twice, once with weight 1 and once with
 //     weight 128 (u8), concatenated along K: 4 int32 accumulators instead of 7, each an EXACT integer
-//   * one CTA owns a tile of 128 datapoints = the 128 TMEM lanes, so every epilogue thread owns ONE datapoint and walks
-//     the states as TMEM columns: running maximum, partition sum and posterior need no cross-thread traffic at all
+//   * one CTA owns a tile of 128 datapoints = the 128 TMEM lanes; four warps share a lane quadrant and split the 64
+//     columns of a chunk, so an epilogue thread owns ONE datapoint and 16 states per chunk: running maximum, partition
+//     sum and posterior need no cross-thread traffic until the tile is finished
 //   * pass 1 (top two accumulators only) bounds the maximum of F(s) from above to ~1e-5 of the feature scale; pass 2
 //     evaluates exp(F(s) - bound) in float64, cuts the posterior into 6 digits of 7 bits (42 bits) and writes them as
 //     the A operand of the reverse product, whose 3 accumulators (78 features x 128 datapoints) stay in TMEM for the
@@ -43,13 +44,14 @@ constexpr int KFC = KF / 16;            // 16-byte K chunks per digit plane
 constexpr int NDF = 8;                  // digits of the features (56 bits)
 constexpr int NDP = 6;                  // digits of the posterior (42 bits)
 constexpr int NOUT = TC_NOUT;           // outputs of the reverse product, padded (MMA N)
-constexpr int THREADS = 256;
+constexpr int NPART = 4;                // warps per TMEM lane quadrant: each owns 16 of the 64 columns of a chunk
+constexpr int THREADS = 128 * NPART;
 constexpr int CSTR = 13;                // stride of the candidate rows in shared memory (conflict-free)
 constexpr double EXP_CUTOFF = -100.0;   // as gl_kernel.cu
 constexpr int XB = 7 * NDF - 1;         // the features are scaled to integers below 2^XB and offset by 2^XB
 constexpr int OFFB = XB - 28;           // ... which is 2^OFFB in units of the upper half (accumulators 2, 3: weight 2^28)
 
-constexpr int A_FWD_BYTES = NDF * KFC * TM * 16;            // 86016
+constexpr int A_FWD_BYTES = NDF * KFC * TM * 16;            // 98304
 constexpr int B_FWD_BYTES = TC_BFWD_BYTES;                  // 2 * KF * NC = 12288 per chunk
 constexpr int A_REV_BYTES = NDP * (NC / 16) * TM * 16;      // 49152
 constexpr int B_REV_BYTES = TC_BREV_BYTES;                  // 2 * NC * NOUT = 10240 per chunk
@@ -58,13 +60,14 @@ constexpr int OFF_B_FWD = OFF_A_FWD + A_FWD_BYTES;
 constexpr int OFF_A_REV = OFF_B_FWD + 2 * B_FWD_BYTES;
 constexpr int OFF_B_REV = OFF_A_REV + A_REV_BYTES;
 constexpr int OFF_CAND = OFF_B_REV + 2 * B_REV_BYTES;       // int [TM][CSTR]
-constexpr int OFF_DBL = OFF_CAND + TM * CSTR * 4;           // double arrays, see below
-constexpr int N_DBL = 8 * TM;                               // rowmax[2][TM], scale[TM], bias[TM], part[2][2][TM]
-constexpr int OFF_INT = OFF_DBL + N_DBL * 8;                // int imax[2][TM]
-constexpr int OFF_FEAT = OFF_INT + 2 * TM * 4;              // uint8 fj[KF], fk[KF]
+constexpr int OFF_DBL = OFF_CAND + TM * CSTR * 4;           // double arrays, see the kernel
+constexpr int N_DBL = (NPART + 2 + 2 * NPART + 3) * TM + 32; // rowmax[NPART], scale, bias, part[2][NPART], fin[3], exp table
+constexpr int OFF_INT = OFF_DBL + N_DBL * 8;                // int imax[NPART][TM]
+constexpr int OFF_FEAT = OFF_INT + NPART * TM * 4;          // uint8 fj[KF], fk[KF]
 constexpr int OFF_BAR = OFF_FEAT + 2 * KF;                  // 3 mbarriers + tmem slot
 constexpr int SMEM_BYTES = OFF_BAR + 64;
 static_assert(OFF_BAR % 8 == 0 && OFF_DBL % 8 == 0, "alignment");
+static_assert(SMEM_BYTES + 128 <= 227 * 1024, "shared memory");
 
 __device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -118,6 +121,11 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
         : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
           "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
         : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr) : "memory");
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -191,12 +199,21 @@ __global__ void __launch_bounds__(THREADS, 1) gl_state_tc_kernel(const __grid_co
     const GLStatic &st = a.st;
     const GLIter &it = a.it;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int q = warp & 3, hf = warp >> 2;               // TMEM lane quadrant; which half of the columns / features
+    const int q = warp & 3, part = warp >> 2;             // TMEM lane quadrant; which 16 of the 64 columns of a chunk
     const int r = q * 32 + lane;                          // datapoint of this thread within the tile
     const int Hp = st.Hp, nf = t.n_feat;
     uint64_t *bar_tab = sm.bars();                        // [2] table buffers landed
     uint64_t *bar_mma = sm.bars() + 2;                    // MMAs issued so far have completed
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(sm.bars() + 3);
+
+    double *rowmax_s = sm.dbl();                          // [NPART][TM]
+    double *scale_s = rowmax_s + NPART * TM;              // [TM]
+    double *bias_s = scale_s + TM;                        // [TM]
+    double *part_s = bias_s + TM;                         // [2 (Z, SF)][NPART][TM]
+    double *fin_s = part_s + 2 * NPART * TM;              // [3 (1/Z or 0, singleton scale, keep)][TM]
+    double *exptab = fin_s + 3 * TM;                      // [32] 2^(j/32)
+    int *imax_s = sm.imax();                              // [NPART][TM]
+    int *cand_s = sm.cand() + r * CSTR;
 
     if (tid == 0) {
         mbar_init(&bar_tab[0], 1);
@@ -209,6 +226,7 @@ __global__ void __launch_bounds__(THREADS, 1) gl_state_tc_kernel(const __grid_co
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     for (int i = tid; i < 2 * KF; i += THREADS) sm.feat()[i] = t.feat[i];
+    exp_tab32_init(exptab);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -221,13 +239,8 @@ __global__ void __launch_bounds__(THREADS, 1) gl_state_tc_kernel(const __grid_co
     const bool fold = (a.flags & GLF_FOLD_SCALE) != 0;
     const bool use_cut = STATS && (a.flags & GLF_USE_CUT);
     const double cut = use_cut ? *a.cut : 0.0;
-
-    double *rowmax_s = sm.dbl();                 // [2][TM]
-    double *scale_s = sm.dbl() + 2 * TM;         // [TM]
-    double *bias_s = sm.dbl() + 3 * TM;          // [TM]
-    double *part_s = sm.dbl() + 4 * TM;          // [2 (Z, SF)][2 (hf)][TM]
-    int *imax_s = sm.imax();                     // [2][TM]
-    int *cand_s = sm.cand() + r * CSTR;
+    // K chunks of the feature operand built by this thread: parts 0, 1 two each, parts 2, 3 one each
+    const int kc0 = (part < 2) ? 2 * part : part + 2, nkc = (part < 2) ? 2 : 1;
 
     double acc_n = 0.0, acc_lse = 0.0, acc_sig = 0.0, acc_cnt = 0.0;
     uint32_t item = 0;            // table fetches issued so far (thread 0), = items consumed by everybody
@@ -246,21 +259,21 @@ __global__ void __launch_bounds__(THREADS, 1) gl_state_tc_kernel(const __grid_co
             bulk_g2s(sm.b_fwd(b), t.bfwd, B_FWD_BYTES, &bar_tab[b]);
         }
 
-        // ---- features: gather, scale, 7 digits -> A operand of the forward product ----
-        if (hf == 0) {
+        // ---- features: gather, scale, 8 digits -> A operand of the forward product ----
+        if (part == 0) {
 #pragma unroll 4
             for (int j = 0; j < Hp; ++j) cand_s[j] = valid ? a.cand[n * Hp + j] : 0;
         }
         __syncthreads();
-        double v[48];
+        double v[32];
         double vmax = 0.0;
         {
             const uint8_t *fj = sm.feat(), *fk = sm.feat() + KF;
 #pragma unroll
-            for (int i = 0; i < 48; ++i) {
-                const int f = hf * 48 + i;
+            for (int i = 0; i < 32; ++i) {
+                const int f = kc0 * 16 + i;
                 double x = 0.0;
-                if (valid && f < nf) {
+                if (valid && f < nf && i < nkc * 16) {
                     const int cj = cand_s[fj[f]], ck = cand_s[fk[f]];
                     const double g = a.G[int64_t(cj) * st.ldH + ck];
                     x = (f < Hp) ? fma(cq, fma(-2.0, a.ywc[n * Hp + f], g), lpm) : 2.0 * cq * g;
@@ -269,35 +282,39 @@ __global__ void __launch_bounds__(THREADS, 1) gl_state_tc_kernel(const __grid_co
                 vmax = fmax(vmax, fabs(x));
             }
         }
-        rowmax_s[hf * TM + r] = vmax;
+        rowmax_s[part * TM + r] = vmax;
         __syncthreads();
         {
-            const double m = fmax(rowmax_s[r], rowmax_s[TM + r]);
+            double m = rowmax_s[r];
+#pragma unroll
+            for (int pp = 1; pp < NPART; ++pp) m = fmax(m, rowmax_s[pp * TM + r]);
             int e = 0;
             if (m > 0.0 && m < INFINITY) frexp(m, &e);                   // m = f 2^e, f in [0.5, 1): |v| 2^-e < 1
             const double up = ldexp(1.0, XB - e);                        // x = rint(v 2^(XB-e)) in (-2^XB, 2^XB)
-            if (hf == 0) scale_s[r] = ldexp(1.0, e - XB);
+            if (part == 0) scale_s[r] = ldexp(1.0, e - XB);
 #pragma unroll
-            for (int kc = 0; kc < 3; ++kc) {
-                uint32_t lo[16], hi[16];
+            for (int kk = 0; kk < 2; ++kk) {
+                if (kk < nkc) {
+                    uint32_t lo[16], hi[16];
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const int f = hf * 48 + kc * 16 + i;
-                    long long xi = (f < nf) ? __double2ll_rn(v[kc * 16 + i] * up) + (1ll << XB) : 0ll;   // padding features: digit 0
-                    if (xi < 0) xi = 0;                                   // (NaN / inf inputs: keep the digits in range)
-                    if (xi >= (2ll << XB)) xi = (2ll << XB) - 1;
-                    lo[i] = uint32_t(xi);
-                    hi[i] = uint32_t(xi >> 32);
+                    for (int i = 0; i < 16; ++i) {
+                        const int f = (kc0 + kk) * 16 + i;
+                        long long xi = (f < nf) ? __double2ll_rn(v[kk * 16 + i] * up) + (1ll << XB) : 0ll;   // padding features: digit 0
+                        if (xi < 0) xi = 0;                               // (NaN / inf inputs: keep the digits in range)
+                        if (xi >= (2ll << XB)) xi = (2ll << XB) - 1;
+                        lo[i] = uint32_t(xi);
+                        hi[i] = uint32_t(xi >> 32);
+                    }
+                    uint8_t *dst = sm.a_fwd() + (kc0 + kk) * (TM * 16) + r * 16;
+                    *reinterpret_cast<uint4 *>(dst + 0 * KFC * TM * 16) = pack_digit16<0, false>(lo, hi);
+                    *reinterpret_cast<uint4 *>(dst + 1 * KFC * TM * 16) = pack_digit16<1, false>(lo, hi);
+                    *reinterpret_cast<uint4 *>(dst + 2 * KFC * TM * 16) = pack_digit16<2, false>(lo, hi);
+                    *reinterpret_cast<uint4 *>(dst + 3 * KFC * TM * 16) = pack_digit16<3, false>(lo, hi);
+                    *reinterpret_cast<uint4 *>(dst + 4 * KFC * TM * 16) = pack_digit16<4, false>(lo, hi);
+                    *reinterpret_cast<uint4 *>(dst + 5 * KFC * TM * 16) = pack_digit16<5, false>(lo, hi);
+                    *reinterpret_cast<uint4 *>(dst + 6 * KFC * TM * 16) = pack_digit16<6, false>(lo, hi);
+                    if (NDF == 8) *reinterpret_cast<uint4 *>(dst + 7 * KFC * TM * 16) = pack_digit16<7, false>(lo, hi);
                 }
-                uint8_t *dst = sm.a_fwd() + (hf * 3 + kc) * (TM * 16) + r * 16;
-                *reinterpret_cast<uint4 *>(dst + 0 * KFC * TM * 16) = pack_digit16<0, false>(lo, hi);
-                *reinterpret_cast<uint4 *>(dst + 1 * KFC * TM * 16) = pack_digit16<1, false>(lo, hi);
-                *reinterpret_cast<uint4 *>(dst + 2 * KFC * TM * 16) = pack_digit16<2, false>(lo, hi);
-                *reinterpret_cast<uint4 *>(dst + 3 * KFC * TM * 16) = pack_digit16<3, false>(lo, hi);
-                *reinterpret_cast<uint4 *>(dst + 4 * KFC * TM * 16) = pack_digit16<4, false>(lo, hi);
-                *reinterpret_cast<uint4 *>(dst + 5 * KFC * TM * 16) = pack_digit16<5, false>(lo, hi);
-                *reinterpret_cast<uint4 *>(dst + 6 * KFC * TM * 16) = pack_digit16<6, false>(lo, hi);
-                if (NDF == 8) *reinterpret_cast<uint4 *>(dst + 7 * KFC * TM * 16) = pack_digit16<7, false>(lo, hi);
             }
         }
         fence_async_smem();
@@ -329,11 +346,10 @@ __global__ void __launch_bounds__(THREADS, 1) gl_state_tc_kernel(const __grid_co
             ++item;
             __syncwarp();                                     // the TMEM loads below are warp-collective
             const uint32_t off = uint32_t(t.chunk_nfeat[c]) << OFFB;    // the digits carry v 2^(XB-e) + 2^XB per feature
-#pragma unroll
-            for (int bt = 0; bt < 2; ++bt) {
+            {
                 uint32_t a2[16], a3[16];
-                tmem_ld16(tlane + 2 * NC + hf * 32 + bt * 16, a2);
-                tmem_ld16(tlane + 3 * NC + hf * 32 + bt * 16, a3);
+                tmem_ld16(tlane + 2 * NC + part * 16, a2);
+                tmem_ld16(tlane + 3 * NC + part * 16, a3);
                 tmem_wait_ld();
 #pragma unroll
                 for (int i = 0; i < 16; ++i) imax = max(imax, int(a3[i] * 16384u + a2[i] - off));
@@ -341,10 +357,12 @@ __global__ void __launch_bounds__(THREADS, 1) gl_state_tc_kernel(const __grid_co
             tc_fence_before();
             __syncthreads();
         }
-        imax_s[hf * TM + r] = imax;
+        imax_s[part * TM + r] = imax;
         __syncthreads();
-        if (hf == 0) {
-            const int im = max(imax_s[r], imax_s[TM + r]);
+        if (part == 0) {
+            int im = imax_s[r];
+#pragma unroll
+            for (int pp = 1; pp < NPART; ++pp) im = max(im, imax_s[pp * TM + r]);
             const double yy = valid ? a.yy[n] : 0.0;
             const double m1 = valid ? a.rs[n * (4 + PET_MAXV)] : 0.0;
             // F(s) - c yy = scale (hi 2^28 + lo),  0 <= lo < n_feat 2^28
@@ -379,44 +397,44 @@ __global__ void __launch_bounds__(THREADS, 1) gl_state_tc_kernel(const __grid_co
             __syncwarp();
             const uint32_t off = uint32_t(t.chunk_nfeat[c]) << OFFB;
             const int cnt = t.chunk_cnt[c];
+            uint32_t ylo[16], yhi[16];
 #pragma unroll
-            for (int bt = 0; bt < 2; ++bt) {
-                const int col0 = hf * 32 + bt * 16;
-                uint32_t a0[16], a1[16], a2[16], a3[16];
-                tmem_ld16(tlane + 0 * NC + col0, a0);
-                tmem_ld16(tlane + 1 * NC + col0, a1);
-                tmem_ld16(tlane + 2 * NC + col0, a2);
-                tmem_ld16(tlane + 3 * NC + col0, a3);
+            for (int sb = 0; sb < 2; ++sb) {
+                const int col0 = part * 16 + sb * 8;
+                uint32_t a0[8], a1[8], a2[8], a3[8];
+                tmem_ld8(tlane + 0 * NC + col0, a0);
+                tmem_ld8(tlane + 1 * NC + col0, a1);
+                tmem_ld8(tlane + 2 * NC + col0, a2);
+                tmem_ld8(tlane + 3 * NC + col0, a3);
                 tmem_wait_ld();
-                uint32_t ylo[16], yhi[16];
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
+                for (int i = 0; i < 8; ++i) {
                     const int hi = int(a3[i] * 16384u + a2[i] - off);
                     const uint32_t lo = a1[i] * 16384u + a0[i];
                     const double f = fma(double(hi), 268435456.0, double(lo));
                     const double x = fma(f, scale, bias);
-                    double p = exp_nonpos(fmax(x, -700.0));
+                    double p = exp_tab32(fmax(x, -700.0), exptab);
                     p = (x > EXP_CUTOFF && col0 + i < cnt) ? p : 0.0;
                     Z2 += p;
                     SF = fma(p, x, SF);
                     if (STATS) {
                         const double T = fma(p, 4398046511104.0, 4503599627370496.0);    // p 2^42 + 2^52: mantissa = rint(p 2^42)
-                        ylo[i] = uint32_t(__double2loint(T));
-                        yhi[i] = uint32_t(__double2hiint(T)) & 0xFFFFFu;
+                        ylo[sb * 8 + i] = uint32_t(__double2loint(T));
+                        yhi[sb * 8 + i] = uint32_t(__double2hiint(T)) & 0xFFFFFu;
                     }
                 }
-                if (STATS) {
-                    uint8_t *dst = sm.a_rev() + (hf * 2 + bt) * (TM * 16) + r * 16;
-                    constexpr int PL = (NC / 16) * TM * 16;
-                    *reinterpret_cast<uint4 *>(dst + 0 * PL) = pack_digit16<0, false>(ylo, yhi);
-                    *reinterpret_cast<uint4 *>(dst + 1 * PL) = pack_digit16<1, false>(ylo, yhi);
-                    *reinterpret_cast<uint4 *>(dst + 2 * PL) = pack_digit16<2, false>(ylo, yhi);
-                    *reinterpret_cast<uint4 *>(dst + 3 * PL) = pack_digit16<3, false>(ylo, yhi);
-                    *reinterpret_cast<uint4 *>(dst + 4 * PL) = pack_digit16<4, false>(ylo, yhi);
-                    *reinterpret_cast<uint4 *>(dst + 5 * PL) = pack_digit16<5, true>(ylo, yhi);
-                }
             }
-            if (STATS) fence_async_smem();
+            if (STATS) {
+                uint8_t *dst = sm.a_rev() + part * (TM * 16) + r * 16;
+                constexpr int PL = (NC / 16) * TM * 16;
+                *reinterpret_cast<uint4 *>(dst + 0 * PL) = pack_digit16<0, false>(ylo, yhi);
+                *reinterpret_cast<uint4 *>(dst + 1 * PL) = pack_digit16<1, false>(ylo, yhi);
+                *reinterpret_cast<uint4 *>(dst + 2 * PL) = pack_digit16<2, false>(ylo, yhi);
+                *reinterpret_cast<uint4 *>(dst + 3 * PL) = pack_digit16<3, false>(ylo, yhi);
+                *reinterpret_cast<uint4 *>(dst + 4 * PL) = pack_digit16<4, false>(ylo, yhi);
+                *reinterpret_cast<uint4 *>(dst + 5 * PL) = pack_digit16<5, true>(ylo, yhi);
+                fence_async_smem();
+            }
             tc_fence_before();
             __syncthreads();
         }
@@ -430,13 +448,15 @@ __global__ void __launch_bounds__(THREADS, 1) gl_state_tc_kernel(const __grid_co
             ++mma_phase;
             tc_fence_after();
         }
-        part_s[(0 * 2 + hf) * TM + r] = Z2;
-        part_s[(1 * 2 + hf) * TM + r] = SF;
+        part_s[(0 * NPART + part) * TM + r] = Z2;
+        part_s[(1 * NPART + part) * TM + r] = SF;
         __syncthreads();
 
-        // ---- per-datapoint results (one thread per datapoint; the TMEM loads are warp-collective, so every lane of
-        // warps 0..3 walks the accumulators and only the side effects are predicated) ----
-        if (hf == 0) {
+        // ---- per-datapoint results.  Part 0 owns the scalars of its datapoint; the four parts then share the 80 columns
+        // of the reverse accumulators (the TMEM loads are warp-collective: every lane walks them, side effects are
+        // predicated) ----
+        double m1 = 0.0, sig1 = 0.0, cnt1 = 0.0, mx = 0.0, e1 = 0.0, lse = 0.0;
+        if (part == 0) {
             bool keep = valid;
             if (valid && use_cut) {
                 const double l = a.lse[n];
@@ -445,75 +465,83 @@ __global__ void __launch_bounds__(THREADS, 1) gl_state_tc_kernel(const __grid_co
             double *scl = a.scl + n * (1 + PET_MAXHP);
             if (valid && !keep)                               // truncated away: contributes nothing (bsc_et.py:254-257)
                 for (int j = 0; j <= Hp; ++j) scl[j] = 0.0;
-            double m1 = 0.0, Z1 = 0.0, sig1 = 0.0, cnt1 = 0.0, mx = 0.0, e1 = 0.0, inv = 0.0, sce = 1.0, lse = 0.0;
-            double *Srow = a.S + rr * st.ldH;
+            double inv = 0.0, sce = 1.0;
             if (keep) {
                 const double *rs = a.rs + n * (4 + PET_MAXV);
-                m1 = rs[0]; Z1 = rs[1]; sig1 = rs[2]; cnt1 = rs[4];
+                m1 = rs[0]; sig1 = rs[2]; cnt1 = rs[4];
                 mx = cq * a.yy[n] - bias;
-                Z2 = part_s[r] + part_s[TM + r];
-                SF = part_s[2 * TM + r] + part_s[3 * TM + r];
+                Z2 = 0.0; SF = 0.0;
+#pragma unroll
+                for (int pp = 0; pp < NPART; ++pp) { Z2 += part_s[pp * TM + r]; SF += part_s[(NPART + pp) * TM + r]; }
                 e1 = (m1 == -INFINITY) ? 0.0 : exp(m1 - mx);
-                const double Z = fma(Z1, e1, Z2);
+                const double Z = fma(rs[1], e1, Z2);
                 lse = mx + log(Z);
                 a.lse[n] = lse;
                 if (STATS) {
                     inv = 1.0 / Z;
                     sce = e1 * inv;
                     if (fold && sce == 0.0) {      // the singletons vanish next to the multi-cause states: zero row, unit scale
+                        double *Srow = a.S + rr * st.ldH;
                         for (int h = 0; h < st.ldH; ++h) Srow[h] = 0.0;
                         sce = 1.0;
                     }
                     scl[0] = sce;
                 }
             }
-            if (STATS) {
-                // reverse accumulators: value = (a2 2^28 + a1 2^14 + a0) 2^-42, columns = features
-                double sum_marg = 0.0;
-                int pj = 0, pk = 1;                           // pair of the current pair feature
+            fin_s[r] = inv; fin_s[TM + r] = sce; fin_s[2 * TM + r] = keep ? 1.0 : 0.0;
+        }
+        if (STATS) {
+            __syncthreads();
+            const double inv = fin_s[r], sce = fin_s[TM + r];
+            const bool keep = fin_s[2 * TM + r] != 0.0;
+            double *scl = a.scl + n * (1 + PET_MAXHP);
+            double *Srow = a.S + rr * st.ldH;
+            const uint8_t *fj = sm.feat(), *fk = sm.feat() + KF;
+            double sum_marg = 0.0;
+            // reverse accumulators: value = (a2 2^28 + a1 2^14 + a0) 2^-42, columns = features; part p reads columns
+            // 16 p .. 16 p + 15, part 0 also 64 .. 79
 #pragma unroll 1
-                for (int c0 = 0; c0 < NOUT; c0 += 16) {
-                    uint32_t r0[16], r1[16], r2[16];
-                    tmem_ld16(tlane + 4 * NC + 0 * NOUT + c0, r0);
-                    tmem_ld16(tlane + 4 * NC + 1 * NOUT + c0, r1);
-                    tmem_ld16(tlane + 4 * NC + 2 * NOUT + c0, r2);
-                    tmem_wait_ld();
-                    if (keep) {
+            for (int c0 = 16 * part; c0 < NOUT; c0 += 64) {
+                uint32_t r0[16], r1[16], r2[16];
+                tmem_ld16(tlane + 4 * NC + 0 * NOUT + c0, r0);
+                tmem_ld16(tlane + 4 * NC + 1 * NOUT + c0, r1);
+                tmem_ld16(tlane + 4 * NC + 2 * NOUT + c0, r2);
+                tmem_wait_ld();
+                if (keep) {
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) {
-                            const int f = c0 + i;
-                            if (f >= nf) continue;
-                            const long long R = ((long long)r2[i] << 28) + ((long long)r1[i] << 14) + (long long)r0[i];
-                            const double val = double(R) * 2.2737367544323206e-13;            // 2^-42
-                            if (f < Hp) {
-                                sum_marg += val;
-                                const double mj = val * inv;
-                                if (fold) {
-                                    if (mj != 0.0) Srow[cand_s[f]] += mj / sce;
-                                    scl[1 + f] = 0.0;
-                                } else {
-                                    scl[1 + f] = mj;
-                                }
+                    for (int i = 0; i < 16; ++i) {
+                        const int f = c0 + i;
+                        if (f >= nf) continue;
+                        const long long R = ((long long)r2[i] << 28) + ((long long)r1[i] << 14) + (long long)r0[i];
+                        const double val = double(R) * 2.2737367544323206e-13;            // 2^-42
+                        if (f < Hp) {                                                     // (Hp <= 12: all in part 0's first batch)
+                            sum_marg += val;
+                            const double mj = val * inv;
+                            if (fold) {
+                                if (mj != 0.0) Srow[cand_s[f]] += mj / sce;
+                                scl[1 + f] = 0.0;
                             } else {
-                                const double w = val * inv;
-                                if (w != 0.0) {
-                                    const int cj = cand_s[pj], ck = cand_s[pk];
-                                    atomicAdd(&a.Wq[int64_t(cj) * st.ldH + ck], w);
-                                    atomicAdd(&a.Wq[int64_t(ck) * st.ldH + cj], w);
-                                }
-                                if (++pk == Hp) { ++pj; pk = pj + 1; }
+                                scl[1 + f] = mj;
+                            }
+                        } else {
+                            const double w = val * inv;
+                            if (w != 0.0) {
+                                const int cj = cand_s[fj[f]], ck = cand_s[fk[f]];
+                                atomicAdd(&a.Wq[int64_t(cj) * st.ldH + ck], w);
+                                atomicAdd(&a.Wq[int64_t(ck) * st.ldH + cj], w);
                             }
                         }
                     }
                 }
-                if (keep) {
-                    // sum_s p_s q_s from sum_s p_s (F_s - mx):  F_s = c q_s + lpm |s|,  sum_s p_s |s| = sum_j marginal_j
-                    const double sig2 = (fma(mx, Z2, SF) - lpm * sum_marg) / cq;
-                    acc_n += 1.0;
-                    acc_lse += lse;
-                    acc_sig += fma(sig1, e1, sig2) * inv;
-                    acc_cnt += fma(cnt1, e1, sum_marg) * inv;
-                }
+                if (part != 0) break;                         // parts 1..3: one batch; part 0: columns 0..15 and 64..79
+            }
+            if (part == 0 && keep) {
+                // sum_s p_s q_s from sum_s p_s (F_s - mx):  F_s = c q_s + lpm |s|,  sum_s p_s |s| = sum_j marginal_j
+                const double sig2 = (fma(mx, Z2, SF) - lpm * sum_marg) / cq;
+                acc_n += 1.0;
+                acc_lse += lse;
+                acc_sig += fma(sig1, e1, sig2) * inv;
+                acc_cnt += fma(cnt1, e1, sum_marg) * inv;
             }
         }
         tc_fence_before();
@@ -523,7 +551,7 @@ __global__ void __launch_bounds__(THREADS, 1) gl_state_tc_kernel(const __grid_co
 
     if (STATS) {
         acc_n = warp_sum(acc_n); acc_lse = warp_sum(acc_lse); acc_sig = warp_sum(acc_sig); acc_cnt = warp_sum(acc_cnt);
-        if (lane == 0 && hf == 0) {
+        if (lane == 0 && part == 0) {
             atomicAdd(&a.scalars[0], acc_n);
             atomicAdd(&a.scalars[1], acc_lse);
             atomicAdd(&a.scalars[2], acc_sig);

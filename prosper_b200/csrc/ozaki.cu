@@ -444,12 +444,14 @@ __global__ void add_slabs_kernel(double *dst, const double *slabs, int64_t count
 int ozaki_kp(int64_t K) { return int(round_up(K, oz::KB)); }
 
 // split-K factor for an (M, N, Kp) product: whole waves of (tile, split) units, each unit paying a fixed epilogue
-int ozaki_splits(int64_t M, int64_t N, int Kp, int sm_count) {
+int ozaki_splits(int64_t M, int64_t N, int Kp, int sm_count, int max_kb_per_split) {
     const int64_t tiles = ceil_div(M, oz::BM) * ceil_div(N, oz::BN);
     const int kblocks = Kp / oz::KB;
-    int best = std::max(1, int(ceil_div(kblocks, 1024)));
+    int best = std::max(1, int(ceil_div(kblocks, max_kb_per_split)));
     double best_cost = 1e300;
-    const int s_min = int(ceil_div(kblocks, 1024));        // int32 accumulators: at most 1170 K blocks per split
+    // int32 accumulators: at most 1170 K blocks per split with |slices| <= 64 on both sides, 589 when one side holds
+    // unsigned 7-bit digits (<= 127)
+    const int s_min = int(ceil_div(kblocks, max_kb_per_split));
     for (int s = s_min; s <= std::max(16, 4 * s_min) && s <= kblocks; ++s) {
         const int kbs = int(ceil_div(kblocks, s));
         if (kbs < 16 && s > s_min) break;
@@ -501,7 +503,7 @@ int ozaki_slice_rows(const double *X, int64_t ldx, int64_t rows, int K, int ns, 
 // C(M,N) (+)= A . B^T from pre-sliced operands (slice rows Kp bytes apart, Kp a multiple of 64).  ns in {6, 7}.
 // splits > 1: split s covers an equal share of the K blocks and writes C + s * split_stride.
 int ozaki_gemm(int64_t M, int64_t N, int Kp, int ns, const OzOperand &A, const OzOperand &B, double *C, int64_t ldc, int splits,
-               int64_t split_stride, bool accumulate, int sm_count, cudaStream_t st) {
+               int64_t split_stride, bool accumulate, int sm_count, cudaStream_t st, int max_pair_product) {
     if (M <= 0 || N <= 0) return PET_OK;
     if ((ldc & 1) || (split_stride & 1) || (reinterpret_cast<uintptr_t>(C) & 15)) {
         set_error("ozaki_gemm: C must be 16-byte aligned with even ldc");
@@ -513,7 +515,7 @@ int ozaki_gemm(int64_t M, int64_t N, int Kp, int ns, const OzOperand &A, const O
     if (splits > kblocks) splits = kblocks;
     const int kbs = int(ceil_div(kblocks, splits));
     splits = int(ceil_div(kblocks, kbs));                  // no empty split
-    if (int64_t(kbs) * oz::KB * ns * 4096 >= (int64_t(1) << 31)) {
+    if (int64_t(kbs) * oz::KB * ns * max_pair_product >= (int64_t(1) << 31)) {
         set_error("ozaki_gemm: %d K elements per split overflow the int32 accumulators", kbs * oz::KB);
         return PET_EINVAL;
     }

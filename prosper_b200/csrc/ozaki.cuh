@@ -12,14 +12,16 @@ struct OzOperand {
 };
 
 int ozaki_kp(int64_t K);
-int ozaki_splits(int64_t M, int64_t N, int Kp, int sm_count);
+// max_kb_per_split: 1024 K blocks of 64 when both operands hold signed slices in [-64, 64]; 512 when one of them holds
+// unsigned 7-bit digits (gl_post_slice: products up to 64 * 127)
+int ozaki_splits(int64_t M, int64_t N, int Kp, int sm_count, int max_kb_per_split = 1024);
 int ozaki_slice_rows(const double *X, int64_t ldx, int64_t rows, int K, int ns, int8_t *out, int64_t slice_stride, double *scale,
                      cudaStream_t st);
 int ozaki_slice_cols(const double *X, int64_t ldx, int64_t rows, int cols, int ns, unsigned long long *colmax, bool have_colmax, int8_t *out,
                      int64_t row_stride, int64_t slice_stride, double *scale, cudaStream_t st,
                      const double *rowscale = nullptr, int64_t rs_stride = 0);
 int ozaki_gemm(int64_t M, int64_t N, int Kp, int ns, const OzOperand &A, const OzOperand &B, double *C, int64_t ldc, int splits,
-               int64_t split_stride, bool accumulate, int sm_count, cudaStream_t st);
+               int64_t split_stride, bool accumulate, int sm_count, cudaStream_t st, int max_pair_product = 4096);
 int ozaki_add_slabs(double *dst, const double *slabs, int64_t count, int n_slabs, cudaStream_t st);
 
 }  // namespace pet

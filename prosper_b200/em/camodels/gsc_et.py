@@ -294,23 +294,24 @@ class GSC(CAModel):
         return B[:, :H].clone()
 
     def _inv_szsz(self, sum_szsz, Wp, model_params, eps):
-        """W_n = Wp . inv(sum <sz sz^T>) with the reference's fallbacks for a singular matrix (gsc_et.py:623-637):
-        np.linalg.inv raises on an exactly singular matrix (a dead unit: zero row and column) -> pinv of the matrix
-        plus an eps-sized rank-one perturbation -> if that fails too, the old W plus eps noise.  Here "singular" is
-        the Cholesky dropping a pivot; pinv is a symmetric eigendecomposition with NumPy's cutoff (1e-15 sigma_max)."""
-        inv = self._inv(sum_szsz)
-        if self._inv_dropped == 0:
+        """W_n = Wp . inv(sum <sz sz^T>) with the reference's fallbacks (gsc_et.py:623-637).  The reference calls
+        np.linalg.inv (LU with partial pivoting), which only raises for an EXACTLY singular matrix and otherwise returns
+        whatever the factorisation gives, however ill conditioned; the same factorisation is used here
+        (torch.linalg.inv_ex on the device: a data-independent H x H operation) so that near-singular iterations follow
+        the reference instead of a truncated Cholesky.  Singular -> pinv of the matrix plus an eps-sized rank-one
+        perturbation -> if that fails too, the old W plus eps noise."""
+        inv, info = torch.linalg.inv_ex(sum_szsz)
+        self._inv_dropped = int(info.item())
+        if self._inv_dropped == 0 and bool(torch.isfinite(inv).all()):
             return Wp @ inv
         dev, H = sum_szsz.device, self.H
         noise = self.comm.bcast(np.random.normal(0, eps, H) if self.comm.rank == 0 else None)
         noise = torch.as_tensor(np.outer(noise, noise), dtype=torch.float64, device=dev)
         try:
-            M = sum_szsz + noise
-            lam, V = torch.linalg.eigh(0.5 * (M + M.T))
-            keep = lam.abs() > 1e-15 * lam.abs().max()
-            if not bool(torch.isfinite(lam).all()) or not bool(keep.any()):
-                raise RuntimeError("eigendecomposition of sum_szsz failed")
-            return ((Wp @ V[:, keep]) / lam[keep]) @ V[:, keep].T
+            pinv = torch.linalg.pinv(sum_szsz + noise, rtol=1e-15)
+            if not bool(torch.isfinite(pinv).all()):
+                raise RuntimeError("pinv of sum_szsz failed")
+            return Wp @ pinv
         except RuntimeError:
             W_old = torch.as_tensor(np.asarray(model_params['W'], dtype=np.float64), device=dev)
             jitter = self.comm.bcast(np.random.normal(0, 1, [self.D, H]) if self.comm.rank == 0 else None)
