@@ -257,6 +257,10 @@ int  pet_generate_data(int32_t combine, int64_t n, int64_t row0, int32_t D, int3
  * (camodels/__init__.py:224-226) and parameter noise (em/__init__.py:63-107) */
 int  pet_normal_fill(double *X_dev, int64_t ld, int64_t rows, int64_t cols,
                      const double *row_base_dev, double scale, uint64_t seed, void *stream);
+/* dst[i][:] = src[idx[i]][:] for i < n_sel: the random datapoint subset of CAModel.select_partial_data
+ * (camodels/__init__.py:125-152) taken from a device-resident shard, no host round trip. */
+int  pet_gather_rows(int64_t n_sel, int64_t n_src, int64_t cols, const double *src_dev, int64_t ld_src,
+                     const int64_t *idx_dev, double *dst_dev, int64_t ld_dst, void *stream);
 /* out[c] += sum_r (M[r][c] - mean[c])^2: data variance of standard_init (:220) */
 int  pet_col_centered_sumsq(int64_t rows, int64_t cols, const double *M_dev, int64_t ld,
                             const double *mean_dev, double *out_dev, void *stream);

@@ -92,6 +92,7 @@ SIGNATURES = {
                                     c_double_p, c_double_p, C.c_double, C.c_uint64, C.c_void_p, C.c_int64, C.c_void_p,
                                     C.c_int64, C.c_void_p]),
     "pet_normal_fill": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_double, C.c_uint64, C.c_void_p]),
+    "pet_gather_rows": (C.c_int, [C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "pet_col_centered_sumsq": (C.c_int, [C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "pet_data_sum": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "pet_mix_posterior": (C.c_int, [C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_double, C.c_double, C.c_void_p,

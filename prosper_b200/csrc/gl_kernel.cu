@@ -571,6 +571,171 @@ __global__ void __launch_bounds__(ROW_WARPS * 32, 3) gl_row_select_kernel(const 
     }
 }
 
+// -------------------------------------------------------------------------------------------------
+// Selection and singleton reductions in ONE pass over the score row (used whenever the <s> row is not written: the
+// int8 statistics path, the log-denominator sweep, select_Hprimes).  The row lives in registers (32 scores per lane).
+//   * selection by threshold on FLOAT32 keys, exact ranking in float64: rounding to float32 is monotone, so with tau =
+//     the H'-th best of the 32 lane maxima (H' rounds of two 32-bit warp REDUX.MAX; each lane contributes one item, no
+//     refills) every item whose key is below tau is below at least H' others in float64 as well.  The items with
+//     key >= tau (H' + a few) are compacted into a shared-memory list with their float64 keys and ranked exactly there
+//     (score descending, ties -> the larger item index first, as everywhere).  A list overflow (massive float32 ties)
+//     falls back to the generic selection.
+//   * null + all-H singleton log-joints from the same registers, F_h = (B + A yy) + A wn2_h - 2 A v_h with
+//     A = beta pre1: max, partition sum, sigma / prior partial sums (table-based exp); nothing of length H is written.
+// -------------------------------------------------------------------------------------------------
+constexpr int ROWF_WARPS = 8, ROWF_LIST = 32 * PET_MAXHP;
+
+__device__ __forceinline__ bool item_ge(unsigned long long ka, int ia, unsigned long long kb, int ib) {
+    return ka > kb || (ka == kb && ia >= ib);
+}
+// selection score of item h from its score-row entry; sc1 = 1/||W_h|| (BSC) or ||W_h||^2 (NEGDIST), sc0 = W_h . mu (BSC)
+template <int MODE, bool WMU>
+__device__ __forceinline__ double row_score(double vk, double sc0, double sc1) {
+    double s = (MODE == SEL_BSC) ? (WMU ? vk + sc0 : vk) * sc1 : (MODE == SEL_NEGDIST) ? 2.0 * vk - sc1 : -vk;
+    s += 0.0;                                          // -0.0 ties with +0.0, as in a floating-point compare
+    return (s != s) ? -INFINITY : s;                   // NaN scores never win
+}
+__device__ __forceinline__ unsigned key32(double s) {  // order-preserving image of the score rounded to float32; > 0
+    const int b = __float_as_int(__double2float_rn(s));
+    return unsigned(b ^ ((b >> 31) | int(0x80000000)));
+}
+
+template <int MODE, bool WMU>
+__global__ void __launch_bounds__(ROWF_WARPS * 32, 2) gl_row_threshold_kernel(const __grid_constant__ GLArgs a) {
+    __shared__ double exptab[32];
+    __shared__ unsigned long long list_key[ROWF_WARPS][ROWF_LIST];
+    __shared__ short list_idx[ROWF_WARPS][ROWF_LIST];
+    __shared__ int cand_all[ROWF_WARPS][PET_MAXHP];
+    constexpr int HC = 32;
+    const GLStatic &st = a.st;
+    const GLIter &it = a.it;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int H = st.H, Hp = st.Hp;
+    int *cand_s = cand_all[warp];
+    unsigned long long *lk = list_key[warp];
+    short *li = list_idx[warp];
+    // combine(prior, q) = B + A q
+    const double A = it.beta * it.pre1, invA = 1.0 / A;
+    const double Bp = it.anneal_prior ? it.beta * it.prior_block[0] : it.prior_block[0];
+    const double B0 = it.anneal_prior ? it.beta * it.prior_null : it.prior_null;
+    const double m2A = -2.0 * A;
+    const double *sc1p = ((MODE == SEL_BSC) ? a.invn : a.wn2) + lane, *sc0p = (WMU ? a.wmu : a.wn2) + lane, *wn2p = a.wn2 + lane;
+    const int nk = (H - lane + 31) >> 5;               // items of this lane: h = k * 32 + lane < H  <=>  k < nk
+    const bool do_select = (a.flags & GLF_SELECT) != 0, select_only = (a.flags & GLF_SELECT_ONLY) != 0;
+    exp_tab32_init(exptab);
+    __syncthreads();
+    const int64_t wstride = int64_t(gridDim.x) * ROWF_WARPS;
+    for (int64_t r = int64_t(blockIdx.x) * ROWF_WARPS + warp; r < a.n_rows; r += wstride) {
+        const int64_t n = a.row0 + r;
+        const double *yw = a.YW + r * st.ldH;
+        const double *ywl = yw + lane;
+        double v[HC];
+#pragma unroll
+        for (int k = 0; k < HC; ++k) v[k] = (k < nk) ? ywl[k * 32] : 0.0;
+        if (do_select) {
+            // ---- float32 keys, best item of every lane ----
+            unsigned key[HC];
+            unsigned bk = 0u;
+            int bidx = lane;
+#pragma unroll
+            for (int k = 0; k < HC; ++k) {
+                unsigned kk = 0u;
+                if (k < nk) kk = key32(row_score<MODE, WMU>(v[k], WMU ? sc0p[k * 32] : 0.0, (MODE == SEL_GIVEN) ? 0.0 : sc1p[k * 32]));
+                key[k] = kk;
+                if (kk >= bk) { bk = kk; bidx = k * 32 + lane; }
+            }
+            // ---- tau = the H'-th best lane maximum ----
+            unsigned tk = 0u;
+            {
+                unsigned ck = bk;
+                for (int rnd = 0; rnd < Hp; ++rnd) {
+                    tk = __reduce_max_sync(0xffffffffu, ck);
+                    const unsigned mi = __reduce_max_sync(0xffffffffu, ck == tk ? unsigned(bidx) + 1u : 0u);
+                    if (ck == tk && unsigned(bidx) + 1u == mi) ck = 0u;       // this lane's maximum is out
+                }
+            }
+            // ---- compact the items with key >= tau ----
+            unsigned mask = 0u;
+#pragma unroll
+            for (int k = 0; k < HC; ++k) mask |= (key[k] != 0u && key[k] >= tk) ? (1u << k) : 0u;
+            const int cnt = __popc(mask);
+            int incl = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t2 = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t2;
+            }
+            const int M = __shfl_sync(0xffffffffu, incl, 31);
+            if (M <= ROWF_LIST) {
+                int off = incl - cnt;
+                while (mask) {
+                    const int k = __ffs(mask) - 1;
+                    mask &= mask - 1;
+                    li[off++] = short(k * 32 + lane);
+                }
+                __syncwarp();
+                // ---- float64 keys of the listed items, exact rank inside the list (M >= H') ----
+                for (int e = lane; e < M; e += 32) {
+                    const int h = li[e];
+                    lk[e] = order_key(row_score<MODE, WMU>(yw[h], WMU ? a.wmu[h] : 0.0,
+                                                           (MODE == SEL_BSC) ? a.invn[h] : (MODE == SEL_NEGDIST) ? a.wn2[h] : 0.0));
+                }
+                __syncwarp();
+                for (int e = lane; e < M; e += 32) {
+                    const unsigned long long mk = lk[e];
+                    const int mi = li[e];
+                    int rank = 0;
+                    for (int j = 0; j < M; ++j) rank += (j != e && item_ge(lk[j], li[j], mk, mi)) ? 1 : 0;
+                    if (rank < Hp) store_cand(st, cand_s, rank, mi);
+                }
+            } else {
+                select_generic(a, yw, a.yy[n], H, cand_s);
+            }
+            __syncwarp();
+            if (lane < Hp) a.cand[n * Hp + lane] = cand_s[lane];
+        } else {
+            if (lane < Hp) cand_s[lane] = a.cand[n * Hp + lane];
+            __syncwarp();
+        }
+        if (select_only) { __syncwarp(); continue; }
+        if (lane < Hp) a.ywc[n * Hp + lane] = yw[cand_s[lane]];
+
+        // ---- null state + all-H singletons: max, partition sum, sigma / prior partial sums ----
+        const double yy = a.yy[n];
+        double tmax = -INFINITY;
+#pragma unroll
+        for (int k = 0; k < HC; ++k) {
+            v[k] = (k < nk) ? fma(m2A, v[k], A * wn2p[k * 32]) : -INFINITY;    // t_h = F_h - (B + A yy)
+            tmax = fmax(tmax, v[k]);
+        }
+        tmax = warp_max(tmax);
+        const double Ryy = fma(A, yy, Bp), F0 = fma(A, yy, B0);
+        const double m1 = fmax(F0, Ryy + tmax);
+        const double d = Ryy - m1;
+        double Zs = 0.0, S1 = 0.0;
+#pragma unroll
+        for (int k = 0; k < HC; ++k) {
+            if (k < nk) {
+                const double p = exp_tab32(fmax(v[k] + d, GL_EXP_CUTOFF), exptab);
+                Zs += p;
+                S1 = fma(p, v[k], S1);
+            }
+        }
+        Zs = warp_sum(Zs);
+        S1 = warp_sum(S1);
+        if (lane == 0) {
+            const double x0 = F0 - m1;
+            const double p0 = (x0 > GL_EXP_CUTOFF) ? exp_tab32(x0, exptab) : 0.0;
+            double *rs = a.rs + n * RS;
+            rs[0] = m1;
+            rs[1] = Zs + p0;
+            rs[2] = fma(p0 + Zs, yy, S1 * invA);             // sum_c p_c q_c,  q_h = yy + t_h / A
+            rs[4] = Zs;
+        }
+        __syncwarp();
+    }
+}
+
 // null state + all-H singletons of one datapoint per warp: max, partition sum, sigma / prior partial sums and the
 // un-normalised posterior row.  F_h decreases with q_h = yy + wn2_h - 2 yw_h (beta pre1 < 0), so the maximum is the
 // log-joint of the smallest q_h.
@@ -980,35 +1145,40 @@ __global__ void __launch_bounds__(256) gl_scale_kernel(const __grid_constant__ G
 // loads (score rows) and the stores (slice rows, datapoints contiguous) are coalesced.
 // =================================================================================================
 constexpr int PS_R = 128, PS_C = 32, PS_PITCH = PS_R + 4;
+// FULL: the tile lies inside the chunk and the cause range (no bounds checks in the element loop)
+template <bool FULL>
 __global__ void __launch_bounds__(256) gl_post_slice_kernel(const __grid_constant__ GLArgs a, int ns, int Kp, int8_t *out,
-                                                            int64_t row_stride, int64_t slice_stride, double *scale_out) {
+                                                            int64_t row_stride, int64_t slice_stride, double *scale_out,
+                                                            int col_tile0, int row_tile0) {
     extern __shared__ __align__(16) int8_t ps_smem[];
     double *add = reinterpret_cast<double *>(ps_smem);                     // [PS_R][PS_C + 1] candidate marginals
-    double *rowc = add + PS_R * (PS_C + 1);                                // [PS_R][3]  m1, scale, yy
-    double *exptab = rowc + PS_R * 3;                                      // [32]
+    double *rowc = add + PS_R * (PS_C + 1);                                // [PS_R][2]  (B + A yy - m1), scale
+    double *exptab = rowc + PS_R * 2;                                      // [32]
     int32_t *tile32 = reinterpret_cast<int32_t *>(exptab + 32);            // [ns][PS_C][PS_PITCH] bytes
-    exp_tab32_init(exptab);
     const GLStatic &st = a.st;
     const GLIter &it = a.it;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    const int c0 = blockIdx.x * PS_C, c = c0 + tx;
-    const int64_t r0 = int64_t(blockIdx.y) * PS_R;
+    const int c0 = (blockIdx.x + col_tile0) * PS_C, c = c0 + tx;
+    const int64_t r0 = int64_t(blockIdx.y + row_tile0) * PS_R;
     const int Hp = st.Hp;
+    // combine(prior, q) = B + A q,  q = yy + wn2_h - 2 v:  x = F_h - m1 = (B + A yy - m1) + A wn2_h - 2 A v
+    const double A = it.beta * it.pre1, m2A = -2.0 * A;
+    const double Bp = it.anneal_prior ? it.beta * it.prior_block[0] : it.prior_block[0];
+    exp_tab32_init(exptab);
     for (int i = threadIdx.x; i < PS_R * (PS_C + 1); i += 256) add[i] = 0.0;
     if (threadIdx.x < PS_R) {
         const int64_t rr = r0 + threadIdx.x;
-        double m1 = 0.0, sc = 0.0, yy = 0.0;
+        double rt = -1.0e300, sc = 0.0;                                    // rows beyond the chunk: exp -> cutoff, scale 0
         if (rr < a.n_rows) {
             const int64_t n = a.row0 + rr;
-            m1 = a.rs[n * RS];
+            rt = fma(A, a.yy[n], Bp) - a.rs[n * RS];
             sc = a.scl[n * (1 + PET_MAXHP)];
-            yy = a.yy[n];
         }
-        rowc[threadIdx.x * 3 + 0] = m1; rowc[threadIdx.x * 3 + 1] = sc; rowc[threadIdx.x * 3 + 2] = yy;
+        rowc[threadIdx.x * 2 + 0] = rt; rowc[threadIdx.x * 2 + 1] = sc;
     }
     __syncthreads();
     for (int i = threadIdx.x; i < PS_R * Hp; i += 256) {                   // candidates are distinct: plain stores
-        const int rl = i / Hp, j = i % Hp;
+        const int rl = i / Hp, j = i - rl * Hp;
         const int64_t rr = r0 + rl;
         if (rr < a.n_rows) {
             const int64_t n = a.row0 + rr;
@@ -1017,28 +1187,26 @@ __global__ void __launch_bounds__(256) gl_post_slice_kernel(const __grid_constan
         }
     }
     __syncthreads();
-    const double pb = it.prior_block[0];
-    const double wn2 = (c < st.H) ? a.wn2[c] : 0.0;
+    const bool col_ok = FULL || c < st.H;
+    const double awn2 = col_ok ? A * a.wn2[c] : 0.0;
     // <s> in [0, 1] as the integer rint(<s> 2^48): slice 0 = bits 42.. (<= 64), slice t = the 7 bits below (0..127, valid
     // as signed bytes); value = sum_t slice_t 2^-(6+7t), i.e. the slicing convention of ozaki.cu with column scale 1
+    const double *ywp = a.YW + (r0 + ty * 16) * st.ldH + c;
+    const double *rc = rowc + ty * 32, *ad = add + ty * 16 * (PS_C + 1) + tx;
     uint32_t lo[16], hi[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
-        const int rl = ty * 16 + i;
-        const int64_t rr = r0 + rl;
-        double val = 0.0;
-        if (c < st.H && rr < a.n_rows) {
-            const double q = rowc[rl * 3 + 2] + (wn2 - 2.0 * a.YW[rr * st.ldH + c]);
-            const double x = combine(it, pb, q) - rowc[rl * 3 + 0];
-            const double p = (x > GL_EXP_CUTOFF) ? exp_tab32(x, exptab) : 0.0;
-            val = fma(p, rowc[rl * 3 + 1], add[rl * (PS_C + 1) + tx]);
-        }
-        long long xi = __double2ll_rn(val * 281474976710656.0);            // 2^48
-        xi = xi < 0 ? 0 : (xi > (1ll << 48) ? (1ll << 48) : xi);           // (rounding noise around 0 and 1)
+        double vv = 0.0;
+        if (FULL || (col_ok && r0 + ty * 16 + i < a.n_rows)) vv = ywp[int64_t(i) * st.ldH];
+        const double x = fmax(fma(m2A, vv, awn2 + rc[2 * i]), GL_EXP_CUTOFF);
+        const double p = exp_tab32(x, exptab);                             // e^-100 2^48 rounds to 0: no select needed
+        double val = fma(p, rc[2 * i + 1], ad[i * (PS_C + 1)]);
+        if (!FULL && !col_ok) val = 0.0;
+        const long long xi = __double2ll_rn(val * 281474976710656.0);      // 2^48; val in [0, 1 + eps]
         lo[i] = uint32_t(xi);
         hi[i] = uint32_t(xi >> 32);
     }
-    if (blockIdx.y == 0 && ty == 0 && c < st.H) scale_out[c] = 1.0;
+    if (blockIdx.y + row_tile0 == 0 && ty == 0 && col_ok) scale_out[c] = 1.0;
 #pragma unroll
     for (int t = 0; t < 7; ++t) {
         if (t < ns) {
@@ -1065,7 +1233,7 @@ __global__ void __launch_bounds__(256) gl_post_slice_kernel(const __grid_constan
         const int t = ro / PS_C, cc = ro % PS_C;
         const int col = c0 + cc;
         const int64_t r = r0 + tx * 4;
-        if (col < st.H && r < Kp)
+        if ((FULL || col < st.H) && r < Kp)
             *reinterpret_cast<int32_t *>(out + t * slice_stride + col * row_stride + r) = tile32[((t * PS_C + cc) * PS_PITCH) / 4 + tx];
     }
 }
@@ -1073,15 +1241,30 @@ __global__ void __launch_bounds__(256) gl_post_slice_kernel(const __grid_constan
 int launch_gl_post_slice(const GLArgs &a, int ns, int Kp, int8_t *out, int64_t row_stride, int64_t slice_stride, double *scale_out,
                          cudaStream_t st) {
     if (a.n_rows <= 0) return PET_OK;
-    const size_t smem = size_t(PS_R) * (PS_C + 1) * 8 + size_t(PS_R) * 3 * 8 + 32 * 8 + size_t(ns) * PS_C * PS_PITCH;
+    const size_t smem = size_t(PS_R) * (PS_C + 1) * 8 + size_t(PS_R) * 2 * 8 + 32 * 8 + size_t(ns) * PS_C * PS_PITCH;
     static size_t configured = 0;
     if (smem > configured) {
-        PET_CUDA(cudaFuncSetAttribute(gl_post_slice_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        PET_CUDA(cudaFuncSetAttribute(gl_post_slice_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        PET_CUDA(cudaFuncSetAttribute(gl_post_slice_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
         configured = smem;
     }
-    dim3 grid((unsigned)ceil_div(a.st.H, PS_C), (unsigned)ceil_div(Kp, PS_R));
-    gl_post_slice_kernel<<<grid, 256, smem, st>>>(a, ns, Kp, out, row_stride, slice_stride, scale_out);
-    PET_LAUNCH_CHECK();
+    // interior tiles (whole 128-row, 32-cause tiles) without bounds checks, then the ragged right / bottom borders
+    const unsigned cols_full = unsigned(a.st.H / PS_C), rows_full = unsigned(a.n_rows / PS_R);
+    const unsigned cols_all = (unsigned)ceil_div(a.st.H, PS_C), rows_all = (unsigned)ceil_div(Kp, PS_R);
+    if (cols_full > 0 && rows_full > 0) {
+        gl_post_slice_kernel<true><<<dim3(cols_full, rows_full), 256, smem, st>>>(a, ns, Kp, out, row_stride, slice_stride, scale_out, 0, 0);
+        PET_LAUNCH_CHECK();
+    }
+    if (cols_all > cols_full && rows_full > 0) {                           // right border: the last, partial cause tile
+        gl_post_slice_kernel<false><<<dim3(cols_all - cols_full, rows_full), 256, smem, st>>>(a, ns, Kp, out, row_stride, slice_stride,
+                                                                                               scale_out, int(cols_full), 0);
+        PET_LAUNCH_CHECK();
+    }
+    if (rows_all > rows_full) {                                            // bottom border: all cause tiles of the last rows
+        gl_post_slice_kernel<false><<<dim3(cols_all, rows_all - rows_full), 256, smem, st>>>(a, ns, Kp, out, row_stride, slice_stride,
+                                                                                              scale_out, 0, int(rows_full));
+        PET_LAUNCH_CHECK();
+    }
     return PET_OK;
 }
 
@@ -1148,6 +1331,16 @@ int launch_gl_row(const GLArgs &a, int sm_count, cudaStream_t stream) {
         static const bool one_kernel = getenv("PET_GL_ROW_FUSED") != nullptr;
         if (one_kernel) {
             gl_row_fast_kernel<<<(unsigned)grid, ROW_WARPS * 32, smem, stream>>>(a);
+            PET_LAUNCH_CHECK();
+            return PET_OK;
+        }
+        static const bool no_threshold = getenv("PET_GL_NO_THRESHOLD_ROW") != nullptr;
+        if (!no_threshold && (a.flags & (GLF_NO_SROW | GLF_LSE_ONLY | GLF_SELECT_ONLY))) {      // nothing of length H to write
+            grid = std::min<int64_t>(ceil_div(a.n_rows, ROWF_WARPS), int64_t(sm_count) * 2 * 4);
+            if (a.st.select_mode == SEL_BSC && a.wmu) gl_row_threshold_kernel<SEL_BSC, true><<<(unsigned)grid, ROWF_WARPS * 32, 0, stream>>>(a);
+            else if (a.st.select_mode == SEL_BSC) gl_row_threshold_kernel<SEL_BSC, false><<<(unsigned)grid, ROWF_WARPS * 32, 0, stream>>>(a);
+            else if (a.st.select_mode == SEL_NEGDIST) gl_row_threshold_kernel<SEL_NEGDIST, false><<<(unsigned)grid, ROWF_WARPS * 32, 0, stream>>>(a);
+            else gl_row_threshold_kernel<SEL_GIVEN, false><<<(unsigned)grid, ROWF_WARPS * 32, 0, stream>>>(a);
             PET_LAUNCH_CHECK();
             return PET_OK;
         }

@@ -171,6 +171,31 @@ extern "C" int pet_normal_fill(double *X_dev, int64_t ld, int64_t rows, int64_t 
     return PET_OK;
 }
 
+// dst[i][:] = src[idx[i]][:]: the datapoint subset of select_partial_data (camodels/__init__.py:125-152) taken from the
+// device-resident shard, one warp per destination row
+__global__ void gather_rows_kernel(double *dst, int64_t ld_dst, const double *src, int64_t ld_src, const int64_t *idx,
+                                   int64_t n_sel, int64_t n_src, int cols) {
+    const int64_t i = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (i >= n_sel) return;
+    int64_t r = idx[i];
+    r = r < 0 ? 0 : (r >= n_src ? n_src - 1 : r);
+    for (int c = lane; c < cols; c += 32) dst[i * ld_dst + c] = src[r * ld_src + c];
+}
+
+extern "C" int pet_gather_rows(int64_t n_sel, int64_t n_src, int64_t cols, const double *src_dev, int64_t ld_src,
+                               const int64_t *idx_dev, double *dst_dev, int64_t ld_dst, void *stream) {
+    if (!src_dev || !idx_dev || !dst_dev || n_sel < 0 || n_src < 1 || cols < 1 || ld_src < cols || ld_dst < cols) {
+        set_error("pet_gather_rows: bad arguments");
+        return PET_EINVAL;
+    }
+    if (n_sel == 0) return PET_OK;
+    gather_rows_kernel<<<(unsigned)ceil_div(n_sel * 32, 256), 256, 0, (cudaStream_t)stream>>>(dst_dev, ld_dst, src_dev, ld_src, idx_dev,
+                                                                                             n_sel, n_src, (int)cols);
+    PET_LAUNCH_CHECK();
+    return PET_OK;
+}
+
 extern "C" int pet_col_centered_sumsq(int64_t rows, int64_t cols, const double *M_dev, int64_t ld, const double *mean_dev,
                                       double *out_dev, void *stream) {
     if (!M_dev || !mean_dev || !out_dev || rows < 0 || cols < 1 || ld < cols) { set_error("pet_col_centered_sumsq: bad arguments"); return PET_EINVAL; }

@@ -36,8 +36,11 @@ class Model(object):
         for param, policy in self.noise_policy.items():
             pvalue = model_params[param]
             scale = anneal[param + "_noise"]
+            if scale != 0.0 and hasattr(pvalue, 'is_cuda') and pvalue.is_cuda and pvalue.dim() == 2 and pvalue.dtype.is_floating_point:
+                model_params[param] = self._noisify_device(pvalue, scale, policy)
+                continue
             on_device = None
-            if scale != 0.0 and hasattr(pvalue, 'detach') and hasattr(pvalue, 'cpu'):   # device-resident parameter
+            if scale != 0.0 and hasattr(pvalue, 'detach') and hasattr(pvalue, 'cpu'):   # other device-resident parameters
                 on_device = pvalue.device
                 pvalue = pvalue.detach().cpu().numpy()
             if scale != 0.0:
@@ -62,6 +65,28 @@ class Model(object):
                 pvalue = torch.as_tensor(pvalue).to(on_device)
             model_params[param] = pvalue
         return model_params
+
+    def _noisify_device(self, pvalue, scale, policy):
+        """Parameter noise for a matrix that lives on the device (em/__init__.py:82-103): rank 0 draws a SEED, every rank
+        runs the same counter-based generator (`pet_normal_fill`, Philox keyed by seed and element index), so all
+        ranks add identical noise and nothing but the seed is broadcast; clamp and abs follow on the device."""
+        import ctypes as C
+        import torch
+        from .. import _lib
+        seed = self.comm.bcast(int(np.random.randint(0, 2 ** 31 - 1)) if self.comm.rank == 0 else None)
+        lib = _lib.load()
+        src = pvalue if pvalue.dtype == torch.float64 else pvalue.to(torch.float64)
+        noise = torch.empty(src.shape, dtype=torch.float64, device=src.device)
+        st = C.c_void_p(torch.cuda.current_stream(src.device).cuda_stream)
+        _lib.check(lib.pet_normal_fill(C.c_void_p(noise.data_ptr()), noise.stride(0), noise.shape[0], noise.shape[1], None,
+                                       float(scale), seed, st))
+        low, up, absify = policy
+        out = src + noise
+        if np.isfinite(low) or np.isfinite(up):
+            out = torch.clamp(out, min=(low if np.isfinite(low) else None), max=(up if np.isfinite(up) else None))
+        if absify:
+            out = torch.abs(out)
+        return out.to(pvalue.dtype)
 
     def gain(self, old_params, new_params):
         return 0.

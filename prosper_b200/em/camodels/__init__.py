@@ -304,7 +304,10 @@ class CAModel(Model):
         return self.generate_from_hidden(model_params, {'s': s})
 
     def select_partial_data(self, anneal, my_data):
-        """camodels/__init__.py:125-152."""
+        """camodels/__init__.py:125-152: a random subset of ceil(partial * my_N) datapoints, in ascending order.
+        A shard that lives on the device (CUDA tensors) is subsampled there: the permutation comes from the device RNG
+        (seeded from np.random, so runs stay reproducible; SURVEY 8 f3: parity with np.random's stream is not required)
+        and the rows are gathered by `pet_gather_rows` -- nothing returns to the host."""
         partial = anneal['partial']
         if partial == 0 or partial == 1:
             return my_data
@@ -312,6 +315,24 @@ class CAModel(Model):
         my_pN = int(np.ceil(my_N * partial))
         if my_N == my_pN:
             return my_data
+        y = my_data['y']
+        if isinstance(y, torch.Tensor) and y.is_cuda:
+            gen = torch.Generator(device=y.device)
+            gen.manual_seed(int(np.random.randint(0, 2 ** 31 - 1)))
+            sel = torch.sort(torch.randperm(my_N, device=y.device, generator=gen)[:my_pN]).values
+            lib = _lib.load()
+            st = C.c_void_p(torch.cuda.current_stream(y.device).cuda_stream)
+            out = {}
+            for k, v in my_data.items():
+                if (isinstance(v, torch.Tensor) and v.is_cuda and v.dim() == 2 and v.dtype == torch.float64 and v.stride(1) == 1):
+                    dst = torch.empty((my_pN, v.shape[1]), dtype=torch.float64, device=v.device)
+                    _lib.check(lib.pet_gather_rows(my_pN, my_N, v.shape[1], _ptr(v), v.stride(0), _ptr(sel), _ptr(dst), dst.stride(0), st))
+                    out[k] = dst
+                elif isinstance(v, torch.Tensor):
+                    out[k] = v[sel.to(v.device)]
+                else:
+                    out[k] = v[sel.cpu().numpy()]
+            return out
         sel = np.random.permutation(my_N)[:my_pN]
         sel.sort()
         return dict((k, v[sel]) for k, v in my_data.items())

@@ -86,3 +86,51 @@ def test_standard_init_on_device_matches_host_formula():
     np.random.seed(5)
     again = m.standard_init({'y': y})['W']                                          # seeded through np.random on rank 0
     assert np.allclose(again, p['W'], rtol=0, atol=1e-12)                           # (column sums use atomics: last-bit noise)
+
+
+def test_select_partial_data_on_the_device():
+    """camodels/__init__.py:125-152 for a shard that lives on the device: ceil(partial N) distinct rows in ascending
+    order, gathered by pet_gather_rows; reproducible from np.random's seed; the host path is untouched."""
+    from prosper_b200.em.camodels.bsc_et import BSC_ET
+    from oracle.common import DictAnneal
+    m = BSC_ET(20, 8, 4, 2)
+    dev = torch.device('cuda', 0)
+    y = torch.arange(1000 * 20, dtype=torch.float64, device=dev).reshape(1000, 20)
+    an = DictAnneal(partial=0.3)
+    np.random.seed(3)
+    a = m.select_partial_data(an, {'y': y})['y']
+    np.random.seed(3)
+    b = m.select_partial_data(an, {'y': y})['y']
+    assert a.is_cuda and a.shape == (300, 20) and torch.equal(a, b)
+    rows = (a[:, 0] / 20).round().long()
+    assert torch.equal(a, y[rows]) and bool((rows[1:] > rows[:-1]).all())
+    c = m.select_partial_data(an, {'y': y})['y']
+    assert not torch.equal(a, c)
+    assert m.select_partial_data(DictAnneal(partial=1.0), {'y': y})['y'] is y
+    yh = y.cpu().numpy()
+    np.random.seed(5)
+    h = m.select_partial_data(an, {'y': yh})['y']
+    np.random.seed(5)
+    sel = np.sort(np.random.permutation(1000)[:300])
+    assert np.array_equal(h, yh[sel])
+
+
+def test_noisify_params_on_the_device():
+    """em/__init__.py:63-107 for a parameter matrix that lives on the device: noise of the annealed scale from the
+    counter-based generator (every rank draws the same), bounds of the noise policy applied, host scalars as before."""
+    from prosper_b200.em.camodels.bsc_et import BSC_ET
+    from oracle.common import DictAnneal
+    m = BSC_ET(64, 32, 4, 2)
+    dev = torch.device('cuda', 0)
+    W = torch.zeros((64, 32), dtype=torch.float64, device=dev)
+    an = DictAnneal(W_noise=0.5)
+    np.random.seed(1)
+    p1 = m.noisify_params({'W': W, 'pi': 0.1, 'sigma': 1.0}, an)
+    np.random.seed(1)
+    p2 = m.noisify_params({'W': W, 'pi': 0.1, 'sigma': 1.0}, an)
+    assert p1['W'].is_cuda and torch.equal(p1['W'], p2['W']) and p1['pi'] == 0.1 and p1['sigma'] == 1.0
+    assert abs(float(p1['W'].std()) - 0.5) < 0.05 and abs(float(p1['W'].mean())) < 0.05
+    m.noise_policy['W'] = (-0.2, 0.3, False)
+    p3 = m.noisify_params({'W': W, 'pi': 0.1, 'sigma': 1.0}, an)
+    assert float(p3['W'].min()) >= -0.2 and float(p3['W'].max()) <= 0.3
+    assert m.noisify_params({'W': W, 'pi': 0.1, 'sigma': 1.0}, DictAnneal())['W'] is W
