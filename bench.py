@@ -479,7 +479,15 @@ def run_gpu(args):
             achieved = 2.0 * D * H * rows_per_launch / (avg_launch_ms / 1e3) / 1e12
             if ns > 0:
                 pairs = ns * (ns + 1) // 2
-                int8_peak = 2.0 * bf16            # kind::i8 issues at twice the bf16 rate on B200 (4.5 vs 2.25 PFLOP/s nominal)
+                # int8 tensor-pipe peak MEASURED on this pool's B200 (tools/ubench/umma_probe.cu, profiles/r02_int8_peak.json):
+                # the sustained figure, because the GEMMs run inside a long step
+                int8_peak, int8_src = 2.0 * bf16, "2 x %s bf16_tflops_sustained (no measured int8 peak found)" % peak_src
+                try:
+                    ip = json.load(open(os.path.join(ROOT, "profiles", "r02_int8_peak.json")))
+                    int8_peak = ip["int8_tops_sustained"]
+                    int8_src = "profiles/r02_int8_peak.json int8_tops_sustained (measured: tcgen05 kind::i8 M128 N256 K32 back to back on all SMs)"
+                except Exception:
+                    pass
                 roof = {"kernel": "oz::gemm_kernel<%d> (score + statistics GEMM)" % ns, "bound": "tensor",
                         "pipe": "tcgen05.mma kind::i8 + TMEM: %d int8 slice products per FP64 product" % pairs,
                         "achieved": achieved, "peak": int8_peak / pairs, "unit": "TFLOP/s", "frac": achieved * pairs / int8_peak,
@@ -487,8 +495,8 @@ def run_gpu(args):
                         "pipe_nominal_tops": 4500.0, "frac_of_nominal": achieved * pairs / 4500.0,
                         "ncu_tensor_pipe_active": {"score_shape": 0.66, "statistics_shape": 0.73,
                                                    "source": "profiles/r01i_ncu_oz_gemm_kernel.txt"},
-                        "peak_source": "2 x %s bf16_tflops_sustained (int8 dense rate), divided by the %d slice products; "
-                                       "cuBLAS DGEMM measured in this run: %.1f TFLOP/s" % (peak_src, pairs, peak),
+                        "peak_source": int8_src + ", divided by the %d slice products; cuBLAS DGEMM measured in this run: %.1f TFLOP/s"
+                                       % (pairs, peak),
                         "traffic": ncu_traffic()}
             else:
                 roof = {"kernel": "dgemm_kernel (FP64 DMMA, score + statistics GEMM)", "bound": "tensor",

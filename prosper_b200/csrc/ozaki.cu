@@ -27,7 +27,7 @@ namespace pet {
 namespace oz {
 constexpr int BM = 128, BN = 64, KB = 64;          // tile rows, tile cols, bytes (= int8 elements) of K per stage
 constexpr int UMMA_K = 32;                         // K of one kind::i8 MMA
-constexpr int THREADS = 256;
+constexpr int THREADS = 384;                       // 4 control warps + 8 epilogue warps (two per TMEM lane quadrant)
 
 __device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -94,6 +94,14 @@ __device__ __forceinline__ void mma_i8(uint32_t tmem_d, uint64_t desc_a, uint64_
 __device__ __forceinline__ void mma_commit(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, int32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, int32_t (&v)[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -136,7 +144,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_kernel(const __grid_constant_
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         mbar_init(tmem_full, 1);
-        mbar_init(tmem_empty, 4);
+        mbar_init(tmem_empty, 8);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -215,8 +223,9 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_kernel(const __grid_constant_
     } else if (warp >= 4) {
         // ===== epilogue: TMEM -> exact int64 combination -> FP64 -> global =====
         // sum_t v_t 2^-(12+7t) = 2^-33 (hi + lo 2^-(7 (NS-4))),  hi = sum_{t<4} v_t 2^(7(3-t)) (< 2^53, exact in FP64),
-        // lo = sum_{t>=4} v_t 2^(7(NS-1-t))
-        const int q = warp & 3;                              // TMEM lane quadrant of this warp
+        // lo = sum_{t>=4} v_t 2^(7(NS-1-t)).  Eight warps: warp 4 + q and 8 + q share TMEM lane quadrant q and take one
+        // 32-column half of the tile each (two warps per scheduler hide the conversion and store latencies).
+        const int q = warp & 3, half = (warp - 4) >> 2;
         uint32_t tphase = 0;
         const double w_hi = __longlong_as_double((long long)(1023 - 33) << 52);
         const double w_lo = __longlong_as_double((long long)(1023 - 7 * (NS - 4)) << 52);
@@ -225,63 +234,64 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_kernel(const __grid_constant_
             const int split = int(u / tiles);
             const int64_t m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
             // column scales of this tile through shared memory (one global load per column and tile instead of one per
-            // element); double buffered by tile parity, one barrier of the 128 epilogue threads per tile
+            // element); double buffered by tile parity, one barrier of the 256 epilogue threads per tile
             double *sBt = sB_s + (tphase ? BN : 0);
             {
                 const int et = threadIdx.x - 128;
                 if (et < BN) sBt[et] = (n0 + et < a.N) ? a.sB[n0 + et] : 0.0;
-                asm volatile("bar.sync 1, 128;" ::: "memory");
+                asm volatile("bar.sync 1, 256;" ::: "memory");
             }
             mbar_wait_relaxed(tmem_full, tphase);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const int64_t row = m0 + q * 32 + lane;
             const double sa = (row < a.M) ? a.sA[row] * w_hi : 0.0;
-            double *crow = a.C + split * a.split_stride + row * a.ldc + n0;
+            double *crow = a.C + split * a.split_stride + row * a.ldc + n0 + half * 32;
 #pragma unroll 1
-            for (int half = 0; half < 2; ++half) {
-                const uint32_t tcol = tmem_base + (uint32_t(q * 32) << 16) + half * 32;
-                long long hi[32], lo[32];
+            for (int sub = 0; sub < 2; ++sub) {
+                const uint32_t tcol = tmem_base + (uint32_t(q * 32) << 16) + half * 32 + sub * 16;
+                long long hi[16], lo[16];
                 {
-                    int32_t v0[32], v1[32], v2[32], v3[32];
-                    tmem_ld32(tcol + 0 * BN, v0);
-                    tmem_ld32(tcol + 1 * BN, v1);
-                    tmem_ld32(tcol + 2 * BN, v2);
-                    tmem_ld32(tcol + 3 * BN, v3);
+                    int32_t v0[16], v1[16], v2[16], v3[16];
+                    tmem_ld16(tcol + 0 * BN, v0);
+                    tmem_ld16(tcol + 1 * BN, v1);
+                    tmem_ld16(tcol + 2 * BN, v2);
+                    tmem_ld16(tcol + 3 * BN, v3);
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-                    for (int c = 0; c < 32; ++c)
+                    for (int c = 0; c < 16; ++c)
                         hi[c] = ((long long)v0[c] << 21) + ((long long)v1[c] << 14) + ((long long)v2[c] << 7) + (long long)v3[c];
                 }
                 {
-                    int32_t v4[32], v5[32], v6[32];
-                    tmem_ld32(tcol + 4 * BN, v4);
-                    tmem_ld32(tcol + 5 * BN, v5);
-                    if (NS == 7) tmem_ld32(tcol + 6 * BN, v6);
+                    int32_t v4[16], v5[16], v6[16];
+                    tmem_ld16(tcol + 4 * BN, v4);
+                    tmem_ld16(tcol + 5 * BN, v5);
+                    if (NS == 7) tmem_ld16(tcol + 6 * BN, v6);
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-                    for (int c = 0; c < 32; ++c)
+                    for (int c = 0; c < 16; ++c)
                         lo[c] = (NS == 7) ? ((long long)v4[c] << 14) + ((long long)v5[c] << 7) + (long long)v6[c]
                                           : ((long long)v4[c] << 7) + (long long)v5[c];
                 }
-                if (half == 1) {                             // all TMEM reads of this tile are done
+                if (sub == 1) {                              // all TMEM reads of this warp's half are done
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                     __syncwarp();
                     if (lane == 0) mbar_arrive(tmem_empty);
                 }
                 if (row < a.M) {
-                    const int64_t nb = n0 + half * 32;
-                    double *cp = crow + half * 32;
+                    const int64_t nb = n0 + half * 32 + sub * 16;
+                    double *cp = crow + sub * 16;
+                    const double *sbp = sBt + half * 32 + sub * 16;
 #pragma unroll
-                    for (int c = 0; c < 32; c += 2) {
+                    for (int c = 0; c < 16; c += 2) {
                         double o0 = fma(double(lo[c]), w_lo, double(hi[c])) * sa;
                         double o1 = fma(double(lo[c + 1]), w_lo, double(hi[c + 1])) * sa;
                         if (nb + c + 1 < a.N) {
-                            o0 *= sBt[half * 32 + c]; o1 *= sBt[half * 32 + c + 1];
+                            o0 *= sbp[c]; o1 *= sbp[c + 1];
                             double2 *dst = reinterpret_cast<double2 *>(cp + c);
                             if (a.accumulate) { double2 old = *dst; o0 += old.x; o1 += old.y; }
                             *dst = make_double2(o0, o1);
                         } else if (nb + c < a.N) {
-                            o0 *= sBt[half * 32 + c];
+                            o0 *= sbp[c];
                             if (a.accumulate) o0 += cp[c];
                             cp[c] = o0;
                         }
