@@ -29,7 +29,8 @@ def main():
     keep = dlog.set_handler('*', Keep)
     worst = 0.0
     for (D, H, Hp, g, N, T, ncut) in [(25, 10, 6, 3, 1001, 1.0, 0.0), (25, 10, 6, 3, 1001, 2.0, 0.7),
-                                      (100, 50, 8, 4, 3000, 1.2, 1.0), (676, 1000, 12, 5, 333, 1.0, 1.0)]:
+                                      (100, 50, 8, 4, 3000, 1.2, 1.0), (676, 1000, 12, 5, 333, 1.0, 1.0),
+                                      (60, 40, 12, 5, 24000, 1.3, 1.0)]:      # 12 000 datapoints per rank at 2 ranks: tensor-core state kernel
         bars = D == 25
         y, params, _ = bsc_problem(D, H, N, 3, bars=bars, pi=(0.2 if bars else None), sigma=(2.0 if bars else 1.0))
         f, l = parallel.stride_data(N, comm=comm)
@@ -47,6 +48,10 @@ def main():
                 errs = [rel_err(p['W'], po['W']), abs(p['pi'] - po['pi']) / po['pi'], abs(p['sigma'] - po['sigma']) / po['sigma'],
                         abs(keep.last('L') - o.log['L']) / abs(o.log['L'])]
                 assert keep.last('N_use') == o.log['N_use'], (keep.last('N_use'), o.log['N_use'])
+                # N < H: rank-deficient Wq, minimum-norm update (see tests/test_bsc_gpu.py): W to 1e-6, the rest to 1e-8
+                if N < H:
+                    assert errs[0] < 1e-6, errs
+                    errs = errs[1:]
                 worst = max(worst, max(errs))
                 print("BSC D=%d H=%d N=%d ranks=%d it=%d: max rel err %.2e N_use %d" % (D, H, N, comm.size, it, max(errs), o.log['N_use']), flush=True)
     # every rank ends with identical parameters

@@ -172,3 +172,30 @@ def test_ozaki_gemm_is_deterministic_and_exact_on_integers(lib, dev):
         outs.append(Cm[:, :N].clone())
     assert torch.equal(outs[0], outs[1])
     assert torch.equal(outs[0], A @ B.T)
+
+
+def test_ozaki_gemm_heavy_tailed_rows(lib, dev):
+    """Rows whose entries span six decades (one dominant entry per row): the slices are cut relative to the LARGEST
+    entry of a row, so the error is bounded by K 2^-45 rowmax(A) rowmax(B) -- relative to |C| that is only small when
+    the dominant entries contribute to C, which is what this test pins down from both sides: the absolute bound always
+    holds, and the error relative to |C| degrades by exactly the dynamic range when the dominant entry is multiplied by
+    zero.  (The EM path slices datapoints and dictionary columns, whose entries share one scale)"""
+    M, N, K = 512, 256, 676
+    g = torch.Generator(device=dev); g.manual_seed(9)
+    A = torch.randn(M, K, dtype=torch.float64, device=dev, generator=g)
+    B = torch.randn(N, K, dtype=torch.float64, device=dev, generator=g)
+    A[:, 0] *= 1e6                                              # the dominant column
+    Cm = torch.zeros((M, N), dtype=torch.float64, device=dev)
+    assert lib.pet_ozaki_gemm_kk(M, N, K, P(A), K, P(B), K, P(Cm), N, 7, 1, stream()) == 0
+    ref = A @ B.T
+    bound = K * A.abs().amax(1, keepdim=True) * B.abs().amax(1)[None, :]
+    assert float(((Cm - ref).abs() / bound).max()) < OZ_TOL[7]                     # the model's bound
+    assert float(((Cm - ref).abs() / ref.abs().clamp_min(1e-300)).median()) < 1e-12   # |C| is dominated by the big entries
+    # the same rows against a B whose dominant-direction entries are zero: |C| ~ 1e-6 rowmax, the ABSOLUTE error stays
+    B0 = B.clone(); B0[:, 0] = 0.0
+    assert lib.pet_ozaki_gemm_kk(M, N, K, P(A), K, P(B0), K, P(Cm), N, 7, 1, stream()) == 0
+    ref0 = A @ B0.T
+    err0 = (Cm - ref0).abs()
+    assert float((err0 / bound).max()) < OZ_TOL[7]
+    rel0 = float((err0 / ref0.abs().clamp_min(1e-300)).median())
+    assert 1e-12 < rel0 < 1e-6, rel0                            # ~2^-45 x 1e6: the documented loss, not more

@@ -22,11 +22,10 @@ def test_example_reaches_the_engine_and_fails_loudly_without_a_gpu(tmp_path):
 
 
 @pytest.mark.gpu
-@pytest.mark.skipif(not os.environ.get("PET_RUN_EXAMPLES"),
-                    reason="end-to-end example: written after the round's GPU budget was spent, not yet run on hardware "
-                           "(set PET_RUN_EXAMPLES=1)")
 @pytest.mark.parametrize("kind", ["bsc", "mca", "dsc"])
 def test_example_recovers_the_bars(tmp_path, kind):
+    """examples/bars_learning.py end to end on the device (flow of examples/barstests/bars-learning.py:23-88): run on a
+    B200 in round 2, 15 s for the three models."""
     out = subprocess.run([sys.executable, SCRIPT, kind, "1000"], cwd=str(tmp_path), capture_output=True, text=True, timeout=900)
     assert out.returncode == 0, out.stderr[-3000:]
     mae = float(re.search(r"generating bars: ([0-9.]+)", out.stdout).group(1))
