@@ -75,9 +75,12 @@ __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, u
 }
 // K-major SWIZZLE_64B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address >> 4,
 // LBO = 1, SBO = 8 rows * 64 B = 512 B, version 1 (Blackwell), layout type 4 (SWIZZLE_64B)
+template <int KBLK>
 __device__ __forceinline__ uint64_t make_desc(const void *smem_ptr) {
+    // rows of KBLK bytes: SWIZZLE_64B (layout type 4, SBO = 8 x 64 B) or SWIZZLE_32B (layout type 6, SBO = 8 x 32 B)
     uint64_t addr = smem_u32(smem_ptr);
-    return ((addr & 0x3FFFFull) >> 4) | (1ull << 16) | (uint64_t(512 >> 4) << 32) | (1ull << 46) | (4ull << 61);
+    return ((addr & 0x3FFFFull) >> 4) | (1ull << 16) | (uint64_t((8 * KBLK) >> 4) << 32) | (1ull << 46) |
+           ((KBLK == 64 ? 4ull : 6ull) << 61);
 }
 // instruction descriptor (cute::UMMA::InstrDescriptor) for kind::i8: D = S32 (2 << 4), A = B = signed int8 (1 << 7,
 // 1 << 10), both K-major, N >> 3 at bit 17, M >> 4 at bit 24: make_idesc_n below
@@ -128,9 +131,12 @@ __device__ __forceinline__ uint32_t make_idesc_n(int n) {
     return (2u << 4) | (1u << 7) | (1u << 10) | (uint32_t(n >> 3) << 17) | (uint32_t(BM >> 4) << 24);
 }
 
-template <int NS, int STAGES>
+// KBLK: bytes of K per pipeline stage (Args.kblocks / kb_per_split count blocks of KBLK).  64: two stages of 86 KB
+// (the default); 32: five stages of 43 KB -- the same bytes in flight in finer grains (measured slower, see ozaki_gemm)
+template <int NS, int STAGES, int KBLK>
 __global__ void __launch_bounds__(THREADS, 1) gemm_kernel(const __grid_constant__ CUtensorMap mapA,
                                                           const __grid_constant__ CUtensorMap mapB, const Args a) {
+    constexpr int KB = KBLK;
     constexpr int A_SLICE = BM * KB, B_SLICE = BN * KB;                 // bytes per slice tile
     constexpr int STAGE_BYTES = NS * (A_SLICE + B_SLICE);
     extern __shared__ uint8_t smem_raw[];
@@ -202,13 +208,13 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_kernel(const __grid_constant_
                     for (int kk = 0; kk < KB / UMMA_K; ++kk) {
 #pragma unroll
                         for (int i = 0; i < NS; ++i) {
-                            const uint64_t da = make_desc(sa + i * A_SLICE + kk * UMMA_K);
+                            const uint64_t da = make_desc<KBLK>(sa + i * A_SLICE + kk * UMMA_K);
                             const uint32_t acc = (i != 0 || kb != kb0 || kk != 0) ? 1u : 0u;
                             constexpr int MAXJ = 256 / BN;                       // B slices per MMA (N <= 256)
 #pragma unroll
                             for (int j0 = 0; j0 < NS - i; j0 += MAXJ) {
                                 const int cnt = (NS - i - j0 < MAXJ) ? NS - i - j0 : MAXJ;
-                                const uint64_t db = make_desc(sb + j0 * B_SLICE + kk * UMMA_K);
+                                const uint64_t db = make_desc<KBLK>(sb + j0 * B_SLICE + kk * UMMA_K);
                                 mma_i8(tmem_base + (i + j0) * BN, da, db, make_idesc_n(cnt * BN), acc);
                             }
                         }
@@ -349,7 +355,7 @@ static EncodeTiledFn get_encode() {
 
 // slices: ns planes of (rows, Kp) int8, rows `row_stride` bytes apart, planes `slice_stride` bytes apart
 static int make_map(CUtensorMap *map, const int8_t *slices, int64_t rows, int Kp, int64_t row_stride, int64_t slice_stride,
-                    int ns, int box_rows) {
+                    int ns, int box_rows, int kblk) {
     EncodeTiledFn enc = get_encode();
     if (!enc) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return PET_ECUDA; }
     if ((row_stride & 15) || (slice_stride & 15) || (reinterpret_cast<uintptr_t>(slices) & 15)) {
@@ -358,10 +364,11 @@ static int make_map(CUtensorMap *map, const int8_t *slices, int64_t rows, int Kp
     }
     cuuint64_t dims[3] = {(cuuint64_t)Kp, (cuuint64_t)rows, (cuuint64_t)ns};
     cuuint64_t strides[2] = {(cuuint64_t)row_stride, (cuuint64_t)slice_stride};
-    cuuint32_t box[3] = {(cuuint32_t)KB, (cuuint32_t)box_rows, 1};
+    cuuint32_t box[3] = {(cuuint32_t)kblk, (cuuint32_t)box_rows, 1};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<int8_t *>(slices), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, kblk == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", int(r)); return PET_ECUDA; }
     return PET_OK;
@@ -529,25 +536,28 @@ int ozaki_gemm(int64_t M, int64_t N, int Kp, int ns, const OzOperand &A, const O
         set_error("ozaki_gemm: %d K elements per split overflow the int32 accumulators", kbs * oz::KB);
         return PET_EINVAL;
     }
+    // stage granularity: 64-byte K blocks, two stages of 86 KB (default), or 32-byte blocks, five stages of 43 KB
+    // (PET_OZ_KB=32).  Measured at the north-star shape (round 2): 14.1 / 13.9 ms (score / statistics GEMM) against
+    // 16.7 / 16.9 ms -- finer grains cost more TMA requests and barrier round trips than the deeper pipeline hides.
+    static const int kblk = []() { const char *e = getenv("PET_OZ_KB"); return (e && atoi(e) == 32) ? 32 : 64; }();
     CUtensorMap mapA, mapB;
-    PET_CHECK(oz::make_map(&mapA, A.slices, M, Kp, A.row_stride, A.slice_stride, ns, oz::BM));
-    PET_CHECK(oz::make_map(&mapB, B.slices, N, Kp, B.row_stride, B.slice_stride, ns, oz::BN));
-    oz::Args a{M, N, kblocks, splits, kbs, accumulate ? 1 : 0, A.scale, B.scale, C, ldc, split_stride};
+    PET_CHECK(oz::make_map(&mapA, A.slices, M, Kp, A.row_stride, A.slice_stride, ns, oz::BM, kblk));
+    PET_CHECK(oz::make_map(&mapB, B.slices, N, Kp, B.row_stride, B.slice_stride, ns, oz::BN, kblk));
+    const int per = oz::KB / kblk;                               // pipeline blocks per 64-byte K block
+    oz::Args a{M, N, kblocks * per, splits, kbs * per, accumulate ? 1 : 0, A.scale, B.scale, C, ldc, split_stride};
     const int64_t units = ceil_div(M, oz::BM) * ceil_div(N, oz::BN) * splits;
     const unsigned grid = (unsigned)std::min<int64_t>(units, sm_count);
-    if (ns == 7) {
-        constexpr int ST = 2;
-        const size_t smem = size_t(ST) * 7 * (oz::BM + oz::BN) * oz::KB + 1024 + 256 + 2 * oz::BN * 8;
-        static bool cfg = false;
-        if (!cfg) { PET_CUDA(cudaFuncSetAttribute(oz::gemm_kernel<7, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem))); cfg = true; }
-        oz::gemm_kernel<7, ST><<<grid, oz::THREADS, smem, st>>>(mapA, mapB, a);
-    } else if (ns == 6) {
-        constexpr int ST = 3;
-        const size_t smem = size_t(ST) * 6 * (oz::BM + oz::BN) * oz::KB + 1024 + 256 + 2 * oz::BN * 8;
-        static bool cfg = false;
-        if (!cfg) { PET_CUDA(cudaFuncSetAttribute(oz::gemm_kernel<6, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem))); cfg = true; }
-        oz::gemm_kernel<6, ST><<<grid, oz::THREADS, smem, st>>>(mapA, mapB, a);
-    } else {
+    auto launch = [&](auto kern, int stages) -> int {
+        const size_t smem = size_t(stages) * ns * (oz::BM + oz::BN) * kblk + 1024 + 256 + 2 * oz::BN * 8;
+        PET_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        kern<<<grid, oz::THREADS, smem, st>>>(mapA, mapB, a);
+        return PET_OK;
+    };
+    if (ns == 7 && kblk == 32) PET_CHECK(launch(oz::gemm_kernel<7, 5, 32>, 5));
+    else if (ns == 7) PET_CHECK(launch(oz::gemm_kernel<7, 2, 64>, 2));
+    else if (ns == 6 && kblk == 32) PET_CHECK(launch(oz::gemm_kernel<6, 6, 32>, 6));
+    else if (ns == 6) PET_CHECK(launch(oz::gemm_kernel<6, 3, 64>, 3));
+    else {
         set_error("ozaki_gemm: ns must be 6 or 7");
         return PET_EINVAL;
     }
