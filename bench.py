@@ -303,13 +303,14 @@ def synth_shard(model, n_local, first, dev):
 
 
 def ncu_traffic():
-    """DRAM bytes per launch of the sliced GEMM kernel from the committed ncu --set full capture (mean of the
-    score and the statistics shape, the two launches the roofline line averages over); None if not recorded."""
+    """DRAM bytes per launch of the sliced GEMM kernel (mean of the score and the statistics shape, the two launches
+    the roofline line averages over) and of the whole EM iteration, from the committed ncu launch list of one step
+    (profiles/r02_launches_step_n1.csv: dram__bytes_read.sum + dram__bytes_write.sum per launch); None if not recorded."""
     try:
-        t = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")))
-        return 0.5 * (t["oz_gemm_score_bytes"] + t["oz_gemm_stats_bytes"])
+        t = json.load(open(os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")))
+        return t["oz_gemm_bytes_per_launch"], t["step_dram_bytes"]
     except Exception:
-        return None
+        return None, None
 
 
 def measure_fp64_peak(dev):
@@ -494,10 +495,11 @@ def run_gpu(args):
                         "pipe_achieved_tops": achieved * pairs, "pipe_peak_tops": int8_peak,
                         "pipe_nominal_tops": 4500.0, "frac_of_nominal": achieved * pairs / 4500.0,
                         "ncu_tensor_pipe_active": {"score_shape": 0.66, "statistics_shape": 0.73,
-                                                   "source": "profiles/r01i_ncu_oz_gemm_kernel.txt"},
+                                                   "source": "profiles/r01i_ncu_oz_gemm_kernel.txt (main loop unchanged in round 2)"},
                         "peak_source": int8_src + ", divided by the %d slice products; cuBLAS DGEMM measured in this run: %.1f TFLOP/s"
                                        % (pairs, peak),
-                        "traffic": ncu_traffic()}
+                        "traffic": ncu_traffic()[0], "step_traffic_bytes": ncu_traffic()[1],
+                        "step_algorithmic_bytes": 2.0 * 8 * D * N_TOTAL / world}
             else:
                 roof = {"kernel": "dgemm_kernel (FP64 DMMA, score + statistics GEMM)", "bound": "tensor",
                         "pipe": "fp64 mma.sync m8n8k4", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
