@@ -629,6 +629,8 @@ __global__ void __launch_bounds__(ROWF_WARPS * 32, 2) gl_row_threshold_kernel(co
         const int64_t n = a.row0 + r;
         const double *yw = a.YW + r * st.ldH;
         const double *ywl = yw + lane;
+        // straight-line code over the 32 items of the lane: out-of-range items (h >= H) are masked by selects, never by
+        // branches, so that the 32 dependency chains interleave
         double v[HC];
 #pragma unroll
         for (int k = 0; k < HC; ++k) v[k] = (k < nk) ? ywl[k * 32] : 0.0;
@@ -639,10 +641,14 @@ __global__ void __launch_bounds__(ROWF_WARPS * 32, 2) gl_row_threshold_kernel(co
             int bidx = lane;
 #pragma unroll
             for (int k = 0; k < HC; ++k) {
-                unsigned kk = 0u;
-                if (k < nk) kk = key32(row_score<MODE, WMU>(v[k], WMU ? sc0p[k * 32] : 0.0, (MODE == SEL_GIVEN) ? 0.0 : sc1p[k * 32]));
+                const double s0 = (WMU && k < nk) ? sc0p[k * 32] : 0.0;
+                const double s1 = (MODE != SEL_GIVEN && k < nk) ? sc1p[k * 32] : 0.0;
+                unsigned kk = key32(row_score<MODE, WMU>(v[k], s0, s1));
+                kk = (k < nk) ? kk : 0u;
                 key[k] = kk;
-                if (kk >= bk) { bk = kk; bidx = k * 32 + lane; }
+                const bool better = kk >= bk;
+                bk = better ? kk : bk;
+                bidx = better ? k * 32 + lane : bidx;
             }
             // ---- tau = the H'-th best lane maximum ----
             unsigned tk = 0u;
@@ -705,7 +711,9 @@ __global__ void __launch_bounds__(ROWF_WARPS * 32, 2) gl_row_threshold_kernel(co
         double tmax = -INFINITY;
 #pragma unroll
         for (int k = 0; k < HC; ++k) {
-            v[k] = (k < nk) ? fma(m2A, v[k], A * wn2p[k * 32]) : -INFINITY;    // t_h = F_h - (B + A yy)
+            const double w2 = (k < nk) ? wn2p[k * 32] : 0.0;
+            const double th = fma(m2A, v[k], A * w2);                          // t_h = F_h - (B + A yy)
+            v[k] = (k < nk) ? th : -1.0e300;
             tmax = fmax(tmax, v[k]);
         }
         tmax = warp_max(tmax);
@@ -714,12 +722,15 @@ __global__ void __launch_bounds__(ROWF_WARPS * 32, 2) gl_row_threshold_kernel(co
         const double d = Ryy - m1;
         double Zs = 0.0, S1 = 0.0;
 #pragma unroll
-        for (int k = 0; k < HC; ++k) {
-            if (k < nk) {
-                const double p = exp_tab32(fmax(v[k] + d, GL_EXP_CUTOFF), exptab);
+        for (int g = 0; g < HC / 8; ++g) {                                      // eight interleaved chains at a time
+#pragma unroll
+            for (int k = 8 * g; k < 8 * g + 8; ++k) {
+                double p = exp_tab32(fmax(v[k] + d, GL_EXP_CUTOFF), exptab);
+                p = (k < nk) ? p : 0.0;                                         // (masked items: t = -1e300 -> cutoff -> 0)
                 Zs += p;
-                S1 = fma(p, v[k], S1);
+                S1 = fma(p, (k < nk) ? v[k] : 0.0, S1);
             }
+            asm volatile("" ::: "memory");                                      // keep the groups apart: register pressure
         }
         Zs = warp_sum(Zs);
         S1 = warp_sum(S1);

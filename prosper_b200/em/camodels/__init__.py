@@ -195,7 +195,10 @@ class Engine(object):
         if add_colsum_diag:
             Wq += torch.diag(A[D])
         lam, V = torch.linalg.eigh(0.5 * (Wq + Wq.T))
-        keep = lam.abs() > rcond * lam.abs().max()
+        # an exactly singular direction comes back from eigh as an eigenvalue of a few eps * lambda_max whose size depends
+        # on the summation order of the statistics (atomics): cut at 32 eps so that the null space is recognised on every
+        # run (LAPACK's gelsd sees an exact zero there; values between eps and 32 eps of lambda_max are rounding noise)
+        keep = lam.abs() > max(rcond, 32 * 2.220446049250313e-16) * lam.abs().max()
         Vk = V[:, keep]
         return (A[:D] @ Vk) / lam[keep] @ Vk.T
 
