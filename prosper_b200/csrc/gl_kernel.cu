@@ -1188,13 +1188,15 @@ __global__ void __launch_bounds__(256) gl_post_slice_kernel(const __grid_constan
         rowc[threadIdx.x * 2 + 0] = rt; rowc[threadIdx.x * 2 + 1] = sc;
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < PS_R * Hp; i += 256) {                   // candidates are distinct: plain stores
-        const int rl = i / Hp, j = i - rl * Hp;
+    {                                                                      // candidates are distinct: plain stores
+        const int rl = threadIdx.x >> 1;                                   // two threads per datapoint, alternate candidates
         const int64_t rr = r0 + rl;
         if (rr < a.n_rows) {
             const int64_t n = a.row0 + rr;
-            const int h = a.cand[n * Hp + j] - c0;
-            if (h >= 0 && h < PS_C) add[rl * (PS_C + 1) + h] = a.scl[n * (1 + PET_MAXHP) + 1 + j];
+            for (int j = threadIdx.x & 1; j < Hp; j += 2) {
+                const int h = a.cand[n * Hp + j] - c0;
+                if (h >= 0 && h < PS_C) add[rl * (PS_C + 1) + h] = a.scl[n * (1 + PET_MAXHP) + 1 + j];
+            }
         }
     }
     __syncthreads();

@@ -48,6 +48,7 @@ constexpr int NPART = 4;                // warps per TMEM lane quadrant: each ow
 constexpr int THREADS = 128 * NPART;
 constexpr int CSTR = 13;                // stride of the candidate rows in shared memory (conflict-free)
 constexpr double EXP_CUTOFF = -100.0;   // as gl_kernel.cu
+constexpr double SKIP_CUTOFF = -45.0;   // a batch whose posteriors all lie below e^-45 of the largest one is skipped
 constexpr int XB = 7 * NDF - 1;         // the features are scaled to integers below 2^XB and offset by 2^XB
 constexpr int OFFB = XB - 28;           // ... which is 2^OFFB in units of the upper half (accumulators 2, 3: weight 2^28)
 
@@ -268,16 +269,20 @@ __global__ void __launch_bounds__(THREADS, 1) gl_state_tc_kernel(const __grid_co
         double v[32];
         double vmax = 0.0;
         {
+            // straight-line gathers (a branch per feature would serialise 32 L2 round trips): out-of-range features and
+            // rows read a safe address and are zeroed by a select
             const uint8_t *fj = sm.feat(), *fk = sm.feat() + KF;
+            const int64_t nn = valid ? n : a.row0;
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
                 const int f = kc0 * 16 + i;
-                double x = 0.0;
-                if (valid && f < nf && i < nkc * 16) {
-                    const int cj = cand_s[fj[f]], ck = cand_s[fk[f]];
-                    const double g = a.G[int64_t(cj) * st.ldH + ck];
-                    x = (f < Hp) ? fma(cq, fma(-2.0, a.ywc[n * Hp + f], g), lpm) : 2.0 * cq * g;
-                }
+                const bool on = valid && f < nf && i < nkc * 16;
+                const int fs = on ? f : 0;
+                const int cj = cand_s[fj[fs]], ck = cand_s[fk[fs]];
+                const double g = a.G[int64_t(cj) * st.ldH + ck];
+                const double yw = a.ywc[nn * Hp + (fs < Hp ? fs : 0)];
+                double x = (fs < Hp) ? fma(cq, fma(-2.0, yw, g), lpm) : 2.0 * cq * g;
+                x = on ? x : 0.0;
                 v[i] = x;
                 vmax = fmax(vmax, fabs(x));
             }
@@ -398,6 +403,7 @@ __global__ void __launch_bounds__(THREADS, 1) gl_state_tc_kernel(const __grid_co
             const uint32_t off = uint32_t(t.chunk_nfeat[c]) << OFFB;
             const int cnt = t.chunk_cnt[c];
             uint32_t ylo[16], yhi[16];
+            bool live = false;                                // warp-uniform: some posterior of the 16 states is not negligible
 #pragma unroll
             for (int sb = 0; sb < 2; ++sb) {
                 const int col0 = part * 16 + sb * 8;
@@ -407,32 +413,51 @@ __global__ void __launch_bounds__(THREADS, 1) gl_state_tc_kernel(const __grid_co
                 tmem_ld8(tlane + 2 * NC + col0, a2);
                 tmem_ld8(tlane + 3 * NC + col0, a3);
                 tmem_wait_ld();
+                double x8[8];
+                double xm = -INFINITY;
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const int hi = int(a3[i] * 16384u + a2[i] - off);
                     const uint32_t lo = a1[i] * 16384u + a0[i];
                     const double f = fma(double(hi), 268435456.0, double(lo));
-                    const double x = fma(f, scale, bias);
-                    double p = exp_tab32(fmax(x, -700.0), exptab);
-                    p = (x > EXP_CUTOFF && col0 + i < cnt) ? p : 0.0;
-                    Z2 += p;
-                    SF = fma(p, x, SF);
-                    if (STATS) {
-                        const double T = fma(p, 4398046511104.0, 4503599627370496.0);    // p 2^42 + 2^52: mantissa = rint(p 2^42)
-                        ylo[sb * 8 + i] = uint32_t(__double2loint(T));
-                        yhi[sb * 8 + i] = uint32_t(__double2hiint(T)) & 0xFFFFFu;
+                    x8[i] = (col0 + i < cnt) ? fma(f, scale, bias) : -INFINITY;      // padding columns of a partial chunk
+                    xm = fmax(xm, x8[i]);
+                }
+                // one warp-uniform decision per batch of 8 states x 32 datapoints: either nobody is within e^-45 of its
+                // largest posterior (2.9e-20: below the last bit of the partition sum even when all 1573 states add up),
+                // or the eight exps run as straight-line code so that their dependency chains interleave
+                if (__any_sync(0xffffffffu, xm > SKIP_CUTOFF)) {
+                    live = true;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const double p = exp_tab32(fmax(x8[i], EXP_CUTOFF), exptab);     // (x = -inf: e^-100 = 4e-44, harmless)
+                        Z2 += p;
+                        SF = fma(p, fmax(x8[i], EXP_CUTOFF), SF);
+                        if (STATS) {
+                            const double T = fma(p, 4398046511104.0, 4503599627370496.0);    // p 2^42 + 2^52: mantissa = rint(p 2^42)
+                            ylo[sb * 8 + i] = uint32_t(__double2loint(T));
+                            yhi[sb * 8 + i] = uint32_t(__double2hiint(T)) & 0xFFFFFu;
+                        }
                     }
+                } else if (STATS) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) { ylo[sb * 8 + i] = 0u; yhi[sb * 8 + i] = 0u; }
                 }
             }
             if (STATS) {
                 uint8_t *dst = sm.a_rev() + part * (TM * 16) + r * 16;
                 constexpr int PL = (NC / 16) * TM * 16;
-                *reinterpret_cast<uint4 *>(dst + 0 * PL) = pack_digit16<0, false>(ylo, yhi);
-                *reinterpret_cast<uint4 *>(dst + 1 * PL) = pack_digit16<1, false>(ylo, yhi);
-                *reinterpret_cast<uint4 *>(dst + 2 * PL) = pack_digit16<2, false>(ylo, yhi);
-                *reinterpret_cast<uint4 *>(dst + 3 * PL) = pack_digit16<3, false>(ylo, yhi);
-                *reinterpret_cast<uint4 *>(dst + 4 * PL) = pack_digit16<4, false>(ylo, yhi);
-                *reinterpret_cast<uint4 *>(dst + 5 * PL) = pack_digit16<5, true>(ylo, yhi);
+                if (live) {
+                    *reinterpret_cast<uint4 *>(dst + 0 * PL) = pack_digit16<0, false>(ylo, yhi);
+                    *reinterpret_cast<uint4 *>(dst + 1 * PL) = pack_digit16<1, false>(ylo, yhi);
+                    *reinterpret_cast<uint4 *>(dst + 2 * PL) = pack_digit16<2, false>(ylo, yhi);
+                    *reinterpret_cast<uint4 *>(dst + 3 * PL) = pack_digit16<3, false>(ylo, yhi);
+                    *reinterpret_cast<uint4 *>(dst + 4 * PL) = pack_digit16<4, false>(ylo, yhi);
+                    *reinterpret_cast<uint4 *>(dst + 5 * PL) = pack_digit16<5, true>(ylo, yhi);
+                } else {
+#pragma unroll
+                    for (int pl = 0; pl < NDP; ++pl) *reinterpret_cast<uint4 *>(dst + pl * PL) = make_uint4(0u, 0u, 0u, 0u);
+                }
                 fence_async_smem();
             }
             tc_fence_before();
