@@ -404,7 +404,7 @@ def run_gpu(args):
     ms = e0.elapsed_time(e1)
     launches = eng.launch_count() - launches0
     stages = eng.stage_times()
-    gemm_slices = eng.gemm_path()
+    gemm_slices = eng.gemm_slices()
     eng.enable_timing(False)
     clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
@@ -459,7 +459,7 @@ def run_gpu(args):
     if rank == 0:
         peak = measure_fp64_peak(dev)
         per_step = dict((k, v['ms'] / args.steps) for k, v in stages.items())
-        ns = gemm_slices
+        ns_score, ns = gemm_slices
         # kernels by total time: both GEMM stages run the same kernel template
         kernel_ms = {'gemm': per_step['score_gemm'] + per_step['stats_gemm'], 'state_kernel': per_step['state_kernel'],
                      'row_kernel': per_step['row_kernel']}
@@ -479,7 +479,8 @@ def run_gpu(args):
             # algorithmic work: 2*D*H flop per datapoint per GEMM, whatever pipe executes it
             achieved = 2.0 * D * H * rows_per_launch / (avg_launch_ms / 1e3) / 1e12
             if ns > 0:
-                pairs = ns * (ns + 1) // 2
+                # slice products per FP64 product, averaged over the two GEMMs of an iteration (equal algorithmic work)
+                pairs = (ns_score * (ns_score + 1) // 2 + ns * (ns + 1) // 2) / 2.0
                 # int8 tensor-pipe peak MEASURED on this pool's B200 (tools/ubench/umma_probe.cu, profiles/r02_int8_peak.json):
                 # the sustained figure, because the GEMMs run inside a long step
                 int8_peak, int8_src = 2.0 * bf16, "2 x %s bf16_tflops_sustained (no measured int8 peak found)" % peak_src
@@ -489,14 +490,15 @@ def run_gpu(args):
                     int8_src = "profiles/r02_int8_peak.json int8_tops_sustained (measured: tcgen05 kind::i8 M128 N256 K32 back to back on all SMs)"
                 except Exception:
                     pass
-                roof = {"kernel": "oz::gemm_kernel<%d> (score + statistics GEMM)" % ns, "bound": "tensor",
-                        "pipe": "tcgen05.mma kind::i8 + TMEM: %d int8 slice products per FP64 product" % pairs,
+                roof = {"kernel": "oz::gemm_kernel<%d> (score GEMM) + oz::gemm_kernel<%d> (statistics GEMM)" % (ns_score, ns), "bound": "tensor",
+                        "pipe": "tcgen05.mma kind::i8 + TMEM: %d (score, %d slices) and %d (statistics, %d slices) int8 slice "
+                                "products per FP64 product" % (ns_score * (ns_score + 1) // 2, ns_score, ns * (ns + 1) // 2, ns),
                         "achieved": achieved, "peak": int8_peak / pairs, "unit": "TFLOP/s", "frac": achieved * pairs / int8_peak,
                         "pipe_achieved_tops": achieved * pairs, "pipe_peak_tops": int8_peak,
                         "pipe_nominal_tops": 4500.0, "frac_of_nominal": achieved * pairs / 4500.0,
                         "ncu_tensor_pipe_active": {"score_shape": 0.66, "statistics_shape": 0.73,
                                                    "source": "profiles/r01i_ncu_oz_gemm_kernel.txt (main loop unchanged in round 2)"},
-                        "peak_source": int8_src + ", divided by the %d slice products; cuBLAS DGEMM measured in this run: %.1f TFLOP/s"
+                        "peak_source": int8_src + ", divided by the %.1f slice products (mean of the two GEMMs); cuBLAS DGEMM measured in this run: %.1f TFLOP/s"
                                        % (pairs, peak),
                         "traffic": ncu_traffic()[0], "step_traffic_bytes": ncu_traffic()[1],
                         "step_algorithmic_bytes": 2.0 * 8 * D * N_TOTAL / world}

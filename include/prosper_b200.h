@@ -325,8 +325,12 @@ int64_t pet_spd_solve_work_doubles(int64_t n, int64_t lda);   /* size of work_de
  * out[PET_N_STAGES..2*PET_N_STAGES-1] = how many spans each total sums.  Synchronises. */
 #define PET_N_STAGES 10
 /* which kernels run the score / statistics GEMMs for the bound shard: 0 = FP64 DMMA
- * (dgemm.cu), n > 0 = int8 tcgen05 with n slices per operand (ozaki.cu) */
+ * (dgemm.cu), n > 0 = int8 tcgen05 with n slices per operand of the statistics GEMM (ozaki.cu) */
 int32_t pet_gemm_path(const pet_engine *e);
+/* slices per operand of the score GEMM y.W (bsc_et.py:107, default 6: 42 bits) and of the statistics GEMM
+ * sum_n y <s>^T (bsc_et.py:366, default 7: 49 bits); 0, 0 on the FP64 DMMA path.  Environment: PET_OZAKI_SLICES=6|7
+ * (both), PET_OZAKI_SLICES_SCORE, PET_OZAKI_SLICES_STATS. */
+int32_t pet_gemm_slices(const pet_engine *e, int32_t *score, int32_t *stats);
 /* Which kernel evaluates the multi-cause states of the fused BSC path (bsc_et.py:180-185, 349-366): mode 0 = automatic
  * (tensor cores once the state space has >= 256 states and a chunk of the shard fills half a wave of 128-datapoint
  * tiles), 1 = the scalar FP64 kernel, 2 = the int8 tensor-core kernel (binary states, H' <= 12, gamma <= 5; PET_EINVAL

@@ -114,6 +114,7 @@ SIGNATURES = {
                                       C.c_void_p, C.POINTER(C.c_int32), C.c_void_p]),
     "pet_spd_solve_work_doubles": (C.c_int64, [C.c_int64, C.c_int64]),
     "pet_gemm_path": (C.c_int32, [C.c_void_p]),
+    "pet_gemm_slices": (C.c_int32, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "pet_set_state_kernel": (C.c_int, [C.c_void_p, C.c_int32]),
     "pet_state_kernel_path": (C.c_int32, [C.c_void_p]),
     "pet_stage_times_ms": (C.c_int, [C.c_void_p, c_double_p]),

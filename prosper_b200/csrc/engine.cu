@@ -150,7 +150,7 @@ struct pet_engine {
     GLTcHost tc_host; uint8_t *d_tc_fwd = nullptr, *d_tc_rev = nullptr; bool tc_ok = false; int tc_mode = 0;
 
     // int8-sliced operands of the two large GEMMs (ozaki.cu); oz_on = buffers present and the path selected
-    bool oz_want = false, oz_on = false; int oz_ns = 7, oz_kpd = 0, oz_splits = 1; int64_t oz_rows = 0;
+    bool oz_want = false, oz_on = false; int oz_ns = 7, oz_ns2 = 7, oz_kpd = 0, oz_splits = 1; int64_t oz_rows = 0;
     int8_t *ozY = nullptr, *ozYT = nullptr, *ozW = nullptr, *ozS = nullptr;
     double *ozYs = nullptr, *ozYTs = nullptr, *ozWs = nullptr, *ozSs = nullptr, *oz_slabs = nullptr;
     unsigned long long *oz_colmax = nullptr;
@@ -368,7 +368,16 @@ extern "C" int pet_create(const pet_config *cfg, pet_engine **out) {
         // score and statistics GEMMs on the int8 tensor cores (PET_OZAKI=0 keeps the FP64 DMMA kernels)
         const char *env = getenv("PET_OZAKI"), *envs = getenv("PET_OZAKI_SLICES");
         e->oz_want = !(env && atoi(env) == 0);
-        e->oz_ns = (envs && atoi(envs) == 6) ? 6 : 7;
+        // Slices per operand.  The score GEMM y.W feeds log-joints: 6 slices (42 bits below the row / column maxima, an
+        // absolute error ~1e-10 in F and so ~1e-10 relative in every posterior) leave the parity unchanged and cost 21
+        // slice products with a three-stage pipeline instead of 28 with two.  The statistics GEMM feeds the H x H solve,
+        // which amplifies its rounding by the condition number of sum <s s^T>, and its <s> operand is fixed point
+        // (scale 1): it keeps all 7 slices (49 bits).  PET_OZAKI_SLICES=6|7 sets both, _SCORE / _STATS one of them.
+        e->oz_ns = 6;
+        e->oz_ns2 = 7;
+        if (envs) e->oz_ns = e->oz_ns2 = (atoi(envs) == 6) ? 6 : 7;
+        if (const char *v = getenv("PET_OZAKI_SLICES_SCORE")) e->oz_ns = (atoi(v) == 6) ? 6 : 7;
+        if (const char *v = getenv("PET_OZAKI_SLICES_STATS")) e->oz_ns2 = (atoi(v) == 6) ? 6 : 7;
         if (e->oz_want) {
             e->oz_kpd = ozaki_kp(e->D);
             TRY(dev_alloc(&e->ozW, (int64_t)e->oz_ns * e->H * e->oz_kpd));
@@ -400,7 +409,13 @@ extern "C" int pet_state_matrix(const pet_engine *e, double *out_host) {
     memcpy(out_host, e->ss.matrix.data(), e->ss.matrix.size() * sizeof(double));
     return PET_OK;
 }
-extern "C" int32_t pet_gemm_path(const pet_engine *e) { return (e && e->oz_on) ? e->oz_ns : 0; }
+extern "C" int32_t pet_gemm_path(const pet_engine *e) { return (e && e->oz_on) ? e->oz_ns2 : 0; }
+extern "C" int32_t pet_gemm_slices(const pet_engine *e, int32_t *score, int32_t *stats) {
+    if (!e || !score || !stats) return PET_EINVAL;
+    *score = e->oz_on ? e->oz_ns : 0;
+    *stats = e->oz_on ? e->oz_ns2 : 0;
+    return PET_OK;
+}
 // the tensor-core state kernel pays off once the state space fills a few 64-state chunks
 // (a 128-datapoint tile is one CTA's sequential work: ~250 us at 1573 states) and the chunk fills at least half a wave of
 // tiles; below that the scalar kernel (8 datapoints per CTA pass) finishes sooner
@@ -478,7 +493,7 @@ static int size_chunks(pet_engine *e, int64_t n) {
     }
     if (e->oz_want) {
         e->oz_splits = ozaki_splits(e->D + 1, e->H, ozaki_kp(cr), e->sm_count, 512);      // <s> may arrive as unsigned digits
-        PET_CHECK(dev_alloc(&e->ozS, (int64_t)e->oz_ns * e->H * cr));
+        PET_CHECK(dev_alloc(&e->ozS, (int64_t)e->oz_ns2 * e->H * cr));
         PET_CHECK(dev_alloc(&e->oz_slabs, (int64_t)e->oz_splits * (e->D + 1) * e->ldH));
     }
     return PET_OK;
@@ -516,7 +531,7 @@ static int ensure_rows(pet_engine *e, int64_t n) {
         // row slices (score GEMM) and per-chunk transposed column slices (statistics GEMM) of the shard;
         // without room for them the FP64 kernels take over
         const int64_t nchunks = ceil_div(n, e->chunk_rows) + 4;      // + the short chunks of a ramped chunk table
-        const int64_t b1 = (int64_t)e->oz_ns * n * e->oz_kpd, b2 = (int64_t)e->oz_ns * nchunks * (e->D + 1) * e->chunk_rows;
+        const int64_t b1 = (int64_t)e->oz_ns * n * e->oz_kpd, b2 = (int64_t)e->oz_ns2 * nchunks * (e->D + 1) * e->chunk_rows;
         cudaMemGetInfo(&free_b, &total_b);
         if (b1 + b2 + (int64_t(1) << 30) < (int64_t)free_b &&
             dev_alloc(&e->ozY, b1) == PET_OK && dev_alloc(&e->ozYT, b2) == PET_OK &&
@@ -767,8 +782,8 @@ static int ensure_chunk_inputs(pet_engine *e, int64_t c, int64_t r0, int64_t row
             PET_CHECK(ozaki_slice_rows(e->Y + r0 * e->ldY, e->ldY, rows, e->D, e->oz_ns, e->ozY + r0 * e->oz_kpd,
                                        e->oz_rows * e->oz_kpd, e->ozYs + r0, st));
             const int64_t plane = (int64_t)(e->D + 1) * e->chunk_rows;
-            PET_CHECK(ozaki_slice_cols(e->Y + r0 * e->ldY, e->ldY, rows, e->D + 1, e->oz_ns, e->oz_colmax, false,
-                                       e->ozYT + c * e->oz_ns * plane, e->chunk_rows, plane, e->ozYTs + c * e->ldY, st));
+            PET_CHECK(ozaki_slice_cols(e->Y + r0 * e->ldY, e->ldY, rows, e->D + 1, e->oz_ns2, e->oz_colmax, false,
+                                       e->ozYT + c * e->oz_ns2 * plane, e->chunk_rows, plane, e->ozYTs + c * e->ldY, st));
         }
     }
     return PET_OK;
@@ -882,17 +897,17 @@ static int sweep_gl(pet_engine *e, const pet_anneal *a, const pet_params *p, int
                 e->timer.end(st);
                 e->timer.begin(ST_SLICE, st);
                 if (defer_s)
-                    PET_CHECK(launch_gl_post_slice(ga, e->oz_ns, ozaki_kp(rows), e->ozS, e->chunk_rows, (int64_t)e->H * e->chunk_rows,
+                    PET_CHECK(launch_gl_post_slice(ga, e->oz_ns2, ozaki_kp(rows), e->ozS, e->chunk_rows, (int64_t)e->H * e->chunk_rows,
                                                    e->ozSs, st));
                 else
-                    PET_CHECK(ozaki_slice_cols(e->Sbuf, e->ldH, rows, e->H, e->oz_ns, e->oz_colmax, false, e->ozS,
+                    PET_CHECK(ozaki_slice_cols(e->Sbuf, e->ldH, rows, e->H, e->oz_ns2, e->oz_colmax, false, e->ozS,
                                                e->chunk_rows, (int64_t)e->H * e->chunk_rows, e->ozSs, st,
                                                fold_scale ? e->scl + r0 * (1 + PET_MAXHP) : nullptr, 1 + PET_MAXHP));
                 e->timer.end(st);
                 e->timer.begin(ST_STATS, st);
-                const OzOperand oy{e->ozYT + c * e->oz_ns * plane, e->chunk_rows, plane, e->ozYTs + c * e->ldY};
+                const OzOperand oy{e->ozYT + c * e->oz_ns2 * plane, e->chunk_rows, plane, e->ozYTs + c * e->ldY};
                 const OzOperand os{e->ozS, e->chunk_rows, (int64_t)e->H * e->chunk_rows, e->ozSs};
-                PET_CHECK(ozaki_gemm(e->D + 1, e->H, ozaki_kp(rows), e->oz_ns, oy, os, e->oz_slabs, e->ldH, e->oz_splits, wp,
+                PET_CHECK(ozaki_gemm(e->D + 1, e->H, ozaki_kp(rows), e->oz_ns2, oy, os, e->oz_slabs, e->ldH, e->oz_splits, wp,
                                      true, e->sm_count, st, defer_s ? 64 * 127 : 4096));
             } else {
                 PET_CHECK(dgemm_mn(e->D + 1, e->H, rows, e->Y + r0 * e->ldY, e->ldY, e->Sbuf, e->ldH,

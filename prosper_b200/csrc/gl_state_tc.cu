@@ -65,8 +65,8 @@ constexpr int OFF_DBL = OFF_CAND + TM * CSTR * 4;           // double arrays, se
 constexpr int N_DBL = (NPART + 2 + 2 * NPART + 3) * TM + 32; // rowmax[NPART], scale, bias, part[2][NPART], fin[3], exp table
 constexpr int OFF_INT = OFF_DBL + N_DBL * 8;                // int imax[NPART][TM]
 constexpr int OFF_FEAT = OFF_INT + NPART * TM * 4;          // uint8 fj[KF], fk[KF]
-constexpr int OFF_BAR = OFF_FEAT + 2 * KF;                  // 8 mbarriers + tmem slot
-constexpr int SMEM_BYTES = OFF_BAR + 128;
+constexpr int OFF_BAR = OFF_FEAT + 2 * KF;                  // 3 mbarriers + tmem slot
+constexpr int SMEM_BYTES = OFF_BAR + 64;
 static_assert(OFF_BAR % 8 == 0 && OFF_DBL % 8 == 0, "alignment");
 static_assert(SMEM_BYTES + 128 <= 227 * 1024, "shared memory");
 
@@ -93,9 +93,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity, int wh
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity))
         if (++spins > (1u << 22)) mbar_timeout(which, parity);
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -172,24 +169,27 @@ struct Smem {
     __device__ __forceinline__ uint64_t *bars() const { return reinterpret_cast<uint64_t *>(base + OFF_BAR); }
 };
 
-// forward product of one chunk, accumulator u, table slot b
-__device__ __forceinline__ void issue_fwd(const Smem &sm, uint32_t tmem, int b, int u) {
+// forward product of one chunk: accumulators U0 .. 3 (pass 1: the top two only), table buffer b
+__device__ __forceinline__ void issue_fwd(const Smem &sm, uint32_t tmem, int b, int u0) {
     const uint32_t a0 = smem_u32(sm.a_fwd()), b0 = smem_u32(sm.b_fwd(b));
-    const int nk = (2 * u + 1 < NDF) ? 2 * KF / 32 : KF / 32;              // a lone top digit uses the weight-1 half only
-    for (int kk = 0; kk < nk; ++kk) {
-        const uint64_t da = make_desc(a0 + (2 * u * KFC + 2 * kk) * (TM * 16), TM * 16, 128);
-        const uint64_t db = make_desc(b0 + (2 * kk) * (NC * 16), NC * 16, 128);
-        mma_u8(tmem + u * NC, da, db, make_idesc(NC), kk > 0 ? 1u : 0u);
+    for (int u = u0; u < 4; ++u) {
+        const int nk = (2 * u + 1 < NDF) ? 2 * KF / 32 : KF / 32;          // a lone top digit uses the weight-1 half only
+        for (int kk = 0; kk < nk; ++kk) {
+            const uint64_t da = make_desc(a0 + (2 * u * KFC + 2 * kk) * (TM * 16), TM * 16, 128);
+            const uint64_t db = make_desc(b0 + (2 * kk) * (NC * 16), NC * 16, 128);
+            mma_u8(tmem + u * NC, da, db, make_idesc(NC), kk > 0 ? 1u : 0u);
+        }
     }
 }
-// reverse product of one chunk into tile-long accumulator v
-__device__ __forceinline__ void issue_rev(const Smem &sm, uint32_t tmem, int b, bool first, int v) {
+// reverse product of one chunk into the three tile-long accumulators
+__device__ __forceinline__ void issue_rev(const Smem &sm, uint32_t tmem, int b, bool first) {
     const uint32_t a0 = smem_u32(sm.a_rev()), b0 = smem_u32(sm.b_rev(b));
-    for (int kk = 0; kk < 2 * NC / 32; ++kk) {
-        const uint64_t da = make_desc(a0 + (2 * v * (NC / 16) + 2 * kk) * (TM * 16), TM * 16, 128);
-        const uint64_t db = make_desc(b0 + (2 * kk) * (NOUT * 16), NOUT * 16, 128);
-        mma_u8(tmem + 4 * NC + v * NOUT, da, db, make_idesc(NOUT), (first && kk == 0) ? 0u : 1u);
-    }
+    for (int v = 0; v < NDP / 2; ++v)
+        for (int kk = 0; kk < 2 * NC / 32; ++kk) {
+            const uint64_t da = make_desc(a0 + (2 * v * (NC / 16) + 2 * kk) * (TM * 16), TM * 16, 128);
+            const uint64_t db = make_desc(b0 + (2 * kk) * (NOUT * 16), NOUT * 16, 128);
+            mma_u8(tmem + 4 * NC + v * NOUT, da, db, make_idesc(NOUT), (first && kk == 0) ? 0u : 1u);
+        }
 }
 
 // STATS = false: log-denominators only (first sweep of a truncated iteration)
@@ -203,10 +203,9 @@ __global__ void __launch_bounds__(THREADS, 1) gl_state_tc_kernel(const __grid_co
     const int q = warp & 3, part = warp >> 2;             // TMEM lane quadrant; which 16 of the 64 columns of a chunk
     const int r = q * 32 + lane;                          // datapoint of this thread within the tile
     const int Hp = st.Hp, nf = t.n_feat;
-    uint64_t *bar_tabf = sm.bars();                       // [2] forward table slots landed
-    uint64_t *bar_tabr = sm.bars() + 2;                   // [2] reverse table slots landed
-    uint64_t *bar_fwd = sm.bars() + 4, *bar_rev = sm.bars() + 5, *bar_free = sm.bars() + 6, *bar_done = sm.bars() + 7;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(sm.bars() + 8);
+    uint64_t *bar_tab = sm.bars();                        // [2] table buffers landed
+    uint64_t *bar_mma = sm.bars() + 2;                    // MMAs issued so far have completed
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(sm.bars() + 3);
 
     double *rowmax_s = sm.dbl();                          // [NPART][TM]
     double *scale_s = rowmax_s + NPART * TM;              // [TM]
@@ -218,14 +217,9 @@ __global__ void __launch_bounds__(THREADS, 1) gl_state_tc_kernel(const __grid_co
     int *cand_s = sm.cand() + r * CSTR;
 
     if (tid == 0) {
-        mbar_init(&bar_tabf[0], 1);
-        mbar_init(&bar_tabf[1], 1);
-        mbar_init(&bar_tabr[0], 1);
-        mbar_init(&bar_tabr[1], 1);
-        mbar_init(bar_fwd, 4);                            // one commit (or plain arrival) per forward issuer
-        mbar_init(bar_rev, NDP / 2);                      // one commit per reverse issuer
-        mbar_init(bar_free, THREADS / 32);
-        mbar_init(bar_done, THREADS / 32);
+        mbar_init(&bar_tab[0], 1);
+        mbar_init(&bar_tab[1], 1);
+        mbar_init(bar_mma, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -250,8 +244,8 @@ __global__ void __launch_bounds__(THREADS, 1) gl_state_tc_kernel(const __grid_co
     const int kc0 = (part < 2) ? 2 * part : part + 2, nkc = (part < 2) ? 2 : 1;
 
     double acc_n = 0.0, acc_lse = 0.0, acc_sig = 0.0, acc_cnt = 0.0;
-    uint32_t item = 0;            // forward products consumed so far (slot and phase of the tables, bar_fwd, bar_free)
-    uint32_t rchunk = 0;          // reverse products started so far (slot and phase of the tables, bar_done, bar_rev)
+    uint32_t item = 0;            // table fetches issued so far (thread 0), = items consumed by everybody
+    uint32_t mma_phase = 0;       // commits waited for so far (all threads)
 
     const int64_t n_tiles = (a.n_rows + TM - 1) / TM;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -259,17 +253,11 @@ __global__ void __launch_bounds__(THREADS, 1) gl_state_tc_kernel(const __grid_co
         const bool valid = rr < a.n_rows;
         const int64_t n = a.row0 + rr;                    // global datapoint index
 
-        // ---- table fetches for the first two items of this tile (overlap the feature build) ----
+        // ---- table fetch for the first item of this tile (overlaps the feature build) ----
         if (tid == 0) {
-            for (int i = 0; i < 2; ++i) {
-                const uint32_t g = item + i;
-                mbar_expect_tx(&bar_tabf[g & 1], B_FWD_BYTES);
-                bulk_g2s(sm.b_fwd(g & 1), t.bfwd + size_t(i < t.n_chunks ? i : 0) * B_FWD_BYTES, B_FWD_BYTES, &bar_tabf[g & 1]);
-            }
-            if (STATS) {
-                mbar_expect_tx(&bar_tabr[rchunk & 1], B_REV_BYTES);
-                bulk_g2s(sm.b_rev(rchunk & 1), t.brev, B_REV_BYTES, &bar_tabr[rchunk & 1]);
-            }
+            const int b = item & 1;
+            mbar_expect_tx(&bar_tab[b], B_FWD_BYTES);
+            bulk_g2s(sm.b_fwd(b), t.bfwd, B_FWD_BYTES, &bar_tab[b]);
         }
 
         // ---- features: gather, scale, 8 digits -> A operand of the forward product ----
@@ -339,63 +327,40 @@ __global__ void __launch_bounds__(THREADS, 1) gl_state_tc_kernel(const __grid_co
         __syncthreads();
         tc_fence_after();
 
-        // Pipeline of the 2 n_chunks items of a tile (pass 1, then pass 2, chunk by chunk).  No block-wide barrier inside:
-        //   bar_fwd   forward product of the item has completed               (one tcgen05.commit per accumulator)
-        //   bar_free  every warp has read the item's accumulators out of TMEM (one arrival per warp)
-        //             -> the NEXT item's forward product starts and runs under this item's arithmetic
-        //   bar_done  every warp has stored its posterior digits of the chunk  (one arrival per warp)
-        //             -> the chunk's reverse product starts and runs under the next chunk
-        //   bar_rev   reverse product of the chunk has completed: the digit operand and its table slot are free again
-        // tcgen05.mma issue blocks the issuing thread at the execution rate (~54 cycles per M128 N64 K32 instruction), so
-        // the accumulators are spread over issuer threads: lane 0 of warp u issues forward accumulator u, lane 0 of warp
-        // 4 + v reverse accumulator v; an accumulate chain stays in one thread, which keeps it ordered.
-        const int nch = t.n_chunks, n_items = 2 * nch;
-        auto fetch_fwd = [&](uint32_t g, int i) {             // thread 0: table of item i of this tile (global item g)
-            const int cn = (i < nch) ? i : i - nch;
-            mbar_expect_tx(&bar_tabf[g & 1], B_FWD_BYTES);
-            bulk_g2s(sm.b_fwd(g & 1), t.bfwd + size_t(cn) * B_FWD_BYTES, B_FWD_BYTES, &bar_tabf[g & 1]);
-        };
-        auto start_fwd = [&](uint32_t g, int i) {             // lane 0 of warps 0..3: accumulator `warp` of item i
-            if (i < nch && warp < 2) { mbar_arrive(bar_fwd); return; }      // pass 1 needs the two leading accumulators only
-            mbar_wait(&bar_tabf[g & 1], (g >> 1) & 1, int(g & 1));
-            tc_fence_after();
-            issue_fwd(sm, tmem, g & 1, warp);
-            mma_commit(bar_fwd);
-        };
-        auto fetch_rev = [&](uint32_t g, int c) {             // reverse table of chunk c (global chunk g)
-            mbar_expect_tx(&bar_tabr[g & 1], B_REV_BYTES);
-            bulk_g2s(sm.b_rev(g & 1), t.brev + size_t(c) * B_REV_BYTES, B_REV_BYTES, &bar_tabr[g & 1]);
-        };
-        // the accumulators of item i have been read: release them, start item i + 1 and fetch the table of item i + 2
-        auto release_fwd = [&](uint32_t g, int i) {
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) {
-                mbar_arrive(bar_free);
-                if (warp < 4 && i + 1 < n_items) {
-                    mbar_wait(bar_free, g & 1, 5);
-                    start_fwd(g + 1, i + 1);
-                    if (warp == 0 && i + 2 < n_items) fetch_fwd(g + 2, i + 2);
-                }
-            }
-        };
-        if (lane == 0 && warp < 4) start_fwd(item, 0);
-
         // ---- pass 1: upper bound of max_s F(s) from the two leading accumulators ----
         int imax = INT_MIN;
-        for (int c = 0; c < nch; ++c) {
-            mbar_wait(bar_fwd, item & 1, 2);
+        for (int c = 0; c < t.n_chunks; ++c) {
+            if (tid == 0) {
+                const int b = item & 1;
+                mbar_wait(&bar_tab[b], (item >> 1) & 1, b);
+                tc_fence_after();
+                issue_fwd(sm, tmem, b, 2);
+                mma_commit(bar_mma);
+            }
+            mbar_wait(bar_mma, mma_phase & 1, 2);
+            ++mma_phase;
             tc_fence_after();
+            if (tid == 0) {                                   // next item: chunk c + 1 of pass 1, or chunk 0 of pass 2
+                const int b = (item + 1) & 1;
+                const int cn = (c + 1 < t.n_chunks) ? c + 1 : 0;
+                const bool rev_too = STATS && (c + 1 == t.n_chunks);
+                mbar_expect_tx(&bar_tab[b], B_FWD_BYTES + (rev_too ? B_REV_BYTES : 0));
+                bulk_g2s(sm.b_fwd(b), t.bfwd + size_t(cn) * B_FWD_BYTES, B_FWD_BYTES, &bar_tab[b]);
+                if (rev_too) bulk_g2s(sm.b_rev(b), t.brev + size_t(cn) * B_REV_BYTES, B_REV_BYTES, &bar_tab[b]);
+            }
+            ++item;
             __syncwarp();                                     // the TMEM loads below are warp-collective
             const uint32_t off = uint32_t(t.chunk_nfeat[c]) << OFFB;    // the digits carry v 2^(XB-e) + 2^XB per feature
-            uint32_t a2[16], a3[16];
-            tmem_ld16(tlane + 2 * NC + part * 16, a2);
-            tmem_ld16(tlane + 3 * NC + part * 16, a3);
-            tmem_wait_ld();
-            release_fwd(item, c);
-            ++item;
+            {
+                uint32_t a2[16], a3[16];
+                tmem_ld16(tlane + 2 * NC + part * 16, a2);
+                tmem_ld16(tlane + 3 * NC + part * 16, a3);
+                tmem_wait_ld();
 #pragma unroll
-            for (int i = 0; i < 16; ++i) imax = max(imax, int(a3[i] * 16384u + a2[i] - off));
+                for (int i = 0; i < 16; ++i) imax = max(imax, int(a3[i] * 16384u + a2[i] - off));
+            }
+            tc_fence_before();
+            __syncthreads();
         }
         imax_s[part * TM + r] = imax;
         __syncthreads();
@@ -415,13 +380,30 @@ __global__ void __launch_bounds__(THREADS, 1) gl_state_tc_kernel(const __grid_co
 
         // ---- pass 2: posterior, partition sum, digits of the posterior -> reverse product ----
         double Z2 = 0.0, SF = 0.0;
-        for (int c = 0; c < nch; ++c) {
-            mbar_wait(bar_fwd, item & 1, 2);
+        for (int c = 0; c < t.n_chunks; ++c) {
+            if (tid == 0) {
+                const int b = item & 1;
+                mbar_wait(&bar_tab[b], (item >> 1) & 1, b);
+                tc_fence_after();
+                if (STATS && c > 0) issue_rev(sm, tmem, b ^ 1, c == 1);
+                issue_fwd(sm, tmem, b, 0);
+                mma_commit(bar_mma);
+            }
+            mbar_wait(bar_mma, mma_phase & 1, 2);
+            ++mma_phase;
             tc_fence_after();
+            if (tid == 0 && c + 1 < t.n_chunks) {
+                const int b = (item + 1) & 1;
+                mbar_expect_tx(&bar_tab[b], B_FWD_BYTES + (STATS ? B_REV_BYTES : 0));
+                bulk_g2s(sm.b_fwd(b), t.bfwd + size_t(c + 1) * B_FWD_BYTES, B_FWD_BYTES, &bar_tab[b]);
+                if (STATS) bulk_g2s(sm.b_rev(b), t.brev + size_t(c + 1) * B_REV_BYTES, B_REV_BYTES, &bar_tab[b]);
+            }
+            ++item;
             __syncwarp();
             const uint32_t off = uint32_t(t.chunk_nfeat[c]) << OFFB;
             const int cnt = t.chunk_cnt[c];
-            double x16[16];
+            uint32_t ylo[16], yhi[16];
+            bool live = false;                                // warp-uniform: some posterior of the 16 states is not negligible
 #pragma unroll
             for (int sb = 0; sb < 2; ++sb) {
                 const int col0 = part * 16 + sb * 8;
@@ -431,23 +413,16 @@ __global__ void __launch_bounds__(THREADS, 1) gl_state_tc_kernel(const __grid_co
                 tmem_ld8(tlane + 2 * NC + col0, a2);
                 tmem_ld8(tlane + 3 * NC + col0, a3);
                 tmem_wait_ld();
+                double x8[8];
+                double xm = -INFINITY;
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const int hi = int(a3[i] * 16384u + a2[i] - off);
                     const uint32_t lo = a1[i] * 16384u + a0[i];
                     const double f = fma(double(hi), 268435456.0, double(lo));
-                    x16[sb * 8 + i] = (col0 + i < cnt) ? fma(f, scale, bias) : -INFINITY;      // padding columns of a partial chunk
+                    x8[i] = (col0 + i < cnt) ? fma(f, scale, bias) : -INFINITY;      // padding columns of a partial chunk
+                    xm = fmax(xm, x8[i]);
                 }
-            }
-            release_fwd(item, nch + c);
-            ++item;
-            uint32_t ylo[16], yhi[16];
-            bool live = false;                                // warp-uniform: some posterior of the 16 states is not negligible
-#pragma unroll
-            for (int sb = 0; sb < 2; ++sb) {
-                double xm = x16[sb * 8];
-#pragma unroll
-                for (int i = 1; i < 8; ++i) xm = fmax(xm, x16[sb * 8 + i]);
                 // one warp-uniform decision per batch of 8 states x 32 datapoints: either nobody is within e^-45 of its
                 // largest posterior (2.9e-20: below the last bit of the partition sum even when all 1573 states add up),
                 // or the eight exps run as straight-line code so that their dependency chains interleave
@@ -455,10 +430,9 @@ __global__ void __launch_bounds__(THREADS, 1) gl_state_tc_kernel(const __grid_co
                     live = true;
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
-                        const double xc = fmax(x16[sb * 8 + i], EXP_CUTOFF);              // (x = -inf: e^-100 = 4e-44, harmless)
-                        const double p = exp_tab32(xc, exptab);
+                        const double p = exp_tab32(fmax(x8[i], EXP_CUTOFF), exptab);     // (x = -inf: e^-100 = 4e-44, harmless)
                         Z2 += p;
-                        SF = fma(p, xc, SF);
+                        SF = fma(p, fmax(x8[i], EXP_CUTOFF), SF);
                         if (STATS) {
                             const double T = fma(p, 4398046511104.0, 4503599627370496.0);    // p 2^42 + 2^52: mantissa = rint(p 2^42)
                             ylo[sb * 8 + i] = uint32_t(__double2loint(T));
@@ -471,8 +445,6 @@ __global__ void __launch_bounds__(THREADS, 1) gl_state_tc_kernel(const __grid_co
                 }
             }
             if (STATS) {
-                if (c > 0) mbar_wait(bar_rev, (rchunk - 1) & 1, 3);      // the previous chunk's digits have been consumed
-                if (tid == 4 * 32 && c + 1 < nch) fetch_rev(rchunk + 1, c + 1);
                 uint8_t *dst = sm.a_rev() + part * (TM * 16) + r * 16;
                 constexpr int PL = (NC / 16) * TM * 16;
                 if (live) {
@@ -487,22 +459,18 @@ __global__ void __launch_bounds__(THREADS, 1) gl_state_tc_kernel(const __grid_co
                     for (int pl = 0; pl < NDP; ++pl) *reinterpret_cast<uint4 *>(dst + pl * PL) = make_uint4(0u, 0u, 0u, 0u);
                 }
                 fence_async_smem();
-                __syncwarp();
-                if (lane == 0) {
-                    mbar_arrive(bar_done);
-                    if (warp >= 4 && warp < 4 + NDP / 2) {
-                        mbar_wait(bar_done, rchunk & 1, 4);
-                        mbar_wait(&bar_tabr[rchunk & 1], (rchunk >> 1) & 1, 6 + int(rchunk & 1));
-                        tc_fence_after();
-                        issue_rev(sm, tmem, rchunk & 1, c == 0, warp - 4);
-                        mma_commit(bar_rev);
-                    }
-                }
-                ++rchunk;
             }
+            tc_fence_before();
+            __syncthreads();
         }
         if (STATS) {
-            mbar_wait(bar_rev, (rchunk - 1) & 1, 3);
+            if (tid == 0) {
+                tc_fence_after();
+                issue_rev(sm, tmem, (item & 1) ^ 1, t.n_chunks == 1);
+                mma_commit(bar_mma);
+            }
+            mbar_wait(bar_mma, mma_phase & 1, 2);
+            ++mma_phase;
             tc_fence_after();
         }
         part_s[(0 * NPART + part) * TM + r] = Z2;

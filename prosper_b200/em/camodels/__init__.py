@@ -221,6 +221,13 @@ class Engine(object):
         """0 = FP64 DMMA kernels, n > 0 = int8 tcgen05 kernels with n slices per operand."""
         return int(self.lib.pet_gemm_path(self.h))
 
+    def gemm_slices(self):
+        """(score GEMM, statistics GEMM) int8 slices per operand; (0, 0) on the FP64 DMMA path."""
+        import ctypes as C
+        a, b = C.c_int32(0), C.c_int32(0)
+        _lib.check(self.lib.pet_gemm_slices(self.h, C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
+
     def set_state_kernel(self, mode):
         """0 = automatic, 1 = scalar FP64 state kernel, 2 = int8 tensor-core state kernel (fused BSC path)."""
         _lib.check(self.lib.pet_set_state_kernel(self.h, int(mode)))

@@ -347,13 +347,14 @@ def test_bsc_learns_mu_like_the_reference(ncut):
     assert np.abs(pm['mu']).max() > 0.5                      # it moved towards the offset
 
 
-@pytest.mark.parametrize("slices", ["0", "6"])
+@pytest.mark.parametrize("slices", ["0", "6", "7", "default"])
 def test_gemm_fallback_paths_agree_with_oracle(monkeypatch, slices):
-    """The FP64 DMMA kernels (PET_OZAKI=0: what runs when the int8 slices do not fit in memory) and the 6-slice int8
-    variant go through the same pipeline; both must reproduce the oracle (6 slices: ~1e-12 per product)."""
+    """The FP64 DMMA kernels (PET_OZAKI=0: what runs when the int8 slices do not fit in memory), the all-6-slice and
+    all-7-slice int8 variants and the default (score GEMM 6 slices, statistics GEMM 7) go through the same pipeline; all
+    must reproduce the oracle (6 slices: ~1e-12 per product)."""
     if slices == "0":
         monkeypatch.setenv("PET_OZAKI", "0")
-    else:
+    elif slices != "default":
         monkeypatch.setenv("PET_OZAKI_SLICES", slices)
     D, H, Hp, gam, N = 40, 24, 8, 4, 3000
     y, params, _ = bsc_problem(D, H, N, 11)
@@ -362,8 +363,10 @@ def test_gemm_fallback_paths_agree_with_oracle(monkeypatch, slices):
     onew = o.step(an, copy_params(params), {'y': y.copy()})
     m = model(D, H, Hp, gam)
     got = m._fused_step(an, copy_params(params), {'y': y.copy()})
-    assert m.engine.gemm_path() == (0 if slices == "0" else 6)      # known once a shard is bound
-    tol = TOL if slices == "0" else 1e-7
+    want = {"0": (0, 0), "6": (6, 6), "7": (7, 7), "default": (6, 7)}[slices]
+    assert m.engine.gemm_slices() == want                           # known once a shard is bound
+    assert m.engine.gemm_path() == want[1]
+    tol = 1e-7 if slices == "6" else TOL
     assert rel_err(got['W'], onew['W']) < tol
     assert abs(got['pi'] - onew['pi']) < tol * onew['pi'] and abs(got['sigma'] - onew['sigma']) < tol * onew['sigma']
 
