@@ -539,7 +539,7 @@ def run_gpu(args):
             "truncated_iteration": {"Ncut_factor": 1.0, "value": N_TOTAL / (cut_ms / 1e3), "unit": "datapoints/s",
                                     "ms_per_step": cut_ms, "steps": cut_steps,
                                     "note": "same step with the reference's datapoint truncation (bsc_et.py:247-260): "
-                                            "two sweeps + distributed k-th largest; not part of `value`"},
+                                            "one posterior evaluation (statistics parked per datapoint, added up after the distributed k-th largest gives the cut); not part of `value`"},
             "roofline": roof,
             "cpu_baseline": cpu,
             "result_check": {"pi": float(params['pi']), "sigma": float(params['sigma'])},

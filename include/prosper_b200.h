@@ -159,6 +159,8 @@ const double *pet_log_denominators_ptr(const pet_engine *e);
 /* `flags` of pet_log_denominators / pet_m_step_stats */
 #define PET_PASS_SELECT        1  /* (re)run select_Hprimes inside this pass (fused step)      */
 #define PET_PASS_REUSE_SCORES  2  /* same params as the previous pass: reuse its score matrix  */
+#define PET_PASS_DEFER_STATS   4  /* pet_log_denominators: a pet_m_step_stats(use_cut, REUSE_SCORES) with the same params
+                                   * follows -- evaluate the posterior once and park the per-datapoint statistics   */
 
 /* k-th largest of n device doubles (replaces parallel.allsort(...)[-k], parallel.py:87-110).
  * Result written to *out_dev (device). */

@@ -14,6 +14,7 @@ c_int64_p = C.POINTER(C.c_int64)
 MODEL_BSC, MODEL_MCA, MODEL_MMCA, MODEL_TSC, MODEL_DSC, MODEL_GSC = range(6)
 PASS_SELECT = 1
 PASS_REUSE_SCORES = 2
+PASS_DEFER_STATS = 4
 N_STAGES = 10          # PET_N_STAGES
 MAX_HPRIME, MAX_GAMMA = 16, 8     # engine limits (gl_kernel.cuh)
 

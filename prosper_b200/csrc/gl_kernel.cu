@@ -1382,6 +1382,61 @@ int launch_gl_state(const GLArgs &a, int gamma, bool binary, int sm_count, cudaS
     return launch_state<8, false>(a, sm_count, stream);
 }
 
+// Second half of a GLF_DEFER_STATS evaluation: one thread per datapoint of the chunk.
+__global__ void __launch_bounds__(256) gl_finalize_cut_kernel(const __grid_constant__ GLArgs a) {
+    __shared__ double red[4][8];
+    const GLStatic &st = a.st;
+    const int Hp = st.Hp;
+    const int64_t rr = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    double acc_n = 0.0, acc_lse = 0.0, acc_sig = 0.0, acc_cnt = 0.0;
+    if (rr < a.n_rows) {
+        const int64_t n = a.row0 + rr;
+        const double l = a.lse[n];
+        bool keep = true;
+        if (a.flags & GLF_USE_CUT) {
+            const double cut = *a.cut;
+            keep = (a.flags & GLF_CUT_STRICT) ? (l > cut) : (l >= cut);
+        }
+        double *scl = a.scl + n * (1 + PET_MAXHP);
+        if (!keep) {                                          // truncated away: contributes nothing (bsc_et.py:254-257)
+            for (int j = 0; j <= Hp; ++j) scl[j] = 0.0;
+        } else {
+            const int *cand = a.cand + n * Hp;
+            int f = 0;
+            for (int j = 0; j < Hp; ++j) {
+                const int cj = cand[j];
+                for (int k = j + 1; k < Hp; ++k, ++f) {
+                    const double w = a.pairs[int64_t(f) * a.pairs_ld + n];
+                    if (w != 0.0) {
+                        const int ck = cand[k];
+                        atomicAdd(&a.Wq[int64_t(cj) * st.ldH + ck], w);
+                        atomicAdd(&a.Wq[int64_t(ck) * st.ldH + cj], w);
+                    }
+                }
+            }
+            const double *rs = a.rs + n * (4 + PET_MAXV);
+            acc_n = 1.0; acc_lse = l; acc_sig = rs[5]; acc_cnt = rs[6];
+        }
+    }
+    acc_n = warp_sum(acc_n); acc_lse = warp_sum(acc_lse); acc_sig = warp_sum(acc_sig); acc_cnt = warp_sum(acc_cnt);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) { red[0][warp] = acc_n; red[1][warp] = acc_lse; red[2][warp] = acc_sig; red[3][warp] = acc_cnt; }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        double s = 0.0;
+        for (int w = 0; w < 8; ++w) s += red[threadIdx.x][w];
+        if (s != 0.0) atomicAdd(&a.scalars[threadIdx.x], s);
+    }
+}
+
+int launch_gl_finalize_cut(const GLArgs &a, cudaStream_t st) {
+    if (a.n_rows <= 0) return PET_OK;
+    if (!a.pairs || !a.Wq || !a.scalars) { set_error("gl_finalize_cut: missing buffers"); return PET_EINVAL; }
+    gl_finalize_cut_kernel<<<(unsigned)ceil_div(a.n_rows, 256), 256, 0, st>>>(a);
+    PET_LAUNCH_CHECK();
+    return PET_OK;
+}
+
 int launch_gl_scale(const GLArgs &a, cudaStream_t stream) {
     if (a.n_rows <= 0 || (a.flags & (GLF_LSE_ONLY | GLF_SELECT_ONLY))) return PET_OK;
     gl_scale_kernel<<<(unsigned)ceil_div(a.n_rows * 32, 256), 256, 0, stream>>>(a);

@@ -30,6 +30,9 @@ enum {
     GLF_NO_SROW     = 1 << 8,   // the <s> chunk is never materialised: the singleton kernel only reduces, the state kernel
                                 // leaves scl[n] = {e^(m1-m)/Z, candidate marginals} and gl_post_slice recomputes the
                                 // singleton posteriors from the score row while it cuts them into int8 slices
+    GLF_DEFER_STATS = 1 << 9,   // truncated iteration, first sweep: the state kernel evaluates the posterior once and parks the
+                                // per-datapoint statistics (pair sums in `pairs`, scalar contributions in rs[5], rs[6]); once
+                                // the cut is known gl_finalize_cut adds up the datapoints that stay and zeroes scl of the rest
     GLF_FOLD_SCALE  = 1 << 7,   // no scale kernel: the state kernel folds the candidate marginals into the un-normalised
                                 // <s> row (divided by the row's scale); consumers multiply rows by scl[n][0] on load
 };
@@ -94,12 +97,17 @@ struct GLArgs {
     double *rs;                   // (n, 4+PET_MAXV) row-kernel partial sums {m1, Z1, sig1, -, cnt1[..]}, global index
     double *ywc;                  // (n, Hp) scores of the candidates, global index
     double *scl;                  // (n, 1+PET_MAXHP) {scale of the singleton row, candidate marginals}, global index
+    double *pairs;                // GLF_DEFER_STATS: (H'(H'-1)/2, pairs_ld) normalised pair sums <s_j s_k>, feature major, global index
+    int64_t pairs_ld;
 };
 
 int launch_gl_kernel(const GLArgs &a, int gamma, bool binary, int sm_count, cudaStream_t st);
 int launch_gl_row(const GLArgs &a, int sm_count, cudaStream_t st);
 int launch_gl_state(const GLArgs &a, int gamma, bool binary, int sm_count, cudaStream_t st);
 int launch_gl_scale(const GLArgs &a, cudaStream_t st);
+// second half of a GLF_DEFER_STATS evaluation (bsc_et.py:250-257, 349-366): datapoints at or above the cut scatter their parked
+// pair sums into Wq and add their scalars; the others get scl = 0, so the slicer gives them an all-zero <s> row
+int launch_gl_finalize_cut(const GLArgs &a, cudaStream_t st);
 // <s>[n,h] = exp(F_h - m1[n]) scl[n][0] (+ scl[n][1+j] if h = cand[n][j]) cut into ns signed 7-bit slices relative to the
 // fixed scale 1 (a posterior mean lies in [0, 1]: slice 0 <= 64, the others are UNSIGNED 7-bit digits 0..127, so the
 // int32 accumulators of ozaki_gemm hold K <= 37 000 terms per split) and stored transposed, out[t][h][r] (r < Kp, zero

@@ -239,6 +239,7 @@ __global__ void __launch_bounds__(THREADS, 1) gl_state_tc_kernel(const __grid_co
     const double lpm = it.anneal_prior ? it.beta * it.lp[0] : it.lp[0];
     const bool fold = (a.flags & GLF_FOLD_SCALE) != 0;
     const bool use_cut = STATS && (a.flags & GLF_USE_CUT);
+    const bool defer = STATS && (a.flags & GLF_DEFER_STATS);      // park the statistics per datapoint (see GLF_DEFER_STATS)
     const double cut = use_cut ? *a.cut : 0.0;
     // K chunks of the feature operand built by this thread: parts 0, 1 two each, parts 2, 3 one each
     const int kc0 = (part < 2) ? 2 * part : part + 2, nkc = (part < 2) ? 2 : 1;
@@ -550,7 +551,9 @@ __global__ void __launch_bounds__(THREADS, 1) gl_state_tc_kernel(const __grid_co
                             }
                         } else {
                             const double w = val * inv;
-                            if (w != 0.0) {
+                            if (defer) {
+                                a.pairs[int64_t(f - Hp) * a.pairs_ld + n] = w;
+                            } else if (w != 0.0) {
                                 const int cj = cand_s[fj[f]], ck = cand_s[fk[f]];
                                 atomicAdd(&a.Wq[int64_t(cj) * st.ldH + ck], w);
                                 atomicAdd(&a.Wq[int64_t(ck) * st.ldH + cj], w);
@@ -563,10 +566,16 @@ __global__ void __launch_bounds__(THREADS, 1) gl_state_tc_kernel(const __grid_co
             if (part == 0 && keep) {
                 // sum_s p_s q_s from sum_s p_s (F_s - mx):  F_s = c q_s + lpm |s|,  sum_s p_s |s| = sum_j marginal_j
                 const double sig2 = (fma(mx, Z2, SF) - lpm * sum_marg) / cq;
-                acc_n += 1.0;
-                acc_lse += lse;
-                acc_sig += fma(sig1, e1, sig2) * inv;
-                acc_cnt += fma(cnt1, e1, sum_marg) * inv;
+                if (defer) {
+                    double *rs = a.rs + n * (4 + PET_MAXV);
+                    rs[5] = fma(sig1, e1, sig2) * inv;
+                    rs[6] = fma(cnt1, e1, sum_marg) * inv;
+                } else {
+                    acc_n += 1.0;
+                    acc_lse += lse;
+                    acc_sig += fma(sig1, e1, sig2) * inv;
+                    acc_cnt += fma(cnt1, e1, sum_marg) * inv;
+                }
             }
         }
         tc_fence_before();
@@ -574,7 +583,7 @@ __global__ void __launch_bounds__(THREADS, 1) gl_state_tc_kernel(const __grid_co
         tc_fence_after();
     }
 
-    if (STATS) {
+    if (STATS && !defer) {
         acc_n = warp_sum(acc_n); acc_lse = warp_sum(acc_lse); acc_sig = warp_sum(acc_sig); acc_cnt = warp_sum(acc_cnt);
         if (lane == 0 && part == 0) {
             atomicAdd(&a.scalars[0], acc_n);

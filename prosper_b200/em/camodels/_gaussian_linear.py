@@ -73,7 +73,9 @@ class GaussianLinearET(CAModel):
             N = comm.allreduce(eng.n)            # without a cut N = N_use comes back with the packed statistics
             N_use_target = int(N * (1 - (1 - A) * anneal['Ncut_factor']))
         if N_use_target > 0:                     # allsort(...)[-0] is the smallest denominator: N_use <= 0 keeps every point
-            lse = eng.log_denominators(a, p, logpj, sel)
+            # fused: the same parameters come back for the statistics right after the cut -- the engine may evaluate the
+            # posterior once and park the per-datapoint statistics (PET_PASS_DEFER_STATS)
+            lse = eng.log_denominators(a, p, logpj, sel | (_lib.PASS_DEFER_STATS if fused else 0))
             self._global_cut(lse, N_use_target)
             stats = eng.m_step_stats(a, p, logpj, _lib.PASS_REUSE_SCORES if fused else 0, use_cut=True)
         else:

@@ -103,3 +103,37 @@ def test_tensor_state_kernel_heavy_tailed_features():
     assert rel_err(got['W'], want['W']) < 1e-7
     assert abs(got['pi'] - want['pi']) < 1e-7 * want['pi']
     assert abs(got['sigma'] - want['sigma']) < 1e-7 * want['sigma']
+
+
+def test_truncated_iteration_evaluates_the_posterior_once(monkeypatch):
+    """bsc_et.py:250-257 needs every log-denominator before the cut is known.  With the tensor-core state kernel the
+    log-denominator sweep parks the per-datapoint statistics and the statistics sweep only adds up the datapoints that
+    stay (GLF_DEFER_STATS + gl_finalize_cut): same result as the two-evaluation form and as the oracle, over several
+    chunks with a ragged last one, and the row / state kernels run once per chunk instead of twice."""
+    D, H, Hp, gam, N = 60, 40, 12, 5, 1400
+    y, params, _ = bsc_problem(D, H, N, 21)
+    an = DictAnneal(T=1.1, Ncut_factor=0.8, anneal_prior=False)
+    want = BSC(D, H, Hp, gam).step(an, copy_params(params), {'y': y.copy()})
+    got, spans = {}, {}
+    for single in (True, False):
+        if single:
+            monkeypatch.delenv("PET_GL_NO_SINGLE_EVAL", raising=False)
+        else:
+            monkeypatch.setenv("PET_GL_NO_SINGLE_EVAL", "1")
+        monkeypatch.setenv("PET_CHUNK_ROWS", "512")
+        m = model(D, H, Hp, gam, 2)
+        m._bind({'y': y})
+        m.engine.enable_timing(True)
+        got[single] = m._fused_step(an, copy_params(params), {'y': y})
+        st = m.engine.stage_times()
+        m.engine.enable_timing(False)
+        spans[single] = (st['row_kernel']['spans'], st['state_kernel']['spans'], st['score_gemm']['spans'])
+    for single in (True, False):
+        assert rel_err(got[single]['W'], want['W']) < TOL, single
+        assert abs(got[single]['pi'] - want['pi']) < TOL * want['pi'], single
+        assert abs(got[single]['sigma'] - want['sigma']) < TOL * want['sigma'], single
+    assert rel_err(got[True]['W'], got[False]['W']) < 1e-10
+    nchunks = spans[True][2]
+    assert nchunks >= 3                                                   # several chunks, the last one ragged
+    assert spans[False][0] == 2 * nchunks and spans[True][0] == nchunks   # one selection + singleton pass per chunk
+    assert spans[True][1] == 2 * nchunks                                  # state kernel once, then gl_finalize_cut
