@@ -275,14 +275,15 @@ int dgemm_mn_splits(int64_t M, int64_t N, int64_t K, int sm_count) {
     int64_t bm = mn_tile_m(M, N), bn = (big && !(bm == 136 && mn_variant() == 2)) ? 128 : 64;
     int64_t tiles = ceil_div(M, bm) * ceil_div(N, bn);
     int64_t max_by_k = std::max<int64_t>(1, K / 512);               // >= 512 rows per split
+    // time model in units of one row of K: the CTAs run in ceil(tiles s / SMs) waves of K / s rows each, and every split
+    // costs one more slab for splitk_reduce to read.  (A single 64 x 64 output tile -- the H x H statistics of GSC --
+    // spreads over all the SMs this way; the previous rule left it on one CTA.)
     int best = 1;
-    double best_score = -1.0;
-    for (int64_t s = 1; s <= std::min<int64_t>(max_by_k, 64); ++s) {
-        int64_t ctas = tiles * s;
-        double waves = double(ctas) / sm_count;
-        double eff = waves / ceil(waves);                           // wave quantisation
-        double score = eff - 0.01 * s - (waves < 1.5 ? 0.5 : 0.0);  // prefer few splits, at least ~2 waves
-        if (score > best_score) { best_score = score; best = int(s); }
+    double best_cost = 1e300;
+    for (int64_t s = 1; s <= std::min<int64_t>(max_by_k, 2 * sm_count); ++s) {
+        const double waves = ceil(double(tiles * s) / sm_count);
+        const double cost = waves * double(ceil_div(std::max<int64_t>(K, 1), s)) + 24.0 * double(s);
+        if (cost < best_cost) { best_cost = cost; best = int(s); }
     }
     return best;
 }
@@ -297,7 +298,8 @@ int dgemm_mn(int64_t M, int64_t N, int64_t K, const double *A, int64_t lda, cons
     }
     int splits = dgemm_mn_splits(M, N, K, sm_count);
     int64_t stride = M * ldc;
-    if (splits > 1 && (work == nullptr || work_doubles < stride * splits)) splits = 1;
+    if (splits > 1 && (work == nullptr || work_doubles < stride * splits))      // as many splits as the workspace holds
+        splits = (work && stride > 0) ? int(std::max<int64_t>(1, work_doubles / stride)) : 1;
     int64_t kps = round_up(ceil_div(std::max<int64_t>(K, 1), splits), 16);
     const int64_t bm = mn_tile_m(M, N);
     auto launch = [&](const GemmArgs &g, int sp) -> int {
