@@ -30,12 +30,16 @@ def main():
     worst = 0.0
     for (D, H, Hp, g, N, T, ncut) in [(25, 10, 6, 3, 1001, 1.0, 0.0), (25, 10, 6, 3, 1001, 2.0, 0.7),
                                       (100, 50, 8, 4, 3000, 1.2, 1.0), (676, 1000, 12, 5, 333, 1.0, 1.0),
-                                      (60, 40, 12, 5, 24000, 1.3, 1.0)]:      # 12 000 datapoints per rank at 2 ranks: tensor-core state kernel
+                                      (60, 40, 12, 5, 24000, 1.3, 1.0)]:      # tensor-core state kernel on every rank (forced below:
+                                                                              # at 8 ranks 3 000 datapoints would pick the scalar one),
+                                                                              # truncation with ONE posterior evaluation
         bars = D == 25
         y, params, _ = bsc_problem(D, H, N, 3, bars=bars, pi=(0.2 if bars else None), sigma=(2.0 if bars else 1.0))
         f, l = parallel.stride_data(N, comm=comm)
         an = DictAnneal(T=T, Ncut_factor=ncut, anneal_prior=False)
         m = BSC_ET(D, H, Hp, g, comm=comm)
+        if N == 24000:
+            m.engine.set_state_kernel(2)
         p = dict(params)
         po = dict(params)
         o = BSC(D, H, Hp, g)
