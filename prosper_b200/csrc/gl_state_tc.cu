@@ -7,16 +7,19 @@
 // feature vector v, and the statistics the M-step needs (bsc_et.py:349-366, 395-415) are the reverse product
 //     [ <s_j> , <s_j s_k> ]  =  p^T M_f ,   p_s = exp(F(s) - max).
 // Both run as tcgen05.mma kind::i8 with float64 accuracy:
-//   * v is scaled per datapoint by a power of two, offset to be non-negative and cut into 7 digits of 7 bits; digits
+//   * v is scaled per datapoint by a power of two, offset to be non-negative and cut into 8 digits of 7 bits; digits
 //     2u and 2u+1 share accumulator u because the membership operand is stored twice, once with weight 1 and once with
-//     weight 128 (u8), concatenated along K: 4 int32 accumulators instead of 7, each an EXACT integer
-//   * one CTA owns a tile of 128 datapoints = the 128 TMEM lanes; four warps share a lane quadrant and split the 64
-//     columns of a chunk, so an epilogue thread owns ONE datapoint and 16 states per chunk: running maximum, partition
-//     sum and posterior need no cross-thread traffic until the tile is finished
-//   * pass 1 (top two accumulators only) bounds the maximum of F(s) from above to ~1e-5 of the feature scale; pass 2
-//     evaluates exp(F(s) - bound) in float64, cuts the posterior into 6 digits of 7 bits (42 bits) and writes them as
-//     the A operand of the reverse product, whose 3 accumulators (78 features x 128 datapoints) stay in TMEM for the
-//     whole tile
+//     weight 128 (u8), concatenated along K: 4 int32 accumulators instead of 8, each an EXACT integer
+//   * one CTA (16 warps) owns a tile of 128 datapoints = the 128 TMEM lanes; four warps share a lane quadrant and split
+//     the 64 columns of a chunk, so an epilogue thread owns ONE datapoint and 16 states per chunk: running maximum,
+//     partition sum and posterior need no cross-thread traffic until the tile is finished
+//   * pass 1 (top two accumulators only) bounds the maximum of F(s) from above to 2^-20 of the feature scale; pass 2
+//     evaluates exp(F(s) - bound) in float64 (batches of 8 states x 32 datapoints that are all below e^-45 of their
+//     maximum are skipped by one warp-uniform test), cuts the posterior into 6 digits of 7 bits (42 bits) and writes
+//     them as the A operand of the reverse product, whose 3 accumulators (78 features x 128 datapoints) stay in TMEM
+//     for the whole tile
+//   * GLF_DEFER_STATS (first sweep of a truncated iteration): the pair sums and scalar contributions are parked per
+//     datapoint instead of being added to Wq / scalars; gl_finalize_cut adds up the datapoints that survive the cut
 //   * operands are written by the threads in the un-swizzled K-major core-matrix layout (row r of K chunk kc at
 //     kc * rows * 16 + r * 16: consecutive lanes store consecutive 16-byte units, no bank conflicts); the constant
 //     membership tables are kept in global memory as shared-memory images and fetched per 64-state chunk with
