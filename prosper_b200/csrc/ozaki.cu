@@ -133,22 +133,29 @@ __device__ __forceinline__ uint32_t make_idesc_n(int n) {
 
 // KBLK: bytes of K per pipeline stage (Args.kblocks / kb_per_split count blocks of KBLK).  64: two stages of 86 KB
 // (the default); 32: five stages of 43 KB -- the same bytes in flight in finer grains (measured slower, see ozaki_gemm)
-template <int NS, int STAGES, int KBLK>
+// SA / SB: ring depths of the A (128-row) and the B (64-row) slice tiles.  The rings are independent, because with 7
+// slices three whole stages (3 x 84 KB) do not fit: two A stages (2 x 56 KB) + four B stages (4 x 28 KB) do.  Measured at
+// the north-star statistics shape (7 slices): rings 2+2 14.3 ms, 3+2 14.4 ms, 2+4 12.8 ms; 6 slices: 2+2 12.4, 2+5 11.2,
+// 3+3 9.2 ms -- the depth of the pipeline, not the operand bandwidth, is what the 2-stage kernel of round 1 was short of.
+template <int NS, int SA, int SB, int KBLK>
 __global__ void __launch_bounds__(THREADS, 1) gemm_kernel(const __grid_constant__ CUtensorMap mapA,
                                                           const __grid_constant__ CUtensorMap mapB, const Args a) {
     constexpr int KB = KBLK;
     constexpr int A_SLICE = BM * KB, B_SLICE = BN * KB;                 // bytes per slice tile
-    constexpr int STAGE_BYTES = NS * (A_SLICE + B_SLICE);
+    constexpr int A_STAGE = NS * A_SLICE, B_STAGE = NS * B_SLICE;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + STAGES * STAGE_BYTES);
-    uint64_t *full = bars, *empty = bars + STAGES, *tmem_full = bars + 2 * STAGES, *tmem_empty = bars + 2 * STAGES + 1;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * STAGES + 2);
-    double *sB_s = reinterpret_cast<double *>(bars + 2 * STAGES + 4);      // [2][BN] column scales of the current tile
+    uint8_t *smemB = smem + SA * A_STAGE;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smemB + SB * B_STAGE);
+    uint64_t *fullA = bars, *emptyA = fullA + SA, *fullB = emptyA + SA, *emptyB = fullB + SB;
+    uint64_t *tmem_full = emptyB + SB, *tmem_empty = tmem_full + 1;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_empty + 1);
+    double *sB_s = reinterpret_cast<double *>(tmem_empty + 3);             // [2][BN] column scales of the current tile
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < SA; ++s) { mbar_init(&fullA[s], 1); mbar_init(&emptyA[s], 1); }
+        for (int s = 0; s < SB; ++s) { mbar_init(&fullB[s], 1); mbar_init(&emptyB[s], 1); }
         mbar_init(tmem_full, 1);
         mbar_init(tmem_empty, 8);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -168,23 +175,27 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_kernel(const __grid_constant_
     if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
+            int sta = 0, stb = 0;
+            uint32_t pha = 0, phb = 0;
             for (int64_t u = blockIdx.x; u < units; u += gridDim.x) {
                 const int64_t tile = u % tiles;
                 const int split = int(u / tiles);
                 const int m0 = int(tile / tiles_n) * BM, n0 = int(tile % tiles_n) * BN;
                 const int kb0 = split * a.kb_per_split, kb1 = min(kb0 + a.kb_per_split, a.kblocks);
                 for (int kb = kb0; kb < kb1; ++kb) {
-                    mbar_wait_relaxed(&empty[stage], phase ^ 1);
-                    mbar_expect_tx(&full[stage], STAGE_BYTES);
-                    uint8_t *sa = smem + stage * STAGE_BYTES, *sb = sa + NS * A_SLICE;
+                    // B first: its ring is the shallow one, so its slot is the one the MMAs are waiting for
+                    mbar_wait_relaxed(&emptyB[stb], phb ^ 1);
+                    mbar_expect_tx(&fullB[stb], B_STAGE);
+                    uint8_t *sb = smemB + stb * B_STAGE;
 #pragma unroll
-                    for (int i = 0; i < NS; ++i) {
-                        tma_load_3d(sa + i * A_SLICE, &mapA, &full[stage], kb * KB, m0, i);
-                        tma_load_3d(sb + i * B_SLICE, &mapB, &full[stage], kb * KB, n0, i);
-                    }
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    for (int i = 0; i < NS; ++i) tma_load_3d(sb + i * B_SLICE, &mapB, &fullB[stb], kb * KB, n0, i);
+                    mbar_wait_relaxed(&emptyA[sta], pha ^ 1);
+                    mbar_expect_tx(&fullA[sta], A_STAGE);
+                    uint8_t *sa = smem + sta * A_STAGE;
+#pragma unroll
+                    for (int i = 0; i < NS; ++i) tma_load_3d(sa + i * A_SLICE, &mapA, &fullA[sta], kb * KB, m0, i);
+                    if (++sta == SA) { sta = 0; pha ^= 1; }
+                    if (++stb == SB) { stb = 0; phb ^= 1; }
                 }
             }
         }
@@ -193,17 +204,18 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_kernel(const __grid_constant_
         // A_i multiplies the stacked B slices 0 .. NS-1-i (consecutive 64-row tiles in shared memory) in one or two
         // wide MMAs whose N columns land on the consecutive accumulators t = i .. NS-1.
         if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0, tphase = 0;
+            int sta = 0, stb = 0;
+            uint32_t pha = 0, phb = 0, tphase = 0;
             for (int64_t u = blockIdx.x; u < units; u += gridDim.x) {
                 const int split = int(u / tiles);
                 const int kb0 = split * a.kb_per_split, kb1 = min(kb0 + a.kb_per_split, a.kblocks);
                 mbar_wait_relaxed(tmem_empty, tphase ^ 1);   // epilogue has drained the accumulators
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 for (int kb = kb0; kb < kb1; ++kb) {
-                    mbar_wait(&full[stage], phase);
+                    mbar_wait(&fullB[stb], phb);
+                    mbar_wait(&fullA[sta], pha);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint8_t *sa = smem + stage * STAGE_BYTES, *sb = sa + NS * A_SLICE;
+                    const uint8_t *sa = smem + sta * A_STAGE, *sb = smemB + stb * B_STAGE;
 #pragma unroll
                     for (int kk = 0; kk < KB / UMMA_K; ++kk) {
 #pragma unroll
@@ -219,8 +231,10 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_kernel(const __grid_constant_
                             }
                         }
                     }
-                    mma_commit(&empty[stage]);               // frees the smem stage when these MMAs retire
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    mma_commit(&emptyA[sta]);                // frees the two slots when these MMAs retire
+                    mma_commit(&emptyB[stb]);
+                    if (++sta == SA) { sta = 0; pha ^= 1; }
+                    if (++stb == SB) { stb = 0; phb ^= 1; }
                 }
                 mma_commit(tmem_full);                       // accumulators complete
                 tphase ^= 1;
@@ -547,16 +561,25 @@ int ozaki_gemm(int64_t M, int64_t N, int Kp, int ns, const OzOperand &A, const O
     oz::Args a{M, N, kblocks * per, splits, kbs * per, accumulate ? 1 : 0, A.scale, B.scale, C, ldc, split_stride};
     const int64_t units = ceil_div(M, oz::BM) * ceil_div(N, oz::BN) * splits;
     const unsigned grid = (unsigned)std::min<int64_t>(units, sm_count);
-    auto launch = [&](auto kern, int stages) -> int {
-        const size_t smem = size_t(stages) * ns * (oz::BM + oz::BN) * kblk + 1024 + 256 + 2 * oz::BN * 8;
+    auto launch = [&](auto kern, int sa, int sb) -> int {
+        const size_t smem = size_t(ns) * (size_t(sa) * oz::BM + size_t(sb) * oz::BN) * kblk + 1024 + (2 * (sa + sb) + 4) * 8 +
+                            2 * oz::BN * 8 + 64;
         PET_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
         kern<<<grid, oz::THREADS, smem, st>>>(mapA, mapB, a);
         return PET_OK;
     };
-    if (ns == 7 && kblk == 32) PET_CHECK(launch(oz::gemm_kernel<7, 5, 32>, 5));
-    else if (ns == 7) PET_CHECK(launch(oz::gemm_kernel<7, 2, 64>, 2));
-    else if (ns == 6 && kblk == 32) PET_CHECK(launch(oz::gemm_kernel<6, 6, 32>, 6));
-    else if (ns == 6) PET_CHECK(launch(oz::gemm_kernel<6, 3, 64>, 3));
+    // 7 slices: two A stages + four B stages (229 KB); PET_OZ_RING=22 keeps the two whole stages of round 1
+    static const int ring = []() { const char *e = getenv("PET_OZ_RING"); return e ? atoi(e) : 0; }();
+    const bool ring22 = ring == 22;
+    if (ns == 7 && kblk == 32) PET_CHECK(launch(oz::gemm_kernel<7, 5, 5, 32>, 5, 5));
+    else if (ns == 7 && ring22) PET_CHECK(launch(oz::gemm_kernel<7, 2, 2, 64>, 2, 2));
+    else if (ns == 7 && ring == 24) PET_CHECK(launch(oz::gemm_kernel<7, 2, 4, 64>, 2, 4));
+    else if (ns == 6 && ring22) PET_CHECK(launch(oz::gemm_kernel<6, 2, 2, 64>, 2, 2));
+    else if (ns == 6 && ring == 25) PET_CHECK(launch(oz::gemm_kernel<6, 2, 5, 64>, 2, 5));
+    else if (ns == 7 && ring == 32) PET_CHECK(launch(oz::gemm_kernel<7, 3, 2, 64>, 3, 2));
+    else if (ns == 7) PET_CHECK(launch(oz::gemm_kernel<7, 2, 4, 64>, 2, 4));
+    else if (ns == 6 && kblk == 32) PET_CHECK(launch(oz::gemm_kernel<6, 6, 6, 32>, 6, 6));
+    else if (ns == 6) PET_CHECK(launch(oz::gemm_kernel<6, 3, 3, 64>, 3, 3));
     else {
         set_error("ozaki_gemm: ns must be 6 or 7");
         return PET_EINVAL;
