@@ -137,6 +137,9 @@ __device__ __forceinline__ uint32_t make_idesc_n(int n) {
 // slices three whole stages (3 x 84 KB) do not fit: two A stages (2 x 56 KB) + four B stages (4 x 28 KB) do.  Measured at
 // the north-star statistics shape (7 slices): rings 2+2 14.3 ms, 3+2 14.4 ms, 2+4 12.8 ms; 6 slices: 2+2 12.4, 2+5 11.2,
 // 3+3 9.2 ms -- the depth of the pipeline, not the operand bandwidth, is what the 2-stage kernel of round 1 was short of.
+// (Also measured: cp.async.bulk.prefetch.tensor into L2 a few K blocks ahead of the loads, to make up for the depth that
+// does not fit: 14.7 / 16.9 ms against 11.1 / 12.9 ms whatever the distance -- the prefetches cost the TMA unit as many
+// row requests as the loads themselves.)
 template <int NS, int SA, int SB, int KBLK>
 __global__ void __launch_bounds__(THREADS, 1) gemm_kernel(const __grid_constant__ CUtensorMap mapA,
                                                           const __grid_constant__ CUtensorMap mapB, const Args a) {
