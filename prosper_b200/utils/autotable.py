@@ -5,7 +5,8 @@ context manager): every `append(name, value)` adds one row, so after T iteration
 (T, D, H), `/pi` (T,), ... -- the layout the reference's notebooks read with
 `tables.open_file('result.h5').root.W[:]`.  PyTables is not available here; rows are kept in host
 memory and the file is written by `utils/h5min.py` on `flush()` / `close()` (flat root group,
-contiguous datasets).
+contiguous datasets) and, so that a run that is killed keeps what it has logged (the reference appends to
+on-disk EArrays as it goes), every `flush_interval` seconds from inside `append` (atomic: `.tmp` + `os.replace`).
 """
 import os
 import time
@@ -16,10 +17,12 @@ from . import h5min
 
 
 class AutoTable(object):
-    def __init__(self, fname=None, compression_level=1):
+    def __init__(self, fname=None, compression_level=1, flush_interval=60.0):
         if fname is None:
             fname = self._guess_fname()
         self.fname = fname
+        self.flush_interval = flush_interval             # seconds between automatic flushes; None / <= 0: only on close()
+        self._last_flush = time.time()
         self.compression_level = compression_level       # accepted for compatibility; datasets are stored uncompressed
         self.tables = {}
         self.types = {}
@@ -55,6 +58,8 @@ class AutoTable(object):
         if value.shape != shape or (value.dtype.kind != dt.kind and not (dt.kind in 'fiu' and value.dtype.kind in 'fiub')):
             raise TypeError('Wrong datatype "%s" for "%s" field' % (value.dtype, name))
         self.tables[name].append(np.array(value, copy=True))
+        if self.flush_interval and self.flush_interval > 0 and time.time() - self._last_flush >= self.flush_interval:
+            self.flush()
 
     def appendList(self, name, value):
         """autotable.py:190-223: like `append`, but `value` holds SEVERAL rows (its first axis, or a list of strings)."""
@@ -96,6 +101,7 @@ class AutoTable(object):
     def flush(self):
         h5min.write_h5(self.fname + ".tmp", self._stacked())
         os.replace(self.fname + ".tmp", self.fname)
+        self._last_flush = time.time()
 
     def close(self):
         if not self._closed:

@@ -237,3 +237,23 @@ def test_tracepoints_of_the_stage_methods(tmp_path):
     with tarfile.open(str(tmp_path / "traces.tgz")) as tar:
         text = tar.extractfile("trace-0000.txt").read().decode()
     assert "[work:begin]" in text and "[work:end]" in text and "[custom]" in text and text.startswith("# Start time")
+
+
+def test_autotable_flushes_while_the_run_is_going(tmp_path):
+    """The reference appends to on-disk EArrays (autotable.py:87-127), so a killed run keeps its log.  Here rows are
+    buffered and the file is rewritten atomically every `flush_interval` seconds from inside `append`."""
+    from prosper_b200.utils.autotable import AutoTable
+    from prosper_b200.utils import h5min
+    fn = str(tmp_path / "run.h5")
+    t = AutoTable(fn, flush_interval=1e-9)                 # every append is "due"
+    t.append('pi', 0.25)
+    t.append('W', np.ones((3, 2)))
+    got = h5min.read_h5(fn)                                # no close(), no flush(): the rows are on disk already
+    assert got['pi'].shape == (1,) and got['W'].shape == (1, 3, 2)
+    t.append('pi', 0.5)
+    assert h5min.read_h5(fn)['pi'].tolist() == [0.25, 0.5]
+    t2 = AutoTable(str(tmp_path / "lazy.h5"), flush_interval=None)
+    t2.append('pi', 0.25)
+    assert not (tmp_path / "lazy.h5").exists()
+    t2.close()
+    assert h5min.read_h5(str(tmp_path / "lazy.h5"))['pi'].tolist() == [0.25]
