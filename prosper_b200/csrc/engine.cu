@@ -154,7 +154,7 @@ struct pet_engine {
     GLTcHost tc_host; uint8_t *d_tc_fwd = nullptr, *d_tc_rev = nullptr; bool tc_ok = false; int tc_mode = 0;
 
     // int8-sliced operands of the two large GEMMs (ozaki.cu); oz_on = buffers present and the path selected
-    bool oz_want = false, oz_on = false; int oz_ns = 7, oz_ns2 = 7, oz_kpd = 0, oz_splits = 1; int64_t oz_rows = 0;
+    bool oz_want = false, oz_on = false; int oz_ns = 7, oz_ns2 = 7, oz_kpd = 0, oz_splits = 1; int64_t oz_rows = 0, oz_ldT = 0;
     int8_t *ozY = nullptr, *ozYT = nullptr, *ozW = nullptr, *ozS = nullptr;
     double *ozYs = nullptr, *ozYTs = nullptr, *ozWs = nullptr, *ozSs = nullptr, *oz_slabs = nullptr;
     unsigned long long *oz_colmax = nullptr;
@@ -497,9 +497,14 @@ static int size_chunks(pet_engine *e, int64_t n) {
         PET_CHECK(dev_alloc(&e->gemm_work, e->gemm_work_doubles));
     }
     if (e->oz_want) {
-        e->oz_splits = ozaki_splits(e->D + 1, e->H, ozaki_kp(cr), e->sm_count, 512);      // <s> may arrive as unsigned digits
+        // The statistics GEMM is computed TRANSPOSED, (H, D+1) = <S>^T . Y with <S> as the 128-row operand: 8 x 11 tiles of
+        // 1024 x 704 instead of 6 x 16 tiles of 768 x 1024 for the 677 x 1000 result (8 % less padding) and a split count
+        // that fills whole waves (5 x 88 = 440 units = 2.97 waves instead of 3 x 96 = 1.95); the slabs are summed into
+        // the (D+1, H) layout of the packed statistics by ozaki_add_slabs_t
+        e->oz_ldT = round_up((int64_t)e->D + 1, 8);
+        e->oz_splits = ozaki_splits(e->H, e->D + 1, ozaki_kp(cr), e->sm_count, 512);      // <s> may arrive as unsigned digits
         PET_CHECK(dev_alloc(&e->ozS, (int64_t)e->oz_ns2 * e->H * cr));
-        PET_CHECK(dev_alloc(&e->oz_slabs, (int64_t)e->oz_splits * (e->D + 1) * e->ldH));
+        PET_CHECK(dev_alloc(&e->oz_slabs, (int64_t)e->oz_splits * e->H * e->oz_ldT));
     }
     return PET_OK;
 }
@@ -831,7 +836,7 @@ static int sweep_gl(pet_engine *e, const pet_anneal *a, const pet_params *p, int
         ga.Wq = stats_dev + lay.off_Wq;
         ga.scalars = stats_dev + lay.off_scalars;
         if (e->S2buf) PET_CUDA(cudaMemsetAsync(e->s2sum, 0, e->ldH * 8, st));
-        if (e->oz_on) PET_CUDA(cudaMemsetAsync(e->oz_slabs, 0, (int64_t)e->oz_splits * (e->D + 1) * e->ldH * 8, st));
+        if (e->oz_on) PET_CUDA(cudaMemsetAsync(e->oz_slabs, 0, (int64_t)e->oz_splits * e->H * e->oz_ldT * 8, st));
     }
     const bool user_logpj = (kflags & (GLF_READ_LOGPJ | GLF_WRITE_LOGPJ)) != 0;
     const bool logpj_on_dev = user_logpj && is_device_ptr(logpj_user);
@@ -935,7 +940,7 @@ static int sweep_gl(pet_engine *e, const pet_anneal *a, const pet_params *p, int
             e->timer.begin(ST_STATS, st);
             // Wp^T (D+1, H) += Y_chunk^T . <S>_chunk ; row D (all-ones column of Y) = sum_n <s>
             if (e->oz_on) {
-                const int64_t plane = (int64_t)(e->D + 1) * e->chunk_rows, wp = (int64_t)(e->D + 1) * e->ldH;
+                const int64_t plane = (int64_t)(e->D + 1) * e->chunk_rows;
                 e->timer.end(st);
                 e->timer.begin(ST_SLICE, st);
                 if (defer_s)
@@ -949,8 +954,8 @@ static int sweep_gl(pet_engine *e, const pet_anneal *a, const pet_params *p, int
                 e->timer.begin(ST_STATS, st);
                 const OzOperand oy{e->ozYT + c * e->oz_ns2 * plane, e->chunk_rows, plane, e->ozYTs + c * e->ldY};
                 const OzOperand os{e->ozS, e->chunk_rows, (int64_t)e->H * e->chunk_rows, e->ozSs};
-                PET_CHECK(ozaki_gemm(e->D + 1, e->H, ozaki_kp(rows), e->oz_ns2, oy, os, e->oz_slabs, e->ldH, e->oz_splits, wp,
-                                     true, e->sm_count, st, defer_s ? 64 * 127 : 4096));
+                PET_CHECK(ozaki_gemm(e->H, e->D + 1, ozaki_kp(rows), e->oz_ns2, os, oy, e->oz_slabs, e->oz_ldT, e->oz_splits,
+                                     (int64_t)e->H * e->oz_ldT, true, e->sm_count, st, defer_s ? 64 * 127 : 4096));
             } else {
                 PET_CHECK(dgemm_mn(e->D + 1, e->H, rows, e->Y + r0 * e->ldY, e->ldY, e->Sbuf, e->ldH,
                                    stats_dev + lay.off_Wp, e->ldH, 1, e->gemm_work, e->gemm_work_doubles, e->sm_count, st));
@@ -963,7 +968,8 @@ static int sweep_gl(pet_engine *e, const pet_anneal *a, const pet_params *p, int
     e->defer_valid = defer_eval;
     if (kflags & GLF_SELECT) e->cand_state = 1;
     if (do_stats && e->oz_on)   // Wp^T = sum of the split-K slabs
-        PET_CHECK(ozaki_add_slabs(stats_dev + lay.off_Wp, e->oz_slabs, (int64_t)(e->D + 1) * e->ldH, e->oz_splits, st));
+        PET_CHECK(ozaki_add_slabs_t(stats_dev + lay.off_Wp, e->ldH, e->oz_slabs, e->H, e->D + 1, e->oz_ldT,
+                                    (int64_t)e->H * e->oz_ldT, e->oz_splits, st));
     if (do_stats && e->S2buf)   // DSC: singleton second moments onto the diagonal (dsc_et.py:701)
         PET_CHECK(launch_add_diag(stats_dev + lay.off_Wq, e->ldH, e->s2sum, e->H, st));
     mark_compute_done(e, st);

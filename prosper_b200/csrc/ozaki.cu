@@ -525,6 +525,33 @@ int ozaki_add_slabs(double *dst, const double *slabs, int64_t count, int n_slabs
     return PET_OK;
 }
 
+// dst (cols, ld_dst) = transpose of the sum of n_slabs slabs (rows, ld_src), slab_stride doubles apart
+__global__ void add_slabs_t_kernel(double *dst, int64_t ld_dst, const double *slabs, int rows, int cols, int64_t ld_src,
+                                   int64_t slab_stride, int n_slabs) {
+    __shared__ double t[32][33];
+    const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int r = r0 + i, c = c0 + threadIdx.x;
+        double v = 0.0;
+        if (r < rows && c < cols)
+            for (int s = 0; s < n_slabs; ++s) v += slabs[s * slab_stride + int64_t(r) * ld_src + c];
+        t[i][threadIdx.x] = v;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        const int c = c0 + i, r = r0 + threadIdx.x;
+        if (r < rows && c < cols) dst[int64_t(c) * ld_dst + r] = t[threadIdx.x][i];
+    }
+}
+int ozaki_add_slabs_t(double *dst, int64_t ld_dst, const double *slabs, int rows, int cols, int64_t ld_src, int64_t slab_stride,
+                      int n_slabs, cudaStream_t st) {
+    if (n_slabs <= 0 || rows <= 0 || cols <= 0) return PET_OK;
+    dim3 g((unsigned)ceil_div(cols, 32), (unsigned)ceil_div(rows, 32)), b(32, 8);
+    add_slabs_t_kernel<<<g, b, 0, st>>>(dst, ld_dst, slabs, rows, cols, ld_src, slab_stride, n_slabs);
+    PET_LAUNCH_CHECK();
+    return PET_OK;
+}
+
 // X (rows, K) row-major -> slices out[t][r][k] (rows Kp bytes apart, planes slice_stride bytes apart), per-row scales
 int ozaki_slice_rows(const double *X, int64_t ldx, int64_t rows, int K, int ns, int8_t *out, int64_t slice_stride, double *scale,
                      cudaStream_t st) {

@@ -23,5 +23,8 @@ int ozaki_slice_cols(const double *X, int64_t ldx, int64_t rows, int cols, int n
 int ozaki_gemm(int64_t M, int64_t N, int Kp, int ns, const OzOperand &A, const OzOperand &B, double *C, int64_t ldc, int splits,
                int64_t split_stride, bool accumulate, int sm_count, cudaStream_t st, int max_pair_product = 4096);
 int ozaki_add_slabs(double *dst, const double *slabs, int64_t count, int n_slabs, cudaStream_t st);
+// dst (cols, ld_dst) = transpose of the sum of n_slabs slabs of shape (rows, ld_src), slab_stride doubles apart
+int ozaki_add_slabs_t(double *dst, int64_t ld_dst, const double *slabs, int rows, int cols, int64_t ld_src, int64_t slab_stride,
+                      int n_slabs, cudaStream_t st);
 
 }  // namespace pet
