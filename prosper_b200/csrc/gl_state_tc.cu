@@ -7,7 +7,9 @@
 // feature vector v, and the statistics the M-step needs (bsc_et.py:349-366, 395-415) are the reverse product
 //     [ <s_j> , <s_j s_k> ]  =  p^T M_f ,   p_s = exp(F(s) - max).
 // Both run as tcgen05.mma kind::i8 with float64 accuracy:
-//   * v is scaled per datapoint by a power of two, offset to be non-negative and cut into 8 digits of 7 bits; digits
+//   * v is scaled per datapoint by a power of two and cut into 8 digits of 7 bits in two's complement: seven unsigned
+//     digits and a SIGNED top digit (the MMAs of the top accumulator read the A operand as s8; an unsigned digit
+//     <= 127 is the same byte either way), so no offset has to be added or removed; digits
 //     2u and 2u+1 share accumulator u because the membership operand is stored twice, once with weight 1 and once with
 //     weight 128 (u8), concatenated along K: 4 int32 accumulators instead of 8, each an EXACT integer
 //   * one CTA (16 warps) owns a tile of 128 datapoints = the 128 TMEM lanes; four warps share a lane quadrant and split
@@ -52,8 +54,7 @@ constexpr int THREADS = 128 * NPART;
 constexpr int CSTR = 13;                // stride of the candidate rows in shared memory (conflict-free)
 constexpr double EXP_CUTOFF = -100.0;   // as gl_kernel.cu
 constexpr double SKIP_CUTOFF = -45.0;   // a batch whose posteriors all lie below e^-45 of the largest one is skipped
-constexpr int XB = 7 * NDF - 1;         // the features are scaled to integers below 2^XB and offset by 2^XB
-constexpr int OFFB = XB - 28;           // ... which is 2^OFFB in units of the upper half (accumulators 2, 3: weight 2^28)
+constexpr int XB = 7 * NDF - 1;         // the features are scaled to integers of magnitude below 2^XB (the top digit lies in [-64, 63])
 
 constexpr int A_FWD_BYTES = NDF * KFC * TM * 16;            // 98304
 constexpr int B_FWD_BYTES = TC_BFWD_BYTES;                  // 2 * KF * NC = 12288 per chunk
@@ -106,9 +107,9 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
     return (uint64_t((saddr & 0x3FFFFu) >> 4)) | (uint64_t(lbo >> 4) << 16) | (uint64_t(sbo >> 4) << 32) | (1ull << 46);
 }
-// kind::i8, D = s32, A = B = unsigned 8 bit, both K-major, M = 128
-__device__ __forceinline__ constexpr uint32_t make_idesc(int n) {
-    return (2u << 4) | (uint32_t(n >> 3) << 17) | (uint32_t(TM >> 4) << 24);
+// kind::i8, D = s32, B = unsigned 8 bit, A = unsigned or (a_signed) signed 8 bit, both K-major, M = 128
+__device__ __forceinline__ constexpr uint32_t make_idesc(int n, bool a_signed = false) {
+    return (2u << 4) | (a_signed ? (1u << 7) : 0u) | (uint32_t(n >> 3) << 17) | (uint32_t(TM >> 4) << 24);
 }
 __device__ __forceinline__ void mma_u8(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
     asm volatile(
@@ -180,7 +181,7 @@ __device__ __forceinline__ void issue_fwd(const Smem &sm, uint32_t tmem, int b, 
         for (int kk = 0; kk < nk; ++kk) {
             const uint64_t da = make_desc(a0 + (2 * u * KFC + 2 * kk) * (TM * 16), TM * 16, 128);
             const uint64_t db = make_desc(b0 + (2 * kk) * (NC * 16), NC * 16, 128);
-            mma_u8(tmem + u * NC, da, db, make_idesc(NC), kk > 0 ? 1u : 0u);
+            mma_u8(tmem + u * NC, da, db, make_idesc(NC, 2 * u + 2 == NDF), kk > 0 ? 1u : 0u);    // top accumulator: signed top digit
         }
     }
 }
@@ -308,9 +309,8 @@ __global__ void __launch_bounds__(THREADS, 1) gl_state_tc_kernel(const __grid_co
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
                         const int f = (kc0 + kk) * 16 + i;
-                        long long xi = (f < nf) ? __double2ll_rn(v[kk * 16 + i] * up) + (1ll << XB) : 0ll;   // padding features: digit 0
-                        if (xi < 0) xi = 0;                               // (NaN / inf inputs: keep the digits in range)
-                        if (xi >= (2ll << XB)) xi = (2ll << XB) - 1;
+                        long long xi = __double2ll_rn(v[kk * 16 + i] * up);      // (padding features are 0)
+                        xi = max(min(xi, (1ll << XB) - 1), 1 - (1ll << XB));     // (NaN / inf inputs: keep the digits in range)
                         lo[i] = uint32_t(xi);
                         hi[i] = uint32_t(xi >> 32);
                     }
@@ -322,7 +322,8 @@ __global__ void __launch_bounds__(THREADS, 1) gl_state_tc_kernel(const __grid_co
                     *reinterpret_cast<uint4 *>(dst + 4 * KFC * TM * 16) = pack_digit16<4, false>(lo, hi);
                     *reinterpret_cast<uint4 *>(dst + 5 * KFC * TM * 16) = pack_digit16<5, false>(lo, hi);
                     *reinterpret_cast<uint4 *>(dst + 6 * KFC * TM * 16) = pack_digit16<6, false>(lo, hi);
-                    if (NDF == 8) *reinterpret_cast<uint4 *>(dst + 7 * KFC * TM * 16) = pack_digit16<7, false>(lo, hi);
+                    static_assert(NDF == 8, "eight digit planes, the last one signed");
+                    *reinterpret_cast<uint4 *>(dst + 7 * KFC * TM * 16) = pack_digit16<7, true>(lo, hi);    // bits 49..56: s8
                 }
             }
         }
@@ -354,14 +355,17 @@ __global__ void __launch_bounds__(THREADS, 1) gl_state_tc_kernel(const __grid_co
             }
             ++item;
             __syncwarp();                                     // the TMEM loads below are warp-collective
-            const uint32_t off = uint32_t(t.chunk_nfeat[c]) << OFFB;    // the digits carry v 2^(XB-e) + 2^XB per feature
+            const int cnt = t.chunk_cnt[c];
             {
                 uint32_t a2[16], a3[16];
                 tmem_ld16(tlane + 2 * NC + part * 16, a2);
                 tmem_ld16(tlane + 3 * NC + part * 16, a3);
                 tmem_wait_ld();
 #pragma unroll
-                for (int i = 0; i < 16; ++i) imax = max(imax, int(a3[i] * 16384u + a2[i] - off));
+                for (int i = 0; i < 16; ++i) {
+                    const int v = int(a3[i] * 16384u + a2[i]);
+                    imax = max(imax, (part * 16 + i < cnt) ? v : INT_MIN);
+                }
             }
             tc_fence_before();
             __syncthreads();
@@ -404,7 +408,6 @@ __global__ void __launch_bounds__(THREADS, 1) gl_state_tc_kernel(const __grid_co
             }
             ++item;
             __syncwarp();
-            const uint32_t off = uint32_t(t.chunk_nfeat[c]) << OFFB;
             const int cnt = t.chunk_cnt[c];
             uint32_t ylo[16], yhi[16];
             bool live = false;                                // warp-uniform: some posterior of the 16 states is not negligible
@@ -421,7 +424,7 @@ __global__ void __launch_bounds__(THREADS, 1) gl_state_tc_kernel(const __grid_co
                 double xm = -INFINITY;
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    const int hi = int(a3[i] * 16384u + a2[i] - off);
+                    const int hi = int(a3[i] * 16384u + a2[i]);
                     const uint32_t lo = a1[i] * 16384u + a0[i];
                     const double f = fma(double(hi), 268435456.0, double(lo));
                     x8[i] = (col0 + i < cnt) ? fma(f, scale, bias) : -INFINITY;      // padding columns of a partial chunk
@@ -621,22 +624,17 @@ int gl_tc_build_tables(const GLStatic &st, int gamma, const std::vector<double> 
         for (int j = 0; j < Hp; ++j)
             for (int k = j + 1; k < Hp; ++k, ++f) { t.feat[f] = uint8_t(j); t.feat[tc::KF + f] = uint8_t(k); }
     }
-    struct Chunk { int first, cnt, g; };
+    // chunks of 64 consecutive multi-cause states, across the size groups (1573 states: 25 chunks)
+    struct Chunk { int first, cnt; };
     std::vector<Chunk> chunks;
-    for (int g = 2; g <= gamma; ++g) {
-        const int s0 = st.size_start[g], s1 = (g < gamma) ? st.size_start[g + 1] : st.S;
-        for (int s = s0; s < s1; s += tc::NC) chunks.push_back({s, std::min(tc::NC, s1 - s), g});
-    }
+    for (int s = st.size_start[2]; s < st.S; s += tc::NC) chunks.push_back({s, std::min(tc::NC, st.S - s)});
     if (chunks.empty() || (int)chunks.size() > TC_MAX_CHUNKS) { set_error("tensor-core state kernel: %zu chunks unsupported", chunks.size()); return PET_EINVAL; }
     t.n_chunks = (int)chunks.size();
     out.bfwd.assign(size_t(t.n_chunks) * TC_BFWD_BYTES, 0);
     out.brev.assign(size_t(t.n_chunks) * TC_BREV_BYTES, 0);
     for (int c = 0; c < t.n_chunks; ++c) {
         const Chunk &ch = chunks[c];
-        const int nfeat = ch.g + ch.g * (ch.g - 1) / 2;
         t.chunk_cnt[c] = uint8_t(ch.cnt);
-        t.chunk_nfeat[c] = uint8_t(nfeat);
-        t.max_nfeat = std::max(t.max_nfeat, nfeat);
         uint8_t *bf = out.bfwd.data() + size_t(c) * TC_BFWD_BYTES, *br = out.brev.data() + size_t(c) * TC_BREV_BYTES;
         for (int i = 0; i < ch.cnt; ++i) {
             const double *row = matrix.data() + size_t(ch.first + i) * Hp;
@@ -646,7 +644,9 @@ int gl_tc_build_tables(const GLStatic &st, int gamma, const std::vector<double> 
             int f = Hp;
             for (int j = 0; j < Hp; ++j)
                 for (int k = j + 1; k < Hp; ++k, ++f) member[f] = (row[j] != 0.0 && row[k] != 0.0) ? 1 : 0;
-            if (cnt_members != ch.g) { set_error("tensor-core state kernel: states are not ordered by size"); return PET_EINVAL; }
+            if (cnt_members < 2 || cnt_members > gamma) { set_error("tensor-core state kernel: unexpected state size %d", cnt_members); return PET_EINVAL; }
+            const int nfeat = cnt_members + cnt_members * (cnt_members - 1) / 2;
+            t.max_nfeat = std::max(t.max_nfeat, nfeat);
             for (int ft = 0; ft < nf; ++ft) {
                 if (!member[ft]) continue;
                 // forward operand: row = state i, K = [feature (weight 1) | feature (weight 128)], K chunk major

@@ -17,7 +17,6 @@ struct GLTc {                                      // kernel parameter
     int n_chunks, n_feat, max_nfeat;
     const uint8_t *bfwd, *brev;                    // device images, n_chunks x TC_BFWD_BYTES / TC_BREV_BYTES
     uint8_t chunk_cnt[TC_MAX_CHUNKS];              // valid states of a chunk (the rest is padding)
-    uint8_t chunk_nfeat[TC_MAX_CHUNKS];            // features per state of the chunk: g + g (g - 1) / 2
     uint8_t feat[2 * TC_KF];                       // feature f -> candidate positions (j, k); j == k: linear term
 };
 
