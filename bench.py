@@ -305,7 +305,7 @@ def synth_shard(model, n_local, first, dev):
 def ncu_traffic():
     """DRAM bytes per launch of the sliced GEMM kernel (mean of the score and the statistics shape, the two launches
     the roofline line averages over) and of the whole EM iteration, from the committed ncu launch list of one step
-    (profiles/r02_launches_step_n1.csv: dram__bytes_read.sum + dram__bytes_write.sum per launch); None if not recorded."""
+    (profiles/r02d_launches_step_n1.csv: dram__bytes_read.sum + dram__bytes_write.sum per launch); None if not recorded."""
     try:
         t = json.load(open(os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")))
         return t["oz_gemm_bytes_per_launch"], t["step_dram_bytes"]
@@ -496,8 +496,8 @@ def run_gpu(args):
                         "achieved": achieved, "peak": int8_peak / pairs, "unit": "TFLOP/s", "frac": achieved * pairs / int8_peak,
                         "pipe_achieved_tops": achieved * pairs, "pipe_peak_tops": int8_peak,
                         "pipe_nominal_tops": 4500.0, "frac_of_nominal": achieved * pairs / 4500.0,
-                        "ncu_tensor_pipe_active": {"score_shape": 0.66, "statistics_shape": 0.73,
-                                                   "source": "profiles/r01i_ncu_oz_gemm_kernel.txt (main loop unchanged in round 2)"},
+                        "ncu_tensor_pipe_active": {"score_shape": 0.64, "statistics_shape": 0.80,
+                                                   "source": "profiles/r02d_ncu_hot_kernels.txt (oz::gemm_kernel<6,3,3,64> / <7,2,4,64>)"},
                         "peak_source": int8_src + ", divided by the %.1f slice products (mean of the two GEMMs); cuBLAS DGEMM measured in this run: %.1f TFLOP/s"
                                        % (pairs, peak),
                         "traffic": ncu_traffic()[0], "step_traffic_bytes": ncu_traffic()[1],

@@ -13,3 +13,5 @@ timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__byte
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:'gemm_kernel|gl_state_tc|gl_row_threshold|gl_post_slice_kernel' -c 8 \
   -o gpurun_out/final/hot python tools/profile_step.py 75776 1 > gpurun_out/final/hot.log 2>&1
 tail -2 gpurun_out/final/pytest_gpu.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('SMOKE_OK')" > gpurun_out/final/smoke.log 2>&1; tail -1 gpurun_out/final/smoke.log
+timeout 600 python bench.py --impl reference --steps 2 --warmup 1 2>gpurun_out/final/bench_ref.err | tail -1 > gpurun_out/final/bench_reference_arm.json; head -c 300 gpurun_out/final/bench_reference_arm.json

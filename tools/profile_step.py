@@ -12,7 +12,7 @@ from prosper_b200.em.camodels.bsc_et import BSC_ET  # noqa: E402
 
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 16384
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 2
-D, H, Hp, g = 676, 1000, 12, 5
+D, H, Hp, g = 676, 1000, 12, int(os.environ.get('PET_PROF_GAMMA', 5))
 dev = torch.device('cuda', 0)
 gen = torch.Generator(device=dev); gen.manual_seed(5)
 rng = np.random.RandomState(5)
@@ -23,6 +23,8 @@ yt = s @ Wg.T + torch.randn((N, D), dtype=torch.float64, device=dev, generator=g
 W0 = (yt.mean(0)[:, None] + 0.25 * torch.randn((D, H), dtype=torch.float64, device=dev, generator=gen)).cpu().numpy()
 params = {'W': W0, 'pi': 1. / H, 'sigma': 1.2}
 m = BSC_ET(D, H, Hp, g)
+if os.environ.get('PET_PROF_FORCE_TC'):
+    m.engine.set_state_kernel(2)
 an = DictAnneal(T=1.0, Ncut_factor=0.0, anneal_prior=False)
 for _ in range(reps):
     new = m._fused_step(an, dict(params), {'y': yt})
