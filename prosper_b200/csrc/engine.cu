@@ -129,6 +129,7 @@ struct pet_engine {
     // single-evaluation truncated iteration (GLF_DEFER_STATS): parked pair sums (H'(H'-1)/2, pairs_ld), which chunks of the
     // last log-denominator sweep parked their statistics, and whether that record is still current
     double *pairs = nullptr; int64_t pairs_ld = 0;
+    int *tile_counter = nullptr;                               // dynamic tile hand-out of the tensor-core state kernel
     std::vector<char> chunk_deferred; bool defer_valid = false;
     bool yy_valid = false, wmu_nonzero = false; int cand_state = 0;
     std::vector<double> mu_applied;
@@ -195,6 +196,7 @@ extern "C" void pet_destroy(pet_engine *e) {
     cudaDeviceSynchronize();
     free_dev(e->Y); free_dev(e->yy); free_dev(e->cand); free_dev(e->lse); free_dev(e->rs); free_dev(e->ywc); free_dev(e->scl);
     free_dev(e->pairs);
+    if (e->tile_counter) cudaFree(e->tile_counter);
     free_dev(e->Wt); free_dev(e->G); free_dev(e->wn2); free_dev(e->invn); free_dev(e->Wtmp); free_dev(e->mu_dev); free_dev(e->wmu); free_dev(e->mu_full);
     free_dev(e->YW); free_dev(e->Sbuf); free_dev(e->S2buf); free_dev(e->gemm_work);
     free_dev(e->solveA); free_dev(e->solve_work); free_dev(e->s2sum);
@@ -453,7 +455,10 @@ extern "C" int pet_stage_times_ms(pet_engine *e, double *out) {
 // ---- data ------------------------------------------------------------------------------
 // Chunk length for a shard of n datapoints and the buffers that scale with it.  Long chunks amortise the wave tails of
 // every kernel of the pipeline (measured at the north-star shape: 83 ms per iteration with 128 MB chunks of <S>, 73 ms
-// with 600 MB), so the default aims at ~600 MB of <S> per chunk, bounded by the shard itself; the length is then tuned
+// with 600 MB in round 1), so the default aims at ~600 MB of <S> per chunk (75 776 datapoints at H = 1000), bounded by
+// the shard itself.  (Round 2: 1200 MB chunks looked 2 ms faster until the state kernel handed out its tiles
+// dynamically -- it was load imbalance between CTAs with 4 instead of 8 tiles each; with that fixed 600 and 1200 MB are
+// equal, 45.0 / 44.8 ms, and the shorter chunk overlaps a host upload better.)  The length is then tuned
 // so that the 128 x 64 tiles of the score GEMM fill whole waves of sm_count persistent CTAs.
 static int size_chunks(pet_engine *e, int64_t n) {
     int64_t cr;
@@ -884,6 +889,8 @@ static int sweep_gl(pet_engine *e, const pet_anneal *a, const pet_params *p, int
         e->chunk_deferred.assign(nchunks, 0);
     }
     ga.pairs = e->pairs; ga.pairs_ld = e->pairs_ld;
+    if (!e->tile_counter) PET_CUDA(cudaMalloc(&e->tile_counter, 64));
+    ga.tile_counter = e->tile_counter;
     for (int64_t c = 0; c < nchunks; ++c) {
         const int64_t r0 = e->chunk_start[c], rows = e->chunk_start[c + 1] - r0;
         PET_CHECK(ensure_chunk_inputs(e, c, r0, rows, st));

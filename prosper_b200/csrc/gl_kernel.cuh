@@ -97,6 +97,7 @@ struct GLArgs {
     double *rs;                   // (n, 4+PET_MAXV) row-kernel partial sums {m1, Z1, sig1, -, cnt1[..]}, global index
     double *ywc;                  // (n, Hp) scores of the candidates, global index
     double *scl;                  // (n, 1+PET_MAXHP) {scale of the singleton row, candidate marginals}, global index
+    int *tile_counter;            // tensor-core state kernel: next 128-datapoint tile to hand out (zeroed before the launch)
     double *pairs;                // GLF_DEFER_STATS: (H'(H'-1)/2, pairs_ld) normalised pair sums <s_j s_k>, feature major, global index
     int64_t pairs_ld;
 };
