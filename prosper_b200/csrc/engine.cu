@@ -456,8 +456,8 @@ extern "C" int pet_stage_times_ms(pet_engine *e, double *out) {
 // Chunk length for a shard of n datapoints and the buffers that scale with it.  Long chunks amortise the wave tails of
 // every kernel of the pipeline (measured at the north-star shape: 83 ms per iteration with 128 MB chunks of <S>, 73 ms
 // with 600 MB in round 1), so the default aims at ~600 MB of <S> per chunk (75 776 datapoints at H = 1000), bounded by
-// the shard itself.  (Round 2: 1200 MB chunks looked 2 ms faster until the state kernel handed out its tiles
-// dynamically -- it was load imbalance between CTAs with 4 instead of 8 tiles each; with that fixed 600 and 1200 MB are
+// the shard itself.  (Round 2: 1200 MB chunks looked 2 ms faster; the cause was the wave quantisation of the state
+// kernel's 128-datapoint tiles at the chunk length the tuner had picked, see below -- with that fixed 600 and 1200 MB are
 // equal, 45.0 / 44.8 ms, and the shorter chunk overlaps a host upload better.)  The length is then tuned
 // so that the 128 x 64 tiles of the score GEMM fill whole waves of sm_count persistent CTAs.
 static int size_chunks(pet_engine *e, int64_t n) {
@@ -473,7 +473,11 @@ static int size_chunks(pet_engine *e, int64_t n) {
             int64_t best = cr;
             for (int64_t c = round_up(target * 3 / 4, 128); c <= target * 5 / 4; c += 128) {
                 const int64_t tiles = (c / 128) * ntile, waves = ceil_div(tiles, e->sm_count);
-                const double eff = double(tiles) / double(waves * e->sm_count);
+                // ... and the 128-datapoint tiles of the tensor-core state kernel (one CTA per SM) whole waves as well:
+                // 80 512 rows = 629 tiles = 4.25 waves cost that kernel 10.2 ms per iteration, 75 776 = 4 waves 8.9 ms
+                const int64_t stiles = c / 128, swaves = ceil_div(stiles, e->sm_count);
+                const double eff = double(tiles) / double(waves * e->sm_count) *
+                                   (e->tc_ok ? double(stiles) / double(swaves * e->sm_count) : 1.0);
                 if (eff > best_eff + 1e-9 || (eff > best_eff - 1e-9 && llabs(c - target) < llabs(best - target))) { best_eff = eff; best = c; }
             }
             cr = best;
