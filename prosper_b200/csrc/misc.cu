@@ -172,11 +172,49 @@ __global__ void ksel_pick_kernel(unsigned long long *state, int pass, double *ou
     state[2 + threadIdx.x] = 0ull;
 }
 
+// the same select for small arrays in ONE launch (the bars configurations are launch bound: 17 launches -> 1)
+constexpr int KSEL_SMALL_N = 65536;
+__global__ void __launch_bounds__(1024) ksel_small_kernel(const double *v, int n, unsigned long long k, double *out) {
+    __shared__ unsigned int h[256];
+    __shared__ unsigned long long s_prefix, s_k;
+    if (threadIdx.x == 0) { s_prefix = 0ull; s_k = k; }
+    for (int pass = 0; pass < 8; ++pass) {
+        if (threadIdx.x < 256) h[threadIdx.x] = 0u;
+        __syncthreads();
+        const int shift = 56 - 8 * pass;
+        const unsigned long long prefix = s_prefix;
+        const unsigned long long mask = pass == 0 ? 0ull : (~0ull << (shift + 8));
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            const unsigned long long key = key_of(v[i]);
+            if ((key & mask) == prefix) atomicAdd(&h[(key >> shift) & 0xFF], 1u);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned long long kk = s_k, cum = 0;
+            int d = 255;
+            for (; d > 0; --d) {
+                const unsigned long long c = h[d];
+                if (cum + c >= kk) break;
+                cum += c;
+            }
+            s_k = kk - cum;
+            s_prefix = prefix | ((unsigned long long)d << shift);
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *out = val_of(s_prefix);
+}
+
 int kth_largest(const double *vals, int64_t n, int64_t k, double *out, unsigned long long *state, int sm_count,
                 cudaStream_t st) {
     if (n <= 0 || k < 1 || k > n) {
         set_error("kth_largest: need 1 <= k <= n (k=%lld, n=%lld)", (long long)k, (long long)n);
         return PET_EINVAL;
+    }
+    if (n <= KSEL_SMALL_N) {
+        ksel_small_kernel<<<1, 1024, 0, st>>>(vals, int(n), (unsigned long long)k, out);
+        PET_LAUNCH_CHECK();
+        return PET_OK;
     }
     ksel_init_kernel<<<1, 256, 0, st>>>(state, (unsigned long long)k);
     PET_LAUNCH_CHECK();

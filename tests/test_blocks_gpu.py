@@ -104,7 +104,7 @@ def test_spd_solve_dead_unit_gives_lstsq_answer(lib, dev, stacked):
     assert rel_err(Bd.cpu().numpy(), ref) < 1e-10
 
 
-@pytest.mark.parametrize("n,k", [(1, 1), (1000, 1), (1000, 1000), (1000, 337), (1 << 20, 12345)])
+@pytest.mark.parametrize("n,k", [(1, 1), (1000, 1), (1000, 1000), (1000, 337), (65536, 40000), (65537, 40000), (1 << 20, 12345)])
 def test_kth_largest_bit_exact(dev, n, k):
     from prosper_b200 import _lib
     from prosper_b200.em.camodels import Engine
